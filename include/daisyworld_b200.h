@@ -1,0 +1,160 @@
+/*
+ * daisyworld_b200.h -- C ABI of the B200-native RLDaisyWorld simulation step.
+ *
+ * The reference (riveSunder/therldaisyworld) has no FFI: its boundary is the Python surface of
+ * class RLDaisyWorld (daisy/daisy_world_rl.py:13-501).  Each entry point below names the reference
+ * method / attribute it stands in for.  The Python drop-in (therldaisyworld_b200/env.py) binds these
+ * symbols with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success, <0 on error (DW_E_*); text via dw_last_error().
+ *   - the caller owns every host buffer; the library owns all device memory.
+ *   - state-changing calls are enqueued on the handle's CUDA stream (dw_set_stream; default: the
+ *     legacy default stream) and return without waiting; getters synchronise that stream.
+ *   - a handle is bound to one CUDA device, is not thread-safe; distinct handles are independent.
+ *   - no host RNG, no global state, no CPU fallback: if no CUDA device is usable dw_create fails.
+ *   - array layouts are the reference's: grid[B,7,N,N] f64 (channels: 0 bare, 1 light, 2 dark,
+ *     3 T, 4 T_light/agent stamp, 5 T_dark, 6 unused), agent_indices[B,n,2] i64 (x = axis -2,
+ *     y = axis -1), agent_states[B,n] f64, obs[B,n,7,3,3] f64.
+ */
+#ifndef DAISYWORLD_B200_H
+#define DAISYWORLD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DW_ABI_VERSION 1
+
+enum {
+    DW_OK = 0,
+    DW_E_INVALID = -1,      /* bad argument / shape */
+    DW_E_CUDA = -2,         /* CUDA runtime error (message has the CUDA string) */
+    DW_E_UNSUPPORTED = -3,  /* configuration outside what the kernels implement */
+    DW_E_STATE = -4         /* call not valid in the current state */
+};
+
+/* Policies executed on the device inside dw_step_policy / dw_run. */
+enum {
+    DW_POLICY_NONE = 0,       /* step(None): all-zero action when n_agents>0 (daisy_world_rl.py:477-478) */
+    DW_POLICY_GREEDY = 1,     /* Greedy(eps=0), argmax branch (daisy/agents/greedy.py:16-30) */
+    DW_POLICY_ANTIGREEDY = 2, /* Greedy(greedy=False), argmin branch (greedy.py:27-28) */
+    DW_POLICY_REPLAY = 3,     /* actions[K,B,n] supplied by the caller (stochastic policies replayed) */
+    DW_POLICY_RANDOM = 4      /* uniform 0..8 per agent-step from a device counter RNG (throughput runs;
+                                 not stream-compatible with numpy's MT19937) */
+};
+
+/* dw_get_diag selectors: unrounded side-effect attributes of the last forward
+   (daisy_world_rl.py:345-347,373,404,415-419). Each is [B,1,N,N] except growth [B,2,N,N]. */
+enum {
+    DW_DIAG_TEMP = 0, DW_DIAG_TEMP_LIGHT = 1, DW_DIAG_TEMP_DARK = 2, DW_DIAG_TEMP_EFFECTIVE = 3,
+    DW_DIAG_BETA = 4, DW_DIAG_BETA_L = 5, DW_DIAG_BETA_D = 6, DW_DIAG_GROWTH = 7
+};
+
+/* Model constants: the mutable public attributes of RLDaisyWorld (daisy_world_rl.py:32-77) that the
+   step reads.  batch/dim/n_agents fix the shapes of a handle (the reference re-reads them at reset();
+   the Python front re-creates the handle there). */
+typedef struct dw_config {
+    int32_t batch;        /* env.batch_size (worlds owned by this handle / rank) */
+    int32_t dim;          /* env.dim  (grid side N) */
+    int32_t n_agents;     /* env.n_agents */
+    int32_t device;       /* CUDA device ordinal */
+    double p, g, S, sigma, gamma, q, q2, temp_optimal, dt, agent_gamma;
+    double albedo_bare, albedo_light, albedo_dark;
+    double daisy_kernel[9];     /* env.daisy_kernel, row-major 3x3 (daisy_world_rl.py:270-273) */
+    double adjacent_kernel[9];  /* env.adjacent_albedo_kernel (daisy_world_rl.py:278-281) */
+    double obs_mask[9];         /* env.neighborhood for kr=1 (daisy/nn/functional.py:93-103) */
+} dw_config;
+
+/* Luminosity clock: env.L, dL, min_L, max_L, ddL, step_count, ramp_period, ramp_up_down
+   (daisy_world_rl.py:329-332, 463-473). Shared by every world of the handle. */
+typedef struct dw_clock {
+    double L, dL, min_L, max_L, ddL;
+    int64_t step_count, ramp_period;
+    int32_t ramp_up_down, _pad;
+} dw_clock;
+
+/* Result of dw_run. */
+typedef struct dw_run_result {
+    int64_t steps_run;        /* env steps executed */
+    int64_t worlds_alive;     /* worlds with max(grid[:,1:3]) > 0.005 after the last step */
+    int32_t all_done_hit;     /* 1 if the run stopped because every world was grid_done in one step */
+    int32_t _pad;
+} dw_run_result;
+
+typedef struct dw_handle dw_handle;
+
+int dw_abi_version(void);
+const char *dw_last_error(const dw_handle *h);   /* h may be NULL: error of the last failed dw_create */
+
+/* RLDaisyWorld.__init__ shapes + constants (daisy_world_rl.py:15-83). Fails if no CUDA device. */
+int dw_create(const dw_config *cfg, dw_handle **out);
+int dw_destroy(dw_handle *h);
+/* attribute mutation after construction (env.albedo_dark = ..., env.dt = ...); shapes must not change */
+int dw_set_config(dw_handle *h, const dw_config *cfg);
+int dw_set_clock(dw_handle *h, const dw_clock *clk);
+int dw_get_clock(dw_handle *h, dw_clock *clk);
+/* luminosity the last forward pass used (the L behind env.temp / env.dead_temp, daisy_world_rl.py:403-416) */
+int dw_get_last_L(dw_handle *h, double *L);
+int dw_set_stream(dw_handle *h, void *cuda_stream);
+
+/* env.grid / env.agent_indices / env.agent_states assignment (any of the pointers may be NULL = keep).
+   Host -> device; pinned host memory makes the copy asynchronous. */
+int dw_upload_state(dw_handle *h, const double *grid, const int64_t *agent_indices, const double *agent_states);
+
+/* initialize_grid's field fill (daisy_world_rl.py:304-324): ch0 = p-l-d and ch3..5 = UNROUNDED T, T_light,
+   T_dark of the uploaded covers at the current clock L. Called by reset() after dw_upload_state. */
+int dw_init_temperatures(dw_handle *h);
+
+/* RLDaisyWorld.step(action) (daisy_world_rl.py:475-497): update_agents -> forward -> get_obs ->
+   reward/done -> update_L, all on the device.  action: host int64 [ab,am] (ab<=B, am<=n, values 0..8)
+   or NULL for step(None). */
+int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t am);
+/* Same step with the action chosen on the device by DW_POLICY_* (Greedy.__call__ fused in). */
+int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed);
+
+/* Pieces of step(), exposed because callers use them standalone:
+   RLDaisyWorld.update_agents(action) (:181-244) */
+int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab, int32_t am);
+/* RLDaisyWorld.forward(grid) (:434-461) on a caller grid (host in, host out) with the handle's agents/L;
+   writes the mutated ch0 back into grid_in like the reference (:381). Does not advance the state. */
+int dw_forward(dw_handle *h, double *grid_in, double *grid_out);
+/* RLDaisyWorld.get_obs(agent_indices) (:246-263) at caller-supplied positions [b,m,2] -> obs[b,m,7,3,3] */
+int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t b, int32_t m, double *obs);
+
+/* Getters (device -> host, synchronise). */
+int dw_get_grid(dw_handle *h, double *grid);                              /* env.grid */
+int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states);
+int dw_get_obs(dw_handle *h, double *obs);                                /* obs of the last step / current state */
+int dw_get_reward_done(dw_handle *h, double *reward, uint8_t *done);      /* [B,n] (or [B,2] when n_agents==0) */
+int dw_get_diag(dw_handle *h, int32_t which, double *out);                /* env.temp, env.beta_l, env.growth ... */
+
+/* K fused steps with an on-device policy and the notebook lifespan counters
+   (notebooks/greedy_longevity_abatement.ipynb cell 2): done_at[b] += !grid_done, agents_done_at[b,i] += !done.
+   actions: host int8 [K,B,n] for DW_POLICY_REPLAY, else NULL.  stop_all_done: stop after the first step in
+   which every world of this handle is grid_done (the notebook's loop condition). */
+int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed, int32_t stop_all_done,
+           dw_run_result *res);
+/* Multi-rank variant: run exactly `K` (<=64) steps and return, per step, whether every world of THIS handle
+   was grid_done (bit j of *done_mask = step j); the caller ANDs masks across ranks and decides. */
+int dw_run_chunk(dw_handle *h, int32_t K, int32_t policy, const int8_t *actions, uint64_t seed, uint64_t *done_mask);
+int dw_reset_lifespans(dw_handle *h);
+int dw_get_lifespans(dw_handle *h, int64_t *done_at /*[B]*/, int64_t *agents_done_at /*[B,n]*/);
+/* Ensemble statistics of the lifespan counters on the DEVICE, for an NCCL all-reduce by the caller:
+   out_dev (device pointer, 8 doubles) = {count, sum life, sum life^2, n_agents_total, sum agent_life,
+   sum agent_life^2, worlds_alive, 0}. */
+int dw_lifespan_stats_device(dw_handle *h, double *out_dev);
+
+/* Device-side state checkpoint (grid/lattice, agents, clock, counters): used to rewind a chunk and by the
+   benchmark to restart from the same initial state without host traffic. */
+int dw_checkpoint_save(dw_handle *h);
+int dw_checkpoint_restore(dw_handle *h);
+
+int dw_synchronize(dw_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAISYWORLD_B200_H */

@@ -1,0 +1,78 @@
+"""GPU parity of dw_run (K fused steps, on-device policy, lifespan counters) against the reference-recorded
+fixtures and the C oracle.  Integer lifespans must be identical; grids value-identical."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, product_env_from_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("greedy_n16_b4_todeath", "greedy"), ("antigreedy_n8_b16_todeath", "antigreedy"),
+         ("random_n8_b8_todeath", "replay"), ("greedy_n5_b3_n2_todeath", "greedy"),
+         ("cfg1_n16_b1_noagents_todeath", "none"), ("halfrandom_n16_b4_300", "replay"),
+         ("greedy_n64_b2_120", "greedy"), ("neutral_antigreedy_n64_b1_40", "antigreedy"),
+         ("randint_n7_b3_n16_200", "replay"), ("greedy_n17_b2_params_200", "greedy"),
+         ("none_n16_b2_n4_40", "none"), ("rampupdown_n8_b2_100", "greedy")]
+
+
+@pytest.mark.parametrize("name,policy", CASES)
+def test_run_reproduces_reference_lifespans_and_final_state(name, policy):
+    z, meta = load_golden(name)
+    env = product_env_from_golden(z, meta)
+    env.reset_lifespans()
+    K = meta["steps"]
+    actions = z["actions"] if policy == "replay" else None
+    steps, alive, hit = env.run(100000 if meta["to_death"] and policy != "replay" else K, policy=policy, actions=actions,
+                                stop_all_done=meta["to_death"])
+    assert steps == K
+    if meta["to_death"]:
+        assert hit and alive == 0
+    done_at, agents_done_at = env.lifespans()
+    np.testing.assert_array_equal(done_at, z["done_at"])
+    np.testing.assert_array_equal(agents_done_at, z["agents_done_at"])
+    np.testing.assert_array_equal(env.agent_indices, z["agent_indices"][-1])
+    np.testing.assert_array_equal(env.agent_states, z["agent_states"][-1])
+    np.testing.assert_array_equal(env.grid, z["ckpt_grid"][-1])
+    np.testing.assert_array_equal(env.get_obs(env.agent_indices), z["ckpt_obs"][-1])
+    assert env.L == z["L"][K] and env.step_count == meta["final_step_count"]
+    np.testing.assert_allclose(env.temp, z["diag_temp"], rtol=1e-9)
+    np.testing.assert_allclose(env.growth, z["diag_growth"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,policy", [("greedy_n16_b4_todeath", "greedy"), ("greedy_n64_b2_120", "greedy"),
+                                         ("random_n8_b8_todeath", "replay")])
+def test_run_in_pieces_equals_single_steps(name, policy):
+    """Chunk boundaries and mixing run()/step() must not change anything: compare checkpoints on the way."""
+    z, meta = load_golden(name)
+    env = product_env_from_golden(z, meta)
+    t = 0
+    for s, i in sorted((int(s), i) for i, s in enumerate(z["ckpt_steps"])):
+        k = s - t
+        if k:
+            acts = z["actions"][t:s] if policy == "replay" else None
+            env.run(k, policy=policy, actions=acts)
+            t = s
+        np.testing.assert_array_equal(env.grid, z["ckpt_grid"][i])
+        np.testing.assert_array_equal(env.get_obs(env.agent_indices), z["ckpt_obs"][i])
+        if t < meta["steps"]:   # interleave one materialising step
+            a = z["actions"][t]
+            obs, reward, done, _ = env.step(None if a[0, 0, 0] == -1 else a)
+            np.testing.assert_array_equal(reward, z["reward"][t])
+            t += 1
+
+
+def test_run_large_ensemble_matches_c_oracle():
+    """BASELINE config 2 shape at reduced batch (64 worlds, 64x64, greedy) against the C oracle, full life."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_c import COracleWorld
+    np.random.seed(13)
+    env = RLDaisyWorld(grid_dimension=64)
+    env.batch_size = 64
+    env.reset()
+    ref = COracleWorld(env)
+    done_at, agents_done_at = env.simulate_lifespan(policy="greedy")
+    steps, d2, a2 = ref.run(100000, "greedy", stop_all_done=True)
+    assert env.step_count == steps
+    np.testing.assert_array_equal(done_at, d2)
+    np.testing.assert_array_equal(agents_done_at, a2)
+    np.testing.assert_array_equal(env.grid, ref.grid)

@@ -1,0 +1,182 @@
+"""GPU parity of the single-step (materialising) CUDA path, called through the C-ABI via the drop-in class.
+
+Bar (BASELINE north_star): fp64 fields within 1e-9 relative of the reference; in practice -- and asserted
+here -- value-identical (==) to the reference-recorded fixtures and to the C oracle, because the kernels
+follow the oracle's IEEE operation order."""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+from helpers import golden_action, load_golden, product_env_from_golden, apply_attrs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_step_replays_reference_trajectory(name):
+    z, meta = load_golden(name)
+    env = product_env_from_golden(z, meta)
+    np.testing.assert_array_equal(env.get_obs(env.agent_indices), z["init_obs"])
+    ck = {int(s): i for i, s in enumerate(z["ckpt_steps"])}
+    for t in range(meta["steps"]):
+        assert env.L == z["L"][t]
+        obs, reward, done, info = env.step(golden_action(z, t))
+        assert info == {}
+        np.testing.assert_array_equal(reward, z["reward"][t])
+        np.testing.assert_array_equal(done, z["done"][t])
+        assert reward.dtype == z["reward"][t].dtype and done.dtype == np.bool_
+        if (t + 1) in ck or t % 37 == 0:
+            np.testing.assert_array_equal(env.agent_indices, z["agent_indices"][t])
+            np.testing.assert_array_equal(env.agent_states, z["agent_states"][t])
+            np.testing.assert_array_equal(env.grid.sum(axis=(-2, -1)), z["chan_sum"][t])
+        if (t + 1) in ck:
+            np.testing.assert_array_equal(env.grid, z["ckpt_grid"][ck[t + 1]])
+            np.testing.assert_array_equal(obs, z["ckpt_obs"][ck[t + 1]])
+    assert env.L == z["L"][meta["steps"]]
+    assert env.step_count == meta["final_step_count"]
+    np.testing.assert_array_equal(env.agent_indices, z["agent_indices"][-1])
+    np.testing.assert_array_equal(env.agent_states, z["agent_states"][-1])
+    for key, attr in [("diag_temp", "temp"), ("diag_temp_light", "temp_light"), ("diag_temp_dark", "temp_dark"),
+                      ("diag_temp_effective", "temp_effective"), ("diag_dead_temp", "dead_temp"),
+                      ("diag_beta", "beta"), ("diag_beta_l", "beta_l"), ("diag_beta_d", "beta_d"),
+                      ("diag_growth", "growth")]:
+        got = getattr(env, attr)
+        assert got.shape == z[key].shape, key
+        np.testing.assert_allclose(got, z[key], rtol=1e-9, atol=1e-12, err_msg=key)   # FFT round-off in the reference
+
+
+@pytest.mark.parametrize("name", ["cfg1_n16_b1_noagents_todeath", "greedy_n16_b4_todeath", "randint_n7_b3_n16_200",
+                                  "greedy_n17_b2_params_200", "greedy_n64_b2_120"])
+def test_reset_reproduces_reference_rng_order_and_init_fields(name):
+    from therldaisyworld_b200 import RLDaisyWorld
+    z, meta = load_golden(name)
+    np.random.seed(meta["seed"])
+    env = RLDaisyWorld(**meta["ctor"])
+    apply_attrs(env, meta["attrs"])
+    obs = env.reset()
+    np.testing.assert_array_equal(env.agent_indices, z["init_agent_indices"])
+    np.testing.assert_array_equal(env.agent_states, z["init_agent_states"])
+    np.testing.assert_array_equal(env.grid[:, :3], z["init_grid"][:, :3])
+    np.testing.assert_array_equal(env.grid[:, 6], 0.0)
+    np.testing.assert_allclose(env.grid[:, 3:6], z["init_grid"][:, 3:6], rtol=1e-12)   # unrounded; FFT vs stencil
+    np.testing.assert_allclose(obs, z["init_obs"], rtol=1e-12)
+    assert env.step_count == 0 and env.L == env.min_L
+
+
+def test_offlattice_states_match_c_oracle_bitwise():
+    """Arbitrary covers, odd/small N (where the reference's FFT path fails), many agents, every action."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_c import COracleWorld
+    rng = np.random.RandomState(7)
+    for N, B, n in [(1, 2, 1), (2, 3, 2), (3, 2, 1), (4, 2, 3), (6, 3, 2), (9, 2, 5), (33, 2, 7), (64, 3, 4), (100, 1, 9)]:
+        np.random.seed(N)
+        env = RLDaisyWorld(grid_dimension=N, n_agents=n)
+        env.batch_size = B
+        env.reset()
+        g = env.grid.copy()
+        g[:, 1] = rng.rand(B, N, N) * 0.6
+        g[:, 2] = rng.rand(B, N, N) * 0.4
+        env.grid = g
+        w = COracleWorld(env, grid=g)
+        for t in range(6):
+            action = rng.randint(9, size=(B, n, 1))
+            o1, r1, d1, _ = env.step(action)
+            o2, r2, d2, _ = w.step(action)
+            np.testing.assert_array_equal(env.grid, w.grid)
+            np.testing.assert_array_equal(o1, o2)
+            np.testing.assert_array_equal(r1, r2)
+            np.testing.assert_array_equal(d1, d2)
+            np.testing.assert_array_equal(env.agent_indices, w.agent_indices)
+            np.testing.assert_array_equal(env.agent_states[..., 0], w.agent_states.reshape(B, n))
+        # unrounded diagnostics of the last forward are bit-identical too (same IEEE op order)
+        diag = COracleWorld(env, grid=None)   # snapshot of current product state
+        # recompute oracle diagnostics from the state BEFORE the last step is not available; instead check a
+        # standalone forward on the current grid
+        cur = env.grid.copy()
+        out = env.forward(cur.copy())
+        wd = COracleWorld(env, grid=cur)
+        d = wd.forward_diag()
+        np.testing.assert_array_equal(env.temp, d[:, 0:1])
+        np.testing.assert_array_equal(env.temp_light, d[:, 1:2])
+        np.testing.assert_array_equal(env.temp_dark, d[:, 2:3])
+        np.testing.assert_array_equal(env.temp_effective, d[:, 3:4])
+        np.testing.assert_array_equal(env.beta, d[:, 4:5])
+        np.testing.assert_array_equal(env.beta_l, d[:, 5:6])
+        np.testing.assert_array_equal(env.beta_d, d[:, 6:7])
+        np.testing.assert_array_equal(env.growth, d[:, 7:9])
+        wd.step(None) if n == 0 else None
+        assert out.shape == cur.shape
+
+
+def test_reference_smoke_tests_restated():
+    """tests/daisy/test_daisy_world_rl.py:14-68 of the reference, against the drop-in."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    env = RLDaisyWorld()
+    a = env.grid
+    b = env.forward(a)
+    for ii in range(9):
+        obs, reward, done, info = env.step(np.array([[[ii]]]))   # (1,1,1) action while B=32, n=4
+    assert not done.mean()
+    assert type(info) == dict
+    assert 0.0 <= reward.mean()
+    assert a.shape == b.shape
+    assert obs.shape[1] == env.n_agents and obs.shape[0] == env.batch_size
+
+    env = RLDaisyWorld()
+    for c in (3, 4, 5):
+        assert 0 < env.grid[:, c].mean()
+    env.reset()
+    for c in (3, 4, 5):
+        assert 0 < env.grid[:, c].mean()
+    obs, reward, done, info = env.step()
+    for c in (3, 4, 5):
+        assert 0 < env.grid[:, c].mean() and 0 < obs[:, :, c].mean()
+    obs, reward, done, info = env.step(np.random.randint(9, size=(env.batch_size, env.n_agents, 1)))
+    for c in (3, 4, 5):
+        assert 0 < env.grid[:, c].mean() and 0 < obs[:, :, c].mean()
+
+
+def test_host_mirror_round_trip_and_attribute_mutation():
+    """Callers mutate attributes and arrays between steps; the device must see it."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_c import COracleWorld
+    np.random.seed(3)
+    env = RLDaisyWorld(grid_dimension=8, n_agents=2)
+    env.batch_size = 3
+    env.reset()
+    g = env.grid
+    g[:, 1:3] *= 0.5                      # in-place edit of the array we were handed
+    env.agent_states[:, 0, 0] = 0.07      # nearly starved agent
+    env.albedo_dark = 0.3
+    env.dt = 0.5
+    env.L = 1.1
+    w = COracleWorld(env, grid=g)
+    a = np.full((3, 2, 1), 6)
+    o1, r1, d1, _ = env.step(a)
+    o2, r2, d2, _ = w.step(a)
+    np.testing.assert_array_equal(env.grid, w.grid)
+    np.testing.assert_array_equal(o1, o2)
+    np.testing.assert_array_equal(r1, r2)
+    np.testing.assert_array_equal(d1, d2)
+    assert env.L == w.L and env.step_count == w.step_count
+
+
+def test_update_agents_and_get_obs_standalone():
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_numpy import OracleDaisyWorld
+    np.random.seed(5)
+    env = RLDaisyWorld(grid_dimension=9, n_agents=3)
+    st = np.random.get_state()
+    np.random.seed(5)
+    ref = OracleDaisyWorld(grid_dimension=9, n_agents=3)
+    np.random.set_state(st)
+    np.testing.assert_array_equal(env.grid[:, :3], ref.grid[:, :3])
+    ref.grid = env.grid.copy()
+    action = np.array([[[5], [8], [2]]] * env.batch_size)
+    env.update_agents(action)
+    ref.update_agents(action)
+    np.testing.assert_array_equal(env.grid, ref.grid)
+    np.testing.assert_array_equal(env.agent_indices, ref.agent_indices)
+    np.testing.assert_array_equal(env.agent_states, ref.agent_states)
+    pos = np.random.randint(9, size=(5, 6, 2))
+    np.testing.assert_array_equal(env.get_obs(pos), ref.get_obs(pos))

@@ -1,0 +1,102 @@
+"""ctypes binding of include/daisyworld_b200.h.  No fallback: if the CUDA library is missing or no
+CUDA device is usable, importing works but creating an environment raises."""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libdaisyworld_b200.so")
+
+DW_POLICY = {"none": 0, "greedy": 1, "antigreedy": 2, "replay": 3, "random": 4}
+DW_DIAG = {"temp": 0, "temp_light": 1, "temp_dark": 2, "temp_effective": 3, "beta": 4, "beta_l": 5, "beta_d": 6,
+           "growth": 7}
+
+
+class DwConfig(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("dim", C.c_int32), ("n_agents", C.c_int32), ("device", C.c_int32)] + \
+               [(k, C.c_double) for k in ("p", "g", "S", "sigma", "gamma", "q", "q2", "temp_optimal", "dt", "agent_gamma",
+                                          "albedo_bare", "albedo_light", "albedo_dark")] + \
+               [("daisy_kernel", C.c_double * 9), ("adjacent_kernel", C.c_double * 9), ("obs_mask", C.c_double * 9)]
+
+
+class DwClock(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("L", "dL", "min_L", "max_L", "ddL")] + \
+               [("step_count", C.c_int64), ("ramp_period", C.c_int64), ("ramp_up_down", C.c_int32), ("_pad", C.c_int32)]
+
+
+class DwRunResult(C.Structure):
+    _fields_ = [("steps_run", C.c_int64), ("worlds_alive", C.c_int64), ("all_done_hit", C.c_int32), ("_pad", C.c_int32)]
+
+
+# every symbol include/daisyworld_b200.h declares (tests/test_abi.py checks the list against the header)
+SYMBOLS = [
+    "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
+    "dw_set_stream", "dw_upload_state", "dw_init_temperatures", "dw_step", "dw_step_policy", "dw_update_agents",
+    "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
+    "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
+    "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize",
+]
+
+_lib = None
+
+
+class DaisyWorldError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the C-ABI library; raises if it has not been built (python -m therldaisyworld_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DaisyWorldError(f"{LIB_PATH} not found: build it with `python -m therldaisyworld_b200.build` "
+                              "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    pd, pi64, pu8, pi8 = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_int8)
+    sig = {
+        "dw_abi_version": (C.c_int, []),
+        "dw_last_error": (C.c_char_p, [vp]),
+        "dw_create": (C.c_int, [C.POINTER(DwConfig), C.POINTER(vp)]),
+        "dw_destroy": (C.c_int, [vp]),
+        "dw_set_config": (C.c_int, [vp, C.POINTER(DwConfig)]),
+        "dw_set_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
+        "dw_get_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
+        "dw_get_last_L": (C.c_int, [vp, pd]),
+        "dw_set_stream": (C.c_int, [vp, vp]),
+        "dw_upload_state": (C.c_int, [vp, pd, pi64, pd]),
+        "dw_init_temperatures": (C.c_int, [vp]),
+        "dw_step": (C.c_int, [vp, pi64, i32, i32]),
+        "dw_step_policy": (C.c_int, [vp, i32, u64]),
+        "dw_update_agents": (C.c_int, [vp, pi64, i32, i32]),
+        "dw_forward": (C.c_int, [vp, pd, pd]),
+        "dw_get_obs_at": (C.c_int, [vp, pi64, i32, i32, pd]),
+        "dw_get_grid": (C.c_int, [vp, pd]),
+        "dw_get_agents": (C.c_int, [vp, pi64, pd]),
+        "dw_get_obs": (C.c_int, [vp, pd]),
+        "dw_get_reward_done": (C.c_int, [vp, pd, pu8]),
+        "dw_get_diag": (C.c_int, [vp, i32, pd]),
+        "dw_run": (C.c_int, [vp, i64, i32, pi8, u64, i32, C.POINTER(DwRunResult)]),
+        "dw_run_chunk": (C.c_int, [vp, i32, i32, pi8, u64, C.POINTER(u64)]),
+        "dw_reset_lifespans": (C.c_int, [vp]),
+        "dw_get_lifespans": (C.c_int, [vp, pi64, pi64]),
+        "dw_lifespan_stats_device": (C.c_int, [vp, vp]),
+        "dw_checkpoint_save": (C.c_int, [vp]),
+        "dw_checkpoint_restore": (C.c_int, [vp]),
+        "dw_synchronize": (C.c_int, [vp]),
+    }
+    assert set(sig) == set(SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dw_abi_version() != 1:
+        raise DaisyWorldError("ABI version mismatch between _lib.py and libdaisyworld_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(lib, handle, rc, what):
+    if rc != 0:
+        msg = lib.dw_last_error(handle)
+        raise DaisyWorldError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

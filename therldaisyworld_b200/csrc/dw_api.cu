@@ -1,0 +1,679 @@
+// C-ABI implementation (include/daisyworld_b200.h): handle management, state residency, launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (therldaisyworld_b200/build.py)
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dw_common.cuh"
+#include "dw_generic.cuh"
+#include "dw_fused.cuh"
+
+static thread_local std::string g_create_error;
+
+enum PreKind { PRE_NONE = 0, PRE_GRID = 1, PRE_LAT = 2 };
+
+struct dw_handle {
+    dw_config cfg{};
+    dw_clock clk{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+    size_t NN = 0;
+
+    // fp64 materialised representation (allocated lazily: pure ensemble runs never need it)
+    double *grid[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool grid_valid = false;
+    bool ch6_dirty[2] = {false, false};
+    // packed lattice representation [B,N,N]
+    uint32_t *lat[2] = {nullptr, nullptr};
+    int lcur = 0;
+    bool lat_valid = false;
+    // state the last forward started from (post-graze): source of diagnostics / lazy materialisation
+    PreKind pre = PRE_NONE;
+    const double *pre_grid = nullptr;   // points into grid[] or fwd scratch
+    uint32_t *lat_pre = nullptr;
+    double L_last = 0.0;
+
+    int32_t *agent_xy = nullptr;
+    double *agent_state = nullptr;
+    double *obs = nullptr;
+    bool obs_valid = false;
+    double *reward = nullptr;
+    uint8_t *done = nullptr;
+    unsigned long long *world_max = nullptr;   // [B,2]
+    int64_t *done_at = nullptr, *agents_done_at = nullptr;
+    unsigned int *alive = nullptr;             // [64] per-step alive-world counters of a chunk
+    int8_t *action_dev = nullptr;
+    size_t action_cap = 0;
+    double *scratch = nullptr;                 // diag / forward scratch
+    size_t scratch_cap = 0;
+    double *fwd_in = nullptr, *fwd_out = nullptr;
+
+    // checkpoint
+    struct Ckpt {
+        bool have = false, grid_valid = false, lat_valid = false;
+        double *grid = nullptr;
+        uint32_t *lat = nullptr, *lat_pre = nullptr;
+        int32_t *agent_xy = nullptr;
+        double *agent_state = nullptr;
+        int64_t *done_at = nullptr, *agents_done_at = nullptr;
+        dw_clock clk{};
+        PreKind pre = PRE_NONE;
+        double L_last = 0;
+        bool ch6_dirty[2] = {false, false};
+    } ck[2];   // slot 0: dw_checkpoint_save/restore (caller), slot 1: dw_run's chunk rewind
+};
+
+static int dw_fail(dw_handle *h, int code, const char *what, const char *detail) {
+    std::string m = std::string(what) + ": " + detail;
+    if (h) h->err = m; else g_create_error = m;
+    return code;
+}
+
+static DevParams make_params(const dw_handle *h) {
+    DevParams P{};
+    const dw_config &c = h->cfg;
+    P.B = c.batch; P.N = c.dim; P.n_agents = c.n_agents;
+    P.p = c.p; P.g = c.g; P.S = c.S; P.sigma = c.sigma; P.gamma = c.gamma; P.q = c.q; P.q2 = c.q2;
+    P.temp_optimal = c.temp_optimal; P.dt = c.dt; P.agent_gamma = c.agent_gamma;
+    P.ab = c.albedo_bare; P.al = c.albedo_light; P.ad = c.albedo_dark;
+    for (int i = 0; i < 9; ++i) { P.w[i] = c.daisy_kernel[i]; P.adj[i] = c.adjacent_kernel[i]; P.mask[i] = c.obs_mask[i]; }
+    return P;
+}
+
+static inline int grid_for(size_t total, int block = 256) {
+    size_t g = (total + block - 1) / block;
+    const size_t cap = 148 * 64;   // grid-stride loops: a few waves of 148 SMs
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static void update_L(dw_clock &c) {   // daisy_world_rl.py:463-473
+    c.step_count += 1;
+    if (c.ramp_up_down && c.ramp_period != 0 && c.step_count % c.ramp_period == 0) {
+        c.dL *= -1;
+        c.min_L -= c.ddL;
+        c.max_L += c.ddL;
+    }
+    double L = c.L + c.dL;
+    L = L < c.max_L ? L : c.max_L;
+    c.L = L > c.min_L ? L : c.min_L;
+}
+
+template <class T>
+static int dev_alloc(dw_handle *h, T **p, size_t count) {
+    if (*p) return DW_OK;
+    DW_CUDA_TRY(h, cudaMalloc((void **)p, (count ? count : 1) * sizeof(T)));
+    DW_CUDA_TRY(h, cudaMemsetAsync(*p, 0, (count ? count : 1) * sizeof(T), h->stream));
+    return DW_OK;
+}
+
+static int ensure_grid_buffers(dw_handle *h) {
+    const size_t G = (size_t)h->cfg.batch * 7 * h->NN;
+    for (int i = 0; i < 2; ++i) {
+        int rc = dev_alloc(h, &h->grid[i], G);
+        if (rc) return rc;
+    }
+    return DW_OK;
+}
+
+static int ensure_scratch(dw_handle *h, size_t count) {
+    if (h->scratch_cap >= count) return DW_OK;
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr;
+    DW_CUDA_TRY(h, cudaMalloc((void **)&h->scratch, count * sizeof(double)));
+    h->scratch_cap = count;
+    return DW_OK;
+}
+
+// ---- lazy conversions between the two state representations -----------------------------------------
+static int launch_stamp(dw_handle *h, double *grid, bool counters, unsigned int *alive_slot, bool rewards) {
+    const DevParams P = make_params(h);
+    k_stamp_reward<<<(P.B + 127) / 128, 128, 0, h->stream>>>(
+        P, grid, h->agent_xy, h->agent_state, (counters || P.n_agents == 0) ? h->world_max : nullptr,
+        rewards ? h->reward : nullptr, rewards ? h->done : nullptr, counters ? h->done_at : nullptr,
+        counters ? h->agents_done_at : nullptr, alive_slot);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    return DW_OK;
+}
+
+// make grid[cur] hold the full reference grid of the current state
+static int ensure_grid(dw_handle *h) {
+    if (h->grid_valid) return DW_OK;
+    if (!h->lat_valid) return dw_fail(h, DW_E_STATE, "ensure_grid", "no state uploaded");
+    int rc = ensure_grid_buffers(h);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    const size_t total = (size_t)P.B * h->NN;
+    double *out = h->grid[h->cur];
+    if (h->pre == PRE_LAT) {
+        // full literal forward from the post-graze lattice the last fused step started from: reproduces
+        // b' (rounded from UNROUNDED l',d'), the temperatures of that step, and l',d' (== lat[lcur]).
+        SrcLattice src{h->lat_pre, h->NN};
+        k_forward<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, src, out, nullptr, nullptr,
+                                                                       h->ch6_dirty[h->cur] ? 1 : 0);
+        DW_CUDA_TRY(h, cudaGetLastError());
+        h->ch6_dirty[h->cur] = false;
+        rc = launch_stamp(h, out, false, nullptr, false);
+        if (rc) return rc;
+    } else {
+        return dw_fail(h, DW_E_STATE, "ensure_grid", "lattice state without a recorded pre-state");
+    }
+    h->grid_valid = true;
+    return DW_OK;
+}
+
+// ---- API ------------------------------------------------------------------------------------------------
+extern "C" int dw_abi_version(void) { return DW_ABI_VERSION; }
+
+extern "C" const char *dw_last_error(const dw_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int validate_cfg(dw_handle *h, const dw_config *c) {
+    if (!c) return dw_fail(h, DW_E_INVALID, "config", "NULL");
+    if (c->batch < 1 || c->dim < 1 || c->n_agents < 0) return dw_fail(h, DW_E_INVALID, "config", "batch>=1, dim>=1, n_agents>=0 required");
+    if ((size_t)c->dim >= (1u << 23)) return dw_fail(h, DW_E_INVALID, "config", "dim too large");
+    return DW_OK;
+}
+
+extern "C" int dw_create(const dw_config *cfg, dw_handle **out) {
+    if (!out) return dw_fail(nullptr, DW_E_INVALID, "dw_create", "out is NULL");
+    *out = nullptr;
+    int rc = validate_cfg(nullptr, cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return dw_fail(nullptr, DW_E_CUDA, "dw_create", e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return dw_fail(nullptr, DW_E_INVALID, "dw_create", "bad device ordinal");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return dw_fail(nullptr, DW_E_CUDA, "cudaSetDevice", cudaGetErrorString(e));
+    dw_handle *h = new dw_handle();
+    h->cfg = *cfg;
+    h->NN = (size_t)cfg->dim * cfg->dim;
+    const size_t B = cfg->batch, n = cfg->n_agents;
+    rc = dev_alloc(h, &h->agent_xy, B * n * 2);
+    if (!rc) rc = dev_alloc(h, &h->agent_state, B * n);
+    if (!rc) rc = dev_alloc(h, &h->reward, B * (n ? n : 2));
+    if (!rc) rc = dev_alloc(h, &h->done, B * (n ? n : 2));
+    if (!rc) rc = dev_alloc(h, &h->world_max, B * 2);
+    if (!rc) rc = dev_alloc(h, &h->done_at, B);
+    if (!rc) rc = dev_alloc(h, &h->agents_done_at, B * n);
+    if (!rc) rc = dev_alloc(h, &h->alive, 64);
+    if (rc) { g_create_error = h->err; dw_destroy(h); return rc; }
+    h->clk.L = 0.75; h->clk.min_L = 0.75; h->clk.max_L = 1.5; h->clk.ramp_period = 512;
+    h->clk.dL = (h->clk.max_L - h->clk.min_L) / 512.0;
+    *out = h;
+    return DW_OK;
+}
+
+extern "C" int dw_destroy(dw_handle *h) {
+    if (!h) return DW_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->grid[0], h->grid[1], h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in,
+                    h->fwd_out};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &c : h->ck) {
+        void *cp[] = {c.grid, c.lat, c.lat_pre, c.agent_xy, c.agent_state, c.done_at, c.agents_done_at};
+        for (void *p : cp) if (p) cudaFree(p);
+    }
+    delete h;
+    return DW_OK;
+}
+
+extern "C" int dw_set_config(dw_handle *h, const dw_config *cfg) {
+    if (!h) return DW_E_INVALID;
+    int rc = validate_cfg(h, cfg);
+    if (rc) return rc;
+    if (cfg->batch != h->cfg.batch || cfg->dim != h->cfg.dim || cfg->n_agents != h->cfg.n_agents || cfg->device != h->cfg.device)
+        return dw_fail(h, DW_E_INVALID, "dw_set_config", "shapes/device of a handle are fixed; create a new handle");
+    h->cfg = *cfg;
+    return DW_OK;
+}
+
+extern "C" int dw_set_clock(dw_handle *h, const dw_clock *clk) {
+    if (!h || !clk) return DW_E_INVALID;
+    h->clk = *clk;
+    return DW_OK;
+}
+extern "C" int dw_get_clock(dw_handle *h, dw_clock *clk) {
+    if (!h || !clk) return DW_E_INVALID;
+    *clk = h->clk;
+    return DW_OK;
+}
+extern "C" int dw_get_last_L(dw_handle *h, double *L) {
+    if (!h || !L) return DW_E_INVALID;
+    *L = h->L_last;
+    return DW_OK;
+}
+extern "C" int dw_set_stream(dw_handle *h, void *s) {
+    if (!h) return DW_E_INVALID;
+    h->stream = (cudaStream_t)s;
+    return DW_OK;
+}
+extern "C" int dw_synchronize(dw_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *agent_indices, const double *agent_states) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents, NN = h->NN;
+    if (grid) {
+        int rc = ensure_grid_buffers(h);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->grid[h->cur], grid, B * 7 * NN * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        // channel 6 is "always 0" after any forward (new_grid = 0*grid, :445); only pay for zeroing it when
+        // the caller actually put something there
+        bool dirty = false;
+        for (size_t b = 0; b < B && !dirty; ++b) {
+            const double *c6 = grid + (b * 7 + 6) * NN;
+            for (size_t i = 0; i < NN; ++i) if (c6[i] != 0.0) { dirty = true; break; }
+        }
+        h->ch6_dirty[h->cur] = dirty;   // cleaned (zeroed) the next time a forward writes this buffer
+        h->grid_valid = true;
+        h->lat_valid = false;
+        h->pre = PRE_NONE;
+        h->obs_valid = false;
+    }
+    if (n && agent_indices) {
+        std::vector<int32_t> xy(B * n * 2);
+        for (size_t i = 0; i < xy.size(); ++i) {
+            int64_t v = agent_indices[i] % h->cfg.dim;
+            xy[i] = (int32_t)(v < 0 ? v + h->cfg.dim : v);
+        }
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_xy, xy.data(), xy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // xy is a local
+        h->obs_valid = false;
+    }
+    if (n && agent_states) {
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_state, agent_states, B * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->obs_valid = false;
+    }
+    return DW_OK;
+}
+
+// initialize_grid's temperature fill (daisy_world_rl.py:304-324): ch0 = p-l-d, ch3..5 = unrounded T, Tl, Td at clk.L
+extern "C" int dw_init_temperatures(dw_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->grid_valid) return dw_fail(h, DW_E_STATE, "dw_init_temperatures", "upload a grid first");
+    const DevParams P = make_params(h);
+    k_init_fields<<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, h->grid[h->cur]);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    h->pre = PRE_GRID;
+    h->pre_grid = h->grid[h->cur];
+    h->L_last = h->clk.L;
+    h->obs_valid = false;
+    return DW_OK;
+}
+
+static int stage_action(dw_handle *h, const int64_t *action, size_t count) {
+    if (h->action_cap < count) {
+        if (h->action_dev) cudaFree(h->action_dev);
+        h->action_dev = nullptr;
+        DW_CUDA_TRY(h, cudaMalloc((void **)&h->action_dev, count));
+        h->action_cap = count;
+    }
+    std::vector<int8_t> a8(count);
+    for (size_t i = 0; i < count; ++i) {
+        if (action[i] < 0 || action[i] > 8) return dw_fail(h, DW_E_INVALID, "action", "values must be in 0..8");
+        a8[i] = (int8_t)action[i];
+    }
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->action_dev, a8.data(), count, cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, int policy, uint64_t seed) {
+    if (h->cfg.n_agents == 0) return DW_OK;
+    const DevParams P = make_params(h);
+    k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, h->agent_state, act_dev, ab, am,
+                                                             policy, seed, (uint32_t)h->clk.step_count);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    return DW_OK;
+}
+
+// forward + stamp + reward/done (+ optional lifespan counters) + clock: the tail of step() after update_agents
+static int launch_forward_tail(dw_handle *h, bool counters, unsigned int *alive_slot) {
+    const DevParams P = make_params(h);
+    const size_t total = (size_t)P.B * h->NN;
+    double *in = h->grid[h->cur], *out = h->grid[1 - h->cur];
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->world_max, 0, (size_t)P.B * 2 * sizeof(unsigned long long), h->stream));
+    SrcGrid src{in, 7 * h->NN, h->NN};
+    k_forward<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, out, in, h->world_max,
+                                                                h->ch6_dirty[1 - h->cur] ? 1 : 0);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    h->ch6_dirty[1 - h->cur] = false;
+    h->pre = PRE_GRID;
+    h->pre_grid = in;
+    h->L_last = h->clk.L;
+    h->cur = 1 - h->cur;
+    int rc = launch_stamp(h, out, counters, alive_slot, true);
+    if (rc) return rc;
+    h->grid_valid = true;
+    h->lat_valid = false;
+    h->obs_valid = false;
+    update_L(h->clk);
+    return DW_OK;
+}
+
+extern "C" int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab, int32_t am) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.n_agents == 0) return DW_OK;
+    if (!action || ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents)
+        return dw_fail(h, DW_E_INVALID, "dw_update_agents", "action must be [ab<=B, am<=n]");
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    rc = stage_action(h, action, (size_t)ab * am);
+    if (rc) return rc;
+    rc = launch_agents(h, h->action_dev, ab, am, DW_POLICY_REPLAY, 0);
+    h->lat_valid = false;
+    h->obs_valid = false;
+    return rc;
+}
+
+extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t am) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    if (h->cfg.n_agents > 0) {
+        if (action) {
+            if (ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents)
+                return dw_fail(h, DW_E_INVALID, "dw_step", "action must be [ab<=B, am<=n]");
+            rc = stage_action(h, action, (size_t)ab * am);
+            if (rc) return rc;
+            rc = launch_agents(h, h->action_dev, ab, am, DW_POLICY_REPLAY, 0);
+        } else {
+            rc = launch_agents(h, nullptr, 0, 0, DW_POLICY_NONE, 0);
+        }
+        if (rc) return rc;
+    }
+    return launch_forward_tail(h, false, nullptr);
+}
+
+extern "C" int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (policy == DW_POLICY_REPLAY || policy < 0 || policy > DW_POLICY_RANDOM)
+        return dw_fail(h, DW_E_INVALID, "dw_step_policy", "use dw_step for explicit actions");
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    rc = launch_agents(h, nullptr, 0, 0, policy, seed);
+    if (rc) return rc;
+    return launch_forward_tail(h, false, nullptr);
+}
+
+extern "C" int dw_forward(dw_handle *h, double *grid_in, double *grid_out) {
+    if (!h || !grid_in || !grid_out) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t G = (size_t)h->cfg.batch * 7 * h->NN;
+    int rc = dev_alloc(h, &h->fwd_in, G);
+    if (!rc) rc = dev_alloc(h, &h->fwd_out, G);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->fwd_in, grid_in, G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SrcGrid src{h->fwd_in, 7 * h->NN, h->NN};
+    k_forward<SrcGrid><<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, h->fwd_out, h->fwd_in,
+                                                                            nullptr, 1);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    rc = launch_stamp(h, h->fwd_out, false, nullptr, false);
+    if (rc) return rc;
+    // the reference's forward() refreshes env.temp/beta/growth as a side effect
+    h->pre = PRE_GRID;
+    h->pre_grid = h->fwd_in;
+    h->L_last = h->clk.L;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(grid_out, h->fwd_out, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // ch0 of the argument is mutated in place by the reference (:381)
+    for (int b = 0; b < h->cfg.batch; ++b)
+        DW_CUDA_TRY(h, cudaMemcpyAsync(grid_in + (size_t)b * 7 * h->NN, h->fwd_in + (size_t)b * 7 * h->NN, h->NN * sizeof(double),
+                                       cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+static int compute_obs(dw_handle *h) {
+    if (h->obs_valid) return DW_OK;
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents;
+    if (n == 0) { h->obs_valid = true; return DW_OK; }
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    rc = dev_alloc(h, &h->obs, B * n * 63);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    k_obs<<<grid_for(B * n * 63), 256, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, (int)B, (int)n, h->obs);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    h->obs_valid = true;
+    return DW_OK;
+}
+
+extern "C" int dw_get_obs(dw_handle *h, double *obs) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t count = (size_t)h->cfg.batch * h->cfg.n_agents * 63;
+    int rc = compute_obs(h);
+    if (rc) return rc;
+    if (count && obs) DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->obs, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t b, int32_t m, double *obs) {
+    if (!h || b < 0 || m < 0 || b > h->cfg.batch) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t count = (size_t)b * m * 63;
+    if (!count) return DW_OK;
+    if (!agent_indices || !obs) return DW_E_INVALID;
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    rc = ensure_scratch(h, count + (size_t)b * m);   // obs + positions (int32 pairs fit in one double each)
+    if (rc) return rc;
+    std::vector<int32_t> xy((size_t)b * m * 2);
+    for (size_t i = 0; i < xy.size(); ++i) xy[i] = (int32_t)agent_indices[i];
+    int32_t *pos = (int32_t *)(h->scratch + count);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(pos, xy.data(), xy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    const DevParams P = make_params(h);
+    k_obs<<<grid_for(count), 256, 0, h->stream>>>(P, h->grid[h->cur], pos, b, m, h->scratch);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->scratch, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_grid(dw_handle *h, double *grid) {
+    if (!h || !grid) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(grid, h->grid[h->cur], (size_t)h->cfg.batch * 7 * h->NN * sizeof(double), cudaMemcpyDeviceToHost,
+                                   h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents;
+    if (!n) return DW_OK;
+    std::vector<int32_t> xy(B * n * 2);
+    if (agent_indices) DW_CUDA_TRY(h, cudaMemcpyAsync(xy.data(), h->agent_xy, xy.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (agent_states) DW_CUDA_TRY(h, cudaMemcpyAsync(agent_states, h->agent_state, B * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (agent_indices) for (size_t i = 0; i < xy.size(); ++i) agent_indices[i] = xy[i];
+    return DW_OK;
+}
+
+extern "C" int dw_get_reward_done(dw_handle *h, double *reward, uint8_t *done) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t count = (size_t)h->cfg.batch * (h->cfg.n_agents ? h->cfg.n_agents : 2);
+    if (reward) DW_CUDA_TRY(h, cudaMemcpyAsync(reward, h->reward, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (done) DW_CUDA_TRY(h, cudaMemcpyAsync(done, h->done, count, cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_diag(dw_handle *h, int32_t which, double *out) {
+    if (!h || !out || which < 0 || which > DW_DIAG_GROWTH) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->pre == PRE_NONE) return dw_fail(h, DW_E_STATE, "dw_get_diag", "no forward pass has run on this state yet");
+    const DevParams P = make_params(h);
+    const size_t total = (size_t)P.B * h->NN, count = total * (which == DW_DIAG_GROWTH ? 2 : 1);
+    int rc = ensure_scratch(h, count);
+    if (rc) return rc;
+    const double SL = h->cfg.S * h->L_last;
+    if (h->pre == PRE_GRID) {
+        SrcGrid src{h->pre_grid, 7 * h->NN, h->NN};
+        k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
+    } else {
+        SrcLattice src{h->lat_pre, h->NN};
+        k_diag<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
+    }
+    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_CUDA_TRY(h, cudaMemcpyAsync(out, h->scratch, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+// ---- lifespan runs ---------------------------------------------------------------------------------------
+extern "C" int dw_reset_lifespans(dw_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->done_at, 0, B * sizeof(int64_t), h->stream));
+    if (n) DW_CUDA_TRY(h, cudaMemsetAsync(h->agents_done_at, 0, B * n * sizeof(int64_t), h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_lifespans(dw_handle *h, int64_t *done_at, int64_t *agents_done_at) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents;
+    if (done_at) DW_CUDA_TRY(h, cudaMemcpyAsync(done_at, h->done_at, B * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (agents_done_at && n)
+        DW_CUDA_TRY(h, cudaMemcpyAsync(agents_done_at, h->agents_done_at, B * n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+__global__ void k_lifespan_stats(int B, int n, const int64_t *done_at, const int64_t *agents_done_at, const unsigned int *alive_last,
+                                 double *out) {
+    // single block; exact in fp64 for any realistic ensemble (integers < 2^53)
+    __shared__ double sh[6][32];
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const double v = (double)done_at[b];
+        s[0] += v; s[1] += v * v;
+        for (int i = 0; i < n; ++i) {
+            const double a = (double)agents_done_at[(size_t)b * n + i];
+            s[2] += a; s[3] += a * a;
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = 0; k < 4; ++k) {
+        double v = s[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[k][w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t[k] += sh[k][i];
+        out[0] = (double)B; out[1] = t[0]; out[2] = t[1]; out[3] = (double)B * n; out[4] = t[2]; out[5] = t[3];
+        out[6] = alive_last ? (double)*alive_last : 0.0; out[7] = 0.0;
+    }
+}
+
+extern "C" int dw_lifespan_stats_device(dw_handle *h, double *out_dev) {
+    if (!h || !out_dev) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    k_lifespan_stats<<<1, 1024, 0, h->stream>>>(h->cfg.batch, h->cfg.n_agents, h->done_at, h->agents_done_at, nullptr, out_dev);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    return DW_OK;
+}
+
+// ---- checkpoint ---------------------------------------------------------------------------------------------
+static int ckpt_save(dw_handle *h, int slot) {
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents, NN = h->NN;
+    auto &c = h->ck[slot];
+    int rc = DW_OK;
+    if (h->grid_valid) {
+        rc = dev_alloc(h, &c.grid, B * 7 * NN);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(c.grid, h->grid[h->cur], B * 7 * NN * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->lat_valid) {
+        rc = dev_alloc(h, &c.lat, B * NN);
+        if (!rc) rc = dev_alloc(h, &c.lat_pre, B * NN);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(c.lat, h->lat[h->lcur], B * NN * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        if (h->pre == PRE_LAT)
+            DW_CUDA_TRY(h, cudaMemcpyAsync(c.lat_pre, h->lat_pre, B * NN * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    rc = dev_alloc(h, &c.agent_xy, B * n * 2);
+    if (!rc) rc = dev_alloc(h, &c.agent_state, B * n);
+    if (!rc) rc = dev_alloc(h, &c.done_at, B);
+    if (!rc) rc = dev_alloc(h, &c.agents_done_at, B * n);
+    if (rc) return rc;
+    if (n) {
+        DW_CUDA_TRY(h, cudaMemcpyAsync(c.agent_xy, h->agent_xy, B * n * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+        DW_CUDA_TRY(h, cudaMemcpyAsync(c.agent_state, h->agent_state, B * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        DW_CUDA_TRY(h, cudaMemcpyAsync(c.agents_done_at, h->agents_done_at, B * n * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    DW_CUDA_TRY(h, cudaMemcpyAsync(c.done_at, h->done_at, B * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+    c.have = true; c.grid_valid = h->grid_valid; c.lat_valid = h->lat_valid; c.clk = h->clk;
+    // a PRE_GRID pre-state lives in the other ping-pong buffer and is not checkpointed: diagnostics of the
+    // step before the checkpoint are not restorable, the state itself is.
+    c.pre = (h->pre == PRE_LAT) ? PRE_LAT : PRE_NONE;
+    c.L_last = h->L_last;
+    c.ch6_dirty[0] = h->ch6_dirty[0]; c.ch6_dirty[1] = h->ch6_dirty[1];
+    return DW_OK;
+}
+
+static int ckpt_restore(dw_handle *h, int slot) {
+    auto &c = h->ck[slot];
+    if (!c.have) return dw_fail(h, DW_E_STATE, "dw_checkpoint_restore", "no checkpoint saved");
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents, NN = h->NN;
+    if (c.grid_valid) {
+        int rc = ensure_grid_buffers(h);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->grid[h->cur], c.grid, B * 7 * NN * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (c.lat_valid) {
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->lat[h->lcur], c.lat, B * NN * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        if (c.pre == PRE_LAT)
+            DW_CUDA_TRY(h, cudaMemcpyAsync(h->lat_pre, c.lat_pre, B * NN * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (n) {
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_xy, c.agent_xy, B * n * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_state, c.agent_state, B * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agents_done_at, c.agents_done_at, B * n * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->done_at, c.done_at, B * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+    h->grid_valid = c.grid_valid; h->lat_valid = c.lat_valid; h->clk = c.clk; h->pre = c.pre; h->L_last = c.L_last;
+    h->ch6_dirty[0] = c.ch6_dirty[0]; h->ch6_dirty[1] = c.ch6_dirty[1];
+    h->obs_valid = false;
+    return DW_OK;
+}
+
+extern "C" int dw_checkpoint_save(dw_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    return ckpt_save(h, 0);
+}
+extern "C" int dw_checkpoint_restore(dw_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    return ckpt_restore(h, 0);
+}
+
+// ---- dw_run / dw_run_chunk ----------------------------------------------------------------------------------
+#include "dw_run.inl"

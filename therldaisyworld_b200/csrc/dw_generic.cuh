@@ -1,0 +1,294 @@
+// Materialising ("generic") kernels: one reference step on the fp64 grid[B,7,N,N], any N >= 1,
+// any (off-lattice) cover values.  Used by dw_step / dw_forward / dw_get_grid / dw_get_diag.
+// Roofline: writes 6 live channels + reads 2 => 64 B per cell-update; in literal
+// arithmetic (6 fp64 sqrt pairs, 7 fp64 divides per cell) it is fp64-pipe bound at about the same rate.
+#pragma once
+#include "dw_common.cuh"
+
+// ---- input loaders --------------------------------------------------------------------------------
+struct SrcGrid {           // fp64 grid[B,7,N,N]
+    const double *g;
+    size_t world_stride;   // 7*N*N
+    size_t NN;
+    __device__ __forceinline__ double l(int b, size_t c) const { return g[b * world_stride + NN + c]; }
+    __device__ __forceinline__ double d(int b, size_t c) const { return g[b * world_stride + 2 * NN + c]; }
+};
+struct SrcLattice {        // packed milli-covers [B,N,N]
+    const uint32_t *k;
+    size_t NN;
+    __device__ __forceinline__ double l(int b, size_t c) const { return dw_milli(k[b * NN + c] & 0xffffu); }
+    __device__ __forceinline__ double d(int b, size_t c) const { return dw_milli(k[b * NN + c] >> 16); }
+};
+
+template <class Src>
+__device__ __forceinline__ void dw_load9(const Src &src, int b, int N, int x, int y, double (&l9)[9], double (&d9)[9]) {
+    const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+    const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+    const int xs[3] = {xm, x, xp}, ys[3] = {ym, y, yp};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t k = (size_t)xs[a] * N + ys[c];
+            l9[a * 3 + c] = src.l(b, k);
+            d9[a * 3 + c] = src.d(b, k);
+        }
+}
+
+// order-preserving map of non-negative doubles to u64 for atomicMax
+__device__ __forceinline__ void dw_atomic_max_pos(unsigned long long *addr, double v) {
+    if (v > 0.0) atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// ---- forward (daisy_world_rl.py:434-452) ----------------------------------------------------------
+// One thread per cell. out: grid[B,7,N,N] (channels 0..5 written, 6 written only if zero6).
+// writeback_b0: also store (p-l)-d into channel 0 of the INPUT grid (reference :381 mutates its argument).
+// world_max: [B,2] u64 bit patterns of max(l'), max(d') (rounded), pre-zeroed; may be NULL.
+template <class Src>
+__global__ void __launch_bounds__(256) k_forward(DevParams P, double SL, Src src, double *__restrict__ out,
+                                                 double *writeback_b0, unsigned long long *world_max, int zero6) {
+    const size_t NN = (size_t)P.N * P.N;
+    const size_t total = (size_t)P.B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / NN);
+        const size_t c = i - (size_t)b * NN;
+        const int x = (int)(c / P.N), y = (int)(c - (size_t)x * P.N);
+        double l9[9], d9[9];
+        dw_load9(src, b, P.N, x, y, l9, d9);
+        const LitCell o = dw_literal_cell(P, SL, l9, d9);
+        double *ob = out + (size_t)b * 7 * NN + c;
+        const double rl = dw_round3(o.nl), rd = dw_round3(o.nd);
+        ob[0] = dw_round3(o.nb);
+        ob[NN] = rl;
+        ob[2 * NN] = rd;
+        ob[3 * NN] = dw_round3(o.T);
+        ob[4 * NN] = dw_round3(o.Tl);
+        ob[5 * NN] = dw_round3(o.Td);
+        if (zero6) ob[6 * NN] = 0.0;
+        if (writeback_b0) writeback_b0[(size_t)b * 7 * NN + c] = o.b0;
+        if (world_max) {
+            // warp-level pre-reduction when the whole warp sits in one world
+            const unsigned m = __activemask();
+            const int b0 = __shfl_sync(m, b, 0);
+            double ml = rl, md = rd;
+            if (m == 0xffffffffu && __all_sync(m, b == b0)) {
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    ml = fmax(ml, __shfl_xor_sync(m, ml, s));
+                    md = fmax(md, __shfl_xor_sync(m, md, s));
+                }
+                if ((threadIdx.x & 31) == 0) {
+                    dw_atomic_max_pos(world_max + 2 * b, ml);
+                    dw_atomic_max_pos(world_max + 2 * b + 1, md);
+                }
+            } else {
+                dw_atomic_max_pos(world_max + 2 * b, ml);
+                dw_atomic_max_pos(world_max + 2 * b + 1, md);
+            }
+        }
+    }
+}
+
+// ---- initial temperatures (initialize_grid, daisy_world_rl.py:304-324): ch0 and ch3..5, UNROUNDED ----
+__global__ void __launch_bounds__(256) k_init_fields(DevParams P, double SL, double *grid) {
+    const size_t NN = (size_t)P.N * P.N;
+    const size_t total = (size_t)P.B * NN;
+    SrcGrid src{grid, 7 * NN, NN};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / NN);
+        const size_t c = i - (size_t)b * NN;
+        const int x = (int)(c / P.N), y = (int)(c - (size_t)x * P.N);
+        double l9[9], d9[9];
+        dw_load9(src, b, P.N, x, y, l9, d9);
+        const LitCell o = dw_literal_cell(P, SL, l9, d9);
+        double *ob = grid + (size_t)b * 7 * NN + c;
+        ob[0] = o.b0;
+        ob[3 * NN] = o.T;
+        ob[4 * NN] = o.Tl;
+        ob[5 * NN] = o.Td;
+    }
+}
+
+// ---- diagnostics: unrounded side-effect attributes of the last forward -------------------------
+template <class Src>
+__global__ void __launch_bounds__(256) k_diag(DevParams P, double SL, Src src, int which, double *__restrict__ out) {
+    const size_t NN = (size_t)P.N * P.N;
+    const size_t total = (size_t)P.B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / NN);
+        const size_t c = i - (size_t)b * NN;
+        const int x = (int)(c / P.N), y = (int)(c - (size_t)x * P.N);
+        double l9[9], d9[9];
+        dw_load9(src, b, P.N, x, y, l9, d9);
+        const LitCell o = dw_literal_cell(P, SL, l9, d9);
+        switch (which) {
+            case DW_DIAG_TEMP: out[i] = o.T; break;
+            case DW_DIAG_TEMP_LIGHT: out[i] = o.Tl; break;
+            case DW_DIAG_TEMP_DARK: out[i] = o.Td; break;
+            case DW_DIAG_TEMP_EFFECTIVE: out[i] = o.Te; break;
+            case DW_DIAG_BETA: out[i] = o.beta; break;
+            case DW_DIAG_BETA_L: out[i] = o.beta_l; break;
+            case DW_DIAG_BETA_D: out[i] = o.beta_d; break;
+            default:
+                out[(size_t)b * 2 * NN + c] = o.dl;
+                out[(size_t)b * 2 * NN + NN + c] = o.dd;
+        }
+    }
+}
+
+// ---- agents (update_agents, daisy_world_rl.py:181-244; Greedy, agents/greedy.py:16-30) -------------
+// counter RNG for DW_POLICY_RANDOM (throughput ensembles only; parity for stochastic policies is by replay)
+__device__ __forceinline__ uint32_t dw_hash_rng(uint64_t seed, uint32_t world, uint32_t agent, uint32_t step) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)world * 0x10001ull + agent + 1) + ((uint64_t)step << 32);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+// greedy / anti-greedy choice from the four Von Neumann neighbours' l+d (candidates in action order
+// 4..7 = (x,y-1), (x-1,y), (x+1,y), (x,y+1)); first extremum wins like np.argmax/np.argmin.
+__device__ __forceinline__ int dw_greedy_pick(const double (&food)[4], bool greedy) {
+    int best = 0;
+    double bv = food[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const bool better = greedy ? (food[k] > bv) : (food[k] < bv);
+        if (better) { bv = food[k]; best = k; }
+    }
+    return 4 + best;
+}
+
+// One thread per world, agents strictly in index order (grazing conflicts: lower index eats first).
+// action: device int8 [ab,am] (policy REPLAY/explicit), ignored for other policies.
+__global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *grid, int32_t *agent_xy, double *agent_state,
+                                                     const int8_t *action, int ab, int am, int policy, uint64_t seed,
+                                                     uint32_t step) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int N = P.N, n = P.n_agents;
+    const size_t NN = (size_t)N * N;
+    double *gl = grid + (size_t)b * 7 * NN + NN, *gd = gl + NN;
+    int32_t *xy = agent_xy + (size_t)b * n * 2;
+    double *st = agent_state + (size_t)b * n;
+    for (int i = 0; i < n; ++i) st[i] = st[i] - P.agent_gamma;
+    const int lim_b = (policy == DW_POLICY_REPLAY) ? ab : P.B, lim_m = (policy == DW_POLICY_REPLAY) ? am : n;
+    // Observation-driven policies decide from the grid BEFORE any agent of this step moves or grazes
+    // (obs comes from the previous step). Two passes keep that order: decide all, then apply in order.
+    if (b < lim_b) {
+        for (int i = 0; i < lim_m; ++i) {
+            int a;
+            const int x = xy[2 * i], y = xy[2 * i + 1];
+            if (policy == DW_POLICY_REPLAY) a = action[(size_t)b * am + i];
+            else if (policy == DW_POLICY_NONE) a = 0;
+            else if (policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(seed, b, i, step) % 9u);
+            else {
+                const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+                const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+                const size_t c[4] = {(size_t)x * N + ym, (size_t)xm * N + y, (size_t)xp * N + y, (size_t)x * N + yp};
+                double food[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) food[k] = gl[c[k]] + gd[c[k]];
+                a = dw_greedy_pick(food, policy == DW_POLICY_GREEDY);
+            }
+            // stash the decision in the (unused by now) high bits of x: keeps the kernel free of scratch memory
+            xy[2 * i] = x | (a << 24);
+        }
+        for (int i = 0; i < lim_m; ++i) {
+            const int packed = xy[2 * i];
+            const int a = (packed >> 24) & 0xf;
+            int x = packed & 0xffffff, y = xy[2 * i + 1];
+            if (st[i] > 0.0) {
+                if (a != 8) {
+                    switch (a & 3) {
+                        case 0: y -= 1; break;
+                        case 1: x -= 1; break;
+                        case 2: x += 1; break;
+                        default: y += 1; break;
+                    }
+                }
+                x = x < 0 ? x + N : (x >= N ? x - N : x);
+                y = y < 0 ? y + N : (y >= N ? y - N : y);
+                if (a > 4) {
+                    const size_t c = (size_t)x * N + y;
+                    st[i] = st[i] + (gl[c] + gd[c]);
+                    gl[c] *= 0.0;
+                    gd[c] *= 0.0;
+                }
+            }
+            xy[2 * i] = x;
+            xy[2 * i + 1] = y;
+        }
+    }
+    for (int i = 0; i < n; ++i) st[i] = dw_clip01(st[i]);
+}
+
+// ---- stamp + reward/done + lifespan counters (forward :454-459, step :486-492, notebook cell 2) ----
+// One thread per world. world_max as produced by k_forward (NULL = skip counters / n_agents==0 reward).
+__global__ void __launch_bounds__(128) k_stamp_reward(DevParams P, double *grid, const int32_t *agent_xy,
+                                                      const double *agent_state, const unsigned long long *world_max,
+                                                      double *reward, uint8_t *done, int64_t *done_at,
+                                                      int64_t *agents_done_at, unsigned int *alive_count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int N = P.N, n = P.n_agents;
+    const size_t NN = (size_t)N * N;
+    double *g4 = grid + (size_t)b * 7 * NN + 4 * NN;
+    for (int i = 0; i < n; ++i) {
+        const int x = agent_xy[((size_t)b * n + i) * 2], y = agent_xy[((size_t)b * n + i) * 2 + 1];
+        g4[(size_t)x * N + y] = agent_state[(size_t)b * n + i];
+    }
+    if (n > 0) {
+        for (int i = 0; i < n; ++i) {
+            double r = agent_state[(size_t)b * n + i];
+            r = r * (r > 0.0 ? 1.0 : 0.0);
+            const bool dn = r < 0.1;
+            if (reward) reward[(size_t)b * n + i] = r;
+            if (done) done[(size_t)b * n + i] = dn;
+            if (agents_done_at) agents_done_at[(size_t)b * n + i] += dn ? 0 : 1;
+        }
+    } else if (world_max) {
+        for (int c = 0; c < 2; ++c) {
+            const bool r = __longlong_as_double((long long)world_max[2 * b + c]) > 0.0;
+            if (reward) reward[2 * b + c] = r ? 1.0 : 0.0;
+            if (done) done[2 * b + c] = r ? 0 : 1;
+        }
+    }
+    if (world_max && done_at) {
+        const double m = fmax(__longlong_as_double((long long)world_max[2 * b]),
+                              __longlong_as_double((long long)world_max[2 * b + 1]));
+        const bool grid_done = m <= 0.005;
+        done_at[b] += grid_done ? 0 : 1;
+        if (!grid_done && alive_count) atomicAdd(alive_count, 1u);
+    }
+}
+
+// ---- observations (get_obs, daisy_world_rl.py:246-263) -----------------------------------------------
+// One thread per output element of obs[b,m,7,3,3]; positions: int32 [b,m,2].
+__global__ void __launch_bounds__(256) k_obs(DevParams P, const double *__restrict__ grid, const int32_t *__restrict__ pos,
+                                             int nb, int m, double *__restrict__ obs) {
+    const size_t total = (size_t)nb * m * 63;
+    const int N = P.N;
+    const size_t NN = (size_t)N * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t ag = i / 63;
+        const int e = (int)(i - ag * 63);
+        const int ch = e / 9, a = (e % 9) / 3, c = e % 3;
+        const int b = (int)(ag / m);
+        int x = pos[ag * 2] + a - 1, y = pos[ag * 2 + 1] + c - 1;
+        x = ((x % N) + N) % N;
+        y = ((y % N) + N) % N;
+        obs[i] = grid[((size_t)b * 7 + ch) * NN + (size_t)x * N + y] * P.mask[a * 3 + c];
+    }
+}
+
+// lattice -> fp64 covers (channels 1,2 only) : used when a fused run is followed by single steps
+__global__ void __launch_bounds__(256) k_lattice_to_grid(int B, size_t NN, const uint32_t *__restrict__ lat, double *grid) {
+    const size_t total = (size_t)B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / NN, c = i - b * NN;
+        const uint32_t k = lat[i];
+        grid[b * 7 * NN + NN + c] = dw_milli(k & 0xffffu);
+        grid[b * 7 * NN + 2 * NN + c] = dw_milli(k >> 16);
+    }
+}

@@ -1,0 +1,506 @@
+"""Drop-in ``RLDaisyWorld`` whose simulation step runs on a B200 through the C-ABI.
+
+Mirrors the Python surface of the reference class (``daisy/daisy_world_rl.py:13-501``): same constructor
+kwargs, same mutable public attributes, same ``reset/step/forward/get_obs/update_agents/update_L``
+signatures, array shapes and dtypes, same use of the process-global legacy ``np.random`` stream at
+construction and ``reset()``.  Reference callers (``daisy/agents/greedy.py``, ``daisy/agents/mlp.py``,
+``daisy/evo/sges.py``, the notebooks) keep working unchanged.
+
+State lives on the device.  ``env.grid``, ``env.agent_indices``, ``env.agent_states`` are host mirrors:
+reading one downloads it lazily; assigning one (or mutating the array you were handed) is detected and
+uploaded before the next device operation.
+
+Additions that the reference does not have (they do not change any reference behaviour):
+``run(K, policy=...)`` / ``simulate_lifespan(policy=...)`` -- the fused multi-step path with an on-device
+policy and the notebook's lifespan counters.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import numpy.random as npr
+
+from . import _lib
+from ._lib import DwClock, DwConfig, DwRunResult, DW_DIAG, DW_POLICY
+
+
+def query_kwargs(key, default, **kwargs):
+    """reference: daisy/helpers.py:3-8"""
+    return kwargs[key] if key in kwargs else default
+
+
+def make_neighborhood(radius=1, mode="moore"):
+    """Observation masks (reference: daisy/nn/functional.py:51-103)."""
+    ax = np.arange(-radius, radius + 1)
+    xx, yy = np.meshgrid(ax, ax)
+    if mode == "moore":
+        rr = np.maximum(np.abs(xx), np.abs(yy))
+    elif mode == "circular":
+        rr = np.abs(np.sqrt(xx ** 2 + yy ** 2))
+    else:
+        if mode != "von_neumann":
+            print(f"neighborhood mode {mode} not recognized, using von Neumann default")
+        rr = np.abs(xx) + np.abs(yy)
+    out = np.zeros((2 * radius + 1, 2 * radius + 1))
+    out[rr <= radius] = 1.0
+    return out
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+class _Mirror:
+    """Host mirror of one device array with write detection."""
+    __slots__ = ("pristine", "handed", "assigned")
+
+    def __init__(self):
+        self.pristine = None   # private copy of what the device holds (None = not downloaded)
+        self.handed = None     # the array the user holds (may have been mutated)
+        self.assigned = False  # user assigned a brand-new array
+
+    def invalidate(self):
+        self.pristine = None
+        self.handed = None
+        self.assigned = False
+
+    def dirty(self):
+        if self.assigned:
+            return True
+        if self.handed is None or self.pristine is None:
+            return False
+        return not (self.handed.shape == self.pristine.shape and np.array_equal(self.handed, self.pristine))
+
+
+class RLDaisyWorld:
+    _DIAG_ATTRS = ("temp", "temp_light", "temp_dark", "temp_effective", "beta", "beta_l", "beta_d", "growth")
+
+    def __init__(self, **kwargs):
+        self.ch = 7
+        self.batch_size = 32                      # ctor kwarg is ignored like the reference (:20)
+        self.kr = query_kwargs("kr", 1, **kwargs)
+        self.neighborhood_mode = query_kwargs("neighborhood_mode", "von_neumann", **kwargs)
+        self.neighborhood = make_neighborhood(self.kr, self.neighborhood_mode)
+        self.dim = kwargs["grid_dimension"] if "grid_dimension" in kwargs else 16
+
+        self.p = 1.00
+        self.g = 0.003265
+        self.S = 1000.0
+        self.sigma = 5.67e-8
+        self.gamma = 0.25
+        self.q = 0.2 * self.S / self.sigma
+        self.use_microclimate = True
+        self.collision_mode = query_kwargs("collision_mode", 0, **kwargs)
+        self.q2 = self.q / 8.0 if self.use_microclimate else 0.0
+        self.Toptim = 295.5
+        self.dt = 1.0
+        self.ddL = 0.0
+        self.agent_gamma = 0.05
+        self.max_L = 1.5
+        self.min_L = 0.75
+        self.initial_L = self.min_L
+        self.ramp_period = kwargs["ramp_period"] if "ramp_period" in kwargs else 512
+        self.ramp_up_down = False
+        self.albedo_bare = 0.5
+        self.albedo_light = 0.75
+        self.albedo_dark = 0.25
+        self.temp_optimal = 295.5
+        self.food_chain_penalty = 0.5
+        self.initial_al = 0.2
+        self.initial_ad = 0.2
+        self.light_proportion = 0.33
+        self.dark_proportion = 0.33
+        self.n_agents = query_kwargs("n_agents", 4, **kwargs)
+
+        # additions (not in the reference)
+        self.device = int(kwargs.get("device", os.environ.get("LOCAL_RANK", 0)))
+        self._lib = _lib.load()
+        self._h = None
+        self._shape = None
+        self._m = {"grid": _Mirror(), "agent_indices": _Mirror(), "agent_states": _Mirror()}
+        self._diag_cache = {}
+        self._dead_L = None
+
+        self.initialize_neighborhood()
+        self.initialize_agents()
+        self.reset()
+
+    # ------------------------------------------------------------------ handle / plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.dw_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        _lib.check(self._lib, self._h, rc, what)
+
+    def _config(self):
+        c = DwConfig(batch=int(self.batch_size), dim=int(self.dim), n_agents=int(self.n_agents), device=self.device,
+                     p=self.p, g=self.g, S=self.S, sigma=self.sigma, gamma=self.gamma, q=self.q, q2=self.q2,
+                     temp_optimal=self.temp_optimal, dt=self.dt, agent_gamma=self.agent_gamma,
+                     albedo_bare=self.albedo_bare, albedo_light=self.albedo_light, albedo_dark=self.albedo_dark)
+        c.daisy_kernel[:] = [float(v) for v in np.asarray(self.daisy_kernel, dtype=np.float64).ravel()]
+        c.adjacent_kernel[:] = [float(v) for v in np.asarray(self.adjacent_albedo_kernel, dtype=np.float64).ravel()]
+        mask = np.asarray(self.neighborhood, dtype=np.float64)
+        if mask.shape != (3, 3):
+            raise ValueError("get_obs gathers a 3-wide window (reference :257-258): only kr=1 neighbourhoods work")
+        c.obs_mask[:] = [float(v) for v in mask.ravel()]
+        return c
+
+    def _clock(self):
+        return DwClock(L=float(self.L), dL=float(self.dL), min_L=float(self.min_L), max_L=float(self.max_L),
+                       ddL=float(self.ddL), step_count=int(self.step_count), ramp_period=int(self.ramp_period),
+                       ramp_up_down=int(bool(self.ramp_up_down)))
+
+    def _pull_clock(self):
+        clk = DwClock()
+        self._check(self._lib.dw_get_clock(self._h, C.byref(clk)), "dw_get_clock")
+        self.L, self.dL, self.min_L, self.max_L = clk.L, clk.dL, clk.min_L, clk.max_L
+        self.step_count = int(clk.step_count)
+
+    def _ensure_handle(self, shape):
+        """(Re)create the device handle when batch_size / dim / n_agents changed (they are re-read at reset())."""
+        if self._h is not None and self._shape == shape:
+            return
+        if self._h is not None:
+            self._lib.dw_destroy(self._h)
+            self._h = None
+        saved = (self.batch_size, self.dim, self.n_agents)
+        self.batch_size, self.dim, self.n_agents = shape
+        cfg = self._config()
+        self.batch_size, self.dim, self.n_agents = saved
+        h = C.c_void_p()
+        rc = self._lib.dw_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            msg = self._lib.dw_last_error(None)
+            raise _lib.DaisyWorldError(f"dw_create failed (code {rc}): {msg.decode() if msg else ''}")
+        self._h = h
+        self._shape = shape
+        for m in self._m.values():
+            m.invalidate()
+
+    def _push(self):
+        """Send host-side changes (config, clock, mutated mirrors) to the device before a device operation."""
+        if self._h is None:
+            raise _lib.DaisyWorldError("environment has no device state; call reset()")
+        B, N, n = self._shape
+        cfg = self._config()
+        cfg.batch, cfg.dim, cfg.n_agents = B, N, n      # shapes of live state only change at reset()
+        self._check(self._lib.dw_set_config(self._h, C.byref(cfg)), "dw_set_config")
+        clk = self._clock()
+        self._check(self._lib.dw_set_clock(self._h, C.byref(clk)), "dw_set_clock")
+        g = ai = st = None
+        if self._m["grid"].dirty():
+            g = np.ascontiguousarray(self._m["grid"].handed, dtype=np.float64)
+            if g.shape != (B, self.ch, N, N):
+                raise ValueError(f"env.grid must have shape {(B, self.ch, N, N)}, got {g.shape}")
+        if n and self._m["agent_indices"].dirty():
+            ai = np.ascontiguousarray(self._m["agent_indices"].handed, dtype=np.int64)
+            if ai.shape != (B, n, 2):
+                raise ValueError(f"env.agent_indices must have shape {(B, n, 2)}, got {ai.shape}")
+        if n and self._m["agent_states"].dirty():
+            st = np.ascontiguousarray(self._m["agent_states"].handed, dtype=np.float64).reshape(B, n)
+        if g is not None or ai is not None or st is not None:
+            self._check(self._lib.dw_upload_state(self._h, _ptr(g, C.c_double), _ptr(ai, C.c_int64), _ptr(st, C.c_double)),
+                        "dw_upload_state")
+            for name, arr in (("grid", g), ("agent_indices", ai), ("agent_states", st)):
+                if arr is not None:
+                    m = self._m[name]
+                    m.pristine = np.array(m.handed, copy=True)
+                    m.assigned = False
+
+    def _state_changed(self):
+        for m in self._m.values():
+            m.invalidate()
+        self._diag_cache = {}
+
+    # ------------------------------------------------------------------ host mirrors
+    def _get_mirror(self, name):
+        m = self._m[name]
+        if m.handed is not None:
+            return m.handed
+        B, N, n = self._shape
+        if name == "grid":
+            arr = np.empty((B, self.ch, N, N))
+            self._check(self._lib.dw_get_grid(self._h, _ptr(arr, C.c_double)), "dw_get_grid")
+        else:
+            ai = np.zeros((B, n, 2), dtype=np.int64)
+            st = np.zeros((B, n, 1))
+            if n:
+                self._check(self._lib.dw_get_agents(self._h, _ptr(ai, C.c_int64), _ptr(st, C.c_double)), "dw_get_agents")
+            for nm, a in (("agent_indices", ai), ("agent_states", st)):
+                mm = self._m[nm]
+                if mm.handed is None:
+                    mm.pristine = a.copy()
+                    mm.handed = a
+            return self._m[name].handed
+        m.pristine = arr.copy()
+        m.handed = arr
+        return arr
+
+    def _set_mirror(self, name, value):
+        m = self._m[name]
+        m.handed = np.asarray(value)
+        m.assigned = True
+
+    grid = property(lambda self: self._get_mirror("grid"), lambda self, v: self._set_mirror("grid", v))
+    agent_indices = property(lambda self: self._get_mirror("agent_indices"),
+                             lambda self, v: self._set_mirror("agent_indices", v))
+    agent_states = property(lambda self: self._get_mirror("agent_states"),
+                            lambda self, v: self._set_mirror("agent_states", v))
+
+    # ------------------------------------------------------------------ diagnostics (unrounded, lazy)
+    def _diag(self, name):
+        if name not in self._diag_cache:
+            B, N, _ = self._shape
+            out = np.empty((B, 2 if name == "growth" else 1, N, N))
+            self._check(self._lib.dw_get_diag(self._h, DW_DIAG[name], _ptr(out, C.c_double)), "dw_get_diag")
+            self._diag_cache[name] = out
+        return self._diag_cache[name]
+
+    temp = property(lambda self: self._diag("temp"))
+    temp_light = property(lambda self: self._diag("temp_light"))
+    temp_dark = property(lambda self: self._diag("temp_dark"))
+    temp_effective = property(lambda self: self._diag("temp_effective"))
+    beta = property(lambda self: self._diag("beta"))
+    beta_l = property(lambda self: self._diag("beta_l"))
+    beta_d = property(lambda self: self._diag("beta_d"))
+    growth = property(lambda self: self._diag("growth"))
+
+    @property
+    def dead_temp(self):
+        """reference :406-407,416 -- bare-planet temperature at the L of the last forward."""
+        if self._dead_L is None:
+            last = C.c_double()
+            self._check(self._lib.dw_get_last_L(self._h, C.byref(last)), "dw_get_last_L")
+            self._dead_L = last.value
+        L = self._dead_L
+        return np.array([((self.S * L * (1 - self.albedo_bare)) / self.sigma) ** (1 / 4)])
+
+    # ------------------------------------------------------------------ reference API
+    def set_use_microclimate(self, use_microclimate=True):
+        self.use_microclimate = use_microclimate
+        self.q2 = self.q / 8.0 if self.use_microclimate else 0.0
+
+    _CONFIG_KEYS = ("max_L", "min_L", "initial_L", "ramp_period", "dL", "p", "g", "S", "sigma", "gamma", "albedo_bare",
+                    "albedo_light", "albedo_dark", "temp_optimal", "light_proportion", "dark_proportion", "initial_al",
+                    "initial_ad", "n_agents", "agent_gamma")
+
+    def make_config(self):
+        """reference :94-119"""
+        return {k: getattr(self, k) for k in self._CONFIG_KEYS}
+
+    def save_config(self, filepath=None):
+        if filepath is None:
+            filepath = os.path.join("results", "default_model_config.json")
+        with open(filepath, "w") as f:
+            json.dump(self.make_config(), f)
+
+    def _apply_config(self, config):
+        for k in self._CONFIG_KEYS:
+            setattr(self, k, config[k])
+
+    def load_config(self, filepath=None):
+        if filepath is None:
+            filepath = os.path.join("results", "default_model_config.json")
+        with open(filepath, "r") as f:
+            return json.load(f)
+
+    def restore_config(self, filepath=None):
+        self._apply_config(self.load_config(filepath))
+
+    def initialize_neighborhood(self):
+        """reference :265-283"""
+        self.n_daisies = 2
+        self.daisy_kernel = np.ones((1, 1, 3, 3)) * np.exp(-1)
+        self.daisy_kernel[:, :, 1, 1] = 1.0
+        self.daisy_kernel[:, :, 0::2, 0::2] = np.exp(-2)
+        self.daisy_kernel /= self.daisy_kernel.sum()
+        self.local_albedo_kernel = np.zeros((1, 1, 3, 3))
+        self.local_albedo_kernel[:, :, 1, 1] = 1.0
+        self.adjacent_albedo_kernel = np.ones((1, 1, 3, 3)) / 8.0
+        self.adjacent_albedo_kernel[:, :, 1, 1] = 0.0
+
+    def initialize_agents(self):
+        """reference :173-179 (one randint draw; states = 1)."""
+        ai = np.random.randint(self.dim, size=(self.batch_size, self.n_agents, 2))
+        st = np.ones((self.batch_size, self.n_agents, 1))
+        if self._h is not None and self._shape == (self.batch_size, self.dim, self.n_agents):
+            self.agent_indices = ai
+            self.agent_states = st
+        else:
+            self._pending_agents = (ai, st)   # constructor call before the first reset(): no device state yet
+
+    def initialize_grid(self):
+        """reference :285-324: RNG draw order (dark first), cover init on the host; temperatures on the device."""
+        B, N = self.batch_size, self.dim
+        dark_probability = np.random.rand(B, 2, N, N)
+        light_probability = np.random.rand(B, 2, N, N)
+        dark = 1.0 * (dark_probability[:, 0] < self.dark_proportion) * self.initial_ad * dark_probability[:, 1]
+        light = 1.0 * (light_probability[:, 0] < self.light_proportion) * self.initial_al * light_probability[:, 1]
+        grid = np.zeros((B, self.ch, N, N))
+        grid[:, 0] = self.p - light - dark
+        grid[:, 1] = light
+        grid[:, 2] = dark
+        self._ensure_handle((int(B), int(N), int(self.n_agents)))
+        self.grid = grid
+        self._push()
+        self._check(self._lib.dw_init_temperatures(self._h), "dw_init_temperatures")
+        self._dead_L = self.L
+        self._m["grid"].invalidate()
+        self._diag_cache = {}
+
+    def reset(self):
+        """reference :327-338"""
+        self.L = self.min_L
+        self.dL = (self.max_L - self.min_L) / self.ramp_period
+        self.step_count = 0
+        self.initialize_grid()
+        self.initialize_agents()
+        self._pending_agents = None
+        return self.get_obs(self.agent_indices)
+
+    def update_agents(self, action):
+        """reference :181-244 (collision_mode 0)."""
+        if self.collision_mode == 1:
+            raise NotImplementedError("collision_mode == 1 (stochastic, default off) is not implemented on the device")
+        a = self._action(action)
+        self._push()
+        if self._shape[2]:
+            self._check(self._lib.dw_update_agents(self._h, _ptr(a, C.c_int64), a.shape[0], a.shape[1]), "dw_update_agents")
+        self._state_changed()
+
+    def _action(self, action):
+        a = np.asarray(action)
+        if a.ndim != 3:
+            raise IndexError("action must be indexable as action[b, n, 0] (reference :186-189)")
+        return np.ascontiguousarray(a[:, :, 0], dtype=np.int64)
+
+    def get_obs(self, agent_indices=None):
+        """reference :246-263"""
+        ai = np.ascontiguousarray(np.asarray(agent_indices), dtype=np.int64)
+        b, m = ai.shape[:2]
+        obs = np.zeros((b, m, self.ch, self.kr * 2 + 1, self.kr * 2 + 1))
+        self._push()
+        if b and m:
+            self._check(self._lib.dw_get_obs_at(self._h, _ptr(ai, C.c_int64), b, m, _ptr(obs, C.c_double)), "dw_get_obs_at")
+        return obs
+
+    def forward(self, grid):
+        """reference :434-461; standalone-callable (tests/daisy/test_daisy_world_rl.py:18-19)."""
+        g = np.asarray(grid)
+        B, N, _ = self._shape
+        if g.shape != (B, self.ch, N, N):
+            raise ValueError(f"forward expects a grid of shape {(B, self.ch, N, N)}")
+        work = np.ascontiguousarray(g, dtype=np.float64)
+        out = np.empty_like(work)
+        self._push()
+        self._check(self._lib.dw_forward(self._h, _ptr(work, C.c_double), _ptr(out, C.c_double)), "dw_forward")
+        if work is not g:
+            g[:, 0] = work[:, 0]
+        self._dead_L = self.L
+        self._diag_cache = {}
+        return out
+
+    def update_L(self, L):
+        """reference :463-473"""
+        self.step_count += 1
+        if self.ramp_up_down and self.step_count % self.ramp_period == 0:
+            self.dL *= -1
+            self.min_L -= self.ddL
+            self.max_L += self.ddL
+        L += self.dL
+        return max([min([L, self.max_L]), self.min_L])
+
+    def step(self, action=None):
+        """reference :475-497"""
+        if self.collision_mode == 1:
+            raise NotImplementedError("collision_mode == 1 (stochastic, default off) is not implemented on the device")
+        B, N, n = self._shape
+        a = None
+        if action is not None and n:
+            a = self._action(action)
+        self._push()
+        self._dead_L = self.L
+        if a is None:
+            rc = self._lib.dw_step(self._h, None, 0, 0)
+        else:
+            rc = self._lib.dw_step(self._h, _ptr(a, C.c_int64), a.shape[0], a.shape[1])
+        self._check(rc, "dw_step")
+        self._state_changed()
+        return self._collect()
+
+    def _collect(self):
+        B, N, n = self._shape
+        obs = np.zeros((B, n, self.ch, 3, 3))
+        self._check(self._lib.dw_get_obs(self._h, _ptr(obs, C.c_double)), "dw_get_obs")
+        if n:
+            reward = np.empty((B, n, 1))
+            done = np.empty((B, n, 1), dtype=np.uint8)
+        else:
+            reward = np.empty((B, 2))
+            done = np.empty((B, 2), dtype=np.uint8)
+        self._check(self._lib.dw_get_reward_done(self._h, _ptr(reward, C.c_double), _ptr(done, C.c_uint8)),
+                    "dw_get_reward_done")
+        if not n:
+            reward = reward.astype(bool)
+        self._pull_clock()
+        return obs, reward, done.astype(bool), {}
+
+    def __call__(self, grid):
+        pass
+
+    # ------------------------------------------------------------------ additions: fused path
+    def step_policy(self, policy="greedy", seed=0):
+        """One step with the action chosen on the device (Greedy's deterministic branch fused in)."""
+        self._push()
+        self._dead_L = self.L
+        self._check(self._lib.dw_step_policy(self._h, DW_POLICY[policy], C.c_uint64(seed)), "dw_step_policy")
+        self._state_changed()
+        return self._collect()
+
+    def reset_lifespans(self):
+        self._check(self._lib.dw_reset_lifespans(self._h), "dw_reset_lifespans")
+
+    def lifespans(self):
+        B, N, n = self._shape
+        done_at = np.zeros((B,), dtype=np.int64)
+        agents_done_at = np.zeros((B, n, 1), dtype=np.int64)
+        self._check(self._lib.dw_get_lifespans(self._h, _ptr(done_at, C.c_int64), _ptr(agents_done_at, C.c_int64)),
+                    "dw_get_lifespans")
+        return done_at, agents_done_at
+
+    def run(self, K, policy="greedy", actions=None, seed=0, stop_all_done=False):
+        """K steps on the device with an on-device policy; lifespan counters accumulate (see lifespans()).
+
+        policy: "none" | "greedy" | "antigreedy" | "random" | "replay" (actions[K,B,n(,1)] ints 0..8).
+        Returns (steps_run, worlds_alive, all_done_hit)."""
+        B, N, n = self._shape
+        a8 = None
+        if policy == "replay":
+            a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
+            if a8.shape[0] < K:
+                raise ValueError("replay needs at least K action frames")
+        self._push()
+        res = DwRunResult()
+        rc = self._lib.dw_run(self._h, int(K), DW_POLICY[policy], _ptr(a8, C.c_int8), C.c_uint64(seed),
+                              int(bool(stop_all_done)), C.byref(res))
+        self._check(rc, "dw_run")
+        self._state_changed()
+        self._pull_clock()
+        self._dead_L = None
+        return int(res.steps_run), int(res.worlds_alive), bool(res.all_done_hit)
+
+    def simulate_lifespan(self, policy="greedy", actions=None, seed=0, max_steps=100000):
+        """The notebook's simulate_lifespan (greedy_longevity_abatement.ipynb cell 2) after a reset():
+        returns (done_at[B], agents_done_at[B,n,1])."""
+        self.reset_lifespans()
+        self.run(max_steps, policy=policy, actions=actions, seed=seed, stop_all_done=True)
+        return self.lifespans()
+
+    def synchronize(self):
+        self._check(self._lib.dw_synchronize(self._h), "dw_synchronize")
