@@ -36,7 +36,7 @@ while True:
     if steps % 50 == 0:
         print(steps, time.time() - t0, flush=True)
 meta = dict(seed=seed, B=B, N=64, n=4, policy=policy, steps=steps, seconds=time.time() - t0, numpy=np.__version__)
-out = os.path.join(os.path.dirname(__file__), "..", "tests", "golden_big", f"cfg2_{policy}_n64_b{B}.npz")
+out = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", f"big_cfg2_{policy}_n64_b{B}.npz")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 np.savez_compressed(out, meta=np.array(json.dumps(meta)), done_at=done_at, agents_done_at=agents_done_at,
                     final_chan_sum=env.grid.sum(axis=(-2, -1)), final_agent_states=env.agent_states,

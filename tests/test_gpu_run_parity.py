@@ -76,3 +76,22 @@ def test_run_large_ensemble_matches_c_oracle():
     np.testing.assert_array_equal(done_at, d2)
     np.testing.assert_array_equal(agents_done_at, a2)
     np.testing.assert_array_equal(env.grid, ref.grid)
+
+
+def test_cfg2_full_size_lifespans_identical_to_reference():
+    """BASELINE config 2 at full size through the CUDA path: lifespans and final-state checksums identical to
+    the live reference's (fixture recorded by oracle/gen_golden_cfg2.py)."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    z, meta = load_golden("big_cfg2_greedy_n64_b1000")
+    np.random.seed(13)
+    env = RLDaisyWorld(grid_dimension=64)
+    env.batch_size = 1000
+    env.reset()
+    np.testing.assert_array_equal(env.agent_indices, z["init_agent_indices"])
+    done_at, agents_done_at = env.simulate_lifespan(policy="greedy")
+    assert env.step_count == meta["steps"]
+    np.testing.assert_array_equal(done_at, z["done_at"])
+    np.testing.assert_array_equal(agents_done_at, z["agents_done_at"])
+    np.testing.assert_array_equal(env.grid.sum(axis=(-2, -1)), z["final_chan_sum"])
+    np.testing.assert_array_equal(env.agent_states, z["final_agent_states"])
+    np.testing.assert_array_equal(env.agent_indices, z["final_agent_indices"])
