@@ -154,6 +154,14 @@ int dw_checkpoint_restore(dw_handle *h);
 
 int dw_synchronize(dw_handle *h);
 
+/* Multi-rank ensembles: global index of this handle's first world (only feeds the DW_POLICY_RANDOM counter RNG). */
+int dw_set_world_offset(dw_handle *h, uint32_t world0);
+
+/* Diagnostics of the fused path (tests / profiling): number of cells recomputed in literal order because the fast
+   path landed within the tie filter; and the fast fourth root evaluated on the device (host in, host out). */
+int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset);
+int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,85 @@
+"""Internals of the fused lattice path: accuracy of the fast fourth root (the only approximation in the fast
+path), the tie filter's literal fallback rate, and fused == materialising path on the same inputs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(N=8, B=2, n=2, seed=0):
+    from therldaisyworld_b200 import RLDaisyWorld
+    np.random.seed(seed)
+    env = RLDaisyWorld(grid_dimension=N, n_agents=n)
+    env.batch_size = B
+    env.reset()
+    return env
+
+
+def test_fast_root4_relative_error_bound():
+    """dw_root4_fast must stay far inside the error budget of the tie filter: the filter half-width is
+    3.8e-6 milli-cover and d(milli-cover)/d(relative root error) <= ~4e4, so 1e-11 suffices;
+    the measured error is ~1e-13."""
+    env = _env()
+    rng = np.random.RandomState(0)
+    x = np.concatenate([10.0 ** rng.uniform(8, 11.5, size=400000), np.linspace(3e9, 2e10, 100000)])
+    y = np.empty_like(x)
+    rc = env._lib.dw_debug_root4(env._h, x.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double)), x.size)
+    assert rc == 0
+    ref = np.sqrt(np.sqrt(x))
+    rel = np.abs(y - ref) / ref
+    print("max rel err of dw_root4_fast:", rel.max())
+    assert rel.max() < 2e-12
+
+
+@pytest.mark.parametrize("N,B,n,policy", [(64, 16, 4, "greedy"), (16, 8, 4, "antigreedy"), (33, 4, 7, "random"),
+                                          (5, 3, 2, "greedy"), (2, 2, 1, "greedy"), (1, 2, 1, "none"), (12, 4, 0, "none"),
+                                          (40, 2, 40, "greedy")])
+def test_fused_equals_materialising_path(N, B, n, policy):
+    """Same inputs through dw_run with the fused kernel and with DW_DISABLE_FUSED=1 (materialising kernels only)."""
+    res = []
+    for disable in (False, True):
+        if disable:
+            os.environ["DW_DISABLE_FUSED"] = "1"
+        else:
+            os.environ.pop("DW_DISABLE_FUSED", None)
+        try:
+            env = _env(N, B, n, seed=N)
+            env.reset_lifespans()
+            env.run(150, policy=policy, seed=5)
+            mid = env.grid.copy()
+            env.run(400, policy=policy, seed=5)
+            count = C.c_uint64()
+            assert env._lib.dw_debug_slow_count(env._h, C.byref(count), 0) == 0
+            res.append((mid, env.grid.copy(), env.agent_indices.copy(), env.agent_states.copy(), env.lifespans(),
+                        env.L, env.step_count, env.temp.copy(), count.value))
+        finally:
+            os.environ.pop("DW_DISABLE_FUSED", None)
+    a, b = res
+    for u, v in zip(a[:4], b[:4]):
+        np.testing.assert_array_equal(u, v)
+    np.testing.assert_array_equal(a[4][0], b[4][0])
+    np.testing.assert_array_equal(a[4][1], b[4][1])
+    assert a[5:7] == b[5:7]
+    np.testing.assert_array_equal(a[7], b[7])
+    assert b[8] == 0                      # materialising path never uses the literal fallback counter
+    cells = 549 * B * N * N
+    print(f"literal recomputations: {a[8]} of {cells} cell-updates ({a[8] / cells:.2e})")
+    assert a[8] < 1e-3 * cells + 10
+
+
+def test_unsupported_kernels_use_materialising_path():
+    """An asymmetric daisy kernel is outside the fused fast path; dw_run must still be right (vs single steps)."""
+    env = _env(8, 2, 2, seed=3)
+    k = env.daisy_kernel.copy()
+    k[0, 0, 0, 1] *= 1.5
+    env.daisy_kernel = k / k.sum()
+    env2 = _env(8, 2, 2, seed=3)
+    env2.daisy_kernel = env.daisy_kernel.copy()
+    env.run(20, policy="greedy")
+    for _ in range(20):
+        env2.step_policy("greedy")
+    np.testing.assert_array_equal(env.grid, env2.grid)
+    np.testing.assert_array_equal(env.agent_states, env2.agent_states)

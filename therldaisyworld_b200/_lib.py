@@ -33,7 +33,8 @@ SYMBOLS = [
     "dw_set_stream", "dw_upload_state", "dw_init_temperatures", "dw_step", "dw_step_policy", "dw_update_agents",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
     "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
-    "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize",
+    "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
+    "dw_debug_root4",
 ]
 
 _lib = None
@@ -84,6 +85,9 @@ def load():
         "dw_checkpoint_save": (C.c_int, [vp]),
         "dw_checkpoint_restore": (C.c_int, [vp]),
         "dw_synchronize": (C.c_int, [vp]),
+        "dw_set_world_offset": (C.c_int, [vp, C.c_uint32]),
+        "dw_debug_slow_count": (C.c_int, [vp, C.POINTER(u64), i32]),
+        "dw_debug_root4": (C.c_int, [vp, pd, pd, i32]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():

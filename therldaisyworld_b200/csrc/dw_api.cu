@@ -1,6 +1,7 @@
 // C-ABI implementation (include/daisyworld_b200.h): handle management, state residency, launches.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (therldaisyworld_b200/build.py)
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -50,6 +51,9 @@ struct dw_handle {
     double *scratch = nullptr;                 // diag / forward scratch
     size_t scratch_cap = 0;
     double *fwd_in = nullptr, *fwd_out = nullptr;
+    unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
+    unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
+    bool fused_attr_set = false;
 
     // checkpoint
     struct Ckpt {
@@ -212,7 +216,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->grid[0], h->grid[1], h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {
@@ -673,6 +677,39 @@ extern "C" int dw_checkpoint_restore(dw_handle *h) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     return ckpt_restore(h, 0);
+}
+
+// ---- diagnostics hooks -------------------------------------------------------------------------------------
+extern "C" int dw_set_world_offset(dw_handle *h, uint32_t world0) {
+    if (!h) return DW_E_INVALID;
+    h->world0 = world0;
+    return DW_OK;
+}
+
+extern "C" int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset) {
+    if (!h || !count) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    *count = 0;
+    if (!h->slow_count) return DW_OK;
+    unsigned int c = 0;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(&c, h->slow_count, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *count = c;
+    if (reset) DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count, 0, sizeof(unsigned int), h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n) {
+    if (!h || !x || !y || n < 1) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_scratch(h, 2 * (size_t)n);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->scratch, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_debug_root4<<<(n + 255) / 256, 256, 0, h->stream>>>(h->scratch, h->scratch + n, n);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_CUDA_TRY(h, cudaMemcpyAsync(y, h->scratch + n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
 }
 
 // ---- dw_run / dw_run_chunk ----------------------------------------------------------------------------------

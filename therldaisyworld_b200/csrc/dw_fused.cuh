@@ -1,8 +1,320 @@
-// Fused multi-step lattice kernels (filled in below).
+// Fused multi-step lattice kernels: one CTA owns one world in shared memory and runs K env steps per launch.
+//
+// After the first forward pass every cover value is k/1000 with integer k in [0,1000] (np.round(.,3),
+// daisy_world_rl.py:452), so a world is stored as one packed u32 per cell (light k | dark k << 16): 16 KB for
+// 64x64.  The 3x3 stencils become exact integer sums on the packed words (ALU pipe), and the per-cell physics is
+// a short fp64 sequence ("fast path") that is algebraically equal to the reference formulas but not in the
+// reference's rounding order.  Exactness is restored by a filter: the fast path's result x (in milli-cover
+// units) has a proven error bound far below the filter width; whenever x lies within DW_TIE_EPS of a rounding
+// tie the cell is recomputed by dw_literal_cell() in the oracle's operation order.  Everything else the step
+// needs (agent moves, grazing, greedy argmax, lifespan counters) follows the literal order as well, so a fused
+// run is value-identical to stepping the oracle -- tests/test_gpu_run_parity.py.
+//
+// Roofline: the kernel is bound by the FP64 pipe (64 DFMA/clk/SM); HBM traffic is 8 B per cell per LAUNCH.
 #pragma once
 #include "dw_common.cuh"
 
-struct dw_handle;
-// placeholders until the fused lattice kernel lands: everything runs through the materialising kernels
-static inline bool dw_fused_supported(const dw_handle *) { return false; }
-static inline int run_steps_fused(dw_handle *, int, int, const int8_t *, unsigned long long) { return DW_E_UNSUPPORTED; }
+#define DW_FUSED_MAX_STEPS 64
+#define DW_FUSED_MAX_AGENTS 1024
+#define DW_FIX_BITS 20                 // fixed-point fraction bits of the rounding trick (ulp of 1.5*2^32)
+#define DW_TIE_EPS 4                   // filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover)
+
+struct FastCoef {        // launch-constant coefficients of the fast path (host-computed, fp64)
+    double w0, w12, w2;  // rho (milli) = w0*k + (w1-w2)*E + w2*S8
+    double dtp, dtm, dtg;  // dt*p, dt/1000, dt*gamma
+    double xk_l, xk_d;   // X_l coefficients of the centre covers: (q2-q)*(al-ab)/1000, (q2-q)*(ad-ab)/1000
+    double xdd;          // X_d - X_l = q2*(al-ad)
+    double topt, g;
+};
+struct StepCoef {        // per-step (luminosity dependent) coefficients
+    double x0;           // cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al
+    double xs_l, xs_d;   // (q-cL)*a*(al-ab)/1000, (q-cL)*a*(ad-ab)/1000   (a = adjacent tap)
+    double SL;           // S*L for the literal path
+};
+
+struct FusedArgs {
+    DevParams P;
+    FastCoef F;
+    StepCoef sc[DW_FUSED_MAX_STEPS];
+    const uint32_t *lat_in;     // [B,N,N]
+    uint32_t *lat_out;          // [B,N,N]
+    uint32_t *lat_pre;          // [B,N,N] post-graze state the LAST step of the launch started from
+    int32_t *agent_xy;          // [B,n,2]
+    double *agent_state;        // [B,n]
+    const int8_t *actions;      // [K,B,n] (REPLAY)
+    int64_t *done_at;           // [B]
+    int64_t *agents_done_at;    // [B,n]
+    unsigned int *alive;        // [K] per-step count of worlds that are not grid_done
+    double *reward;             // [B,n] or [B,2]
+    uint8_t *done;
+    unsigned long long seed;
+    unsigned int step0;         // env.step_count at launch (RANDOM policy counter)
+    unsigned int world0;        // global index of this handle's first world (RANDOM policy counter)
+    int K, policy;
+    unsigned int *slow_count;   // diagnostics: number of literal recomputations (may be NULL)
+};
+
+// ---- fast fourth root ------------------------------------------------------------------------------------
+__device__ __forceinline__ double dw_rsqrt_approx(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double dw_rcp_approx(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+// X^(1/4) for X in the physical range (1e8..1e11): two MUFU.RSQ64H seeds + one MUFU.RCP64H, then one Newton step
+// on y^4 = X.  Relative error <= ~1e-12 (measured in tests/test_gpu_fused_internals.py), 6 fp64-pipe ops.
+__device__ __forceinline__ double dw_root4_fast(double X) {
+    const double y0 = dw_rsqrt_approx(dw_rsqrt_approx(X));   // X^(1/4) (1+d), |d| < 2^-21
+    const double c = dw_rcp_approx(y0);
+    const double z = y0 * y0;
+    const double res = __fma_rn(-z, z, X);                    // X - y0^4
+    const double c2 = c * c;
+    const double c3 = c2 * c;
+    return __fma_rn(res * c3, 0.25, y0);
+}
+
+__device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
+    return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
+}
+
+// One cell of the fast path. pc: packed centre, E: packed sum of the 4 edge neighbours, S: packed sum of all 8.
+// Returns the packed new cell; *tie is set when either species sits within the filter of a rounding tie.
+__device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCoef &C, uint32_t pc, uint32_t E, uint32_t S,
+                                                 bool *tie) {
+    const double kl = dw_u2d(pc & 0xffffu), kd = dw_u2d(pc >> 16);
+    const double El = dw_u2d(E & 0xffffu), Ed = dw_u2d(E >> 16);
+    const double Sl = dw_u2d(S & 0xffffu), Sd = dw_u2d(S >> 16);
+    const double Rl = __fma_rn(F.w2, Sl, __fma_rn(F.w12, El, F.w0 * kl));
+    const double Rd = __fma_rn(F.w2, Sd, __fma_rn(F.w12, Ed, F.w0 * kd));
+    const double rb = __fma_rn(-F.dtm, Rl + Rd, F.dtp);                       // dt * bare neighbourhood density
+    const double Xl = __fma_rn(C.xs_l, Sl, __fma_rn(C.xs_d, Sd, __fma_rn(F.xk_l, kl, __fma_rn(F.xk_d, kd, C.x0))));
+    const double Xd = Xl + F.xdd;
+    const double dTl = F.topt - dw_root4_fast(Xl);
+    const double dTd = F.topt - dw_root4_fast(Xd);
+    const double bl = __fma_rn(-F.g, dTl * dTl, 1.0);
+    const double bd = __fma_rn(-F.g, dTd * dTd, 1.0);
+    const double xl = __fma_rn(Rl, __fma_rn(rb, bl, -F.dtg), kl);             // l + dt*dl in milli units
+    const double xd = __fma_rn(Rd, __fma_rn(rb, bd, -F.dtg), kd);
+    // round-to-nearest via the 1.5*2^32 magic: low word = round(x * 2^20) as a signed fixed-point number
+    const double MAGIC = 6442450944.0;
+    const int fl = __double2loint(xl + MAGIC), fd = __double2loint(xd + MAGIC);
+    const int HALF = 1 << (DW_FIX_BITS - 1), MASK = (1 << DW_FIX_BITS) - 1;
+    int ql = (fl + HALF) >> DW_FIX_BITS, qd = (fd + HALF) >> DW_FIX_BITS;
+    const unsigned ul = (unsigned)(fl + HALF + DW_TIE_EPS) & MASK, ud = (unsigned)(fd + HALF + DW_TIE_EPS) & MASK;
+    *tie = (ul < 2u * DW_TIE_EPS) | (ud < 2u * DW_TIE_EPS);
+    ql = min(max(ql, 0), 1000);
+    qd = min(max(qd, 0), 1000);
+    return dw_pack(ql, qd);
+}
+
+// Literal recomputation of one cell from the packed neighbourhood (oracle order). Rare: ~1e-5 of cell-updates.
+__device__ __noinline__ uint32_t dw_slow_cell(const FusedArgs *A, double SL, const uint32_t *cb, int N, int x, int y) {
+    const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+    const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+    const int xs[3] = {xm, x, xp}, ys[3] = {ym, y, yp};
+    double l9[9], d9[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t k = cb[xs[a] * N + ys[c]];
+            l9[a * 3 + c] = dw_milli(k & 0xffffu);
+            d9[a * 3 + c] = dw_milli(k >> 16);
+        }
+    const LitCell o = dw_literal_cell(A->P, SL, l9, d9);
+    // np.round(x,3) = rint(x*1000)/1000  ->  lattice index rint(x*1000)
+    const int ql = (int)rint(o.nl * 1000.0), qd = (int)rint(o.nd * 1000.0);
+    if (A->slow_count) atomicAdd(A->slow_count, 1u);
+    return dw_pack(ql, qd);
+}
+
+// ---- agents on the lattice (warp 0) ------------------------------------------------------------------------
+struct AgentSmem {
+    double *st;     // [n]
+    int *xy;        // [n] x | y << 16
+    int *act;       // [n]
+    int *ada;       // [n] agents_done_at increments of this launch
+};
+
+__device__ __forceinline__ double dw_food(uint32_t pk) { return dw_milli(pk & 0xffffu) + dw_milli(pk >> 16); }
+
+__device__ __forceinline__ void dw_agents_phase(const FusedArgs &A, int j, int b, uint32_t *cb, const AgentSmem &S, int lane) {
+    const int N = A.P.N, n = A.P.n_agents;
+    // pass 1: decisions from the state the previous step left (= the observation the policy would have seen)
+    for (int i = lane; i < n; i += 32) {
+        int a;
+        if (A.policy == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + i];
+        else if (A.policy == DW_POLICY_NONE) a = 0;
+        else if (A.policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, i, A.step0 + j) % 9u);
+        else {
+            const int x = S.xy[i] & 0xffff, y = S.xy[i] >> 16;
+            const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+            const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+            const double food[4] = {dw_food(cb[x * N + ym]), dw_food(cb[xm * N + y]), dw_food(cb[xp * N + y]),
+                                    dw_food(cb[x * N + yp])};
+            a = dw_greedy_pick(food, A.policy == DW_POLICY_GREEDY);
+        }
+        S.act[i] = a;
+    }
+    __syncwarp();
+    // pass 2: move + graze, agents in index order (32 at a time; inside a batch lower lanes eat first)
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool active = i < n;
+        double st = 0.0;
+        int x = 0, y = 0, cell = -1;
+        bool wants = false;
+        if (active) {
+            st = S.st[i] - A.P.agent_gamma;
+            x = S.xy[i] & 0xffff;
+            y = S.xy[i] >> 16;
+            const int a = S.act[i];
+            if (st > 0.0) {
+                if (a != 8) {
+                    switch (a & 3) {
+                        case 0: y = y == 0 ? N - 1 : y - 1; break;
+                        case 1: x = x == 0 ? N - 1 : x - 1; break;
+                        case 2: x = x == N - 1 ? 0 : x + 1; break;
+                        default: y = y == N - 1 ? 0 : y + 1; break;
+                    }
+                }
+                if (a > 4) { wants = true; cell = x * N + y; }
+            }
+        }
+        const uint32_t pk = wants ? cb[cell] : 0u;
+        __syncwarp();
+        bool taken = false;
+        for (int q = 0; q < 31; ++q) {
+            const int cq = __shfl_sync(0xffffffffu, cell, q);
+            if (q < lane && cq == cell && cell >= 0) taken = true;
+        }
+        if (wants) {
+            st = st + (taken ? (0.0 + 0.0) : dw_food(pk));
+            cb[cell] = 0u;
+        }
+        if (active) {
+            S.st[i] = dw_clip01(st);
+            S.xy[i] = x | (y << 16);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- generic-N fused kernel: one CTA per world, cells strided over threads ---------------------------------
+// dynamic smem: 2*N*N u32 | n doubles | 3n ints | 4 ints
+__global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.P.N, n = A.P.n_agents, NN = N * N;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *buf0 = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *buf1 = buf0 + NN;
+    AgentSmem S;
+    S.st = reinterpret_cast<double *>(buf1 + NN);   // 2*NN u32 = 8*NN bytes: 8-byte aligned
+    S.xy = reinterpret_cast<int *>(S.st + n);
+    S.act = S.xy + n;
+    S.ada = S.act + n;
+    int *s_max = S.ada + n;            // [2 parities][2 species]
+
+    const uint32_t *gin = A.lat_in + (size_t)b * NN;
+    for (int c = tid; c < NN; c += blockDim.x) buf0[c] = gin[c];
+    for (int i = tid; i < n; i += blockDim.x) {
+        S.st[i] = A.agent_state[(size_t)b * n + i];
+        S.xy[i] = A.agent_xy[((size_t)b * n + i) * 2] | (A.agent_xy[((size_t)b * n + i) * 2 + 1] << 16);
+        S.ada[i] = 0;
+    }
+    if (tid < 4) s_max[tid] = 0;
+    __syncthreads();
+
+    uint32_t *cb = buf0, *nb = buf1;
+    int life = 0;
+    // per-thread cell walk: c = tid + m*blockDim  ->  (x,y) advanced incrementally
+    const int dx = blockDim.x / N, dy = blockDim.x % N;
+    for (int j = 0; j < A.K; ++j) {
+        if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane);
+        __syncthreads();
+        if (j == A.K - 1) {
+            uint32_t *gp = A.lat_pre + (size_t)b * NN;
+            for (int c = tid; c < NN; c += blockDim.x) gp[c] = cb[c];
+        }
+        const StepCoef C = A.sc[j];
+        uint32_t mx = 0;
+        int x = tid / N, y = tid % N;
+        for (int c = tid; c < NN; c += blockDim.x) {
+            const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+            const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+            const uint32_t *r0 = cb + xm * N, *r1 = cb + x * N, *r2 = cb + xp * N;
+            const uint32_t E = r1[ym] + r1[yp] + r0[y] + r2[y];
+            const uint32_t S8 = E + r0[ym] + r0[yp] + r2[ym] + r2[yp];
+            const uint32_t pc = r1[y];
+            uint32_t q = pc;
+            if ((pc | S8) != 0u) {          // empty neighbourhood: rho = 0 and the cell stays exactly 0
+                bool tie;
+                q = dw_fast_cell(A.F, C, pc, E, S8, &tie);
+                if (tie) q = dw_slow_cell(&A, C.SL, cb, N, x, y);
+            }
+            nb[c] = q;
+            mx = __vmaxu2(mx, q);
+            x += dx; y += dy;
+            if (y >= N) { y -= N; x += 1; }
+        }
+        const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+        int *sm = s_max + 2 * (j & 1);
+        if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+        __syncthreads();
+        if (warp == 0) {
+            // lifespan bookkeeping of step j (notebook cell 2): grid_done = max(grid[:,1:3]) <= 0.005
+            const bool grid_done = max(sm[0], sm[1]) <= 5;
+            if (lane == 0) {
+                if (!grid_done) { life += 1; atomicAdd(A.alive + j, 1u); }
+                s_max[2 * ((j + 1) & 1)] = 0;
+                s_max[2 * ((j + 1) & 1) + 1] = 0;
+            }
+            for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;   // reward = state (clipped >= 0)
+        }
+        uint32_t *t = cb; cb = nb; nb = t;
+    }
+    // write back (warp 0's bookkeeping above is ordered before these reads by the barrier below)
+    __syncthreads();
+    uint32_t *gout = A.lat_out + (size_t)b * NN;
+    for (int c = tid; c < NN; c += blockDim.x) gout[c] = cb[c];
+    for (int i = tid; i < n; i += blockDim.x) {
+        A.agent_state[(size_t)b * n + i] = S.st[i];
+        A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
+        A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
+        A.agents_done_at[(size_t)b * n + i] += S.ada[i];
+        const double r = S.st[i];
+        A.reward[(size_t)b * n + i] = r;
+        A.done[(size_t)b * n + i] = r < 0.1;
+    }
+    if (tid == 0) {
+        A.done_at[b] += life;
+        if (n == 0) {
+            const int *sm = s_max + 2 * ((A.K - 1) & 1);
+            for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
+        }
+    }
+}
+
+// fp64 grid channels 1,2 -> packed lattice; flags worlds whose covers are not exactly k/1000
+__global__ void __launch_bounds__(256) k_grid_to_lattice(int B, size_t NN, const double *__restrict__ grid, uint32_t *__restrict__ lat,
+                                                         unsigned int *off_lattice) {
+    const size_t total = (size_t)B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / NN, c = i - b * NN;
+        const double l = grid[b * 7 * NN + NN + c], d = grid[b * 7 * NN + 2 * NN + c];
+        const double kl = rint(l * 1000.0), kd = rint(d * 1000.0);
+        const bool ok = kl >= 0.0 && kl <= 1000.0 && kd >= 0.0 && kd <= 1000.0 && kl / 1000.0 == l && kd / 1000.0 == d;
+        if (!ok) atomicAdd(off_lattice, 1u);
+        lat[i] = ok ? dw_pack((int)kl, (int)kd) : 0u;
+    }
+}
+
+// debug/measurement hook: y[i] = dw_root4_fast(x[i])
+__global__ void k_debug_root4(const double *x, double *y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = dw_root4_fast(x[i]);
+}

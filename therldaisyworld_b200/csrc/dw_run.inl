@@ -1,6 +1,134 @@
 // dw_run / dw_run_chunk: K steps with an on-device policy and the notebook lifespan counters.
 // Included at the end of dw_api.cu.
 
+// ---- fused lattice path: host side -----------------------------------------------------------------------
+static size_t fused_smem_bytes(int N, int n) {
+    const size_t NN = (size_t)N * N;
+    return 2 * NN * sizeof(uint32_t) + (size_t)n * sizeof(double) + 3 * (size_t)n * sizeof(int) + 4 * sizeof(int);
+}
+
+// The fast path needs D4-symmetric 3x3 kernels (centre / edge / corner classes) and a uniform zero-centre
+// adjacent kernel; anything else (and worlds too large for shared memory) runs through the materialising kernels.
+static bool dw_fused_supported(const dw_handle *h) {
+    const dw_config &c = h->cfg;
+    const double *w = c.daisy_kernel, *a = c.adjacent_kernel;
+    const bool wsym = w[0] == w[2] && w[0] == w[6] && w[0] == w[8] && w[1] == w[3] && w[1] == w[5] && w[1] == w[7];
+    bool asym = a[4] == 0.0;
+    for (int i = 0; i < 9; ++i) if (i != 4 && a[i] != a[0]) asym = false;
+    if (!wsym || !asym) return false;
+    if (c.n_agents > DW_FUSED_MAX_AGENTS) return false;
+    if (getenv("DW_DISABLE_FUSED")) return false;
+    return fused_smem_bytes(c.dim, c.n_agents) <= 200 * 1024;
+}
+
+static void make_fast_coef(const dw_config &c, FastCoef &F) {
+    F.w0 = c.daisy_kernel[4];
+    F.w12 = c.daisy_kernel[1] - c.daisy_kernel[0];
+    F.w2 = c.daisy_kernel[0];
+    F.dtp = c.dt * c.p;
+    F.dtm = c.dt / 1000.0;
+    F.dtg = c.dt * c.gamma;
+    const double cl = (c.albedo_light - c.albedo_bare) / 1000.0, cd = (c.albedo_dark - c.albedo_bare) / 1000.0;
+    F.xk_l = (c.q2 - c.q) * cl;
+    F.xk_d = (c.q2 - c.q) * cd;
+    F.xdd = c.q2 * (c.albedo_light - c.albedo_dark);
+    F.topt = c.temp_optimal;
+    F.g = c.g;
+}
+
+static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
+    const double a = c.adjacent_kernel[0];
+    const double cL = c.S * L / c.sigma;
+    const double Al0 = c.albedo_bare * c.p, A0 = c.albedo_bare * c.p * (8.0 * a);
+    const double cl = (c.albedo_light - c.albedo_bare) / 1000.0, cd = (c.albedo_dark - c.albedo_bare) / 1000.0;
+    s.x0 = cL + (c.q - cL) * A0 + (c.q2 - c.q) * Al0 - c.q2 * c.albedo_light;
+    s.xs_l = (c.q - cL) * a * cl;
+    s.xs_d = (c.q - cL) * a * cd;
+    s.SL = c.S * L;
+}
+
+// bring the state onto the packed lattice; *converted = false if some cover is not an exact k/1000
+static int grid_to_lattice(dw_handle *h, bool *converted) {
+    const size_t B = h->cfg.batch, NN = h->NN;
+    int rc = dev_alloc(h, &h->lat[0], B * NN);
+    if (!rc) rc = dev_alloc(h, &h->lat[1], B * NN);
+    if (!rc) rc = dev_alloc(h, &h->lat_pre, B * NN);
+    if (!rc) rc = dev_alloc(h, &h->slow_count, (size_t)2);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
+    k_grid_to_lattice<<<grid_for(B * NN), 256, 0, h->stream>>>((int)B, NN, h->grid[h->cur], h->lat[h->lcur], h->slow_count + 1);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    unsigned int off = 0;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(&off, h->slow_count + 1, sizeof(off), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *converted = off == 0;
+    if (*converted) h->lat_valid = true;
+    return DW_OK;
+}
+
+static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive) {
+    FusedArgs A{};
+    A.P = make_params(h);
+    make_fast_coef(h->cfg, A.F);
+    dw_clock clk = h->clk;
+    double L_last = clk.L;
+    for (int j = 0; j < K; ++j) {
+        make_step_coef(h->cfg, clk.L, A.sc[j]);
+        L_last = clk.L;
+        update_L(clk);
+    }
+    A.lat_in = h->lat[h->lcur];
+    A.lat_out = h->lat[1 - h->lcur];
+    A.lat_pre = h->lat_pre;
+    A.agent_xy = h->agent_xy; A.agent_state = h->agent_state; A.actions = act_dev;
+    A.done_at = h->done_at; A.agents_done_at = h->agents_done_at; A.alive = alive;
+    A.reward = h->reward; A.done = h->done;
+    A.seed = seed; A.step0 = (unsigned int)h->clk.step_count; A.world0 = h->world0;
+    A.K = K; A.policy = policy;
+    A.slow_count = h->slow_count;
+    const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
+    if (smem > 48 * 1024 && !h->fused_attr_set) {
+        DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        h->fused_attr_set = true;
+    }
+    k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    h->lcur = 1 - h->lcur;
+    h->lat_valid = true;
+    h->grid_valid = false;
+    h->pre = PRE_LAT;
+    h->L_last = L_last;
+    h->obs_valid = false;
+    h->clk = clk;
+    return DW_OK;
+}
+
+static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive);
+
+// K <= 64 steps, fused where the state allows it
+static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed) {
+    unsigned int *alive = h->alive;
+    const size_t per_step = (size_t)h->cfg.batch * h->cfg.n_agents;
+    if (!h->lat_valid) {
+        if (!h->grid_valid) return dw_fail(h, DW_E_STATE, "dw_run", "no state uploaded");
+        bool ok = false;
+        int rc = grid_to_lattice(h, &ok);
+        if (rc) return rc;
+        if (!ok) {
+            // off-lattice covers (the unrounded state right after reset()): the first step must be literal
+            rc = run_steps_generic(h, 1, policy, act_dev, seed, alive);
+            if (rc) return rc;
+            K -= 1; alive += 1;
+            if (act_dev) act_dev += per_step;
+            if (K == 0) return DW_OK;
+            rc = grid_to_lattice(h, &ok);
+            if (rc) return rc;
+            if (!ok) return dw_fail(h, DW_E_STATE, "dw_run", "state is off the 0.001 lattice after a forward step");
+        }
+    }
+    return launch_fused(h, K, policy, act_dev, seed, alive);
+}
+
 static int stage_actions8(dw_handle *h, const int8_t *actions, size_t count) {
     if (h->action_cap < count) {
         if (h->action_dev) cudaFree(h->action_dev);
@@ -13,7 +141,7 @@ static int stage_actions8(dw_handle *h, const int8_t *actions, size_t count) {
 }
 
 // K <= 64 steps through the materialising kernels (any N, any kernels, off-lattice states)
-static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed) {
+static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive) {
     int rc = ensure_grid(h);
     if (rc) return rc;
     const size_t per_step = (size_t)h->cfg.batch * h->cfg.n_agents;
@@ -21,7 +149,7 @@ static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_
         if (policy == DW_POLICY_REPLAY) rc = launch_agents(h, act_dev + (size_t)j * per_step, h->cfg.batch, h->cfg.n_agents, policy, seed);
         else rc = launch_agents(h, nullptr, 0, 0, policy, seed);
         if (rc) return rc;
-        rc = launch_forward_tail(h, true, h->alive + j);
+        rc = launch_forward_tail(h, true, alive + j);
         if (rc) return rc;
     }
     return DW_OK;
@@ -31,7 +159,7 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
                           unsigned int *alive_last) {
     if (K < 1 || K > 64) return dw_fail(h, DW_E_INVALID, "run_chunk", "1 <= K <= 64");
     DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, 64 * sizeof(unsigned int), h->stream));
-    int rc = dw_fused_supported(h) ? run_steps_fused(h, K, policy, act_dev, seed) : run_steps_generic(h, K, policy, act_dev, seed);
+    int rc = dw_fused_supported(h) ? run_steps_fused(h, K, policy, act_dev, seed) : run_steps_generic(h, K, policy, act_dev, seed, h->alive);
     if (rc) return rc;
     unsigned int alive[64];
     DW_CUDA_TRY(h, cudaMemcpyAsync(alive, h->alive, K * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
