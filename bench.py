@@ -1,0 +1,382 @@
+#!/usr/bin/env python3
+"""Benchmark of the RLDaisyWorld simulation step (BASELINE.json metric: cell-updates/s & env-steps/s, batched 64x64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE configs[1] -- a 1000-world ensemble (per GPU), 64x64, light(0.75)/dark(0.25)
+daisies, 4 greedy agents per world, seed 13.  One bench "step" = one pass of the hot path over that batch: the
+whole ensemble advanced by T=384 env steps from the post-reset state (every world is still alive at step 384, so
+no work is skipped): 1 literal materialising step (the reset state is off the 0.001 lattice) + 383 fused steps.
+`value` = cell-updates/s = worlds * 64*64 * T * K / (device time, max over ranks), state resident in HBM.
+`e2e` = the same through the C-ABI with HOST buffers: per step, upload of the two cover planes + agents from pinned
+host memory, the T-step run, and the download of the lifespan counters, all inside the timed region.
+N > 1: one process per GPU (torchrun), worlds sharded (1000 per rank, weak scaling), no data-path collective;
+one NCCL all-reduce of the 8-double lifespan-statistics vector per bench step, inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORLDS = 1000
+N = 64
+N_AGENTS = 4
+T_STEPS = 384
+SEED = 13
+FLOP_PER_CELL_UPDATE = 98          # algorithmic flops of one cell-update
+WORKLOAD = (f"BASELINE configs[1]: {WORLDS}-world ensemble per GPU, {N}x{N}, light/dark daisies, {N_AGENTS} greedy "
+            f"agents, seed {SEED}; one step = {T_STEPS} env steps from the reset state")
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    """One host process: its share of the ensemble stepped by the NumPy port (FFT convolutions like the reference)."""
+    rank, worlds, steps_per_sample, n_samples, warm = args
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy
+    os.environ["OMP_NUM_THREADS"] = "1"
+    np.random.seed(SEED + rank)
+    env = OracleDaisyWorld(conv="fft", grid_dimension=N, n_agents=N_AGENTS)
+    env.batch_size = worlds
+    obs = env.reset()
+    agent = OracleGreedy()
+    out = []
+    for s in range(warm + n_samples):
+        t0 = time.perf_counter()
+        for _ in range(steps_per_sample):
+            obs, _, _, _ = env.step(agent(obs))
+        out.append(time.perf_counter() - t0)
+    return out[warm:]
+
+
+def run_reference(args):
+    """--impl reference: the reference's NumPy CPU path (oracle port: the reference is Python and cannot travel to the
+    GPU box), all host cores, on a bounded sample of the same workload."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32, WORLDS))
+    per = [WORLDS // procs + (1 if i < WORLDS % procs else 0) for i in range(procs)]
+    steps_per_sample = 2                       # env steps per bench step: bounded sample (1000 worlds x 2 steps)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        times = pool.map(_ref_worker, [(i, per[i], steps_per_sample, K, W) for i in range(procs)])
+    per_step = np.max(np.array(times), axis=0)          # slowest process bounds each step
+    total = float(per_step.sum())
+    cells = WORLDS * N * N * steps_per_sample * K
+    value = cells / total
+    sample = f"{WORLDS} worlds x {steps_per_sample} env steps per bench step, split over {procs} processes"
+    line = {
+        "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "env_steps_per_s": WORLDS * steps_per_sample * K / total,
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # "under load": samples in the upper half of the observed power range
+            thr = (min(power) + max(power)) / 2 if power else 0
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=float(max(power)))
+        return out
+
+
+def initial_state(rank):
+    """Post-reset state of this rank's ensemble, produced exactly like RLDaisyWorld.reset() draws it
+    (daisy_world_rl.py:285-302, 173-179) -- synthetic data, seed SEED + rank."""
+    rng = np.random.RandomState(SEED + rank)
+    rng.randint(N, size=(32, N_AGENTS, 2))                # the constructor's extra draw
+    u_dark = rng.rand(WORLDS, 2, N, N)
+    u_light = rng.rand(WORLDS, 2, N, N)
+    dark = 1.0 * (u_dark[:, 0] < 0.33) * 0.2 * u_dark[:, 1]
+    light = 1.0 * (u_light[:, 0] < 0.33) * 0.2 * u_light[:, 1]
+    agents = rng.randint(N, size=(WORLDS, N_AGENTS, 2)).astype(np.int64)
+    states = np.ones((WORLDS, N_AGENTS))
+    return np.ascontiguousarray(light), np.ascontiguousarray(dark), agents, states
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def load_traffic():
+    """DRAM bytes per launch of the fused kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "fused_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_baseline_sample():
+    """Reference NumPy path (oracle port, FFT convolutions, Python agent loops), 1 core, bounded sample."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy
+    np.random.seed(SEED)
+    env = OracleDaisyWorld(conv="fft", grid_dimension=N, n_agents=N_AGENTS)
+    env.batch_size = WORLDS
+    obs = env.reset()
+    agent = OracleGreedy()
+    obs, _, _, _ = env.step(agent(obs))                   # warm-up
+    steps = 5
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        obs, _, _, _ = env.step(agent(obs))
+    dt = time.perf_counter() - t0
+    return {"value": WORLDS * N * N * steps / dt, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"{WORLDS} worlds x {N}x{N} x {steps} env steps after 1 warm-up, NumPy port with FFT convolutions",
+            "env_steps_per_s": WORLDS * steps / dt, "seconds": dt}
+
+
+# ----------------------------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from therldaisyworld_b200 import RLDaisyWorld, _lib
+    from therldaisyworld_b200._lib import DwProfile, DwRunResult, DW_POLICY
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    light, dark, agents, states = initial_state(rank)
+    # the drop-in object gives us a configured handle (constants, kernels, clock); state comes from initial_state()
+    np.random.seed(SEED + rank)
+    env = RLDaisyWorld(grid_dimension=N, n_agents=N_AGENTS, device=local)
+    env.batch_size = WORLDS
+    env.reset()
+    lib, h = env._lib, env._h
+    lib.dw_set_world_offset(h, rank * WORLDS)
+
+    def chk(rc, what):
+        _lib.check(lib, h, rc, what)
+
+    pd = C.POINTER(C.c_double)
+    # pinned host staging for the e2e arm
+    pin_light = torch.from_numpy(light).pin_memory()
+    pin_dark = torch.from_numpy(dark).pin_memory()
+    pin_agents = torch.from_numpy(agents).pin_memory()
+    pin_states = torch.from_numpy(states).pin_memory()
+    out_done_at = torch.zeros(WORLDS, dtype=torch.int64).pin_memory()
+    out_agents = torch.zeros(WORLDS, N_AGENTS, dtype=torch.int64).pin_memory()
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+
+    def upload():
+        chk(lib.dw_upload_covers(h, C.cast(pin_light.data_ptr(), pd), C.cast(pin_dark.data_ptr(), pd)), "dw_upload_covers")
+        chk(lib.dw_upload_state(h, None, C.cast(pin_agents.data_ptr(), C.POINTER(C.c_int64)), C.cast(pin_states.data_ptr(), pd)),
+            "dw_upload_state")
+        env.L, env.step_count = env.min_L, 0
+        env.dL = (env.max_L - env.min_L) / env.ramp_period
+        clk = env._clock()
+        chk(lib.dw_set_clock(h, C.byref(clk)), "dw_set_clock")
+        chk(lib.dw_reset_lifespans(h), "dw_reset_lifespans")
+
+    res = DwRunResult()
+
+    def run_T():
+        chk(lib.dw_run(h, T_STEPS, DW_POLICY["greedy"], None, C.c_uint64(0), 0, C.byref(res)), "dw_run")
+        chk(lib.dw_lifespan_stats_device(h, C.c_void_p(stats.data_ptr())), "dw_lifespan_stats_device")
+        if world > 1:
+            dist.all_reduce(stats)
+
+    def download():
+        chk(lib.dw_get_lifespans(h, C.cast(out_done_at.data_ptr(), C.POINTER(C.c_int64)),
+                                 C.cast(out_agents.data_ptr(), C.POINTER(C.c_int64))), "dw_get_lifespans")
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident arm: state already in HBM (device-side checkpoint), timed with CUDA events on the launch stream
+    upload()
+    chk(lib.dw_checkpoint_save(h), "dw_checkpoint_save")
+    for _ in range(W):
+        chk(lib.dw_checkpoint_restore(h), "dw_checkpoint_restore")
+        run_T()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    chk(lib.dw_set_profiling(h, 1), "dw_set_profiling")
+    t_res = 0.0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    wall0 = time.perf_counter()
+    for k in range(K):
+        chk(lib.dw_checkpoint_restore(h), "dw_checkpoint_restore")
+        flush.fill_(k & 0xff)                                    # L2 flush between timed iterations
+        ev[k][0].record()
+        run_T()
+        ev[k][1].record()
+    barrier()
+    wall_res = time.perf_counter() - wall0
+    t_res = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    prof = DwProfile()
+    chk(lib.dw_get_profile(h, C.byref(prof)), "dw_get_profile")
+    chk(lib.dw_set_profiling(h, 0), "dw_set_profiling")
+    download()
+    mean_life = float(out_done_at.double().mean())               # all alive at T => T_STEPS exactly
+
+    # ---- e2e arm: host buffers in, host results out, every step
+    for _ in range(2):
+        upload(); run_T(); download()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e2e_wall = []
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev2[k][0].record()
+        upload(); run_T(); download()
+        ev2[k][1].record()
+        torch.cuda.synchronize()
+        e2e_wall.append(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t_e2e = float(sum(e2e_wall))
+
+    # ---- max over ranks
+    t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_res, t_e2e = float(t[0]), float(t[1])
+    cells_per_step = world * WORLDS * N * N * T_STEPS
+    value = cells_per_step * K / t_res
+    e2e_value = cells_per_step * K / t_e2e
+    h2d = light.nbytes + dark.nbytes + agents.nbytes + states.nbytes
+    d2h = out_done_at.numel() * 8 + out_agents.numel() * 8
+
+    if rank == 0:
+        peaks = load_peaks()
+        # measured FP64 FMA peak of this device (the fused kernel's roofline denominator)
+        tf, ms = C.c_double(), C.c_double()
+        chk(lib.dw_debug_fp64_peak(h, 20000, 5, C.byref(tf), C.byref(ms)), "dw_debug_fp64_peak")
+        fused_s = prof.fused_ms * 1e-3
+        achieved = prof.fused_cell_updates * FLOP_PER_CELL_UPDATE / fused_s / 1e12 if fused_s > 0 else None
+        roofline = {
+            "bound": "fp64_fma", "kernel": "k_fused (SMEM-resident lattice kernel)",
+            "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+            "frac": (achieved / tf.value) if achieved else None,
+            "peak_source": "measured live: dw_debug_fp64_peak (dependent DFMA chains, full occupancy); MEASURED_PEAKS.json "
+                           "has no FP64 entry",
+            "flop_per_cell_update": FLOP_PER_CELL_UPDATE,
+            "cell_updates_per_launch": prof.fused_cell_updates / max(1, prof.fused_launches),
+            "avg_launch_ms": prof.fused_ms / max(1, prof.fused_launches),
+            "kernel_share_of_step": fused_s / t_res if t_res > 0 else None,
+            "kernel_cell_updates_per_s": prof.fused_cell_updates / fused_s if fused_s > 0 else None,
+            "traffic": load_traffic(),
+            "hbm": {"algorithmic_bytes_per_launch": 8 * WORLDS * N * N * 2, "peak_gbs": peaks.get("hbm_gbs") if peaks else 6650.0,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "note": "8 B/cell/launch read+write of the packed lattice: the kernel is not HBM bound"},
+        }
+        cpu = cpu_baseline_sample() if world == 1 else None
+        line = {
+            "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "worlds_per_gpu": WORLDS, "grid": N, "n_agents": N_AGENTS, "policy": "greedy",
+                       "env_steps_per_bench_step": T_STEPS, "l2": "flushed between timed iterations (256 MB write)",
+                       "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective"},
+            "env_steps_per_s": world * WORLDS * T_STEPS * K / t_res,
+            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / K, "env_steps_per_s": world * WORLDS * T_STEPS * K / t_e2e},
+            "gpu_launches": int(prof.kernel_launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "check": {"mean_done_at_after_T": mean_life, "expected": float(T_STEPS), "ensemble_stats": stats.tolist(),
+                      "wall_s_resident": wall_res},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,15 @@ typedef struct dw_run_result {
     int32_t _pad;
 } dw_run_result;
 
+/* Launch accounting of a handle since dw_set_profiling(h, 1). fused_ms is device time of the fused lattice kernel
+   measured with CUDA events on the handle's stream. */
+typedef struct dw_profile {
+    uint64_t kernel_launches;      /* every kernel this library launched */
+    uint64_t fused_launches;       /* launches of the fused lattice kernel */
+    uint64_t fused_cell_updates;   /* cell-updates those launches performed */
+    double fused_ms;               /* their summed duration */
+} dw_profile;
+
 typedef struct dw_handle dw_handle;
 
 int dw_abi_version(void);
@@ -103,6 +112,10 @@ int dw_set_stream(dw_handle *h, void *cuda_stream);
 /* env.grid / env.agent_indices / env.agent_states assignment (any of the pointers may be NULL = keep).
    Host -> device; pinned host memory makes the copy asynchronous. */
 int dw_upload_state(dw_handle *h, const double *grid, const int64_t *agent_indices, const double *agent_states);
+
+/* initialize_grid's cover assignment (daisy_world_rl.py:304-312): grid = 0, ch1 = light[B,N,N], ch2 = dark[B,N,N]
+   (host planes).  The narrow upload the reset()/ensemble paths use: the step reads nothing else of the grid. */
+int dw_upload_covers(dw_handle *h, const double *light, const double *dark);
 
 /* initialize_grid's field fill (daisy_world_rl.py:304-324): ch0 = p-l-d and ch3..5 = UNROUNDED T, T_light,
    T_dark of the uploaded covers at the current clock L. Called by reset() after dw_upload_state. */
@@ -157,10 +170,16 @@ int dw_synchronize(dw_handle *h);
 /* Multi-rank ensembles: global index of this handle's first world (only feeds the DW_POLICY_RANDOM counter RNG). */
 int dw_set_world_offset(dw_handle *h, uint32_t world0);
 
+int dw_set_profiling(dw_handle *h, int32_t on);      /* resets the counters */
+int dw_get_profile(dw_handle *h, dw_profile *out);
+
 /* Diagnostics of the fused path (tests / profiling): number of cells recomputed in literal order because the fast
    path landed within the tie filter; and the fast fourth root evaluated on the device (host in, host out). */
 int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset);
 int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n);
+/* Measured FP64 FMA peak of the handle's device (dependent DFMA chains, full occupancy): best of `reps` launches of
+   `iters` x 8 FMAs per thread, in TFLOP/s (FMA = 2 flop).  Roofline denominator of the fused kernel. */
+int dw_debug_fp64_peak(dw_handle *h, int32_t iters, int32_t reps, double *tflops_best, double *ms_best);
 
 #ifdef __cplusplus
 }

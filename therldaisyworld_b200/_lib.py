@@ -23,6 +23,11 @@ class DwClock(C.Structure):
                [("step_count", C.c_int64), ("ramp_period", C.c_int64), ("ramp_up_down", C.c_int32), ("_pad", C.c_int32)]
 
 
+class DwProfile(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("fused_launches", C.c_uint64), ("fused_cell_updates", C.c_uint64),
+                ("fused_ms", C.c_double)]
+
+
 class DwRunResult(C.Structure):
     _fields_ = [("steps_run", C.c_int64), ("worlds_alive", C.c_int64), ("all_done_hit", C.c_int32), ("_pad", C.c_int32)]
 
@@ -30,11 +35,11 @@ class DwRunResult(C.Structure):
 # every symbol include/daisyworld_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
-    "dw_set_stream", "dw_upload_state", "dw_init_temperatures", "dw_step", "dw_step_policy", "dw_update_agents",
+    "dw_set_stream", "dw_upload_state", "dw_upload_covers", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
     "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
-    "dw_debug_root4",
+    "dw_debug_root4", "dw_debug_fp64_peak",
 ]
 
 _lib = None
@@ -66,7 +71,10 @@ def load():
         "dw_get_last_L": (C.c_int, [vp, pd]),
         "dw_set_stream": (C.c_int, [vp, vp]),
         "dw_upload_state": (C.c_int, [vp, pd, pi64, pd]),
+        "dw_upload_covers": (C.c_int, [vp, pd, pd]),
         "dw_init_temperatures": (C.c_int, [vp]),
+        "dw_set_profiling": (C.c_int, [vp, i32]),
+        "dw_get_profile": (C.c_int, [vp, C.POINTER(DwProfile)]),
         "dw_step": (C.c_int, [vp, pi64, i32, i32]),
         "dw_step_policy": (C.c_int, [vp, i32, u64]),
         "dw_update_agents": (C.c_int, [vp, pi64, i32, i32]),
@@ -88,6 +96,7 @@ def load():
         "dw_set_world_offset": (C.c_int, [vp, C.c_uint32]),
         "dw_debug_slow_count": (C.c_int, [vp, C.POINTER(u64), i32]),
         "dw_debug_root4": (C.c_int, [vp, pd, pd, i32]),
+        "dw_debug_fp64_peak": (C.c_int, [vp, i32, i32, pd, pd]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():

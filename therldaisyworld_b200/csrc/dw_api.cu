@@ -54,6 +54,12 @@ struct dw_handle {
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     bool fused_attr_set = false;
+    // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
+    dw_profile prof{};
+    bool profiling = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ev_pending = false;
+    uint64_t ev_cells = 0;
 
     // checkpoint
     struct Ckpt {
@@ -70,6 +76,9 @@ struct dw_handle {
     } ck[2];   // slot 0: dw_checkpoint_save/restore (caller), slot 1: dw_run's chunk rewind
 };
 
+#define DW_LAUNCHED(h) do { (h)->prof.kernel_launches += 1; DW_CUDA_TRY((h), cudaGetLastError()); } while (0)
+
+static int dw_fail(dw_handle *h, int code, const char *what, const char *detail);
 static int dw_fail(dw_handle *h, int code, const char *what, const char *detail) {
     std::string m = std::string(what) + ": " + detail;
     if (h) h->err = m; else g_create_error = m;
@@ -138,7 +147,7 @@ static int launch_stamp(dw_handle *h, double *grid, bool counters, unsigned int 
         P, grid, h->agent_xy, h->agent_state, (counters || P.n_agents == 0) ? h->world_max : nullptr,
         rewards ? h->reward : nullptr, rewards ? h->done : nullptr, counters ? h->done_at : nullptr,
         counters ? h->agents_done_at : nullptr, alive_slot);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     return DW_OK;
 }
 
@@ -157,7 +166,7 @@ static int ensure_grid(dw_handle *h) {
         SrcLattice src{h->lat_pre, h->NN};
         k_forward<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, src, out, nullptr, nullptr,
                                                                        h->ch6_dirty[h->cur] ? 1 : 0);
-        DW_CUDA_TRY(h, cudaGetLastError());
+        DW_LAUNCHED(h);
         h->ch6_dirty[h->cur] = false;
         rc = launch_stamp(h, out, false, nullptr, false);
         if (rc) return rc;
@@ -302,6 +311,27 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
     return DW_OK;
 }
 
+// initialize_grid's cover assignment (daisy_world_rl.py:304-312): channels 1,2 from host planes, the rest zero
+extern "C" int dw_upload_covers(dw_handle *h, const double *light, const double *dark) {
+    if (!h || !light || !dark) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_grid_buffers(h);
+    if (rc) return rc;
+    const size_t B = h->cfg.batch, NN = h->NN;
+    double *g = h->grid[h->cur];
+    DW_CUDA_TRY(h, cudaMemsetAsync(g, 0, B * 7 * NN * sizeof(double), h->stream));
+    DW_CUDA_TRY(h, cudaMemcpy2DAsync(g + NN, 7 * NN * sizeof(double), light, NN * sizeof(double), NN * sizeof(double), B,
+                                     cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaMemcpy2DAsync(g + 2 * NN, 7 * NN * sizeof(double), dark, NN * sizeof(double), NN * sizeof(double), B,
+                                     cudaMemcpyHostToDevice, h->stream));
+    h->ch6_dirty[h->cur] = false;
+    h->grid_valid = true;
+    h->lat_valid = false;
+    h->pre = PRE_NONE;
+    h->obs_valid = false;
+    return DW_OK;
+}
+
 // initialize_grid's temperature fill (daisy_world_rl.py:304-324): ch0 = p-l-d, ch3..5 = unrounded T, Tl, Td at clk.L
 extern "C" int dw_init_temperatures(dw_handle *h) {
     if (!h) return DW_E_INVALID;
@@ -309,7 +339,7 @@ extern "C" int dw_init_temperatures(dw_handle *h) {
     if (!h->grid_valid) return dw_fail(h, DW_E_STATE, "dw_init_temperatures", "upload a grid first");
     const DevParams P = make_params(h);
     k_init_fields<<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, h->grid[h->cur]);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     h->pre = PRE_GRID;
     h->pre_grid = h->grid[h->cur];
     h->L_last = h->clk.L;
@@ -339,7 +369,7 @@ static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, in
     const DevParams P = make_params(h);
     k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, h->agent_state, act_dev, ab, am,
                                                              policy, seed, (uint32_t)h->clk.step_count);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     return DW_OK;
 }
 
@@ -352,7 +382,7 @@ static int launch_forward_tail(dw_handle *h, bool counters, unsigned int *alive_
     SrcGrid src{in, 7 * h->NN, h->NN};
     k_forward<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, out, in, h->world_max,
                                                                 h->ch6_dirty[1 - h->cur] ? 1 : 0);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     h->ch6_dirty[1 - h->cur] = false;
     h->pre = PRE_GRID;
     h->pre_grid = in;
@@ -427,7 +457,7 @@ extern "C" int dw_forward(dw_handle *h, double *grid_in, double *grid_out) {
     SrcGrid src{h->fwd_in, 7 * h->NN, h->NN};
     k_forward<SrcGrid><<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, h->fwd_out, h->fwd_in,
                                                                             nullptr, 1);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     rc = launch_stamp(h, h->fwd_out, false, nullptr, false);
     if (rc) return rc;
     // the reference's forward() refreshes env.temp/beta/growth as a side effect
@@ -453,7 +483,7 @@ static int compute_obs(dw_handle *h) {
     if (rc) return rc;
     const DevParams P = make_params(h);
     k_obs<<<grid_for(B * n * 63), 256, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, (int)B, (int)n, h->obs);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     h->obs_valid = true;
     return DW_OK;
 }
@@ -485,7 +515,7 @@ extern "C" int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t
     DW_CUDA_TRY(h, cudaMemcpyAsync(pos, xy.data(), xy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     const DevParams P = make_params(h);
     k_obs<<<grid_for(count), 256, 0, h->stream>>>(P, h->grid[h->cur], pos, b, m, h->scratch);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->scratch, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DW_OK;
@@ -541,7 +571,7 @@ extern "C" int dw_get_diag(dw_handle *h, int32_t which, double *out) {
         SrcLattice src{h->lat_pre, h->NN};
         k_diag<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
     }
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     DW_CUDA_TRY(h, cudaMemcpyAsync(out, h->scratch, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DW_OK;
@@ -600,7 +630,7 @@ extern "C" int dw_lifespan_stats_device(dw_handle *h, double *out_dev) {
     if (!h || !out_dev) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     k_lifespan_stats<<<1, 1024, 0, h->stream>>>(h->cfg.batch, h->cfg.n_agents, h->done_at, h->agents_done_at, nullptr, out_dev);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     return DW_OK;
 }
 
@@ -679,6 +709,70 @@ extern "C" int dw_checkpoint_restore(dw_handle *h) {
     return ckpt_restore(h, 0);
 }
 
+extern "C" int dw_set_profiling(dw_handle *h, int32_t on) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (on && !h->ev[0]) {
+        DW_CUDA_TRY(h, cudaEventCreate(&h->ev[0]));
+        DW_CUDA_TRY(h, cudaEventCreate(&h->ev[1]));
+    }
+    h->profiling = on != 0;
+    h->prof = dw_profile{};
+    h->ev_pending = false;
+    return DW_OK;
+}
+extern "C" int dw_get_profile(dw_handle *h, dw_profile *out) {
+    if (!h || !out) return DW_E_INVALID;
+    *out = h->prof;
+    return DW_OK;
+}
+
+// FP64 FMA peak of the device, measured: the roofline denominator of the fused kernel (MEASURED_PEAKS.json has
+// only HBM and bf16 numbers). 8 independent DFMA chains per thread, 2048 resident threads per SM.
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __fma_rn(v[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    if (s == 12345.678) out[0] = s;   // keep the chains alive
+}
+
+extern "C" int dw_debug_fp64_peak(dw_handle *h, int32_t iters, int32_t reps, double *tflops_best, double *ms_best) {
+    if (!h || iters < 1 || reps < 1 || !tflops_best) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_scratch(h, 16);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    DW_CUDA_TRY(h, cudaEventCreate(&e0));
+    DW_CUDA_TRY(h, cudaEventCreate(&e1));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const int blocks = sms * 8, threads = 256;
+    double best = 1e30;
+    for (int r = 0; r < reps + 1; ++r) {
+        DW_CUDA_TRY(h, cudaEventRecord(e0, h->stream));
+        k_fp64_peak<<<blocks, threads, 0, h->stream>>>(h->scratch, iters, 0.999999, 1e-9);
+        DW_CUDA_TRY(h, cudaGetLastError());
+        DW_CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+        DW_CUDA_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        DW_CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    *tflops_best = flops / (best * 1e-3) / 1e12;
+    if (ms_best) *ms_best = best;
+    return DW_OK;
+}
+
 // ---- diagnostics hooks -------------------------------------------------------------------------------------
 extern "C" int dw_set_world_offset(dw_handle *h, uint32_t world0) {
     if (!h) return DW_E_INVALID;
@@ -706,7 +800,7 @@ extern "C" int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t 
     if (rc) return rc;
     DW_CUDA_TRY(h, cudaMemcpyAsync(h->scratch, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     k_debug_root4<<<(n + 255) / 256, 256, 0, h->stream>>>(h->scratch, h->scratch + n, n);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     DW_CUDA_TRY(h, cudaMemcpyAsync(y, h->scratch + n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DW_OK;

@@ -17,6 +17,9 @@
 #define DW_FUSED_MAX_STEPS 64
 #define DW_FUSED_MAX_AGENTS 1024
 #define DW_FIX_BITS 20                 // fixed-point fraction bits of the rounding trick (ulp of 1.5*2^32)
+#ifndef DW_N64_MIN_BLOCKS
+#define DW_N64_MIN_BLOCKS 4            // resident CTAs per SM the 64x64 kernel is register-budgeted for
+#endif
 #define DW_TIE_EPS 4                   // filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover)
 
 struct FastCoef {        // launch-constant coefficients of the fast path (host-computed, fp64)
@@ -282,6 +285,143 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ F
     uint32_t *gout = A.lat_out + (size_t)b * NN;
     for (int c = tid; c < NN; c += blockDim.x) gout[c] = cb[c];
     for (int i = tid; i < n; i += blockDim.x) {
+        A.agent_state[(size_t)b * n + i] = S.st[i];
+        A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
+        A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
+        A.agents_done_at[(size_t)b * n + i] += S.ada[i];
+        const double r = S.st[i];
+        A.reward[(size_t)b * n + i] = r;
+        A.done[(size_t)b * n + i] = r < 0.1;
+    }
+    if (tid == 0) {
+        A.done_at[b] += life;
+        if (n == 0) {
+            const int *sm = s_max + 2 * ((A.K - 1) & 1);
+            for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
+        }
+    }
+}
+
+// ---- 64x64 specialisation: 256 threads, one 4x4 tile per thread -------------------------------------------------
+// Thread (tx = tid&15, ty = tid>>4) owns rows 4ty..4ty+3, columns 4tx..4tx+3.  A step loads the 6 rows ty*4-1..ty*4+4
+// of its 4 columns with LDS.128 (conflict-free: a half-warp reads one contiguous 256 B row), takes the two halo
+// columns from the neighbouring lanes with SHFL (tile columns wrap inside the half-warp), forms the packed 3x3
+// sums with ~4.5 integer adds per cell, runs dw_fast_cell on 16 cells and writes 4 STS.128.  Cells that hit the
+// tie filter are patched afterwards by the literal path, outside the unrolled code.
+struct Row6 { uint32_t p[4]; uint32_t hp[4]; };
+
+__device__ __forceinline__ Row6 dw_load_row(const uint32_t *cb, int row, int tx, int lane) {
+    Row6 r;
+    const uint4 v = *reinterpret_cast<const uint4 *>(cb + row * 64 + tx * 4);
+    const int base = lane & 16;
+    const uint32_t left = __shfl_sync(0xffffffffu, v.w, base | ((lane - 1) & 15));
+    const uint32_t right = __shfl_sync(0xffffffffu, v.x, base | ((lane + 1) & 15));
+    r.p[0] = v.x; r.p[1] = v.y; r.p[2] = v.z; r.p[3] = v.w;
+    r.hp[0] = left + v.y;
+    r.hp[1] = v.x + v.z;
+    r.hp[2] = v.y + v.w;
+    r.hp[3] = v.z + right;
+    return r;
+}
+
+__global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __grid_constant__ FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = 64, NN = N * N;
+    const int n = A.P.n_agents;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    uint32_t *buf0 = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *buf1 = buf0 + NN;
+    AgentSmem S;
+    S.st = reinterpret_cast<double *>(buf1 + NN);
+    S.xy = reinterpret_cast<int *>(S.st + n);
+    S.act = S.xy + n;
+    S.ada = S.act + n;
+    int *s_max = S.ada + n;
+
+    {
+        const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat_in + (size_t)b * NN);
+        uint4 *d = reinterpret_cast<uint4 *>(buf0);
+#pragma unroll
+        for (int c = 0; c < NN / 4 / 256; ++c) d[tid + c * 256] = gin[tid + c * 256];
+    }
+    for (int i = tid; i < n; i += 256) {
+        S.st[i] = A.agent_state[(size_t)b * n + i];
+        S.xy[i] = A.agent_xy[((size_t)b * n + i) * 2] | (A.agent_xy[((size_t)b * n + i) * 2 + 1] << 16);
+        S.ada[i] = 0;
+    }
+    if (tid < 4) s_max[tid] = 0;
+    __syncthreads();
+
+    uint32_t *cb = buf0, *nb = buf1;
+    int life = 0;
+    const int r0 = ty * 4;
+    for (int j = 0; j < A.K; ++j) {
+        if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane);
+        __syncthreads();
+        if (j == A.K - 1) {
+            uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
+            const uint4 *sc4 = reinterpret_cast<const uint4 *>(cb);
+#pragma unroll
+            for (int c = 0; c < NN / 4 / 256; ++c) gp[tid + c * 256] = sc4[tid + c * 256];
+        }
+        const StepCoef C = A.sc[j];
+        uint32_t mx = 0, tiemask = 0;
+        Row6 top = dw_load_row(cb, (r0 + 63) & 63, tx, lane);
+        Row6 mid = dw_load_row(cb, r0, tx, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const Row6 bot = dw_load_row(cb, (r0 + i + 1) & 63, tx, lane);
+            uint32_t q[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t E = mid.hp[c] + top.p[c] + bot.p[c];
+                const uint32_t S8 = E + top.hp[c] + bot.hp[c];
+                const uint32_t pc = mid.p[c];
+                uint32_t v = pc;
+                if ((pc | S8) != 0u) {
+                    bool tie;
+                    v = dw_fast_cell(A.F, C, pc, E, S8, &tie);
+                    if (tie) tiemask |= 1u << (i * 4 + c);
+                    else mx = __vmaxu2(mx, v);
+                }
+                q[c] = v;
+            }
+            *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
+            top = mid;
+            mid = bot;
+        }
+        while (tiemask) {            // rare (~1e-5 of cells): literal recomputation in the oracle's order
+            const int k = __ffs(tiemask) - 1;
+            tiemask &= tiemask - 1;
+            const int x = r0 + (k >> 2), y = tx * 4 + (k & 3);
+            const uint32_t v = dw_slow_cell(&A, C.SL, cb, N, x, y);
+            nb[x * 64 + y] = v;
+            mx = __vmaxu2(mx, v);
+        }
+        const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+        int *sm = s_max + 2 * (j & 1);
+        if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+        __syncthreads();
+        if (warp == 0) {
+            const bool grid_done = max(sm[0], sm[1]) <= 5;
+            if (lane == 0) {
+                if (!grid_done) { life += 1; atomicAdd(A.alive + j, 1u); }
+                s_max[2 * ((j + 1) & 1)] = 0;
+                s_max[2 * ((j + 1) & 1) + 1] = 0;
+            }
+            for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;
+        }
+        uint32_t *t = cb; cb = nb; nb = t;
+    }
+    __syncthreads();
+    {
+        uint4 *gout = reinterpret_cast<uint4 *>(A.lat_out + (size_t)b * NN);
+        const uint4 *sc4 = reinterpret_cast<const uint4 *>(cb);
+#pragma unroll
+        for (int c = 0; c < NN / 4 / 256; ++c) gout[tid + c * 256] = sc4[tid + c * 256];
+    }
+    for (int i = tid; i < n; i += 256) {
         A.agent_state[(size_t)b * n + i] = S.st[i];
         A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
         A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;

@@ -57,7 +57,7 @@ static int grid_to_lattice(dw_handle *h, bool *converted) {
     if (rc) return rc;
     DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
     k_grid_to_lattice<<<grid_for(B * NN), 256, 0, h->stream>>>((int)B, NN, h->grid[h->cur], h->lat[h->lcur], h->slow_count + 1);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_LAUNCHED(h);
     unsigned int off = 0;
     DW_CUDA_TRY(h, cudaMemcpyAsync(&off, h->slow_count + 1, sizeof(off), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -91,8 +91,15 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         h->fused_attr_set = true;
     }
-    k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
-    DW_CUDA_TRY(h, cudaGetLastError());
+    if (h->profiling) DW_CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+    if (h->cfg.dim == 64 && !getenv("DW_FUSED_GENERIC")) k_fused_n64<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+    else k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+    DW_LAUNCHED(h);
+    if (h->profiling) {
+        DW_CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
+        h->ev_pending = true;
+        h->ev_cells = (uint64_t)h->cfg.batch * h->NN * (uint64_t)K;
+    }
     h->lcur = 1 - h->lcur;
     h->lat_valid = true;
     h->grid_valid = false;
@@ -164,6 +171,14 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
     unsigned int alive[64];
     DW_CUDA_TRY(h, cudaMemcpyAsync(alive, h->alive, K * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->ev_pending) {
+        float ms = 0.f;
+        DW_CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->prof.fused_launches += 1;
+        h->prof.fused_ms += ms;
+        h->prof.fused_cell_updates += h->ev_cells;
+        h->ev_pending = false;
+    }
     uint64_t m = 0;
     for (int j = 0; j < K; ++j) if (alive[j] == 0) m |= (1ull << j);
     if (done_mask) *done_mask = m;

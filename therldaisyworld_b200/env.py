@@ -342,13 +342,13 @@ class RLDaisyWorld:
         light_probability = np.random.rand(B, 2, N, N)
         dark = 1.0 * (dark_probability[:, 0] < self.dark_proportion) * self.initial_ad * dark_probability[:, 1]
         light = 1.0 * (light_probability[:, 0] < self.light_proportion) * self.initial_al * light_probability[:, 1]
-        grid = np.zeros((B, self.ch, N, N))
-        grid[:, 0] = self.p - light - dark
-        grid[:, 1] = light
-        grid[:, 2] = dark
         self._ensure_handle((int(B), int(N), int(self.n_agents)))
-        self.grid = grid
+        self._m["grid"].invalidate()
         self._push()
+        # narrow upload: the step reads only the two cover planes; ch0 and the temperatures are filled on the device
+        light = np.ascontiguousarray(light, dtype=np.float64)
+        dark = np.ascontiguousarray(dark, dtype=np.float64)
+        self._check(self._lib.dw_upload_covers(self._h, _ptr(light, C.c_double), _ptr(dark, C.c_double)), "dw_upload_covers")
         self._check(self._lib.dw_init_temperatures(self._h), "dw_init_temperatures")
         self._dead_L = self.L
         self._m["grid"].invalidate()
