@@ -177,6 +177,9 @@ int dw_get_profile(dw_handle *h, dw_profile *out);
    path landed within the tie filter; and the fast fourth root evaluated on the device (host in, host out). */
 int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset);
 int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n);
+/* number of integers k in [-kmax,kmax] for which the division-free k/1000 used by the kernels differs from the IEEE
+   quotient (must be 0) */
+int dw_debug_markstein(dw_handle *h, uint32_t kmax, uint32_t *bad);
 /* Measured FP64 FMA peak of the handle's device (dependent DFMA chains, full occupancy): best of `reps` launches of
    `iters` x 8 FMAs per thread, in TFLOP/s (FMA = 2 flop).  Roofline denominator of the fused kernel. */
 int dw_debug_fp64_peak(dw_handle *h, int32_t iters, int32_t reps, double *tflops_best, double *ms_best);

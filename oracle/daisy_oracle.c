@@ -267,5 +267,18 @@ int64_t dwo_run(const dwo_params *P, dwo_clock *clk, double *grid, int64_t *agen
     return t;
 }
 
+/* Test support: number of integers k in [0,kmax] for which Markstein's division-free k/1000
+   (q = k*0.001; r = fma(-1000,q,k); q + r*0.001), used by the CUDA kernels, differs from k/1000.0. */
+long dwo_check_markstein(long kmax) {
+    long bad = 0;
+    for (long k = 0; k <= kmax; ++k) {
+        double kd = (double)k, q = kd * 0.001, r = fma(-1000.0, q, kd), f = fma(r, 0.001, q);
+        if (f != kd / 1000.0) ++bad;
+        kd = -kd; q = kd * 0.001; r = fma(-1000.0, q, kd); f = fma(r, 0.001, q);
+        if (f != kd / 1000.0) ++bad;
+    }
+    return bad;
+}
+
 int dwo_sizeof_params(void) { return (int)sizeof(dwo_params); }
 int dwo_sizeof_clock(void) { return (int)sizeof(dwo_clock); }

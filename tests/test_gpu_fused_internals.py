@@ -83,3 +83,10 @@ def test_unsupported_kernels_use_materialising_path():
         env2.step_policy("greedy")
     np.testing.assert_array_equal(env.grid, env2.grid)
     np.testing.assert_array_equal(env.agent_states, env2.agent_states)
+
+
+def test_division_free_rounding_is_exact_on_device():
+    env = _env()
+    bad = C.c_uint32(123)
+    assert env._lib.dw_debug_markstein(env._h, 2000000, C.byref(bad)) == 0
+    assert bad.value == 0

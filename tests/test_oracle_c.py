@@ -77,3 +77,14 @@ def test_c_oracle_matches_numpy_oracle_random_states():
         np.testing.assert_array_equal(diag[:, 0:1], env.temp)
         np.testing.assert_array_equal(diag[:, 5:6], env.beta_l)
         np.testing.assert_array_equal(diag[:, 7:9], env.growth)
+
+
+def test_markstein_division_exhaustive():
+    """The kernels replace rint(x*1000)/1000 by a division-free sequence; it must equal the IEEE quotient for every
+    lattice index that can occur (covers 0..1 -> 0..1000, temperatures up to 2000 K -> 2e6)."""
+    from oracle.daisy_c import lib
+    import ctypes as C
+    fn = lib().dwo_check_markstein
+    fn.restype = C.c_long
+    fn.argtypes = [C.c_long]
+    assert fn(2000000) == 0

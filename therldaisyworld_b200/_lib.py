@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libdaisyworld_b200.so")
+LIB_PATH = os.environ.get("DW_LIB", os.path.join(PKG, "libdaisyworld_b200.so"))   # DW_LIB: kernel-variant experiments
 
 DW_POLICY = {"none": 0, "greedy": 1, "antigreedy": 2, "replay": 3, "random": 4}
 DW_DIAG = {"temp": 0, "temp_light": 1, "temp_dark": 2, "temp_effective": 3, "beta": 4, "beta_l": 5, "beta_d": 6,
@@ -39,7 +39,7 @@ SYMBOLS = [
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
     "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
-    "dw_debug_root4", "dw_debug_fp64_peak",
+    "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak",
 ]
 
 _lib = None
@@ -96,6 +96,7 @@ def load():
         "dw_set_world_offset": (C.c_int, [vp, C.c_uint32]),
         "dw_debug_slow_count": (C.c_int, [vp, C.POINTER(u64), i32]),
         "dw_debug_root4": (C.c_int, [vp, pd, pd, i32]),
+        "dw_debug_markstein": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "dw_debug_fp64_peak": (C.c_int, [vp, i32, i32, pd, pd]),
     }
     assert set(sig) == set(SYMBOLS)

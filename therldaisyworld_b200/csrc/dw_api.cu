@@ -793,6 +793,19 @@ extern "C" int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset)
     return DW_OK;
 }
 
+extern "C" int dw_debug_markstein(dw_handle *h, uint32_t kmax, uint32_t *bad) {
+    if (!h || !bad) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = dev_alloc(h, &h->slow_count, (size_t)2);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
+    k_debug_markstein<<<148 * 4, 256, 0, h->stream>>>(kmax, h->slow_count + 1);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_CUDA_TRY(h, cudaMemcpyAsync(bad, h->slow_count + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
 extern "C" int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n) {
     if (!h || !x || !y || n < 1) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));

@@ -23,7 +23,12 @@ struct DevParams {
 
 __device__ __forceinline__ double dw_root4(double x) { return sqrt(sqrt(x)); }
 __device__ __forceinline__ double dw_pow4(double x) { double x2 = x * x; return x2 * x2; }
-__device__ __forceinline__ double dw_round3(double x) { return rint(x * 1000.0) / 1000.0; }
+__device__ __forceinline__ double dw_div1000(double k);
+// np.round(x, 3) = rint(x*1000)/1000 (true division); the division-free form is exact for |rint(x*1000)| <= 2e6
+__device__ __forceinline__ double dw_round3(double x) {
+    const double k = rint(x * 1000.0);
+    return fabs(k) <= 2.0e6 ? dw_div1000(k) : k / 1000.0;
+}
 __device__ __forceinline__ double dw_clip01(double x) {
     x = x < 0.0 ? 0.0 : x;
     return x > 1.0 ? 1.0 : x;
@@ -79,7 +84,17 @@ __device__ __forceinline__ LitCell dw_literal_cell(const DevParams &P, double SL
 
 // Packed lattice cell: light milli-cover in bits 0..15, dark in bits 16..31 (both 0..1000).
 __device__ __forceinline__ uint32_t dw_pack(int kl, int kd) { return (uint32_t)kl | ((uint32_t)kd << 16); }
-__device__ __forceinline__ double dw_milli(uint32_t k) { return (double)k / 1000.0; }   // == np.round(x,3) value
+// k/1000 correctly rounded (== the value np.round(x,3) stores) without a division: Markstein's sequence
+// q = k*(1/1000), r = k - 1000q (exact in an FMA), q + r*(1/1000).  Verified exhaustively against k/1000.0 for every
+// integer 0 <= k <= 2e6 (tests/test_oracle_c.py::test_markstein_division_exhaustive and the GPU twin).
+__device__ __forceinline__ double dw_div1000(double k) {
+    const double q = k * 0.001;
+    const double r = __fma_rn(-1000.0, q, k);
+    return __fma_rn(r, 0.001, q);
+}
+__device__ __forceinline__ double dw_milli(uint32_t k) {
+    return dw_div1000(__hiloint2double(0x43300000, (int)k) - 4503599627370496.0);
+}
 
 #define DW_CUDA_TRY(h, expr)                                                           \
     do {                                                                               \

@@ -14,11 +14,20 @@
 #pragma once
 #include "dw_common.cuh"
 
+#ifndef DW_N64_ROW_UNROLL
+#define DW_N64_ROW_UNROLL 4             // unroll factor of the 4-row tile loop (1 keeps the body inside the i-cache)
+#endif
+#ifndef DW_N64_MIN_BLOCKS
+#define DW_N64_MIN_BLOCKS 4
+#endif
 #define DW_FUSED_MAX_STEPS 64
 #define DW_FUSED_MAX_AGENTS 1024
 #define DW_FIX_BITS 20                 // fixed-point fraction bits of the rounding trick (ulp of 1.5*2^32)
 #ifndef DW_N64_MIN_BLOCKS
 #define DW_N64_MIN_BLOCKS 4            // resident CTAs per SM the 64x64 kernel is register-budgeted for
+#endif
+#ifndef DW_N64_ROW_UNROLL
+#define DW_N64_ROW_UNROLL 1
 #endif
 #define DW_TIE_EPS 4                   // filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover)
 
@@ -86,6 +95,7 @@ __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f6
 
 // One cell of the fast path. pc: packed centre, E: packed sum of the 4 edge neighbours, S: packed sum of all 8.
 // Returns the packed new cell; *tie is set when either species sits within the filter of a rounding tie.
+// Straight-line (no branches) so that several cells can be interleaved by the scheduler.
 __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCoef &C, uint32_t pc, uint32_t E, uint32_t S,
                                                  bool *tie) {
     const double kl = dw_u2d(pc & 0xffffu), kd = dw_u2d(pc >> 16);
@@ -104,13 +114,12 @@ __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCo
     const double xd = __fma_rn(Rd, __fma_rn(rb, bd, -F.dtg), kd);
     // round-to-nearest via the 1.5*2^32 magic: low word = round(x * 2^20) as a signed fixed-point number
     const double MAGIC = 6442450944.0;
-    const int fl = __double2loint(xl + MAGIC), fd = __double2loint(xd + MAGIC);
-    const int HALF = 1 << (DW_FIX_BITS - 1), MASK = (1 << DW_FIX_BITS) - 1;
-    int ql = (fl + HALF) >> DW_FIX_BITS, qd = (fd + HALF) >> DW_FIX_BITS;
-    const unsigned ul = (unsigned)(fl + HALF + DW_TIE_EPS) & MASK, ud = (unsigned)(fd + HALF + DW_TIE_EPS) & MASK;
-    *tie = (ul < 2u * DW_TIE_EPS) | (ud < 2u * DW_TIE_EPS);
-    ql = min(max(ql, 0), 1000);
-    qd = min(max(qd, 0), 1000);
+    const int HALF = 1 << (DW_FIX_BITS - 1);
+    const int fl = __double2loint(xl + MAGIC) + HALF, fd = __double2loint(xd + MAGIC) + HALF;
+    // tie filter: fraction within DW_TIE_EPS of .5  <=>  ((f + EPS) mod 2^20) < 2 EPS
+    const unsigned ul = (unsigned)(fl + DW_TIE_EPS) << (32 - DW_FIX_BITS), ud = (unsigned)(fd + DW_TIE_EPS) << (32 - DW_FIX_BITS);
+    *tie = min(ul, ud) < ((2u * DW_TIE_EPS) << (32 - DW_FIX_BITS));
+    const int ql = min(max(fl >> DW_FIX_BITS, 0), 1000), qd = min(max(fd >> DW_FIX_BITS, 0), 1000);
     return dw_pack(ql, qd);
 }
 
@@ -369,7 +378,8 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __gr
         uint32_t mx = 0, tiemask = 0;
         Row6 top = dw_load_row(cb, (r0 + 63) & 63, tx, lane);
         Row6 mid = dw_load_row(cb, r0, tx, lane);
-#pragma unroll
+        constexpr int kRowUnroll = DW_N64_ROW_UNROLL;
+#pragma unroll kRowUnroll
         for (int i = 0; i < 4; ++i) {
             const Row6 bot = dw_load_row(cb, (r0 + i + 1) & 63, tx, lane);
             uint32_t q[4];
@@ -378,13 +388,10 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __gr
                 const uint32_t E = mid.hp[c] + top.p[c] + bot.p[c];
                 const uint32_t S8 = E + top.hp[c] + bot.hp[c];
                 const uint32_t pc = mid.p[c];
-                uint32_t v = pc;
-                if ((pc | S8) != 0u) {
-                    bool tie;
-                    v = dw_fast_cell(A.F, C, pc, E, S8, &tie);
-                    if (tie) tiemask |= 1u << (i * 4 + c);
-                    else mx = __vmaxu2(mx, v);
-                }
+                bool tie;
+                const uint32_t v = dw_fast_cell(A.F, C, pc, E, S8, &tie);
+                tiemask |= (tie ? 1u : 0u) << (i * 4 + c);
+                mx = __vmaxu2(mx, tie ? 0u : v);
                 q[c] = v;
             }
             *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
@@ -450,6 +457,14 @@ __global__ void __launch_bounds__(256) k_grid_to_lattice(int B, size_t NN, const
         const bool ok = kl >= 0.0 && kl <= 1000.0 && kd >= 0.0 && kd <= 1000.0 && kl / 1000.0 == l && kd / 1000.0 == d;
         if (!ok) atomicAdd(off_lattice, 1u);
         lat[i] = ok ? dw_pack((int)kl, (int)kd) : 0u;
+    }
+}
+
+// debug hook: count k in [0,kmax] with dw_div1000(k) != k/1000.0 (must be 0: the division-free rounding is exact)
+__global__ void k_debug_markstein(unsigned int kmax, unsigned int *bad) {
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k <= kmax; k += gridDim.x * blockDim.x) {
+        const double kd = (double)k;
+        if (dw_div1000(kd) != kd / 1000.0 || dw_div1000(-kd) != -kd / 1000.0) atomicAdd(bad, 1u);
     }
 }
 
