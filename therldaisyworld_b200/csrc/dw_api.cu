@@ -54,6 +54,9 @@ struct dw_handle {
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     bool fused_attr_set = false;
+    StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
+    unsigned int *pipe_sync = nullptr;         // [1 + pairs] work queue + per-pair progress of the persistent kernel
+    int pipe_blocks = 0, persist_blocks = 0;   // resident CTAs of the persistent kernels on this device
     // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
     dw_profile prof{};
     bool profiling = false;
@@ -212,7 +215,7 @@ extern "C" int dw_create(const dw_config *cfg, dw_handle **out) {
     if (!rc) rc = dev_alloc(h, &h->world_max, B * 2);
     if (!rc) rc = dev_alloc(h, &h->done_at, B);
     if (!rc) rc = dev_alloc(h, &h->agents_done_at, B * n);
-    if (!rc) rc = dev_alloc(h, &h->alive, 64);
+    if (!rc) rc = dev_alloc(h, &h->alive, DW_FUSED_MAX_STEPS);
     if (rc) { g_create_error = h->err; dw_destroy(h); return rc; }
     h->clk.L = 0.75; h->clk.min_L = 0.75; h->clk.max_L = 1.5; h->clk.ramp_period = 512;
     h->clk.dL = (h->clk.max_L - h->clk.min_L) / 512.0;
@@ -225,7 +228,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->grid[0], h->grid[1], h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->pipe_sync,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {

@@ -20,7 +20,13 @@
 #ifndef DW_N64_MIN_BLOCKS
 #define DW_N64_MIN_BLOCKS 4
 #endif
-#define DW_FUSED_MAX_STEPS 64
+#ifndef DW_CELL_ILP
+#define DW_CELL_ILP 2                    // cells advanced in lockstep by the fast path (1, 2 or 4)
+#endif
+#ifndef DW_TILE_WINDOW
+#define DW_TILE_WINDOW 1                 // 1: rolling 3-row register window over the tile; 0: re-read rows per output row
+#endif
+#define DW_FUSED_MAX_STEPS 4096        // longest launch (coefficient table / alive counters)
 #define DW_FUSED_MAX_AGENTS 1024
 #define DW_FIX_BITS 20                 // fixed-point fraction bits of the rounding trick (ulp of 1.5*2^32)
 #ifndef DW_N64_MIN_BLOCKS
@@ -47,8 +53,9 @@ struct StepCoef {        // per-step (luminosity dependent) coefficients
 struct FusedArgs {
     DevParams P;
     FastCoef F;
-    StepCoef sc[DW_FUSED_MAX_STEPS];
+    const StepCoef *sc;         // [K] per-step coefficients (global memory)
     const uint32_t *lat_in;     // [B,N,N]
+    uint32_t *lat;              // [B,N,N] in-place state (persistent kernel)
     uint32_t *lat_out;          // [B,N,N]
     uint32_t *lat_pre;          // [B,N,N] post-graze state the LAST step of the launch started from
     int32_t *agent_xy;          // [B,n,2]
@@ -64,6 +71,11 @@ struct FusedArgs {
     unsigned int world0;        // global index of this handle's first world (RANDOM policy counter)
     int K, policy;
     unsigned int *slow_count;   // diagnostics: number of literal recomputations (may be NULL)
+    // persistent pipelined kernel only
+    int Kc;                     // steps per work item
+    int n_pairs, n_chunks;      // work items = n_pairs * n_chunks, chunk-major
+    unsigned int *queue;        // [1] next work item (zeroed before the launch)
+    unsigned int *pair_done;    // [n_pairs] chunks completed per world pair (zeroed before the launch)
 };
 
 // ---- fast fourth root ------------------------------------------------------------------------------------
@@ -77,16 +89,17 @@ __device__ __forceinline__ double dw_rcp_approx(double x) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     return r;
 }
-// X^(1/4) for X in the physical range (1e8..1e11): two MUFU.RSQ64H seeds + one MUFU.RCP64H, then one Newton step
-// on y^4 = X.  Relative error <= ~1e-12 (measured in tests/test_gpu_fused_internals.py), 6 fp64-pipe ops.
+// X^(1/4) for X in the physical range (1e8..1e11): two MUFU.RSQ64H seeds (s1 ~ X^-1/2, y0 = rsqrt(s1) ~ X^1/4), then
+// one Newton step on y^4 = X with 1/(4 y0^3) approximated by s1*s1*y0/4.  Relative error <= ~2e-12 (measured in
+// tests/test_gpu_fused_internals.py), 6 fp64-pipe ops.
 __device__ __forceinline__ double dw_root4_fast(double X) {
-    const double y0 = dw_rsqrt_approx(dw_rsqrt_approx(X));   // X^(1/4) (1+d), |d| < 2^-21
-    const double c = dw_rcp_approx(y0);
+    const double s1 = dw_rsqrt_approx(X);
+    const double y0 = dw_rsqrt_approx(s1);                    // X^(1/4) (1+d), |d| < 2^-21
     const double z = y0 * y0;
     const double res = __fma_rn(-z, z, X);                    // X - y0^4
-    const double c2 = c * c;
-    const double c3 = c2 * c;
-    return __fma_rn(res * c3, 0.25, y0);
+    const double a = s1 * s1;
+    const double b3 = a * y0;                                 // ~ 1/y0^3
+    return __fma_rn(res * b3, 0.25, y0);
 }
 
 __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
@@ -94,10 +107,12 @@ __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f6
 }
 
 // One cell of the fast path. pc: packed centre, E: packed sum of the 4 edge neighbours, S: packed sum of all 8.
-// Returns the packed new cell; *tie is set when either species sits within the filter of a rounding tie.
+// Returns the packed new cell; *tiemin is lowered below DW_TIE_THRESH when either species sits within the filter of
+// a rounding tie (the caller then recomputes the cell in literal order).
 // Straight-line (no branches) so that several cells can be interleaved by the scheduler.
+#define DW_TIE_THRESH ((2u * DW_TIE_EPS) << (32 - DW_FIX_BITS))
 __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCoef &C, uint32_t pc, uint32_t E, uint32_t S,
-                                                 bool *tie) {
+                                                 unsigned *tiemin) {
     const double kl = dw_u2d(pc & 0xffffu), kd = dw_u2d(pc >> 16);
     const double El = dw_u2d(E & 0xffffu), Ed = dw_u2d(E >> 16);
     const double Sl = dw_u2d(S & 0xffffu), Sd = dw_u2d(S >> 16);
@@ -116,11 +131,77 @@ __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCo
     const double MAGIC = 6442450944.0;
     const int HALF = 1 << (DW_FIX_BITS - 1);
     const int fl = __double2loint(xl + MAGIC) + HALF, fd = __double2loint(xd + MAGIC) + HALF;
-    // tie filter: fraction within DW_TIE_EPS of .5  <=>  ((f + EPS) mod 2^20) < 2 EPS
+    // tie filter: fraction within DW_TIE_EPS of .5  <=>  ((f + EPS) mod 2^20) < 2 EPS; the running minimum over a
+    // tile is compared once against DW_TIE_THRESH
     const unsigned ul = (unsigned)(fl + DW_TIE_EPS) << (32 - DW_FIX_BITS), ud = (unsigned)(fd + DW_TIE_EPS) << (32 - DW_FIX_BITS);
-    *tie = min(ul, ud) < ((2u * DW_TIE_EPS) << (32 - DW_FIX_BITS));
-    const int ql = min(max(fl >> DW_FIX_BITS, 0), 1000), qd = min(max(fd >> DW_FIX_BITS, 0), 1000);
-    return dw_pack(ql, qd);
+    *tiemin = __vimin3_u32(*tiemin, ul, ud);
+    // floor(x + .5) of both species packed as s16x2, clamped to [0,1000] by one VIMNMX.S16x2.RELU
+    const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
+    return __vimin_s16x2_relu(packed, 1000u | (1000u << 16));
+}
+
+// Two cells in explicit lockstep: the fp64 chain of one cell is serial (8-cycle dependent latency, measured), so the
+// source interleaves two independent cells statement by statement to give the scheduler ILP without more warps.
+template <int W>
+__device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef &C, const uint32_t (&pc)[W], const uint32_t (&E)[W],
+                                              const uint32_t (&S)[W], unsigned *tiemin, uint32_t (&out)[W]) {
+    double kl[W], kd[W], El[W], Ed[W], Sl[W], Sd[W], Rl[W], Rd[W], rb[W], Xl[W], Xd[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) { kl[i] = dw_u2d(pc[i] & 0xffffu); kd[i] = dw_u2d(pc[i] >> 16); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { Sl[i] = dw_u2d(S[i] & 0xffffu); Sd[i] = dw_u2d(S[i] >> 16); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(F.xk_l, kl[i], __fma_rn(F.xk_d, kd[i], C.x0));
+#pragma unroll
+    for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(C.xs_l, Sl[i], __fma_rn(C.xs_d, Sd[i], Xl[i]));
+#pragma unroll
+    for (int i = 0; i < W; ++i) Xd[i] = Xl[i] + F.xdd;
+    // seeds first: the MUFU latency (27 cycles) overlaps the rho arithmetic below
+    double s1l[W], s1d[W], y0l[W], y0d[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) { s1l[i] = dw_rsqrt_approx(Xl[i]); s1d[i] = dw_rsqrt_approx(Xd[i]); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { El[i] = dw_u2d(E[i] & 0xffffu); Ed[i] = dw_u2d(E[i] >> 16); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { Rl[i] = F.w0 * kl[i]; Rd[i] = F.w0 * kd[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { y0l[i] = dw_rsqrt_approx(s1l[i]); y0d[i] = dw_rsqrt_approx(s1d[i]); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { Rl[i] = __fma_rn(F.w12, El[i], Rl[i]); Rd[i] = __fma_rn(F.w12, Ed[i], Rd[i]); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { Rl[i] = __fma_rn(F.w2, Sl[i], Rl[i]); Rd[i] = __fma_rn(F.w2, Sd[i], Rd[i]); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) rb[i] = __fma_rn(-F.dtm, Rl[i] + Rd[i], F.dtp);
+    // Newton step on y^4 = X for both species of all cells, stage by stage
+    double zl[W], zd[W], al[W], ad[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = y0l[i] * y0l[i]; zd[i] = y0d[i] * y0d[i]; al[i] = s1l[i] * s1l[i]; ad[i] = s1d[i] * s1d[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-zl[i], zl[i], Xl[i]); zd[i] = __fma_rn(-zd[i], zd[i], Xd[i]); al[i] = al[i] * y0l[i]; ad[i] = ad[i] * y0d[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = zl[i] * al[i]; zd[i] = zd[i] * ad[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(zl[i], 0.25, y0l[i]); zd[i] = __fma_rn(zd[i], 0.25, y0d[i]); }      // T_l, T_d
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = F.topt - zl[i]; zd[i] = F.topt - zd[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = zl[i] * zl[i]; zd[i] = zd[i] * zd[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-F.g, zl[i], 1.0); zd[i] = __fma_rn(-F.g, zd[i], 1.0); }           // beta_l, beta_d
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(rb[i], zl[i], -F.dtg); zd[i] = __fma_rn(rb[i], zd[i], -F.dtg); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(Rl[i], zl[i], kl[i]); zd[i] = __fma_rn(Rd[i], zd[i], kd[i]); }     // l + dt*dl (milli)
+    const double MAGIC = 6442450944.0;
+    const int HALF = 1 << (DW_FIX_BITS - 1);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const int fl = __double2loint(zl[i] + MAGIC) + HALF, fd = __double2loint(zd[i] + MAGIC) + HALF;
+        const unsigned ul = (unsigned)(fl + DW_TIE_EPS) << (32 - DW_FIX_BITS), ud = (unsigned)(fd + DW_TIE_EPS) << (32 - DW_FIX_BITS);
+        *tiemin = __vimin3_u32(*tiemin, ul, ud);
+        const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
+        out[i] = __vimin_s16x2_relu(packed, 1000u | (1000u << 16));
+    }
 }
 
 // Literal recomputation of one cell from the packed neighbourhood (oracle order). Rare: ~1e-5 of cell-updates.
@@ -264,9 +345,9 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ F
             const uint32_t pc = r1[y];
             uint32_t q = pc;
             if ((pc | S8) != 0u) {          // empty neighbourhood: rho = 0 and the cell stays exactly 0
-                bool tie;
-                q = dw_fast_cell(A.F, C, pc, E, S8, &tie);
-                if (tie) q = dw_slow_cell(&A, C.SL, cb, N, x, y);
+                unsigned tiemin = 0xffffffffu;
+                q = dw_fast_cell(A.F, C, pc, E, S8, &tiemin);
+                if (tiemin < DW_TIE_THRESH) q = dw_slow_cell(&A, C.SL, cb, N, x, y);
             }
             nb[c] = q;
             mx = __vmaxu2(mx, q);
@@ -317,6 +398,27 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ F
 // columns from the neighbouring lanes with SHFL (tile columns wrap inside the half-warp), forms the packed 3x3
 // sums with ~4.5 integer adds per cell, runs dw_fast_cell on 16 cells and writes 4 STS.128.  Cells that hit the
 // tie filter are patched afterwards by the literal path, outside the unrolled code.
+// Re-evaluate one 4x4 tile of a 64x64 world cell by cell (generic indexing): cells whose fast result is within the tie
+// filter are recomputed in the oracle's order and patched into nb.  Returns the packed per-species max of the tile.
+__device__ __noinline__ uint32_t dw_fix_tile64(const FusedArgs *A, const StepCoef *C, const uint32_t *cb, uint32_t *nb, int r0, int c0) {
+    uint32_t mx = 0;
+    for (int k = 0; k < 16; ++k) {
+        const int x = r0 + (k >> 2), y = c0 + (k & 3);
+        const int xm = (x + 63) & 63, xp = (x + 1) & 63, ym = (y + 63) & 63, yp = (y + 1) & 63;
+        const uint32_t *q0 = cb + xm * 64, *q1 = cb + x * 64, *q2 = cb + xp * 64;
+        const uint32_t E = q1[ym] + q1[yp] + q0[y] + q2[y];
+        const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
+        unsigned tiemin = 0xffffffffu;
+        uint32_t v = dw_fast_cell(A->F, *C, q1[y], E, S8, &tiemin);
+        if (tiemin < DW_TIE_THRESH) {
+            v = dw_slow_cell(A, C->SL, cb, 64, x, y);
+            nb[x * 64 + y] = v;
+        }
+        mx = __vmaxu2(mx, v);
+    }
+    return mx;
+}
+
 struct Row6 { uint32_t p[4]; uint32_t hp[4]; };
 
 __device__ __forceinline__ Row6 dw_load_row(const uint32_t *cb, int row, int tx, int lane) {
@@ -331,6 +433,60 @@ __device__ __forceinline__ Row6 dw_load_row(const uint32_t *cb, int row, int tx,
     r.hp[2] = v.y + v.w;
     r.hp[3] = v.z + right;
     return r;
+}
+
+// One step of one 4x4 tile of a 64x64 world: cb -> nb. Returns the packed per-species max of the tile's new cells.
+__device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, const uint32_t *cb, uint32_t *nb, int r0, int tx, int lane) {
+    const StepCoef C = A.sc[j];
+    uint32_t mx = 0;
+    unsigned tiemin = 0xffffffffu;
+#if DW_TILE_WINDOW
+    Row6 top = dw_load_row(cb, (r0 + 63) & 63, tx, lane);
+    Row6 mid = dw_load_row(cb, r0, tx, lane);
+#endif
+    constexpr int kRowUnroll = DW_N64_ROW_UNROLL;
+#pragma unroll kRowUnroll
+    for (int i = 0; i < 4; ++i) {
+#if !DW_TILE_WINDOW
+        // no rolling window: 3 rows are re-read per output row (LSU has slack) so that fewer registers stay live across
+        // the fp64 chains and ptxas can interleave two cells
+        const Row6 top = dw_load_row(cb, (r0 + i + 63) & 63, tx, lane);
+        const Row6 mid = dw_load_row(cb, r0 + i, tx, lane);
+#endif
+        const Row6 bot = dw_load_row(cb, (r0 + i + 1) & 63, tx, lane);
+        uint32_t E[4], S8[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            E[c] = mid.hp[c] + top.p[c] + bot.p[c];
+            S8[c] = E[c] + top.hp[c] + bot.hp[c];
+        }
+        uint32_t q[4];
+#if DW_CELL_ILP == 1
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[c] = dw_fast_cell(A.F, C, mid.p[c], E[c], S8[c], &tiemin);
+#elif DW_CELL_ILP == 2
+        {
+            const uint32_t pa[2] = {mid.p[0], mid.p[1]}, ea[2] = {E[0], E[1]}, sa[2] = {S8[0], S8[1]};
+            const uint32_t pb[2] = {mid.p[2], mid.p[3]}, eb[2] = {E[2], E[3]}, sb[2] = {S8[2], S8[3]};
+            uint32_t qa[2], qb[2];
+            dw_fast_cells<2>(A.F, C, pa, ea, sa, &tiemin, qa);
+            dw_fast_cells<2>(A.F, C, pb, eb, sb, &tiemin, qb);
+            q[0] = qa[0]; q[1] = qa[1]; q[2] = qb[0]; q[3] = qb[1];
+        }
+#else
+        dw_fast_cells<4>(A.F, C, mid.p, E, S8, &tiemin, q);
+#endif
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx = __vmaxu2(mx, q[c]);
+        *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
+#if DW_TILE_WINDOW
+        top = mid;
+        mid = bot;
+#endif
+    }
+    // rare (~2e-4 of tile-steps): some cell of this tile sits on a rounding tie -> redo the tile's ties literally
+    if (tiemin < DW_TIE_THRESH) mx = dw_fix_tile64(&A, &A.sc[j], cb, nb, r0, tx * 4);
+    return mx;
 }
 
 __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __grid_constant__ FusedArgs A) {
@@ -374,38 +530,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __gr
 #pragma unroll
             for (int c = 0; c < NN / 4 / 256; ++c) gp[tid + c * 256] = sc4[tid + c * 256];
         }
-        const StepCoef C = A.sc[j];
-        uint32_t mx = 0, tiemask = 0;
-        Row6 top = dw_load_row(cb, (r0 + 63) & 63, tx, lane);
-        Row6 mid = dw_load_row(cb, r0, tx, lane);
-        constexpr int kRowUnroll = DW_N64_ROW_UNROLL;
-#pragma unroll kRowUnroll
-        for (int i = 0; i < 4; ++i) {
-            const Row6 bot = dw_load_row(cb, (r0 + i + 1) & 63, tx, lane);
-            uint32_t q[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t E = mid.hp[c] + top.p[c] + bot.p[c];
-                const uint32_t S8 = E + top.hp[c] + bot.hp[c];
-                const uint32_t pc = mid.p[c];
-                bool tie;
-                const uint32_t v = dw_fast_cell(A.F, C, pc, E, S8, &tie);
-                tiemask |= (tie ? 1u : 0u) << (i * 4 + c);
-                mx = __vmaxu2(mx, tie ? 0u : v);
-                q[c] = v;
-            }
-            *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
-            top = mid;
-            mid = bot;
-        }
-        while (tiemask) {            // rare (~1e-5 of cells): literal recomputation in the oracle's order
-            const int k = __ffs(tiemask) - 1;
-            tiemask &= tiemask - 1;
-            const int x = r0 + (k >> 2), y = tx * 4 + (k & 3);
-            const uint32_t v = dw_slow_cell(&A, C.SL, cb, N, x, y);
-            nb[x * 64 + y] = v;
-            mx = __vmaxu2(mx, v);
-        }
+        const uint32_t mx = dw_tile_step64(A, j, cb, nb, r0, tx, lane);
         const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
         int *sm = s_max + 2 * (j & 1);
         if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
@@ -442,6 +567,296 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __gr
         if (n == 0) {
             const int *sm = s_max + 2 * ((A.K - 1) & 1);
             for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
+        }
+    }
+}
+
+// ---- 64x64, persistent: one world per CTA-item, dynamic work queue ----------------------------------------------------
+// Work item = (world, chunk of Kc steps), handed out chunk-major from a global counter: all worlds of the ensemble
+// advance together and every SM keeps DW_N64_MIN_BLOCKS CTAs busy until the end of the launch, which removes the
+// wave quantisation of a one-CTA-per-world grid (1000 worlds on 148 SMs x 4 CTAs = 1.69 waves).
+__global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(const __grid_constant__ FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NN = 4096;
+    const int n = A.P.n_agents;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, r0 = (tid >> 4) * 4;
+    uint32_t *buf0 = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *buf1 = buf0 + NN;
+    AgentSmem S;
+    S.st = reinterpret_cast<double *>(buf1 + NN);
+    S.xy = reinterpret_cast<int *>(S.st + n);
+    S.act = S.xy + n;
+    S.ada = S.act + n;
+    int *s_max = S.ada + n;                 // [2 parities][2 species]
+    volatile int *s_item = s_max + 4;
+    const int n_items = A.n_pairs * A.n_chunks;      // n_pairs = number of worlds for this kernel
+
+    for (;;) {
+        if (tid == 0) *s_item = (int)atomicAdd(A.queue, 1u);
+        __syncthreads();
+        const int t = *s_item;
+        if (t >= n_items) break;
+        const int c = t / A.n_pairs, b = t - c * A.n_pairs;
+        if (tid == 0) {
+            while (atomicAdd(A.pair_done + b, 0u) < (unsigned)c) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
+        {
+            const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat + (size_t)b * NN);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) reinterpret_cast<uint4 *>(buf0)[tid + k * 256] = __ldcg(gin + tid + k * 256);
+        }
+        for (int i = tid; i < n; i += 256) {
+            const size_t g = (size_t)b * n + i;
+            S.st[i] = __ldcg(A.agent_state + g);
+            S.xy[i] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
+            S.ada[i] = 0;
+        }
+        if (tid < 4) s_max[tid] = 0;
+        __syncthreads();
+
+        uint32_t *cb = buf0, *nb = buf1;
+        int life = 0;
+#pragma unroll 1
+        for (int jl = 0; jl < kc; ++jl) {
+            const int j = j0 + jl;
+            if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane);
+            __syncthreads();
+            if (j == A.K - 1) {
+                uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) gp[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
+            }
+            const uint32_t mx = dw_tile_step64(A, j, cb, nb, r0, tx, lane);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+            int *sm = s_max + 2 * (jl & 1);
+            if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+            __syncthreads();
+            if (warp == 0) {
+                const int m0 = sm[0], m1 = sm[1];
+                __syncwarp();
+                if (lane == 0) {
+                    if (max(m0, m1) > 5) { life += 1; atomicAdd(A.alive + j, 1u); }
+                    int *nx = s_max + 2 * ((jl + 1) & 1);
+                    nx[0] = 0; nx[1] = 0;
+                }
+                for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;
+            }
+            uint32_t *tmp = cb; cb = nb; nb = tmp;
+        }
+        __syncthreads();
+        {
+            uint4 *gout = reinterpret_cast<uint4 *>(A.lat + (size_t)b * NN);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gout[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
+        }
+        for (int i = tid; i < n; i += 256) {
+            const size_t g = (size_t)b * n + i;
+            const double r = S.st[i];
+            A.agent_state[g] = r;
+            A.agent_xy[2 * g] = S.xy[i] & 0xffff;
+            A.agent_xy[2 * g + 1] = S.xy[i] >> 16;
+            A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + S.ada[i];
+            A.reward[g] = r;
+            A.done[g] = r < 0.1;
+        }
+        if (tid == 0) {
+            A.done_at[b] = __ldcg(A.done_at + b) + life;
+            if (n == 0) {
+                const int *sm = s_max + 2 * ((kc - 1) & 1);
+                for (int ch = 0; ch < 2; ++ch) { A.reward[2 * b + ch] = sm[ch] > 0 ? 1.0 : 0.0; A.done[2 * b + ch] = sm[ch] > 0 ? 0 : 1; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicExch(A.pair_done + b, (unsigned)(c + 1));
+        }
+    }
+}
+
+// ---- 64x64, persistent + pipelined: 2 worlds per CTA, 8 compute warps + 1 agent warp, dynamic work queue --------------
+// Work item = (pair of worlds, chunk of Kc steps), handed out chunk-major from a global counter, so all worlds of the
+// ensemble advance together and every SM stays full until the end of the launch (no wave quantisation at B=1000).
+// Inside an item the two worlds A,B are software-pipelined: while the 8 compute warps run the stencil of one world,
+// the 9th warp does the lifespan bookkeeping and the (sequential, latency-bound) agent phase of the other one, so the
+// agents never stall the FP64 pipe and there is one __syncthreads per world-step.
+#define DW_PIPE_THREADS 288
+#ifndef DW_PIPE_MIN_BLOCKS
+#define DW_PIPE_MIN_BLOCKS 3
+#endif
+struct PipeSlot {
+    uint32_t *buf[2];
+    AgentSmem S;
+    int *smax;       // [2 parities][2 species]
+    int *last_max;   // [2] max of the last bookkept step
+};
+
+// shared-memory layout of the pipelined kernel: 4 world buffers | 2n agent states | per slot: 3n ints + smax[4] + last_max[2]
+__device__ __forceinline__ PipeSlot dw_pipe_slot(unsigned char *smem_raw, int n, int s) {
+    PipeSlot W;
+    uint32_t *base = reinterpret_cast<uint32_t *>(smem_raw);
+    W.buf[0] = base + (2 * s) * 4096;
+    W.buf[1] = base + (2 * s + 1) * 4096;
+    double *st = reinterpret_cast<double *>(base + 4 * 4096);
+    W.S.st = st + s * n;
+    int *ip = reinterpret_cast<int *>(st + 2 * n) + s * (3 * n + 6);
+    W.S.xy = ip; W.S.act = ip + n; W.S.ada = ip + 2 * n;
+    W.smax = ip + 3 * n; W.last_max = ip + 3 * n + 4;
+    return W;
+}
+
+__device__ __forceinline__ void dw_pipe_bookkeep(const FusedArgs &A, const PipeSlot &W, int jl, int jg, int n, int lane, int &life) {
+    int *sm = W.smax + 2 * (jl & 1);
+    const int m0 = sm[0], m1 = sm[1];
+    __syncwarp();
+    if (lane == 0) {
+        if (max(m0, m1) > 5) { life += 1; atomicAdd(A.alive + jg, 1u); }     // grid_done = max(grid[:,1:3]) <= 0.005
+        W.last_max[0] = m0; W.last_max[1] = m1;
+        sm[0] = 0; sm[1] = 0;
+    }
+    for (int i = lane; i < n; i += 32) W.S.ada[i] += (W.S.st[i] < 0.1) ? 0 : 1;
+    __syncwarp();
+}
+
+// agent-warp side of one pipeline slot (kept out of line: it must not inflate the register budget of the stencil path)
+__device__ __noinline__ int dw_pipe_agent_slot(const FusedArgs *Ap, unsigned char *smem_raw, int s, int jl, int j0, int kc, int w,
+                                               int lane) {
+    const FusedArgs &A = *Ap;
+    const int n = A.P.n_agents;
+    const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
+    int add = 0;
+    if (jl >= 1) dw_pipe_bookkeep(A, W, jl - 1, j0 + jl - 1, n, lane, add);
+    if (jl < kc && n > 0) dw_agents_phase(A, j0 + jl, w, W.buf[jl & 1], W.S, lane);
+    return add;
+}
+
+// load / store of one work item's two worlds (L2 reads: another SM may have written them)
+__device__ __noinline__ void dw_pipe_load(const FusedArgs *Ap, unsigned char *smem_raw, int wA, bool hasB, int tid) {
+    const FusedArgs &A = *Ap;
+    const int n = A.P.n_agents;
+    for (int i = tid; i < 2048; i += DW_PIPE_THREADS) {
+        const int s = i >> 10, k = i & 1023;
+        if (s == 0 || hasB)
+            reinterpret_cast<uint4 *>(dw_pipe_slot(smem_raw, n, s).buf[0])[k] =
+                __ldcg(reinterpret_cast<const uint4 *>(A.lat + (size_t)(wA + s) * 4096) + k);
+    }
+    for (int i = tid; i < 2 * n; i += DW_PIPE_THREADS) {
+        const int s = i >= n, k = i - s * n;
+        if (s == 0 || hasB) {
+            const size_t g = (size_t)(wA + s) * n + k;
+            const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
+            W.S.st[k] = __ldcg(A.agent_state + g);
+            W.S.xy[k] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
+            W.S.ada[k] = 0;
+        }
+    }
+    if (tid < 12) dw_pipe_slot(smem_raw, n, tid / 6).smax[tid % 6] = 0;
+}
+
+__device__ __noinline__ void dw_pipe_store(const FusedArgs *Ap, unsigned char *smem_raw, int wA, bool hasB, int kc, int tid) {
+    const FusedArgs &A = *Ap;
+    const int n = A.P.n_agents;
+    for (int i = tid; i < 2048; i += DW_PIPE_THREADS) {
+        const int s = i >> 10, k = i & 1023;
+        if (s == 0 || hasB)
+            reinterpret_cast<uint4 *>(A.lat + (size_t)(wA + s) * 4096)[k] =
+                reinterpret_cast<const uint4 *>(dw_pipe_slot(smem_raw, n, s).buf[kc & 1])[k];
+    }
+    for (int i = tid; i < 2 * n; i += DW_PIPE_THREADS) {
+        const int s = i >= n, k = i - s * n;
+        if (s == 0 || hasB) {
+            const size_t g = (size_t)(wA + s) * n + k;
+            const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
+            const double r = W.S.st[k];
+            A.agent_state[g] = r;
+            A.agent_xy[2 * g] = W.S.xy[k] & 0xffff;
+            A.agent_xy[2 * g + 1] = W.S.xy[k] >> 16;
+            A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + W.S.ada[k];
+            A.reward[g] = r;
+            A.done[g] = r < 0.1;
+        }
+    }
+    if (n == 0 && tid < 4) {
+        const int s = tid >> 1, ch = tid & 1;
+        if (s == 0 || hasB) {
+            const int m = dw_pipe_slot(smem_raw, n, s).last_max[ch];
+            A.reward[2 * (wA + s) + ch] = m > 0 ? 1.0 : 0.0;
+            A.done[2 * (wA + s) + ch] = m > 0 ? 0 : 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DW_PIPE_THREADS, DW_PIPE_MIN_BLOCKS) k_fused_n64_pipe(const __grid_constant__ FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = A.P.n_agents;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_agent = warp == 8;
+    const int tx = tid & 15, r0 = ((tid >> 4) & 15) * 4;
+    volatile int *s_item = reinterpret_cast<volatile int *>(dw_pipe_slot(smem_raw, n, 1).last_max + 2);   // work item broadcast
+    const int n_items = A.n_pairs * A.n_chunks;
+
+    for (;;) {
+        if (tid == 0) *s_item = (int)atomicAdd(A.queue, 1u);
+        __syncthreads();
+        const int t = *s_item;
+        if (t >= n_items) break;
+        const int c = t / A.n_pairs, p = t - c * A.n_pairs;
+        if (tid == 0) {
+            while (atomicAdd(A.pair_done + p, 0u) < (unsigned)c) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        const int wA = 2 * p;
+        const bool hasB = wA + 1 < A.P.B;
+        const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
+        dw_pipe_load(&A, smem_raw, wA, hasB, tid);
+        __syncthreads();
+
+        int life0 = 0, life1 = 0;
+#pragma unroll 1
+        for (int slot = 0; slot <= 2 * kc; ++slot) {
+            if (!is_agent) {
+                const int s = (slot - 1) & 1, jl = (slot - 1) >> 1, jg = j0 + jl;
+                if (slot >= 1 && (s == 0 || hasB)) {
+                    const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
+                    const uint32_t *cb = W.buf[jl & 1];
+                    uint32_t *nb = W.buf[(jl + 1) & 1];
+                    if (jg == A.K - 1) {        // post-graze state of the launch's last step (lazy materialisation)
+                        uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)(wA + s) * 4096);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) gp[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
+                    }
+                    const uint32_t mx = dw_tile_step64(A, jg, cb, nb, r0, tx, lane);
+                    const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+                    int *sm = W.smax + 2 * (jl & 1);
+                    if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+                }
+            } else {
+                const int s = slot & 1, jl = slot >> 1;
+                if (s == 0 || hasB) {
+                    const int add = dw_pipe_agent_slot(&A, smem_raw, s, jl, j0, kc, wA + s, lane);
+                    if (s == 0) life0 += add; else life1 += add;
+                }
+            }
+            __syncthreads();
+        }
+        if (is_agent) {
+            if (hasB) life1 += dw_pipe_agent_slot(&A, smem_raw, 1, kc, j0, kc, wA + 1, lane);   // bookkeeping of B's last step
+            if (lane == 0) {
+                A.done_at[wA] = __ldcg(A.done_at + wA) + life0;
+                if (hasB) A.done_at[wA + 1] = __ldcg(A.done_at + wA + 1) + life1;
+            }
+        }
+        __syncthreads();
+        dw_pipe_store(&A, smem_raw, wA, hasB, kc, tid);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicExch(A.pair_done + p, (unsigned)(c + 1));
         }
     }
 }

@@ -4,7 +4,7 @@
 // ---- fused lattice path: host side -----------------------------------------------------------------------
 static size_t fused_smem_bytes(int N, int n) {
     const size_t NN = (size_t)N * N;
-    return 2 * NN * sizeof(uint32_t) + (size_t)n * sizeof(double) + 3 * (size_t)n * sizeof(int) + 4 * sizeof(int);
+    return 2 * NN * sizeof(uint32_t) + (size_t)n * sizeof(double) + 3 * (size_t)n * sizeof(int) + 8 * sizeof(int);
 }
 
 // The fast path needs D4-symmetric 3x3 kernels (centre / edge / corner classes) and a uniform zero-centre
@@ -66,17 +66,28 @@ static int grid_to_lattice(dw_handle *h, bool *converted) {
     return DW_OK;
 }
 
+static size_t pipe_smem_bytes(int n) {
+    return 4 * 4096 * sizeof(uint32_t) + 2 * (size_t)n * sizeof(double) + (6 * (size_t)n + 12 + 4) * sizeof(int);
+}
+
 static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive) {
+    if (K > DW_FUSED_MAX_STEPS) return dw_fail(h, DW_E_INVALID, "launch_fused", "K too large");
     FusedArgs A{};
     A.P = make_params(h);
     make_fast_coef(h->cfg, A.F);
     dw_clock clk = h->clk;
     double L_last = clk.L;
+    std::vector<StepCoef> table(K);
     for (int j = 0; j < K; ++j) {
-        make_step_coef(h->cfg, clk.L, A.sc[j]);
+        make_step_coef(h->cfg, clk.L, table[j]);
         L_last = clk.L;
         update_L(clk);
     }
+    int rc = dev_alloc(h, &h->sc_dev, (size_t)DW_FUSED_MAX_STEPS);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->sc_dev, table.data(), K * sizeof(StepCoef), cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));       // table is a local
+    A.sc = h->sc_dev;
     A.lat_in = h->lat[h->lcur];
     A.lat_out = h->lat[1 - h->lcur];
     A.lat_pre = h->lat_pre;
@@ -86,21 +97,61 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     A.seed = seed; A.step0 = (unsigned int)h->clk.step_count; A.world0 = h->world0;
     A.K = K; A.policy = policy;
     A.slow_count = h->slow_count;
-    const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
-    if (smem > 48 * 1024 && !h->fused_attr_set) {
-        DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        h->fused_attr_set = true;
-    }
+    // kernel selection: 64x64 worlds run the persistent kernel (dynamic work queue); DW_FUSED_IMPL overrides for
+    // experiments: "persist" (default) | "pipe" (2 worlds per CTA + agent warp) | "simple" (one CTA per world) | "generic"
+    const char *impl = getenv("DW_FUSED_IMPL");
+    const bool n64 = h->cfg.dim == 64 && !(impl && !strcmp(impl, "generic"));
+    const bool pipe = n64 && impl && !strcmp(impl, "pipe") && h->cfg.n_agents <= 256;
+    const bool persist = n64 && !pipe && !(impl && !strcmp(impl, "simple"));
     if (h->profiling) DW_CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
-    if (h->cfg.dim == 64 && !getenv("DW_FUSED_GENERIC")) k_fused_n64<<<h->cfg.batch, 256, smem, h->stream>>>(A);
-    else k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+    if (pipe || persist) {
+        const size_t smem = pipe ? pipe_smem_bytes(h->cfg.n_agents) : fused_smem_bytes(64, h->cfg.n_agents);
+        const int threads = pipe ? DW_PIPE_THREADS : 256;
+        int &blocks = pipe ? h->pipe_blocks : h->persist_blocks;
+        if (!blocks) {
+            int per_sm = 0, sms = 0;
+            if (pipe) {
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_pipe, threads, smem));
+            } else {
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist, threads, smem));
+            }
+            DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+            if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "persistent kernel does not fit on an SM");
+            blocks = per_sm * sms;
+        }
+        const char *kc_env = getenv("DW_PIPE_KC");
+        A.Kc = kc_env ? atoi(kc_env) : 16;
+        if (A.Kc < 1) A.Kc = 1;
+        A.n_pairs = pipe ? (h->cfg.batch + 1) / 2 : h->cfg.batch;
+        A.n_chunks = (K + A.Kc - 1) / A.Kc;
+        rc = dev_alloc(h, &h->pipe_sync, (size_t)h->cfg.batch + 1);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemsetAsync(h->pipe_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
+        A.queue = h->pipe_sync;
+        A.pair_done = h->pipe_sync + 1;
+        A.lat = h->lat[h->lcur];                      // in place
+        const long long items = (long long)A.n_pairs * A.n_chunks;
+        const int grid = (int)(items < blocks ? items : blocks);
+        if (pipe) k_fused_n64_pipe<<<grid, threads, smem, h->stream>>>(A);
+        else k_fused_n64_persist<<<grid, threads, smem, h->stream>>>(A);
+    } else {
+        const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
+        if (smem > 48 * 1024 && !h->fused_attr_set) {
+            DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            h->fused_attr_set = true;
+        }
+        if (n64) k_fused_n64<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+        else k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+        h->lcur = 1 - h->lcur;
+    }
     DW_LAUNCHED(h);
     if (h->profiling) {
         DW_CUDA_TRY(h, cudaEventRecord(h->ev[1], h->stream));
         h->ev_pending = true;
         h->ev_cells = (uint64_t)h->cfg.batch * h->NN * (uint64_t)K;
     }
-    h->lcur = 1 - h->lcur;
     h->lat_valid = true;
     h->grid_valid = false;
     h->pre = PRE_LAT;
@@ -163,13 +214,13 @@ static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_
 }
 
 static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, uint64_t *done_mask,
-                          unsigned int *alive_last) {
-    if (K < 1 || K > 64) return dw_fail(h, DW_E_INVALID, "run_chunk", "1 <= K <= 64");
-    DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, 64 * sizeof(unsigned int), h->stream));
+                          unsigned int *alive_last, int *first_all_done = nullptr) {
+    if (K < 1 || K > DW_FUSED_MAX_STEPS) return dw_fail(h, DW_E_INVALID, "run_chunk", "1 <= K <= 4096");
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, DW_FUSED_MAX_STEPS * sizeof(unsigned int), h->stream));
     int rc = dw_fused_supported(h) ? run_steps_fused(h, K, policy, act_dev, seed) : run_steps_generic(h, K, policy, act_dev, seed, h->alive);
     if (rc) return rc;
-    unsigned int alive[64];
-    DW_CUDA_TRY(h, cudaMemcpyAsync(alive, h->alive, K * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<unsigned int> alive(K);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(alive.data(), h->alive, K * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->ev_pending) {
         float ms = 0.f;
@@ -180,8 +231,10 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
         h->ev_pending = false;
     }
     uint64_t m = 0;
-    for (int j = 0; j < K; ++j) if (alive[j] == 0) m |= (1ull << j);
+    int first = -1;
+    for (int j = 0; j < K; ++j) if (alive[j] == 0) { if (j < 64) m |= (1ull << j); if (first < 0) first = j; }
     if (done_mask) *done_mask = m;
+    if (first_all_done) *first_all_done = first;
     if (alive_last) *alive_last = alive[K - 1];
     return DW_OK;
 }
@@ -193,7 +246,7 @@ static int check_policy(dw_handle *h, int policy, const int8_t *actions) {
 }
 
 extern "C" int dw_run_chunk(dw_handle *h, int32_t K, int32_t policy, const int8_t *actions, uint64_t seed, uint64_t *done_mask) {
-    if (!h) return DW_E_INVALID;
+    if (!h || K < 1 || K > 64) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = check_policy(h, policy, actions);
     if (rc) return rc;
@@ -215,8 +268,11 @@ extern "C" int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *act
     int64_t done_steps = 0;
     unsigned int alive_last = (unsigned int)h->cfg.batch;
     int hit = 0;
+    // Segment length: without the stopping rule one launch covers up to DW_FUSED_MAX_STEPS steps; with it, segments
+    // of 64 steps bound the work that has to be replayed when the all-done step falls inside a segment.
+    const int64_t seg = stop_all_done ? 64 : DW_FUSED_MAX_STEPS;
     while (done_steps < K) {
-        const int k = (int)((K - done_steps) < 64 ? (K - done_steps) : 64);
+        const int k = (int)((K - done_steps) < seg ? (K - done_steps) : seg);
         if (policy == DW_POLICY_REPLAY && per_step) {
             rc = stage_actions8(h, actions + (size_t)done_steps * per_step, per_step * k);
             if (rc) return rc;
@@ -225,19 +281,17 @@ extern "C" int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *act
             rc = ckpt_save(h, 1);
             if (rc) return rc;
         }
-        uint64_t mask = 0;
-        rc = run_chunk_impl(h, k, policy, h->action_dev, seed, &mask, &alive_last);
+        int first = -1;
+        rc = run_chunk_impl(h, k, policy, h->action_dev, seed, nullptr, &alive_last, &first);
         if (rc) return rc;
-        if (stop_all_done && mask) {
-            int j = 0;
-            while (!((mask >> j) & 1ull)) ++j;
-            if (j < k - 1) {     // overshot the notebook's stopping step: rewind and replay exactly j+1 steps
+        if (stop_all_done && first >= 0) {
+            if (first < k - 1) {     // overshot the notebook's stopping step: rewind and replay exactly first+1 steps
                 rc = ckpt_restore(h, 1);
                 if (rc) return rc;
-                rc = run_chunk_impl(h, j + 1, policy, h->action_dev, seed, &mask, &alive_last);
+                rc = run_chunk_impl(h, first + 1, policy, h->action_dev, seed, nullptr, &alive_last, nullptr);
                 if (rc) return rc;
             }
-            done_steps += j + 1;
+            done_steps += first + 1;
             hit = 1;
             break;
         }
