@@ -117,6 +117,12 @@ int dw_upload_state(dw_handle *h, const double *grid, const int64_t *agent_indic
    (host planes).  The narrow upload the reset()/ensemble paths use: the step reads nothing else of the grid. */
 int dw_upload_covers(dw_handle *h, const double *light, const double *dark);
 
+/* Device-side synthetic reset for ensembles too large to draw on the host: same distribution as initialize_grid /
+   initialize_agents (daisy_world_rl.py:285-302,173-179) from a counter RNG keyed by (seed, global world index, cell);
+   not stream-compatible with numpy. Channels 3..5 stay 0 until dw_init_temperatures. */
+int dw_init_random(dw_handle *h, uint64_t seed, double light_proportion, double dark_proportion, double initial_al,
+                   double initial_ad);
+
 /* initialize_grid's field fill (daisy_world_rl.py:304-324): ch0 = p-l-d and ch3..5 = UNROUNDED T, T_light,
    T_dark of the uploaded covers at the current clock L. Called by reset() after dw_upload_state. */
 int dw_init_temperatures(dw_handle *h);

@@ -95,3 +95,43 @@ def test_cfg2_full_size_lifespans_identical_to_reference():
     np.testing.assert_array_equal(env.grid.sum(axis=(-2, -1)), z["final_chan_sum"])
     np.testing.assert_array_equal(env.agent_states, z["final_agent_states"])
     np.testing.assert_array_equal(env.agent_indices, z["final_agent_indices"])
+
+
+def test_device_shard_ensemble_single_rank():
+    """ensemble.simulate_lifespan over a DeviceShard == the reference's recorded experiment (statistics included)."""
+    from therldaisyworld_b200.ensemble import DeviceShard, simulate_lifespan
+    z, meta = load_golden("antigreedy_n8_b16_todeath")
+    env = product_env_from_golden(z, meta)
+    out = simulate_lifespan(DeviceShard(env), policy="antigreedy", device="cuda")
+    assert out["steps"] == meta["steps"] and out["all_done"]
+    done_at, agents_done_at = env.lifespans()
+    np.testing.assert_array_equal(done_at, z["done_at"])
+    np.testing.assert_array_equal(agents_done_at, z["agents_done_at"])
+    assert out["biosphere_lifespan_mean"] == pytest.approx(z["done_at"].mean(), rel=1e-12)
+    assert out["agent_lifespan_sem"] == pytest.approx(z["agents_done_at"].std() / 4.0, rel=1e-9)
+
+
+def test_device_side_reset_distribution_and_run():
+    """dw_init_random: same distribution as the reference's reset (different RNG stream); runs through the fused path
+    with the device-side random policy, and the run is reproducible for a fixed seed."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    np.random.seed(0)
+    env = RLDaisyWorld(grid_dimension=64)
+    env.batch_size = 64
+    outs = []
+    for rep in range(2):
+        env.reset_on_device(seed=7)
+        g = env.grid
+        for ch, prop, init in ((1, env.light_proportion, env.initial_al), (2, env.dark_proportion, env.initial_ad)):
+            x = g[:, ch]
+            assert abs((x > 0).mean() - prop) < 0.01
+            assert x.max() < init and abs(x[x > 0].mean() - init / 2) < 0.002
+        np.testing.assert_array_equal(g[:, 0], (env.p - g[:, 1]) - g[:, 2])
+        assert (g[:, 3:6] > 200).all() and (env.agent_states == 1).all()
+        assert env.agent_indices.min() >= 0 and env.agent_indices.max() < 64
+        env.reset_lifespans()
+        env.run(200, policy="random", seed=11)
+        outs.append((env.grid.copy(), env.agent_states.copy(), env.lifespans()[1].copy()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])

@@ -335,6 +335,27 @@ extern "C" int dw_upload_covers(dw_handle *h, const double *light, const double 
     return DW_OK;
 }
 
+// Device-side synthetic reset (same distribution as initialize_grid/initialize_agents, counter RNG instead of
+// numpy's MT19937): for ensembles too large to draw on the host. Temperatures are NOT filled (dw_init_temperatures).
+extern "C" int dw_init_random(dw_handle *h, uint64_t seed, double light_proportion, double dark_proportion, double initial_al,
+                              double initial_ad) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_grid_buffers(h);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    k_init_random<<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, seed, h->world0, light_proportion, dark_proportion,
+                                                                         initial_al, initial_ad, h->grid[h->cur], h->agent_xy,
+                                                                         h->agent_state);
+    DW_LAUNCHED(h);
+    h->ch6_dirty[h->cur] = false;
+    h->grid_valid = true;
+    h->lat_valid = false;
+    h->pre = PRE_NONE;
+    h->obs_valid = false;
+    return DW_OK;
+}
+
 // initialize_grid's temperature fill (daisy_world_rl.py:304-324): ch0 = p-l-d, ch3..5 = unrounded T, Tl, Td at clk.L
 extern "C" int dw_init_temperatures(dw_handle *h) {
     if (!h) return DW_E_INVALID;

@@ -282,6 +282,37 @@ __global__ void __launch_bounds__(256) k_obs(DevParams P, const double *__restri
     }
 }
 
+// ---- device-side synthetic initial state (throughput ensembles; NOT numpy-stream compatible) -----------------------
+// Same distribution as initialize_grid/initialize_agents (daisy_world_rl.py:285-302,173-179): per cell and species
+// u0,u1 ~ U[0,1): cover = (u0 < proportion) * initial * u1; agents uniform on the grid with state 1.
+__device__ __forceinline__ double dw_u01(uint64_t seed, uint64_t idx, uint32_t stream) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx * 4 + stream + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(256) k_init_random(DevParams P, uint64_t seed, uint64_t world0, double prop_l, double prop_d,
+                                                     double init_l, double init_d, double *grid, int32_t *agent_xy, double *agent_state) {
+    const size_t NN = (size_t)P.N * P.N, total = (size_t)P.B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / NN, c = i - b * NN;
+        const uint64_t gidx = (world0 + b) * NN + c;
+        const double d = dw_u01(seed, gidx, 0) < prop_d ? init_d * dw_u01(seed, gidx, 1) : 0.0;
+        const double l = dw_u01(seed, gidx, 2) < prop_l ? init_l * dw_u01(seed, gidx, 3) : 0.0;
+        double *g = grid + b * 7 * NN + c;
+        g[0] = (P.p - l) - d; g[NN] = l; g[2 * NN] = d; g[3 * NN] = 0; g[4 * NN] = 0; g[5 * NN] = 0; g[6 * NN] = 0;
+    }
+    const size_t na = (size_t)P.B * P.n_agents;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t gidx = world0 * P.n_agents + i;
+        agent_xy[2 * i] = (int)(dw_u01(seed ^ 0xA5A5A5A5ull, gidx, 0) * P.N);
+        agent_xy[2 * i + 1] = (int)(dw_u01(seed ^ 0xA5A5A5A5ull, gidx, 1) * P.N);
+        agent_state[i] = 1.0;
+    }
+}
+
 // lattice -> fp64 covers (channels 1,2 only) : used when a fused run is followed by single steps
 __global__ void __launch_bounds__(256) k_lattice_to_grid(int B, size_t NN, const uint32_t *__restrict__ lat, double *grid) {
     const size_t total = (size_t)B * NN;

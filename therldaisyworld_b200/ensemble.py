@@ -1,0 +1,119 @@
+"""Multi-rank lifespan ensembles: worlds are independent, so an ensemble shards contiguously across ranks with NO
+data-path collective.  The only exchanges are (1) a bitwise-AND all-reduce of a 64-bit "every world of my shard was
+grid_done at step j" mask per 64-step segment -- the notebook's loop stops at the first step where ALL worlds are
+done (notebooks/greedy_longevity_abatement.ipynb cell 2) -- and (2) one SUM all-reduce of the 8-double lifespan
+statistics vector at the end.  One process per GPU; torch.distributed is only plumbing (NCCL on GPUs, gloo in the
+CPU tests, where an oracle-backed shard stands in for the device).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import DW_POLICY
+
+
+def shard_range(total, world_size, rank):
+    """Contiguous [lo, hi) slice of `total` worlds owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class DeviceShard:
+    """The worlds of one rank, living in a therldaisyworld_b200.RLDaisyWorld handle on that rank's GPU."""
+
+    def __init__(self, env, world_offset=0):
+        self.env = env
+        env._check(env._lib.dw_set_world_offset(env._h, int(world_offset)), "dw_set_world_offset")
+
+    def begin(self):
+        self.env._push()
+        self.env.reset_lifespans()
+
+    def checkpoint_save(self):
+        self.env._check(self.env._lib.dw_checkpoint_save(self.env._h), "dw_checkpoint_save")
+
+    def checkpoint_restore(self):
+        self.env._check(self.env._lib.dw_checkpoint_restore(self.env._h), "dw_checkpoint_restore")
+
+    def run_chunk(self, K, policy, actions=None, seed=0):
+        env = self.env
+        B, N, n = env._shape
+        a8 = None
+        if policy == "replay":
+            a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
+        mask = C.c_uint64()
+        rc = env._lib.dw_run_chunk(env._h, int(K), DW_POLICY[policy], None if a8 is None else a8.ctypes.data_as(C.POINTER(C.c_int8)),
+                                   C.c_uint64(seed), C.byref(mask))
+        env._check(rc, "dw_run_chunk")
+        env._state_changed()
+        env._pull_clock()
+        return int(mask.value)
+
+    def stats(self, like):
+        """Local {count, sum life, sum life^2, n_agents_total, sum agent_life, sum agent_life^2, 0, 0} written into
+        `like` (a torch CUDA float64 tensor of 8 elements) on the device, ready for an NCCL all-reduce."""
+        self.env._check(self.env._lib.dw_lifespan_stats_device(self.env._h, C.c_void_p(like.data_ptr())),
+                        "dw_lifespan_stats_device")
+        return like
+
+    def lifespans(self):
+        return self.env.lifespans()
+
+
+def _and_reduce(mask, group, dist, device):
+    import torch
+    if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mask
+    # int64 carries the 64 mask bits (two's complement); BAND is supported by both gloo and NCCL
+    t = torch.tensor([mask - (1 << 64) if mask >= (1 << 63) else mask], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.BAND, group=group)
+    v = int(t.item())
+    return v + (1 << 64) if v < 0 else v
+
+
+def simulate_lifespan(shard, policy="greedy", actions=None, seed=0, max_steps=100000, group=None, device="cpu", segment=64):
+    """Run the notebook's lifespan experiment on a sharded ensemble; returns a dict with global statistics.
+
+    Every rank calls this with its own shard. `actions` (replay policy) is this rank's slice [K, B_local, n]."""
+    import torch
+    try:
+        import torch.distributed as dist
+        if not dist.is_available():
+            dist = None
+    except Exception:       # pragma: no cover
+        dist = None
+    shard.begin()
+    if actions is not None:
+        max_steps = min(max_steps, len(actions))      # replay: cannot run past the recorded actions
+    steps = 0
+    hit = False
+    while steps < max_steps:
+        k = min(segment, max_steps - steps)
+        shard.checkpoint_save()
+        a = None if actions is None else actions[steps:steps + k]
+        mask = _and_reduce(shard.run_chunk(k, policy, a, seed), group, dist, device)
+        if mask:
+            j = (mask & -mask).bit_length() - 1           # first step at which every world of every rank was done
+            if j < k - 1:
+                shard.checkpoint_restore()
+                shard.run_chunk(j + 1, policy, a, seed)
+            steps += j + 1
+            hit = True
+            break
+        steps += k
+    s = shard.stats(torch.zeros(8, dtype=torch.float64, device=device))
+    if dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    s = s.tolist()
+    count, n_ag = s[0], s[3]
+    mean = s[1] / count
+    var = max(s[2] / count - mean * mean, 0.0)
+    out = {"steps": steps, "all_done": hit, "worlds": int(count), "biosphere_lifespan_mean": mean,
+           "biosphere_lifespan_sem": (var ** 0.5) / count ** 0.5}
+    if n_ag:
+        am = s[4] / n_ag
+        av = max(s[5] / n_ag - am * am, 0.0)
+        # the notebook divides the agent std by sqrt(number of worlds) (cell 16)
+        out.update(agent_lifespan_mean=am, agent_lifespan_sem=(av ** 0.5) / count ** 0.5)
+    return out

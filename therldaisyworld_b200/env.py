@@ -502,5 +502,23 @@ class RLDaisyWorld:
         self.run(max_steps, policy=policy, actions=actions, seed=seed, stop_all_done=True)
         return self.lifespans()
 
+    def reset_on_device(self, seed=0, world_offset=0):
+        """reset() with the initial state drawn ON THE DEVICE (counter RNG; same distribution as the reference's reset,
+        different stream): for ensembles too large to draw with numpy. Does not touch the global numpy RNG."""
+        self.L = self.min_L
+        self.dL = (self.max_L - self.min_L) / self.ramp_period
+        self.step_count = 0
+        self._ensure_handle((int(self.batch_size), int(self.dim), int(self.n_agents)))
+        for m in self._m.values():
+            m.invalidate()
+        self._push()
+        self._check(self._lib.dw_set_world_offset(self._h, int(world_offset)), "dw_set_world_offset")
+        self._check(self._lib.dw_init_random(self._h, C.c_uint64(seed), self.light_proportion, self.dark_proportion,
+                                             self.initial_al, self.initial_ad), "dw_init_random")
+        self._check(self._lib.dw_init_temperatures(self._h), "dw_init_temperatures")
+        self._dead_L = self.L
+        self._diag_cache = {}
+        self._pending_agents = None
+
     def synchronize(self):
         self._check(self._lib.dw_synchronize(self._h), "dw_synchronize")
