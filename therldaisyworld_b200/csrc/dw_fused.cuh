@@ -37,16 +37,18 @@
 #endif
 #define DW_TIE_EPS 4                   // filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover)
 
+// The fast path works with X' = g^2 * X (X = T_l^4 resp. T_d^4): its fourth root is T' = sqrt(g)*T, so that
+// beta = 1 - g*(Topt-T)^2 = 1 - (sqrt(g)*Topt - T')^2 is ONE fma.  All X coefficients below carry the factor g^2.
 struct FastCoef {        // launch-constant coefficients of the fast path (host-computed, fp64)
     double w0, w12, w2;  // rho (milli) = w0*k + (w1-w2)*E + w2*S8
     double dtp, dtm, dtg;  // dt*p, dt/1000, dt*gamma
-    double xk_l, xk_d;   // X_l coefficients of the centre covers: (q2-q)*(al-ab)/1000, (q2-q)*(ad-ab)/1000
-    double xdd;          // X_d - X_l = q2*(al-ad)
-    double topt, g;
+    double xk_l, xk_d;   // g^2 * X_l coefficients of the centre covers: (q2-q)*(al-ab)/1000, (q2-q)*(ad-ab)/1000
+    double xdd;          // g^2 * (X_d - X_l) = g^2 * q2*(al-ad)
+    double topt;         // sqrt(g) * Topt
 };
 struct StepCoef {        // per-step (luminosity dependent) coefficients
-    double x0;           // cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al
-    double xs_l, xs_d;   // (q-cL)*a*(al-ab)/1000, (q-cL)*a*(ad-ab)/1000   (a = adjacent tap)
+    double x0;           // g^2 * (cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al)
+    double xs_l, xs_d;   // g^2 * (q-cL)*a*(al-ab)/1000, g^2 * (q-cL)*a*(ad-ab)/1000   (a = adjacent tap)
     double SL;           // S*L for the literal path
 };
 
@@ -105,6 +107,28 @@ __device__ __forceinline__ double dw_root4_fast(double X) {
 __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
     return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
 }
+// Packed half -> f64.  Two exact routes on different pipes: the 2^52 trick (LOP + MOV + DADD: 3 issue slots, 2 cycles of
+// the FP64 pipe) or I2F.F64.U16 (1 issue slot, 8 cycles of the XU pipe, which the MUFU seeds also use; measured on
+// B200 with tools/micro/thr.cu).  DW_I2F_MASK picks the route per operand (bit 0..5 = kl,kd,Sl,Sd,El,Ed) to balance
+// the issue port, the FP64 pipe and the XU pipe.
+#ifndef DW_I2F_MASK
+#define DW_I2F_MASK 0x3F
+#endif
+template <int BIT>
+__device__ __forceinline__ double dw_half2d(uint32_t p) {
+    if (BIT & 1) {
+        if (DW_I2F_MASK & (1 << BIT)) return (double)(unsigned short)(p >> 16);
+        return dw_u2d(p >> 16);
+    } else {
+        if (DW_I2F_MASK & (1 << BIT)) return (double)(unsigned short)(p & 0xffffu);
+        return dw_u2d(p & 0xffffu);
+    }
+}
+// Rounding of x (milli units) to the lattice with the tie filter folded into ONE add: f = low word of
+// x + (1.5*2^32 + 0.5 + EPS*2^-FIX) = round((x + 0.5) * 2^FIX) + EPS as a signed fixed-point number.
+//   floor(x + .5) = f >> FIX   unless frac(x + .5) is within EPS*2^-FIX below 1 -- but then the cell is flagged anyway;
+//   tie flag: frac(x + .5) * 2^FIX + EPS (mod 2^FIX) < 2 EPS   <=>   (unsigned)(f << (32-FIX)) < DW_TIE_THRESH.
+#define DW_ROUND_MAGIC (6442450944.0 + 0.5 + (double)DW_TIE_EPS / (double)(1 << DW_FIX_BITS))
 
 // One cell of the fast path. pc: packed centre, E: packed sum of the 4 edge neighbours, S: packed sum of all 8.
 // Returns the packed new cell; *tiemin is lowered below DW_TIE_THRESH when either species sits within the filter of
@@ -121,20 +145,14 @@ __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCo
     const double rb = __fma_rn(-F.dtm, Rl + Rd, F.dtp);                       // dt * bare neighbourhood density
     const double Xl = __fma_rn(C.xs_l, Sl, __fma_rn(C.xs_d, Sd, __fma_rn(F.xk_l, kl, __fma_rn(F.xk_d, kd, C.x0))));
     const double Xd = Xl + F.xdd;
-    const double dTl = F.topt - dw_root4_fast(Xl);
+    const double dTl = F.topt - dw_root4_fast(Xl);                            // sqrt(g) * (Topt - T_l)
     const double dTd = F.topt - dw_root4_fast(Xd);
-    const double bl = __fma_rn(-F.g, dTl * dTl, 1.0);
-    const double bd = __fma_rn(-F.g, dTd * dTd, 1.0);
+    const double bl = __fma_rn(-dTl, dTl, 1.0);
+    const double bd = __fma_rn(-dTd, dTd, 1.0);
     const double xl = __fma_rn(Rl, __fma_rn(rb, bl, -F.dtg), kl);             // l + dt*dl in milli units
     const double xd = __fma_rn(Rd, __fma_rn(rb, bd, -F.dtg), kd);
-    // round-to-nearest via the 1.5*2^32 magic: low word = round(x * 2^20) as a signed fixed-point number
-    const double MAGIC = 6442450944.0;
-    const int HALF = 1 << (DW_FIX_BITS - 1);
-    const int fl = __double2loint(xl + MAGIC) + HALF, fd = __double2loint(xd + MAGIC) + HALF;
-    // tie filter: fraction within DW_TIE_EPS of .5  <=>  ((f + EPS) mod 2^20) < 2 EPS; the running minimum over a
-    // tile is compared once against DW_TIE_THRESH
-    const unsigned ul = (unsigned)(fl + DW_TIE_EPS) << (32 - DW_FIX_BITS), ud = (unsigned)(fd + DW_TIE_EPS) << (32 - DW_FIX_BITS);
-    *tiemin = __vimin3_u32(*tiemin, ul, ud);
+    const int fl = __double2loint(xl + DW_ROUND_MAGIC), fd = __double2loint(xd + DW_ROUND_MAGIC);
+    *tiemin = __vimin3_u32(*tiemin, (unsigned)fl << (32 - DW_FIX_BITS), (unsigned)fd << (32 - DW_FIX_BITS));
     // floor(x + .5) of both species packed as s16x2, clamped to [0,1000] by one VIMNMX.S16x2.RELU
     const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
     return __vimin_s16x2_relu(packed, 1000u | (1000u << 16));
@@ -147,9 +165,9 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
                                               const uint32_t (&S)[W], unsigned *tiemin, uint32_t (&out)[W]) {
     double kl[W], kd[W], El[W], Ed[W], Sl[W], Sd[W], Rl[W], Rd[W], rb[W], Xl[W], Xd[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) { kl[i] = dw_u2d(pc[i] & 0xffffu); kd[i] = dw_u2d(pc[i] >> 16); }
+    for (int i = 0; i < W; ++i) { kl[i] = dw_half2d<0>(pc[i]); kd[i] = dw_half2d<1>(pc[i]); }
 #pragma unroll
-    for (int i = 0; i < W; ++i) { Sl[i] = dw_u2d(S[i] & 0xffffu); Sd[i] = dw_u2d(S[i] >> 16); }
+    for (int i = 0; i < W; ++i) { Sl[i] = dw_half2d<2>(S[i]); Sd[i] = dw_half2d<3>(S[i]); }
 #pragma unroll
     for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(F.xk_l, kl[i], __fma_rn(F.xk_d, kd[i], C.x0));
 #pragma unroll
@@ -161,7 +179,7 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
 #pragma unroll
     for (int i = 0; i < W; ++i) { s1l[i] = dw_rsqrt_approx(Xl[i]); s1d[i] = dw_rsqrt_approx(Xd[i]); }
 #pragma unroll
-    for (int i = 0; i < W; ++i) { El[i] = dw_u2d(E[i] & 0xffffu); Ed[i] = dw_u2d(E[i] >> 16); }
+    for (int i = 0; i < W; ++i) { El[i] = dw_half2d<4>(E[i]); Ed[i] = dw_half2d<5>(E[i]); }
 #pragma unroll
     for (int i = 0; i < W; ++i) { Rl[i] = F.w0 * kl[i]; Rd[i] = F.w0 * kd[i]; }
 #pragma unroll
@@ -183,22 +201,17 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
 #pragma unroll
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(zl[i], 0.25, y0l[i]); zd[i] = __fma_rn(zd[i], 0.25, y0d[i]); }      // T_l, T_d
 #pragma unroll
-    for (int i = 0; i < W; ++i) { zl[i] = F.topt - zl[i]; zd[i] = F.topt - zd[i]; }
+    for (int i = 0; i < W; ++i) { zl[i] = F.topt - zl[i]; zd[i] = F.topt - zd[i]; }                                   // sqrt(g)*(Topt-T)
 #pragma unroll
-    for (int i = 0; i < W; ++i) { zl[i] = zl[i] * zl[i]; zd[i] = zd[i] * zd[i]; }
-#pragma unroll
-    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-F.g, zl[i], 1.0); zd[i] = __fma_rn(-F.g, zd[i], 1.0); }           // beta_l, beta_d
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-zl[i], zl[i], 1.0); zd[i] = __fma_rn(-zd[i], zd[i], 1.0); }       // beta_l, beta_d
 #pragma unroll
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(rb[i], zl[i], -F.dtg); zd[i] = __fma_rn(rb[i], zd[i], -F.dtg); }
 #pragma unroll
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(Rl[i], zl[i], kl[i]); zd[i] = __fma_rn(Rd[i], zd[i], kd[i]); }     // l + dt*dl (milli)
-    const double MAGIC = 6442450944.0;
-    const int HALF = 1 << (DW_FIX_BITS - 1);
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        const int fl = __double2loint(zl[i] + MAGIC) + HALF, fd = __double2loint(zd[i] + MAGIC) + HALF;
-        const unsigned ul = (unsigned)(fl + DW_TIE_EPS) << (32 - DW_FIX_BITS), ud = (unsigned)(fd + DW_TIE_EPS) << (32 - DW_FIX_BITS);
-        *tiemin = __vimin3_u32(*tiemin, ul, ud);
+        const int fl = __double2loint(zl[i] + DW_ROUND_MAGIC), fd = __double2loint(zd[i] + DW_ROUND_MAGIC);
+        *tiemin = __vimin3_u32(*tiemin, (unsigned)fl << (32 - DW_FIX_BITS), (unsigned)fd << (32 - DW_FIX_BITS));
         const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
         out[i] = __vimin_s16x2_relu(packed, 1000u | (1000u << 16));
     }
@@ -575,27 +588,80 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __gr
 // Work item = (world, chunk of Kc steps), handed out chunk-major from a global counter: all worlds of the ensemble
 // advance together and every SM keeps DW_N64_MIN_BLOCKS CTAs busy until the end of the launch, which removes the
 // wave quantisation of a one-CTA-per-world grid (1000 worlds on 148 SMs x 4 CTAs = 1.69 waves).
+// Shared memory is STATIC (compile-time addresses: no pointer registers, immediate LDS/STS offsets) and the agent
+// phase is the single-pass warp version below, so this kernel takes worlds with at most DW_N64_MAX_AGENTS agents;
+// larger agent counts run k_fused_n64.
+#define DW_N64_MAX_AGENTS 32
+struct __align__(16) N64Smem {
+    uint32_t buf[2][4096];
+    double st[DW_N64_MAX_AGENTS];
+    int xy[DW_N64_MAX_AGENTS];      // x | y << 16
+    int ada[DW_N64_MAX_AGENTS];     // agents_done_at increments of this work item
+    int smax[4];                    // [2 parities][2 species]
+    int item;
+};
+
+// Agent phase of one step for n <= 32 agents, one lane per agent, single pass (the reference's sequential loop,
+// daisy_world_rl.py:186-216, resolved in parallel): every lane decides from the pre-move state, moves, and the grazers of
+// one cell are ordered by MATCH.ANY -- the lowest lane eats, later ones find the cell empty and gain 0.0 (App. B.8).
+// Also does the per-step agent bookkeeping (agents_done_at += !done, done = reward < 0.1) since the state is final here.
+__device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int b, uint32_t *cb, N64Smem &sm, int lane, int n) {
+    constexpr int N = 64;
+    const bool active = lane < n;
+    double st = 0.0;
+    int x = 0, y = 0, a = 0;
+    if (active) {
+        st = sm.st[lane];
+        x = sm.xy[lane] & 0xffff;
+        y = sm.xy[lane] >> 16;
+        if (A.policy == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + lane];
+        else if (A.policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, lane, A.step0 + j) % 9u);
+        else if (A.policy != DW_POLICY_NONE) {
+            const int xm = (x + N - 1) & (N - 1), xp = (x + 1) & (N - 1), ym = (y + N - 1) & (N - 1), yp = (y + 1) & (N - 1);
+            const uint32_t c0 = cb[x * N + ym], c1 = cb[xm * N + y], c2 = cb[xp * N + y], c3 = cb[x * N + yp];
+            const double food[4] = {dw_food(c0), dw_food(c1), dw_food(c2), dw_food(c3)};
+            a = dw_greedy_pick(food, A.policy == DW_POLICY_GREEDY);
+        }
+    }
+    st = st - A.P.agent_gamma;
+    int cell = -1 - lane;                    // non-grazers: a private key, so MATCH groups them alone
+    if (active && st > 0.0) {
+        if (a != 8) {
+            const int d = (a & 2) ? 1 : -1;                  // a & 3 = 0: y-1, 1: x-1, 2: x+1, 3: y+1
+            if (((a + 1) & 2) == 0) y = (y + d) & (N - 1);   // a & 3 in {0, 3}
+            else x = (x + d) & (N - 1);
+        }
+        if (a > 4) cell = x * N + y;
+    }
+    const bool wants = cell >= 0;
+    const uint32_t pk = wants ? cb[cell] : 0u;
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    __syncwarp();                            // every read of the pre-graze state is done before any cell is zeroed
+    if (wants) {
+        const bool taken = (peers & ((1u << lane) - 1u)) != 0u;
+        st = st + (taken ? (0.0 + 0.0) : dw_food(pk));
+        cb[cell] = 0u;
+    }
+    if (active) {
+        st = dw_clip01(st);
+        sm.st[lane] = st;
+        sm.xy[lane] = x | (y << 16);
+        sm.ada[lane] += (st < 0.1) ? 0 : 1;
+    }
+}
+
 __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(const __grid_constant__ FusedArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ N64Smem sm;
     constexpr int NN = 4096;
     const int n = A.P.n_agents;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, r0 = (tid >> 4) * 4;
-    uint32_t *buf0 = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *buf1 = buf0 + NN;
-    AgentSmem S;
-    S.st = reinterpret_cast<double *>(buf1 + NN);
-    S.xy = reinterpret_cast<int *>(S.st + n);
-    S.act = S.xy + n;
-    S.ada = S.act + n;
-    int *s_max = S.ada + n;                 // [2 parities][2 species]
-    volatile int *s_item = s_max + 4;
     const int n_items = A.n_pairs * A.n_chunks;      // n_pairs = number of worlds for this kernel
 
     for (;;) {
-        if (tid == 0) *s_item = (int)atomicAdd(A.queue, 1u);
+        if (tid == 0) sm.item = (int)atomicAdd(A.queue, 1u);
         __syncthreads();
-        const int t = *s_item;
+        const int t = sm.item;
         if (t >= n_items) break;
         const int c = t / A.n_pairs, b = t - c * A.n_pairs;
         if (tid == 0) {
@@ -607,23 +673,23 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
         {
             const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat + (size_t)b * NN);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) reinterpret_cast<uint4 *>(buf0)[tid + k * 256] = __ldcg(gin + tid + k * 256);
+            for (int k = 0; k < 4; ++k) reinterpret_cast<uint4 *>(sm.buf[0])[tid + k * 256] = __ldcg(gin + tid + k * 256);
         }
-        for (int i = tid; i < n; i += 256) {
-            const size_t g = (size_t)b * n + i;
-            S.st[i] = __ldcg(A.agent_state + g);
-            S.xy[i] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
-            S.ada[i] = 0;
+        if (tid < n) {
+            const size_t g = (size_t)b * n + tid;
+            sm.st[tid] = __ldcg(A.agent_state + g);
+            sm.xy[tid] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
+            sm.ada[tid] = 0;
         }
-        if (tid < 4) s_max[tid] = 0;
+        if (tid < 4) sm.smax[tid] = 0;
         __syncthreads();
 
-        uint32_t *cb = buf0, *nb = buf1;
         int life = 0;
 #pragma unroll 1
         for (int jl = 0; jl < kc; ++jl) {
             const int j = j0 + jl;
-            if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane);
+            uint32_t *cb = sm.buf[jl & 1], *nb = sm.buf[(jl + 1) & 1];
+            if (warp == 0 && n > 0) dw_agents_phase32(A, j, b, cb, sm, lane, n);
             __syncthreads();
             if (j == A.K - 1) {
                 uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
@@ -632,42 +698,37 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             }
             const uint32_t mx = dw_tile_step64(A, j, cb, nb, r0, tx, lane);
             const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
-            int *sm = s_max + 2 * (jl & 1);
-            if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+            int *smx = sm.smax + 2 * (jl & 1);
+            if (lane == 0) { atomicMax(smx, (int)ml); atomicMax(smx + 1, (int)md); }
             __syncthreads();
-            if (warp == 0) {
-                const int m0 = sm[0], m1 = sm[1];
-                __syncwarp();
-                if (lane == 0) {
-                    if (max(m0, m1) > 5) { life += 1; atomicAdd(A.alive + j, 1u); }
-                    int *nx = s_max + 2 * ((jl + 1) & 1);
-                    nx[0] = 0; nx[1] = 0;
-                }
-                for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;
+            if (tid == 0) {
+                // lifespan bookkeeping of step j (notebook cell 2): grid_done = max(grid[:,1:3]) <= 0.005
+                if (max(smx[0], smx[1]) > 5) { life += 1; atomicAdd(A.alive + j, 1u); }
+                int *nx = sm.smax + 2 * ((jl + 1) & 1);
+                nx[0] = 0; nx[1] = 0;
             }
-            uint32_t *tmp = cb; cb = nb; nb = tmp;
         }
         __syncthreads();
         {
             uint4 *gout = reinterpret_cast<uint4 *>(A.lat + (size_t)b * NN);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gout[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
+            for (int k = 0; k < 4; ++k) gout[tid + k * 256] = reinterpret_cast<const uint4 *>(sm.buf[kc & 1])[tid + k * 256];
         }
-        for (int i = tid; i < n; i += 256) {
-            const size_t g = (size_t)b * n + i;
-            const double r = S.st[i];
+        if (tid < n) {
+            const size_t g = (size_t)b * n + tid;
+            const double r = sm.st[tid];
             A.agent_state[g] = r;
-            A.agent_xy[2 * g] = S.xy[i] & 0xffff;
-            A.agent_xy[2 * g + 1] = S.xy[i] >> 16;
-            A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + S.ada[i];
+            A.agent_xy[2 * g] = sm.xy[tid] & 0xffff;
+            A.agent_xy[2 * g + 1] = sm.xy[tid] >> 16;
+            A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + sm.ada[tid];
             A.reward[g] = r;
             A.done[g] = r < 0.1;
         }
         if (tid == 0) {
             A.done_at[b] = __ldcg(A.done_at + b) + life;
             if (n == 0) {
-                const int *sm = s_max + 2 * ((kc - 1) & 1);
-                for (int ch = 0; ch < 2; ++ch) { A.reward[2 * b + ch] = sm[ch] > 0 ? 1.0 : 0.0; A.done[2 * b + ch] = sm[ch] > 0 ? 0 : 1; }
+                const int *smx = sm.smax + 2 * ((kc - 1) & 1);
+                for (int ch = 0; ch < 2; ++ch) { A.reward[2 * b + ch] = smx[ch] > 0 ? 1.0 : 0.0; A.done[2 * b + ch] = smx[ch] > 0 ? 0 : 1; }
             }
         }
         __syncthreads();

@@ -17,6 +17,7 @@ static bool dw_fused_supported(const dw_handle *h) {
     for (int i = 0; i < 9; ++i) if (i != 4 && a[i] != a[0]) asym = false;
     if (!wsym || !asym) return false;
     if (c.n_agents > DW_FUSED_MAX_AGENTS) return false;
+    if (!(c.g > 0.0)) return false;                    // the fast path scales X by g^2 and T by sqrt(g)
     if (getenv("DW_DISABLE_FUSED")) return false;
     return fused_smem_bytes(c.dim, c.n_agents) <= 200 * 1024;
 }
@@ -29,11 +30,11 @@ static void make_fast_coef(const dw_config &c, FastCoef &F) {
     F.dtm = c.dt / 1000.0;
     F.dtg = c.dt * c.gamma;
     const double cl = (c.albedo_light - c.albedo_bare) / 1000.0, cd = (c.albedo_dark - c.albedo_bare) / 1000.0;
-    F.xk_l = (c.q2 - c.q) * cl;
-    F.xk_d = (c.q2 - c.q) * cd;
-    F.xdd = c.q2 * (c.albedo_light - c.albedo_dark);
-    F.topt = c.temp_optimal;
-    F.g = c.g;
+    const double g2 = c.g * c.g;        // X' = g^2 X, T' = sqrt(g) T (see FastCoef)
+    F.xk_l = g2 * ((c.q2 - c.q) * cl);
+    F.xk_d = g2 * ((c.q2 - c.q) * cd);
+    F.xdd = g2 * (c.q2 * (c.albedo_light - c.albedo_dark));
+    F.topt = sqrt(c.g) * c.temp_optimal;
 }
 
 static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
@@ -41,9 +42,10 @@ static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
     const double cL = c.S * L / c.sigma;
     const double Al0 = c.albedo_bare * c.p, A0 = c.albedo_bare * c.p * (8.0 * a);
     const double cl = (c.albedo_light - c.albedo_bare) / 1000.0, cd = (c.albedo_dark - c.albedo_bare) / 1000.0;
-    s.x0 = cL + (c.q - cL) * A0 + (c.q2 - c.q) * Al0 - c.q2 * c.albedo_light;
-    s.xs_l = (c.q - cL) * a * cl;
-    s.xs_d = (c.q - cL) * a * cd;
+    const double g2 = c.g * c.g;
+    s.x0 = g2 * (cL + (c.q - cL) * A0 + (c.q2 - c.q) * Al0 - c.q2 * c.albedo_light);
+    s.xs_l = g2 * ((c.q - cL) * a * cl);
+    s.xs_d = g2 * ((c.q - cL) * a * cd);
     s.SL = c.S * L;
 }
 
@@ -102,10 +104,10 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     const char *impl = getenv("DW_FUSED_IMPL");
     const bool n64 = h->cfg.dim == 64 && !(impl && !strcmp(impl, "generic"));
     const bool pipe = n64 && impl && !strcmp(impl, "pipe") && h->cfg.n_agents <= 256;
-    const bool persist = n64 && !pipe && !(impl && !strcmp(impl, "simple"));
+    const bool persist = n64 && !pipe && !(impl && !strcmp(impl, "simple")) && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
     if (h->profiling) DW_CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
     if (pipe || persist) {
-        const size_t smem = pipe ? pipe_smem_bytes(h->cfg.n_agents) : fused_smem_bytes(64, h->cfg.n_agents);
+        const size_t smem = pipe ? pipe_smem_bytes(h->cfg.n_agents) : 0;      // the persistent kernel's smem is static
         const int threads = pipe ? DW_PIPE_THREADS : 256;
         int &blocks = pipe ? h->pipe_blocks : h->persist_blocks;
         if (!blocks) {
@@ -114,7 +116,8 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
                 DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_pipe, threads, smem));
             } else {
-                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    cudaSharedmemCarveoutMaxShared));
                 DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist, threads, smem));
             }
             DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
