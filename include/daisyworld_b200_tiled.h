@@ -1,0 +1,98 @@
+/*
+ * daisyworld_b200_tiled.h -- C ABI of the single-giant-grid path (BASELINE config 5): ONE toroidal N x N RLDaisyWorld
+ * (batch_size == 1, daisy/daisy_world_rl.py:13-501) too large for shared memory, optionally split into row bands, one
+ * band per GPU.  Same conventions as daisyworld_b200.h (return codes, ownership, stream semantics, no CPU fallback).
+ *
+ * A handle owns rows [row0, row0 + rows) of the world (rows == N: the whole torus on one GPU) plus one ghost row above
+ * and below.  Agents are replicated: every rank holds all n agents (global coordinates) and runs the same agent
+ * kernels; only the rank that owns a cell eats from it.
+ *
+ * One env step (daisy_world_rl.py:475-497) is the phase sequence below.  With several ranks the caller sums two small
+ * device vectors across ranks between phases and copies two halo rows to the neighbours after the stencil
+ * (therldaisyworld_b200/banded.py does this with torch.distributed: NCCL on GPUs, gloo in the CPU tests):
+ *
+ *   dwt_decide        Greedy.__call__ (agents/greedy.py:16-30) or replay/none/random, owner rank only -> act[n]
+ *                     [ranks > 1 and greedy/antigreedy: all-reduce SUM of act]
+ *   dwt_move_graze    update_agents (:181-216): pay agent_gamma, move, graze in agent-index order -> gain[n]
+ *                     [ranks > 1: all-reduce SUM of gain]
+ *   dwt_finish_agents state += gain, clip (:244), reward/done (:486-492), agents_done_at += !done
+ *   dwt_stencil       forward (:434-452) on the band -> new covers; update_L (:463-473); per-step species max
+ *   dwt_halo_*        ghost rows: toroidal wrap (one rank) or the neighbours' edge rows (caller copies), then
+ *                     dwt_ghost_cols
+ *
+ * Constraints of the tiled kernels: N % 64 == 0, rows % 64 == 0, N >= 64, D4-symmetric kernels (the defaults).
+ */
+#ifndef DAISYWORLD_B200_TILED_H
+#define DAISYWORLD_B200_TILED_H
+
+#include "daisyworld_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dwt_handle dwt_handle;
+
+/* Device pointers a multi-rank driver needs (valid until the next dwt_stencil for the halo rows, for the life of the
+   handle for the rest). Row pointers address N packed u32 cells (light milli-cover | dark << 16). */
+typedef struct dwt_ptrs {
+    double *act;            /* [n]   action + 1 per agent (0 = not decided here) */
+    double *gain;           /* [n]   food eaten per agent on this rank */
+    int32_t *stepmax;       /* [4096, 2] per-step max milli-cover of (light, dark) over this band */
+    uint32_t *send_top;     /* band row 0          -> the rank above's bottom ghost */
+    uint32_t *send_bottom;  /* band row rows-1     -> the rank below's top ghost */
+    uint32_t *recv_top;     /* ghost row above the band */
+    uint32_t *recv_bottom;  /* ghost row below the band */
+} dwt_ptrs;
+
+const char *dwt_last_error(const dwt_handle *h);
+/* cfg->dim = N, cfg->n_agents = n, cfg->batch must be 1; rows/row0: the band of this handle; n_ranks: number of bands */
+int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int32_t n_ranks, dwt_handle **out);
+int dwt_destroy(dwt_handle *h);
+int dwt_set_config(dwt_handle *h, const dw_config *cfg);
+int dwt_set_clock(dwt_handle *h, const dw_clock *clk);
+int dwt_get_clock(dwt_handle *h, dw_clock *clk);
+int dwt_set_stream(dwt_handle *h, void *cuda_stream);
+int dwt_synchronize(dwt_handle *h);
+
+/* reset(): cover planes of the band INCLUDING its two ghost rows, host fp64 [(rows + 2), N] each (row 0 = world row
+   row0 - 1 with toroidal wrap); the state is off the 0.001 lattice until the first step (daisy_world_rl.py:299-302). */
+int dwt_upload_covers(dwt_handle *h, const double *light, const double *dark);
+/* all n agents, global coordinates: agent_indices[n,2] int64, agent_states[n] */
+int dwt_upload_agents(dwt_handle *h, const int64_t *agent_indices, const double *agent_states);
+/* device-side synthetic reset (distribution of initialize_grid/initialize_agents, counter RNG keyed by the global cell /
+   agent index: every banding of the same world gets the same state) */
+int dwt_init_random(dwt_handle *h, uint64_t seed, double light_proportion, double dark_proportion, double initial_al,
+                    double initial_ad);
+
+/* phases of one step (see the header comment). actions: host int8 [n] for DW_POLICY_REPLAY, else NULL. */
+int dwt_decide(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed);
+int dwt_move_graze(dwt_handle *h);
+int dwt_finish_agents(dwt_handle *h);
+int dwt_stencil(dwt_handle *h);
+int dwt_halo_wrap(dwt_handle *h);      /* one rank: ghost rows from the band's own edge rows */
+int dwt_ghost_cols(dwt_handle *h);     /* after the ghost rows are in place */
+int dwt_get_ptrs(dwt_handle *h, dwt_ptrs *out);
+
+/* K whole steps on one rank (rows == N): the phases above back to back on the handle's stream, no host sync. */
+int dwt_run(dwt_handle *h, int64_t K, int32_t policy, const int8_t *actions /*[K,n] or NULL*/, uint64_t seed);
+/* Close a chunk of `K` steps whose per-step maxima sit in stepmax (all-reduced MAX over ranks by the caller when there
+   are several): done_at += #steps whose max(light, dark) > 5 (notebook cell 2: grid_done = max <= 0.005);
+   first_all_done = first step index of the chunk with the world done, or -1. Clears stepmax. */
+int dwt_end_chunk(dwt_handle *h, int32_t K, int32_t *first_all_done);
+int dwt_reset_lifespans(dwt_handle *h);
+int dwt_get_lifespans(dwt_handle *h, int64_t *done_at /*[1]*/, int64_t *agents_done_at /*[n]*/);
+
+/* getters (synchronise) */
+int dwt_get_agents(dwt_handle *h, int64_t *agent_indices, double *agent_states);
+int dwt_get_reward_done(dwt_handle *h, double *reward, uint8_t *done);          /* [n] */
+int dwt_get_covers(dwt_handle *h, double *light, double *dark);                 /* band rows, [rows, N] each */
+/* env.grid of the band: [7, rows, N] (channels as in the reference; ch4 carries the agent stamp), materialised by a
+   literal forward from the post-graze state the last step started from. Needs at least one step. */
+int dwt_get_grid(dwt_handle *h, double *grid);
+int dwt_debug_slow_count(dwt_handle *h, uint64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAISYWORLD_B200_TILED_H */

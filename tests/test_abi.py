@@ -20,10 +20,13 @@ def lib():
     return _lib.load()
 
 
-def header_symbols():
-    src = open(HEADER).read()
+HEADER_TILED = os.path.join(ROOT, "include", "daisyworld_b200_tiled.h")
+
+
+def header_symbols(path=HEADER, prefix="dw_"):
+    src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(dw_[A-Za-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -35,10 +38,15 @@ def test_library_exports_every_declared_symbol(lib):
     exported = set(re.findall(r"\bT (dw_[A-Za-z0-9_]+)", out))
     assert set(declared) <= exported, f"missing: {set(declared) - exported}"
     assert lib.dw_abi_version() == 1
+    tiled = header_symbols(HEADER_TILED, "dwt_")
+    assert tiled and sorted(_lib.TILED_SYMBOLS) == tiled, "_lib.py and daisyworld_b200_tiled.h disagree"
+    exported_t = set(re.findall(r"\bT (dwt_[A-Za-z0-9_]+)", out))
+    assert set(tiled) <= exported_t, f"missing: {set(tiled) - exported_t}"
 
 
 def test_struct_layouts_match_header():
-    from therldaisyworld_b200._lib import DwClock, DwConfig, DwRunResult
+    from therldaisyworld_b200._lib import DwClock, DwConfig, DwRunResult, DwtPtrs
+    assert C.sizeof(DwtPtrs) == 7 * 8
     assert C.sizeof(DwConfig) == 4 * 4 + 13 * 8 + 27 * 8
     assert C.sizeof(DwClock) == 5 * 8 + 2 * 8 + 2 * 4
     assert C.sizeof(DwRunResult) == 24

@@ -42,6 +42,21 @@ SYMBOLS = [
     "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak",
 ]
 
+# every symbol include/daisyworld_b200_tiled.h declares (single giant grid, row bands)
+TILED_SYMBOLS = [
+    "dwt_last_error", "dwt_create", "dwt_destroy", "dwt_set_config", "dwt_set_clock", "dwt_get_clock", "dwt_set_stream",
+    "dwt_synchronize", "dwt_upload_covers", "dwt_upload_agents", "dwt_init_random", "dwt_decide", "dwt_move_graze",
+    "dwt_finish_agents", "dwt_stencil", "dwt_halo_wrap", "dwt_ghost_cols", "dwt_get_ptrs", "dwt_run", "dwt_end_chunk",
+    "dwt_reset_lifespans", "dwt_get_lifespans", "dwt_get_agents", "dwt_get_reward_done", "dwt_get_covers", "dwt_get_grid",
+    "dwt_debug_slow_count",
+]
+
+
+class DwtPtrs(C.Structure):
+    _fields_ = [("act", C.c_void_p), ("gain", C.c_void_p), ("stepmax", C.c_void_p), ("send_top", C.c_void_p),
+                ("send_bottom", C.c_void_p), ("recv_top", C.c_void_p), ("recv_bottom", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -101,6 +116,38 @@ def load():
         "dw_debug_fp64_peak": (C.c_int, [vp, i32, i32, pd, pd]),
     }
     assert set(sig) == set(SYMBOLS)
+    pi32 = C.POINTER(C.c_int32)
+    tsig = {
+        "dwt_last_error": (C.c_char_p, [vp]),
+        "dwt_create": (C.c_int, [C.POINTER(DwConfig), i32, i32, i32, C.POINTER(vp)]),
+        "dwt_destroy": (C.c_int, [vp]),
+        "dwt_set_config": (C.c_int, [vp, C.POINTER(DwConfig)]),
+        "dwt_set_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
+        "dwt_get_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
+        "dwt_set_stream": (C.c_int, [vp, vp]),
+        "dwt_synchronize": (C.c_int, [vp]),
+        "dwt_upload_covers": (C.c_int, [vp, pd, pd]),
+        "dwt_upload_agents": (C.c_int, [vp, pi64, pd]),
+        "dwt_init_random": (C.c_int, [vp, u64, C.c_double, C.c_double, C.c_double, C.c_double]),
+        "dwt_decide": (C.c_int, [vp, i32, pi8, u64]),
+        "dwt_move_graze": (C.c_int, [vp]),
+        "dwt_finish_agents": (C.c_int, [vp]),
+        "dwt_stencil": (C.c_int, [vp]),
+        "dwt_halo_wrap": (C.c_int, [vp]),
+        "dwt_ghost_cols": (C.c_int, [vp]),
+        "dwt_get_ptrs": (C.c_int, [vp, C.POINTER(DwtPtrs)]),
+        "dwt_run": (C.c_int, [vp, i64, i32, pi8, u64]),
+        "dwt_end_chunk": (C.c_int, [vp, i32, pi32]),
+        "dwt_reset_lifespans": (C.c_int, [vp]),
+        "dwt_get_lifespans": (C.c_int, [vp, pi64, pi64]),
+        "dwt_get_agents": (C.c_int, [vp, pi64, pd]),
+        "dwt_get_reward_done": (C.c_int, [vp, pd, pu8]),
+        "dwt_get_covers": (C.c_int, [vp, pd, pd]),
+        "dwt_get_grid": (C.c_int, [vp, pd]),
+        "dwt_debug_slow_count": (C.c_int, [vp, C.POINTER(u64)]),
+    }
+    assert set(tsig) == set(TILED_SYMBOLS)
+    sig.update(tsig)
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
         fn.restype = res
@@ -109,6 +156,12 @@ def load():
         raise DaisyWorldError("ABI version mismatch between _lib.py and libdaisyworld_b200.so")
     _lib = lib
     return lib
+
+
+def check_tiled(lib, handle, rc, what):
+    if rc != 0:
+        msg = lib.dwt_last_error(handle)
+        raise DaisyWorldError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
 
 
 def check(lib, handle, rc, what):

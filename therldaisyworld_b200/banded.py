@@ -1,0 +1,356 @@
+"""A single giant toroidal RLDaisyWorld (BASELINE config 5), row-banded over the ranks of one node.
+
+The world is ONE batch element of the reference environment (``daisy/daisy_world_rl.py``, ``batch_size == 1``) whose
+grid does not fit in shared memory: rank r owns rows ``[r*N/R, (r+1)*N/R)`` on its GPU (a ``dwt_handle`` of
+``include/daisyworld_b200_tiled.h``) plus a ghost row above and below.  Agents are replicated on every rank.
+
+One env step = the phase sequence of the header, with exactly these exchanges between ranks (``torch.distributed``:
+NCCL over NVLink on GPUs, gloo in the CPU tests -- plumbing only, the data path is the CUDA kernels):
+
+  * greedy / anti-greedy: SUM all-reduce of ``act[n]`` (only the owner band of an agent can see its neighbourhood);
+  * SUM all-reduce of ``gain[n]`` (only the owner band of a cell knows what was eaten there);
+  * after the stencil: the band's first/last row goes to the upper/lower neighbour's ghost row (ring, toroidal);
+  * per chunk of steps: MAX all-reduce of the per-step cover maxima (lifespan bookkeeping, ``grid_done``).
+
+``world_size == 1`` needs none of them (``dwt_halo_wrap`` closes the torus locally).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DwClock, DwtPtrs, DW_POLICY
+from .env import make_clock_struct, make_config_struct, set_default_attributes, set_default_kernels
+
+_WORLD_POLICIES = ("greedy", "antigreedy")      # decisions that read the grid (need the act all-reduce)
+
+
+def band_rows(N, world_size, rank):
+    """Rows [lo, hi) of rank's band; N must split into equal multiples of 64."""
+    if N % (64 * world_size):
+        raise ValueError(f"N={N} must be a multiple of 64*world_size={64 * world_size}")
+    R = N // world_size
+    return rank * R, (rank + 1) * R
+
+
+class DistComm:
+    """The three exchanges of a banded step over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, rank, world_size, group=None):
+        import torch.distributed as dist
+        self.dist, self.rank, self.world_size, self.group = dist, int(rank), int(world_size), group
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+
+    def exchange_halos(self, send_top, send_bottom, recv_top, recv_bottom):
+        dist = self.dist
+        up, down = (self.rank - 1) % self.world_size, (self.rank + 1) % self.world_size
+        if self.group is not None:
+            up, down = dist.get_global_rank(self.group, up), dist.get_global_rank(self.group, down)
+        # tag 0: downward message (my last row -> lower neighbour's top ghost); tag 1: upward. Posting order matters for
+        # NCCL when up == down (two ranks): the first send pairs with the peer's first receive.
+        ops = [dist.P2POp(dist.isend, send_bottom, down, group=self.group, tag=0),
+               dist.P2POp(dist.isend, send_top, up, group=self.group, tag=1),
+               dist.P2POp(dist.irecv, recv_top, up, group=self.group, tag=0),
+               dist.P2POp(dist.irecv, recv_bottom, down, group=self.group, tag=1)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class DeviceBand:
+    """One rank's band on its GPU (ctypes over the dwt_* C-ABI)."""
+
+    def __init__(self, params, N, n_agents, row0, rows, n_ranks, device=0):
+        import torch
+        self._torch = torch
+        self._lib = _lib.load()
+        self.N, self.n, self.row0, self.rows, self.n_ranks, self.device = int(N), int(n_agents), int(row0), int(rows), int(n_ranks), int(device)
+        cfg = make_config_struct(params, 1, N, n_agents, device)
+        h = C.c_void_p()
+        rc = self._lib.dwt_create(C.byref(cfg), self.rows, self.row0, self.n_ranks, C.byref(h))
+        if rc != 0:
+            msg = self._lib.dwt_last_error(None)
+            raise _lib.DaisyWorldError(f"dwt_create failed (code {rc}): {msg.decode() if msg else ''}")
+        self._h = h
+        self._views = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.dwt_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        _lib.check_tiled(self._lib, self._h, rc, what)
+
+    # ---- state
+    def set_params(self, params):
+        cfg = make_config_struct(params, 1, self.N, self.n, self.device)
+        self._check(self._lib.dwt_set_config(self._h, C.byref(cfg)), "dwt_set_config")
+
+    def set_clock(self, clk):
+        self._check(self._lib.dwt_set_clock(self._h, C.byref(clk)), "dwt_set_clock")
+
+    def get_clock(self):
+        clk = DwClock()
+        self._check(self._lib.dwt_get_clock(self._h, C.byref(clk)), "dwt_get_clock")
+        return clk
+
+    def upload(self, light_rows, dark_rows, agent_indices, agent_states):
+        """light_rows/dark_rows: [rows + 2, N] (band with its ghost rows); agents: all n, global coordinates."""
+        pd = C.POINTER(C.c_double)
+        l = np.ascontiguousarray(light_rows, dtype=np.float64)
+        d = np.ascontiguousarray(dark_rows, dtype=np.float64)
+        assert l.shape == d.shape == (self.rows + 2, self.N)
+        self._check(self._lib.dwt_upload_covers(self._h, l.ctypes.data_as(pd), d.ctypes.data_as(pd)), "dwt_upload_covers")
+        if self.n:
+            ai = np.ascontiguousarray(agent_indices, dtype=np.int64).reshape(self.n, 2)
+            st = np.ascontiguousarray(agent_states, dtype=np.float64).reshape(self.n)
+            self._check(self._lib.dwt_upload_agents(self._h, ai.ctypes.data_as(C.POINTER(C.c_int64)), st.ctypes.data_as(pd)),
+                        "dwt_upload_agents")
+        self._views = {}
+
+    def init_random(self, seed, params):
+        self._check(self._lib.dwt_init_random(self._h, C.c_uint64(seed), params.light_proportion, params.dark_proportion,
+                                              params.initial_al, params.initial_ad), "dwt_init_random")
+        self._views = {}
+
+    # ---- phases
+    def decide(self, policy, actions_step=None, seed=0):
+        a = None
+        if policy == "replay":
+            a = np.ascontiguousarray(np.asarray(actions_step).reshape(self.n), dtype=np.int8)
+        self._check(self._lib.dwt_decide(self._h, DW_POLICY[policy], None if a is None else a.ctypes.data_as(C.POINTER(C.c_int8)),
+                                         C.c_uint64(seed)), "dwt_decide")
+
+    def move_graze(self):
+        self._check(self._lib.dwt_move_graze(self._h), "dwt_move_graze")
+
+    def finish_agents(self):
+        self._check(self._lib.dwt_finish_agents(self._h), "dwt_finish_agents")
+
+    def stencil(self):
+        self._check(self._lib.dwt_stencil(self._h), "dwt_stencil")
+
+    def halo_wrap(self):
+        self._check(self._lib.dwt_halo_wrap(self._h), "dwt_halo_wrap")
+
+    def ghost_cols(self):
+        self._check(self._lib.dwt_ghost_cols(self._h), "dwt_ghost_cols")
+
+    def run_local(self, K, policy, actions=None, seed=0):
+        """K steps without any exchange (a band that is the whole torus)."""
+        a = None
+        if policy == "replay":
+            a = np.ascontiguousarray(np.asarray(actions).reshape(-1, self.n)[:K], dtype=np.int8)
+            assert a.shape[0] == K
+        self._check(self._lib.dwt_run(self._h, int(K), DW_POLICY[policy], None if a is None else a.ctypes.data_as(C.POINTER(C.c_int8)),
+                                      C.c_uint64(seed)), "dwt_run")
+
+    def end_chunk(self, K):
+        first = C.c_int32(-1)
+        self._check(self._lib.dwt_end_chunk(self._h, int(K), C.byref(first)), "dwt_end_chunk")
+        return int(first.value)
+
+    # ---- exchange buffers as torch CUDA tensors (zero-copy views of library memory)
+    def _ptrs(self):
+        p = DwtPtrs()
+        self._check(self._lib.dwt_get_ptrs(self._h, C.byref(p)), "dwt_get_ptrs")
+        return p
+
+    def _view(self, ptr, shape, typestr):
+        key = (int(ptr), tuple(shape), typestr)
+        t = self._views.get(key)
+        if t is None:
+            t = self._torch.as_tensor(_DevArray(ptr, shape, typestr), device=f"cuda:{self.device}")
+            self._views[key] = t
+        return t
+
+    def act_tensor(self):
+        return self._view(self._ptrs().act, (max(self.n, 1),), "<f8")[:self.n]
+
+    def gain_tensor(self):
+        return self._view(self._ptrs().gain, (max(self.n, 1),), "<f8")[:self.n]
+
+    def stepmax_tensor(self, K):
+        return self._view(self._ptrs().stepmax, (4096 * 2,), "<i4")[:2 * K]
+
+    def halo_tensors(self):
+        """(send_top, send_bottom, recv_top, recv_bottom) rows of the CURRENT lattice buffer, int32 views of N cells."""
+        p = self._ptrs()
+        return tuple(self._view(q, (self.N,), "<i4") for q in (p.send_top, p.send_bottom, p.recv_top, p.recv_bottom))
+
+    # ---- getters
+    def reset_lifespans(self):
+        self._check(self._lib.dwt_reset_lifespans(self._h), "dwt_reset_lifespans")
+
+    def lifespans(self):
+        done_at = C.c_int64(0)
+        ada = np.zeros((self.n,), dtype=np.int64)
+        self._check(self._lib.dwt_get_lifespans(self._h, C.byref(done_at), ada.ctypes.data_as(C.POINTER(C.c_int64))), "dwt_get_lifespans")
+        return int(done_at.value), ada
+
+    def agents(self):
+        ai = np.zeros((self.n, 2), dtype=np.int64)
+        st = np.zeros((self.n,), dtype=np.float64)
+        if self.n:
+            self._check(self._lib.dwt_get_agents(self._h, ai.ctypes.data_as(C.POINTER(C.c_int64)), st.ctypes.data_as(C.POINTER(C.c_double))),
+                        "dwt_get_agents")
+        return ai, st
+
+    def reward_done(self):
+        r = np.zeros((self.n,), dtype=np.float64)
+        d = np.zeros((self.n,), dtype=np.uint8)
+        if self.n:
+            self._check(self._lib.dwt_get_reward_done(self._h, r.ctypes.data_as(C.POINTER(C.c_double)), d.ctypes.data_as(C.POINTER(C.c_uint8))),
+                        "dwt_get_reward_done")
+        return r, d.astype(bool)
+
+    def covers(self):
+        out = np.empty((2, self.rows, self.N))
+        pd = C.POINTER(C.c_double)
+        self._check(self._lib.dwt_get_covers(self._h, out[0].ctypes.data_as(pd), out[1].ctypes.data_as(pd)), "dwt_get_covers")
+        return out
+
+    def grid(self):
+        out = np.empty((7, self.rows, self.N))
+        self._check(self._lib.dwt_get_grid(self._h, out.ctypes.data_as(C.POINTER(C.c_double))), "dwt_get_grid")
+        return out
+
+    def slow_count(self):
+        c = C.c_uint64(0)
+        self._check(self._lib.dwt_debug_slow_count(self._h, C.byref(c)), "dwt_debug_slow_count")
+        return int(c.value)
+
+    def synchronize(self):
+        self._check(self._lib.dwt_synchronize(self._h), "dwt_synchronize")
+
+
+class BandedDaisyWorld:
+    """Host-side driver of one giant world over `world_size` bands.
+
+    Carries the reference's public constants as attributes (same names as RLDaisyWorld; mutate them before reset()).
+    `band_factory(params, N, n_agents, row0, rows, n_ranks)` builds this rank's band: DeviceBand on a GPU (default), an
+    oracle-backed stand-in in the CPU tests."""
+
+    def __init__(self, grid_dimension, n_agents, rank=0, world_size=1, group=None, device=0, band_factory=None, comm=None,
+                 **kwargs):
+        set_default_attributes(self, grid_dimension=grid_dimension, n_agents=n_agents, **kwargs)
+        set_default_kernels(self)
+        self.batch_size = 1
+        self.rank, self.world_size, self.device = int(rank), int(world_size), int(device)
+        self.comm = comm if (comm is not None or self.world_size == 1) else DistComm(rank, world_size, group)
+        self.row0, hi = band_rows(self.dim, self.world_size, self.rank)
+        self.rows = hi - self.row0
+        factory = band_factory or (lambda p, N, n, r0, R, nr: DeviceBand(p, N, n, r0, R, nr, device=self.device))
+        self.band = factory(self, self.dim, self.n_agents, self.row0, self.rows, self.world_size)
+        self.L = self.min_L
+        self.dL = (self.max_L - self.min_L) / self.ramp_period
+        self.step_count = 0
+        self._pending = 0          # steps recorded since the last end_chunk
+        self.first_done_step = None
+
+    # ---- reset
+    def _reset_clock(self):
+        self.L = self.min_L
+        self.dL = (self.max_L - self.min_L) / self.ramp_period
+        self.step_count = 0
+        self.band.set_params(self)
+        self.band.set_clock(make_clock_struct(self))
+        self.band.reset_lifespans()
+        self._pending = 0
+        self.first_done_step = None
+
+    def load_state(self, light, dark, agent_indices, agent_states):
+        """reset() from explicit GLOBAL arrays: light/dark [N,N] (may be off the 0.001 lattice), agents [n,2], [n]."""
+        self._reset_clock()
+        N = self.dim
+        rows = np.arange(self.row0 - 1, self.row0 + self.rows + 1) % N
+        self.band.upload(np.asarray(light)[rows], np.asarray(dark)[rows], agent_indices, agent_states)
+
+    def reset_on_device(self, seed=0):
+        """reset() with the state drawn on the device (same distribution as the reference, counter RNG keyed by the
+        global cell index: identical for every banding)."""
+        self._reset_clock()
+        self.band.init_random(seed, self)
+
+    # ---- stepping
+    def step(self, policy="greedy", actions_step=None, seed=0):
+        b, comm = self.band, self.comm
+        b.decide(policy, actions_step, seed)
+        if comm is not None and policy in _WORLD_POLICIES and self.n_agents:
+            comm.all_reduce_sum(b.act_tensor())
+        b.move_graze()
+        if comm is not None and self.n_agents:
+            comm.all_reduce_sum(b.gain_tensor())
+        b.finish_agents()
+        b.stencil()
+        if comm is None:
+            b.halo_wrap()
+        else:
+            comm.exchange_halos(*b.halo_tensors())
+        b.ghost_cols()
+        self._pending += 1
+
+    def end_chunk(self):
+        """Fold the per-step cover maxima of the steps since the last call into the lifespan counter."""
+        K = self._pending
+        if K == 0:
+            return
+        if self.comm is not None:
+            self.comm.all_reduce_max(self.band.stepmax_tensor(K))
+        first = self.band.end_chunk(K)
+        if first >= 0 and self.first_done_step is None:
+            self.first_done_step = self.step_count + first + 1      # 1-based count of steps at which grid_done first held
+        self.step_count += K
+        self._pending = 0
+        clk = self.band.get_clock()
+        self.L, self.dL, self.min_L, self.max_L = clk.L, clk.dL, clk.min_L, clk.max_L
+
+    def run(self, K, policy="greedy", actions=None, seed=0, chunk=256):
+        """K env steps. actions: [K, n] ints 0..8 for policy='replay'. Lifespan counters are folded every `chunk` steps."""
+        if self.world_size == 1 and hasattr(self.band, "run_local"):
+            done = 0
+            while done < K:
+                k = min(chunk, K - done)
+                self.band.run_local(k, policy, None if actions is None else np.asarray(actions)[done:done + k], seed)
+                self._pending += k
+                self.end_chunk()
+                done += k
+            return K
+        for j in range(K):
+            self.step(policy, None if actions is None else np.asarray(actions)[j], seed)
+            if self._pending >= chunk:
+                self.end_chunk()
+        self.end_chunk()
+        return K
+
+    # ---- results
+    def lifespans(self):
+        """(done_at, agents_done_at[n]) -- the notebook counters (greedy_longevity_abatement.ipynb cell 2)."""
+        self.end_chunk()
+        return self.band.lifespans()
+
+    def agents(self):
+        return self.band.agents()
+
+    def local_covers(self):
+        """[2, rows, N]: light and dark cover of this rank's band."""
+        return self.band.covers()
+
+    def local_grid(self):
+        """[7, rows, N]: env.grid[0] restricted to this rank's rows."""
+        return self.band.grid()

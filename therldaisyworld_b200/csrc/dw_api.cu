@@ -88,9 +88,8 @@ static int dw_fail(dw_handle *h, int code, const char *what, const char *detail)
     return code;
 }
 
-static DevParams make_params(const dw_handle *h) {
+static DevParams make_params_cfg(const dw_config &c) {
     DevParams P{};
-    const dw_config &c = h->cfg;
     P.B = c.batch; P.N = c.dim; P.n_agents = c.n_agents;
     P.p = c.p; P.g = c.g; P.S = c.S; P.sigma = c.sigma; P.gamma = c.gamma; P.q = c.q; P.q2 = c.q2;
     P.temp_optimal = c.temp_optimal; P.dt = c.dt; P.agent_gamma = c.agent_gamma;
@@ -98,6 +97,7 @@ static DevParams make_params(const dw_handle *h) {
     for (int i = 0; i < 9; ++i) { P.w[i] = c.daisy_kernel[i]; P.adj[i] = c.adjacent_kernel[i]; P.mask[i] = c.obs_mask[i]; }
     return P;
 }
+static DevParams make_params(const dw_handle *h) { return make_params_cfg(h->cfg); }
 
 static inline int grid_for(size_t total, int block = 256) {
     size_t g = (total + block - 1) / block;
@@ -845,3 +845,6 @@ extern "C" int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t 
 
 // ---- dw_run / dw_run_chunk ----------------------------------------------------------------------------------
 #include "dw_run.inl"
+
+// ---- single giant grid (include/daisyworld_b200_tiled.h) -----------------------------------------------------
+#include "dw_tiled_api.inl"

@@ -432,14 +432,10 @@ __device__ __noinline__ uint32_t dw_fix_tile64(const FusedArgs *A, const StepCoe
     return mx;
 }
 
-struct Row6 { uint32_t p[4]; uint32_t hp[4]; };
+struct Row6 { uint32_t p[4]; uint32_t hp[4]; };     // 4 packed cells of one row + their horizontal neighbour sums
 
-__device__ __forceinline__ Row6 dw_load_row(const uint32_t *cb, int row, int tx, int lane) {
+__device__ __forceinline__ Row6 dw_make_row(const uint4 v, uint32_t left, uint32_t right) {
     Row6 r;
-    const uint4 v = *reinterpret_cast<const uint4 *>(cb + row * 64 + tx * 4);
-    const int base = lane & 16;
-    const uint32_t left = __shfl_sync(0xffffffffu, v.w, base | ((lane - 1) & 15));
-    const uint32_t right = __shfl_sync(0xffffffffu, v.x, base | ((lane + 1) & 15));
     r.p[0] = v.x; r.p[1] = v.y; r.p[2] = v.z; r.p[3] = v.w;
     r.hp[0] = left + v.y;
     r.hp[1] = v.x + v.z;
@@ -448,25 +444,39 @@ __device__ __forceinline__ Row6 dw_load_row(const uint32_t *cb, int row, int tx,
     return r;
 }
 
-// One step of one 4x4 tile of a 64x64 world: cb -> nb. Returns the packed per-species max of the tile's new cells.
-__device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, const uint32_t *cb, uint32_t *nb, int r0, int tx, int lane) {
-    const StepCoef C = A.sc[j];
+// Row source of a whole 64x64 world in shared memory: rows wrap mod 64, halo columns come from the neighbouring lanes
+// of the half-warp (tile columns wrap inside the half-warp).
+struct RowsWorld64 {
+    const uint32_t *cb;
+    int r0, tx, lane;
+    __device__ __forceinline__ Row6 load(int k) const {          // k = -1..4 relative to the thread's first row
+        const uint4 v = *reinterpret_cast<const uint4 *>(cb + ((r0 + k) & 63) * 64 + tx * 4);
+        const int base = lane & 16;
+        const uint32_t left = __shfl_sync(0xffffffffu, v.w, base | ((lane - 1) & 15));
+        const uint32_t right = __shfl_sync(0xffffffffu, v.x, base | ((lane + 1) & 15));
+        return dw_make_row(v, left, right);
+    }
+};
+struct StoreWorld64 {
+    uint32_t *nb;
+    int r0, tx;
+    __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
+        *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+};
+
+// One step of one 4x4 tile (fast path): rows come from `rows`, results go to `store`. Returns the packed per-species
+// max of the 16 new cells; *tiemin drops below DW_TIE_THRESH if some cell needs the literal recomputation.
+template <class Rows, class Store>
+__device__ __forceinline__ uint32_t dw_tile_core(const FastCoef &F, const StepCoef &C, const Rows &rows, const Store &store,
+                                                 unsigned *tiemin) {
     uint32_t mx = 0;
-    unsigned tiemin = 0xffffffffu;
-#if DW_TILE_WINDOW
-    Row6 top = dw_load_row(cb, (r0 + 63) & 63, tx, lane);
-    Row6 mid = dw_load_row(cb, r0, tx, lane);
-#endif
+    Row6 top = rows.load(-1);
+    Row6 mid = rows.load(0);
     constexpr int kRowUnroll = DW_N64_ROW_UNROLL;
 #pragma unroll kRowUnroll
     for (int i = 0; i < 4; ++i) {
-#if !DW_TILE_WINDOW
-        // no rolling window: 3 rows are re-read per output row (LSU has slack) so that fewer registers stay live across
-        // the fp64 chains and ptxas can interleave two cells
-        const Row6 top = dw_load_row(cb, (r0 + i + 63) & 63, tx, lane);
-        const Row6 mid = dw_load_row(cb, r0 + i, tx, lane);
-#endif
-        const Row6 bot = dw_load_row(cb, (r0 + i + 1) & 63, tx, lane);
+        const Row6 bot = rows.load(i + 1);
         uint32_t E[4], S8[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -476,27 +486,33 @@ __device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, co
         uint32_t q[4];
 #if DW_CELL_ILP == 1
 #pragma unroll
-        for (int c = 0; c < 4; ++c) q[c] = dw_fast_cell(A.F, C, mid.p[c], E[c], S8[c], &tiemin);
+        for (int c = 0; c < 4; ++c) q[c] = dw_fast_cell(F, C, mid.p[c], E[c], S8[c], tiemin);
 #elif DW_CELL_ILP == 2
         {
             const uint32_t pa[2] = {mid.p[0], mid.p[1]}, ea[2] = {E[0], E[1]}, sa[2] = {S8[0], S8[1]};
             const uint32_t pb[2] = {mid.p[2], mid.p[3]}, eb[2] = {E[2], E[3]}, sb[2] = {S8[2], S8[3]};
             uint32_t qa[2], qb[2];
-            dw_fast_cells<2>(A.F, C, pa, ea, sa, &tiemin, qa);
-            dw_fast_cells<2>(A.F, C, pb, eb, sb, &tiemin, qb);
+            dw_fast_cells<2>(F, C, pa, ea, sa, tiemin, qa);
+            dw_fast_cells<2>(F, C, pb, eb, sb, tiemin, qb);
             q[0] = qa[0]; q[1] = qa[1]; q[2] = qb[0]; q[3] = qb[1];
         }
 #else
-        dw_fast_cells<4>(A.F, C, mid.p, E, S8, &tiemin, q);
+        dw_fast_cells<4>(F, C, mid.p, E, S8, tiemin, q);
 #endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) mx = __vmaxu2(mx, q[c]);
-        *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
-#if DW_TILE_WINDOW
+        store(i, q);
         top = mid;
         mid = bot;
-#endif
     }
+    return mx;
+}
+
+// One step of one 4x4 tile of a 64x64 world: cb -> nb. Returns the packed per-species max of the tile's new cells.
+__device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, const uint32_t *cb, uint32_t *nb, int r0, int tx, int lane) {
+    const StepCoef C = A.sc[j];
+    unsigned tiemin = 0xffffffffu;
+    uint32_t mx = dw_tile_core(A.F, C, RowsWorld64{cb, r0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin);
     // rare (~2e-4 of tile-steps): some cell of this tile sits on a rounding tie -> redo the tile's ties literally
     if (tiemin < DW_TIE_THRESH) mx = dw_fix_tile64(&A, &A.sc[j], cb, nb, r0, tx * 4);
     return mx;

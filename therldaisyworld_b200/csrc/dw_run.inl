@@ -9,15 +9,17 @@ static size_t fused_smem_bytes(int N, int n) {
 
 // The fast path needs D4-symmetric 3x3 kernels (centre / edge / corner classes) and a uniform zero-centre
 // adjacent kernel; anything else (and worlds too large for shared memory) runs through the materialising kernels.
-static bool dw_fused_supported(const dw_handle *h) {
-    const dw_config &c = h->cfg;
+static bool dw_fast_path_cfg_ok(const dw_config &c) {
     const double *w = c.daisy_kernel, *a = c.adjacent_kernel;
     const bool wsym = w[0] == w[2] && w[0] == w[6] && w[0] == w[8] && w[1] == w[3] && w[1] == w[5] && w[1] == w[7];
     bool asym = a[4] == 0.0;
     for (int i = 0; i < 9; ++i) if (i != 4 && a[i] != a[0]) asym = false;
-    if (!wsym || !asym) return false;
+    return wsym && asym && c.g > 0.0;                  // the fast path scales X by g^2 and T by sqrt(g)
+}
+static bool dw_fused_supported(const dw_handle *h) {
+    const dw_config &c = h->cfg;
+    if (!dw_fast_path_cfg_ok(c)) return false;
     if (c.n_agents > DW_FUSED_MAX_AGENTS) return false;
-    if (!(c.g > 0.0)) return false;                    // the fast path scales X by g^2 and T by sqrt(g)
     if (getenv("DW_DISABLE_FUSED")) return false;
     return fused_smem_bytes(c.dim, c.n_agents) <= 200 * 1024;
 }

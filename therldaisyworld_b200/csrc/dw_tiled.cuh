@@ -1,0 +1,416 @@
+// Single large world ("giant grid", BASELINE config 5): one toroidal N x N world too large for shared memory, held as a
+// row band of `R` rows per rank (R = N on one GPU) on the packed 0.001 lattice, padded with ghost cells:
+//
+//     lat[(R + 2) x pitch],  pitch = N + 8 words
+//       row 0        ghost: the row above the band (toroidal wrap, or the neighbouring rank's last row)
+//       rows 1..R    the band
+//       row R + 1    ghost: the row below the band
+//       word 3 / words 4..N+3 / word N+4 of a row: ghost of column N-1 / the N columns / ghost of column 0
+//
+// With the ghosts in place every 64x64 output tile needs one in-bounds 66-row x 72-word box of the source, which one
+// elected thread fetches with a single TMA (cp.async.bulk.tensor.2d) into shared memory; 256 threads then run the same
+// 4x4-cells-per-thread fast path as the ensemble kernel (dw_tile_core) and write their rows straight back to HBM.
+// HBM traffic is 8 B per cell-update (4 B in, 4 B out); at the FP64-bound rate that is ~2 TB/s of the 6.5 TB/s measured,
+// so this kernel is bound by the FP64 pipe like the SMEM-resident one.
+//
+// Agents of a giant world are many (thousands) and are replicated on every rank; the reference's sequential loop
+// (daisy_world_rl.py:186-216) is resolved in parallel: decisions from the pre-move state, moves independent, and the
+// grazers of one cell are ordered by an atomicMin claim (claim[(R+2) x N], INT_MAX when idle) on the agent index (the lowest index eats, later ones find the
+// cell empty -- SURVEY App. B.8).  A rank applies the grazes that land in its band; grazes landing in its ghost rows only
+// zero the ghost copy.  Per-agent food gains are summed over ranks by the caller (one all-reduce; exactly one rank
+// contributes a non-zero term).
+#pragma once
+#include <cuda.h>
+
+#include "dw_fused.cuh"
+
+struct BandGeom {
+    int N;       // global grid side
+    int R;       // rows of this band
+    int row0;    // global index of the band's first row
+    int pitch;   // words (or doubles) per stored row
+    int c0;      // index of column 0 inside a stored row (4 for the lattice, 0 for the fp64 planes of the first step)
+};
+
+// local stored-row indices (0..R+1) at which global row x is held by this band: interior and/or ghost copies
+template <class F>
+__device__ __forceinline__ void band_row_images(const BandGeom &G, int x, F f) {
+    int rel = x - G.row0;
+    rel = rel < 0 ? rel + G.N : rel;
+    if (rel < G.R) f(rel + 1);
+    if (rel == G.N - 1) f(0);
+    if (rel == (G.R == G.N ? 0 : G.R)) f(G.R + 1);
+}
+template <class F>
+__device__ __forceinline__ void band_col_images(const BandGeom &G, int y, F f) {
+    f(G.c0 + y);
+    if (G.c0 > 0) {
+        if (y == G.N - 1) f(G.c0 - 1);
+        if (y == 0) f(G.c0 + G.N);
+    }
+}
+// interior stored row of global row x, or -1 if this band does not own it
+__device__ __forceinline__ int band_owned_row(const BandGeom &G, int x) {
+    int rel = x - G.row0;
+    rel = rel < 0 ? rel + G.N : rel;
+    return rel < G.R ? rel + 1 : -1;
+}
+
+// ---- cell accessors: packed lattice (steady state) or fp64 cover planes (the off-lattice state right after reset) ----
+struct LatCells {
+    uint32_t *p;
+    __device__ __forceinline__ double food(size_t i) const { return dw_food(p[i]); }
+    __device__ __forceinline__ void zero(size_t i) const { p[i] = 0u; }
+};
+struct PlaneCells {
+    double *l, *d;
+    __device__ __forceinline__ double food(size_t i) const { return l[i] + d[i]; }
+    __device__ __forceinline__ void zero(size_t i) const { l[i] = 0.0; d[i] = 0.0; }
+};
+// column index with toroidal wrap for planes without column ghosts
+__device__ __forceinline__ int band_col(const BandGeom &G, int y) {
+    if (G.c0 > 0) return G.c0 + y;                       // ghosts at c0-1 and c0+N make y = -1 and y = N valid
+    return y < 0 ? y + G.N : (y >= G.N ? y - G.N : y);
+}
+
+// ---- agents --------------------------------------------------------------------------------------------------------
+// Phase 1: the owner band of each agent decides its action from the pre-move state. act[i] = action + 1 for owned
+// agents, 0 otherwise (the caller sums act over ranks). Policies that do not look at the world (replay, none, random)
+// fill every entry on every rank and need no exchange.
+template <class Cells>
+__global__ void __launch_bounds__(256) k_band_decide(BandGeom G, Cells C, const int32_t *__restrict__ xy, int n, int policy,
+                                                     const int8_t *__restrict__ replay, uint64_t seed, uint32_t step, int n_ranks,
+                                                     double *__restrict__ act) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    const int lr = band_owned_row(G, x);
+    double out = 0.0;
+    if (policy == DW_POLICY_REPLAY || policy == DW_POLICY_NONE || policy == DW_POLICY_RANDOM) {
+        // world-independent: every rank computes the same action for every agent (no exchange needed)
+        int a = 0;
+        if (policy == DW_POLICY_REPLAY) a = replay[i];
+        else if (policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(seed, 0u, (uint32_t)i, step) % 9u);
+        out = (double)(a + 1);
+    } else if (lr >= 0) {
+        const size_t rowm = (size_t)(lr - 1) * G.pitch, row = (size_t)lr * G.pitch, rowp = (size_t)(lr + 1) * G.pitch;
+        const double food[4] = {C.food(row + band_col(G, y - 1)), C.food(rowm + band_col(G, y)), C.food(rowp + band_col(G, y)),
+                                C.food(row + band_col(G, y + 1))};
+        out = (double)(dw_greedy_pick(food, policy == DW_POLICY_GREEDY) + 1);
+    }
+    act[i] = out;
+}
+
+// Phase 2 (replicated on every rank): pay agent_gamma, move the living, and file the graze claims of cells this band owns.
+// gz[i] = 1 if agent i grazes this step.
+__global__ void __launch_bounds__(256) k_band_move_claim(BandGeom G, double agent_gamma, int32_t *xy, double *st, int n,
+                                                         const double *__restrict__ act, int *claim, uint8_t *gz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = (int)act[i] - 1;
+    const double s = st[i] - agent_gamma;
+    st[i] = s;
+    int x = xy[2 * i], y = xy[2 * i + 1];
+    uint8_t g = 0;
+    if (s > 0.0) {
+        if (a != 8) {
+            const int d = (a & 2) ? 1 : -1;              // a & 3 = 0: y-1, 1: x-1, 2: x+1, 3: y+1
+            if (((a + 1) & 2) == 0) { y += d; y = y < 0 ? y + G.N : (y >= G.N ? y - G.N : y); }
+            else { x += d; x = x < 0 ? x + G.N : (x >= G.N ? x - G.N : x); }
+            xy[2 * i] = x;
+            xy[2 * i + 1] = y;
+        }
+        if (a > 4) {
+            g = 1;
+            const int lr = band_owned_row(G, x);
+            if (lr >= 0) atomicMin(claim + (size_t)lr * G.N + y, i);
+        }
+    }
+    gz[i] = g;
+}
+
+// Phase 3: the claim winner of an owned cell eats it and clears every stored copy; grazes that land in a ghost row only
+// clear the ghost copy (the owner rank does the eating). gain[i] = food eaten by agent i on THIS rank (0 elsewhere).
+template <class Cells>
+__global__ void __launch_bounds__(256) k_band_graze(BandGeom G, Cells C, const int32_t *__restrict__ xy, int n,
+                                                    const uint8_t *__restrict__ gz, const int *__restrict__ claim, double *__restrict__ gain) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double got = 0.0;
+    if (gz[i]) {
+        const int x = xy[2 * i], y = xy[2 * i + 1];
+        const int lr = band_owned_row(G, x);
+        bool clear = true;
+        if (lr >= 0) {
+            if (claim[(size_t)lr * G.N + y] == i) got = C.food((size_t)lr * G.pitch + G.c0 + y);
+            else clear = false;                          // a lower-index agent eats here; it also does the clearing
+        }
+        if (clear)
+            band_row_images(G, x, [&](int r) { band_col_images(G, y, [&](int cc) { C.zero((size_t)r * G.pitch + cc); }); });
+    }
+    gain[i] = got;
+}
+
+__global__ void __launch_bounds__(256) k_band_claim_reset(BandGeom G, const int32_t *__restrict__ xy, int n, const uint8_t *__restrict__ gz,
+                                                          int *claim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !gz[i]) return;
+    const int lr = band_owned_row(G, xy[2 * i]);
+    if (lr >= 0) claim[(size_t)lr * G.N + xy[2 * i + 1]] = 0x7fffffff;
+}
+
+// Phase 4 (replicated, after the gains were summed over ranks): state += gain, clip, reward/done, lifespan counter.
+__global__ void __launch_bounds__(256) k_band_finish(double *st, int n, const double *__restrict__ gain, const uint8_t *__restrict__ gz,
+                                                     double *reward, uint8_t *done, int64_t *agents_done_at) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = st[i];
+    if (gz[i]) s = s + gain[i];
+    s = dw_clip01(s);
+    st[i] = s;
+    reward[i] = s;
+    done[i] = s < 0.1;
+    agents_done_at[i] += (s < 0.1) ? 0 : 1;
+}
+
+// ---- ghost maintenance ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_band_ghost_rows_wrap(BandGeom G, uint32_t *lat) {   // single-rank torus: R == N
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= G.N) return;
+    lat[G.c0 + c] = lat[(size_t)G.R * G.pitch + G.c0 + c];
+    lat[(size_t)(G.R + 1) * G.pitch + G.c0 + c] = lat[(size_t)G.pitch + G.c0 + c];
+}
+__global__ void __launch_bounds__(256) k_band_ghost_cols(BandGeom G, uint32_t *lat) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.R + 2) return;
+    uint32_t *row = lat + (size_t)r * G.pitch;
+    row[G.c0 - 1] = row[G.c0 + G.N - 1];
+    row[G.c0 + G.N] = row[G.c0];
+}
+
+// ---- first step: literal forward from the off-lattice fp64 cover planes [(R+2) x N] onto the padded lattice ---------
+__global__ void __launch_bounds__(256) k_band_first_step(DevParams P, double SL, BandGeom Gp, const double *__restrict__ l,
+                                                         const double *__restrict__ d, BandGeom Gl, uint32_t *__restrict__ lat_out,
+                                                         int *stepmax) {
+    const size_t total = (size_t)Gp.R * Gp.N;
+    uint32_t mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Gp.N), y = (int)(i - (size_t)r * Gp.N);
+        const int ys[3] = {y == 0 ? Gp.N - 1 : y - 1, y, y == Gp.N - 1 ? 0 : y + 1};
+        double l9[9], d9[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t k = (size_t)(r + a) * Gp.pitch + ys[c];     // stored rows r .. r+2 = band rows r-1 .. r+1
+                l9[a * 3 + c] = l[k];
+                d9[a * 3 + c] = d[k];
+            }
+        const LitCell o = dw_literal_cell(P, SL, l9, d9);
+        const uint32_t q = dw_pack((int)rint(o.nl * 1000.0), (int)rint(o.nd * 1000.0));
+        lat_out[(size_t)(r + 1) * Gl.pitch + Gl.c0 + y] = q;
+        mx = __vmaxu2(mx, q);
+    }
+    const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+    if ((threadIdx.x & 31) == 0) { atomicMax(stepmax, (int)ml); atomicMax(stepmax + 1, (int)md); }
+}
+
+// ---- steady state: one stencil step of the band, 64x64 tiles, TMA-staged halo tile ---------------------------------
+#define DWT_TILE 64
+#define DWT_TILE_ROWS (DWT_TILE + 2)
+#define DWT_TILE_PITCH (DWT_TILE + 8)
+#define DWT_TILE_BYTES (DWT_TILE_ROWS * DWT_TILE_PITCH * 4)
+
+struct TiledArgs {
+    DevParams P;
+    FastCoef F;
+    StepCoef C;
+    uint32_t *out;          // padded lattice written by this step
+    int pitch;
+    int tiles_x, tiles_y;   // tiles per row / per band column
+    int *stepmax;           // [2] per-species max of the new band (atomicMax)
+    unsigned int *slow_count;
+};
+
+__device__ __forceinline__ uint32_t dwt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct RowsTile72 {
+    const uint32_t *t;      // first cell of the thread's first row inside the staged tile
+    __device__ __forceinline__ Row6 load(int k) const {
+        const uint32_t *p = t + k * DWT_TILE_PITCH;
+        return dw_make_row(*reinterpret_cast<const uint4 *>(p), p[-1], p[4]);
+    }
+};
+struct StoreGlobal {
+    uint32_t *o;            // first cell of the thread's first output row
+    int pitch;
+    __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
+        *reinterpret_cast<uint4 *>(o + (size_t)i * pitch) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+};
+
+// rare path: re-evaluate the thread's 16 cells one by one from the staged tile; cells on a rounding tie are recomputed
+// in literal order and patched in the output. Returns the packed max of the tile.
+__device__ __noinline__ uint32_t dwt_fix_tile(const TiledArgs *A, const uint32_t *t, uint32_t *o) {
+    uint32_t mx = 0;
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t *p = t + (k >> 2) * DWT_TILE_PITCH + (k & 3);
+        const uint32_t *q0 = p - DWT_TILE_PITCH, *q2 = p + DWT_TILE_PITCH;
+        const uint32_t E = p[-1] + p[1] + q0[0] + q2[0];
+        const uint32_t S8 = E + q0[-1] + q0[1] + q2[-1] + q2[1];
+        unsigned tiemin = 0xffffffffu;
+        uint32_t v = dw_fast_cell(A->F, A->C, p[0], E, S8, &tiemin);
+        if (tiemin < DW_TIE_THRESH) {
+            double l9[9], d9[9];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t w = p[(a - 1) * DWT_TILE_PITCH + (c - 1)];
+                    l9[a * 3 + c] = dw_milli(w & 0xffffu);
+                    d9[a * 3 + c] = dw_milli(w >> 16);
+                }
+            const LitCell lc = dw_literal_cell(A->P, A->C.SL, l9, d9);
+            v = dw_pack((int)rint(lc.nl * 1000.0), (int)rint(lc.nd * 1000.0));
+            o[(size_t)(k >> 2) * A->pitch + (k & 3)] = v;
+            if (A->slow_count) atomicAdd(A->slow_count, 1u);
+        }
+        mx = __vmaxu2(mx, v);
+    }
+    return mx;
+}
+
+__global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledArgs A) {
+    __shared__ __align__(128) uint32_t tile[DWT_TILE_ROWS * DWT_TILE_PITCH];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int smax[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx = tid & 15, r0 = (tid >> 4) * 4;
+    const int tc = blockIdx.x % A.tiles_x, tr = blockIdx.x / A.tiles_x;
+    const uint32_t bar_a = dwt_smem_u32(&bar);
+    if (tid == 0) {
+        smax[0] = 0; smax[1] = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)DWT_TILE_BYTES) : "memory");
+        // box origin (word, row) of the padded lattice: tile columns 64*tc-4 .. 64*tc+67, band rows 64*tr-1 .. 64*tr+64
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dwt_smem_u32(tile)), "l"(&tmap), "r"(bar_a), "r"(tc * DWT_TILE), "r"(tr * DWT_TILE)
+                     : "memory");
+    }
+    __syncthreads();                                     // barrier initialised and armed before anyone polls it
+    {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar_a) : "memory");
+    }
+    const uint32_t *t = tile + (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
+    uint32_t *o = A.out + (size_t)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
+    unsigned tiemin = 0xffffffffu;
+    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{t}, StoreGlobal{o, A.pitch}, &tiemin);
+    if (tiemin < DW_TIE_THRESH) mx = dwt_fix_tile(&A, t, o);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+    if (lane == 0) { atomicMax(&smax[0], (int)ml); atomicMax(&smax[1], (int)md); }
+    __syncthreads();
+    if (tid == 0) {
+        if (smax[0] > 0) atomicMax(A.stepmax, smax[0]);
+        if (smax[1] > 0) atomicMax(A.stepmax + 1, smax[1]);
+    }
+}
+
+// ---- materialisation / synthetic reset -------------------------------------------------------------------------------
+// full reference grid [7, R, N] of the band, materialised by a literal forward from the post-graze state the last step
+// started from: the other lattice buffer, or the fp64 planes when that step was the first one after a reset
+struct PreLattice {
+    const uint32_t *p;
+    __device__ __forceinline__ void load9(const BandGeom &G, int r, int y, double (&l9)[9], double (&d9)[9]) const {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t w = p[(size_t)(r + a) * G.pitch + G.c0 + y + c - 1];
+                l9[a * 3 + c] = dw_milli(w & 0xffffu);
+                d9[a * 3 + c] = dw_milli(w >> 16);
+            }
+    }
+};
+struct PrePlanes {
+    const double *l, *d;
+    __device__ __forceinline__ void load9(const BandGeom &G, int r, int y, double (&l9)[9], double (&d9)[9]) const {
+        const int ys[3] = {y == 0 ? G.N - 1 : y - 1, y, y == G.N - 1 ? 0 : y + 1};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t k = (size_t)(r + a) * G.pitch + ys[c];
+                l9[a * 3 + c] = l[k];
+                d9[a * 3 + c] = d[k];
+            }
+    }
+};
+template <class Pre>
+__global__ void __launch_bounds__(256) k_band_materialise(DevParams P, double SL, BandGeom G, Pre pre, double *__restrict__ out) {
+    const size_t RN = (size_t)G.R * G.N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < RN; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / G.N), y = (int)(i - (size_t)r * G.N);
+        double l9[9], d9[9];
+        pre.load9(G, r, y, l9, d9);
+        const LitCell o = dw_literal_cell(P, SL, l9, d9);
+        out[i] = dw_round3(o.nb);
+        out[RN + i] = dw_round3(o.nl);
+        out[2 * RN + i] = dw_round3(o.nd);
+        out[3 * RN + i] = dw_round3(o.T);
+        out[4 * RN + i] = dw_round3(o.Tl);
+        out[5 * RN + i] = dw_round3(o.Td);
+        out[6 * RN + i] = 0.0;
+    }
+}
+// lattice covers of the band as fp64 planes [2, R, N] (k/1000 exactly as np.round stores them)
+__global__ void __launch_bounds__(256) k_band_covers(BandGeom G, const uint32_t *__restrict__ lat, double *__restrict__ out) {
+    const size_t RN = (size_t)G.R * G.N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < RN; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / G.N), y = (int)(i - (size_t)r * G.N);
+        const uint32_t w = lat[(size_t)(r + 1) * G.pitch + G.c0 + y];
+        out[i] = dw_milli(w & 0xffffu);
+        out[RN + i] = dw_milli(w >> 16);
+    }
+}
+// agent stamp of ch4 (forward :454-459): the highest agent index on a cell wins. claim holds INT_MAX outside a stamp.
+__global__ void __launch_bounds__(256) k_band_stamp_claim(BandGeom G, const int32_t *__restrict__ xy, int n, int *claim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int lr = band_owned_row(G, xy[2 * i]);
+    if (lr >= 0) atomicMin(claim + (size_t)lr * G.N + xy[2 * i + 1], n - 1 - i);
+}
+__global__ void __launch_bounds__(256) k_band_stamp_write(BandGeom G, const int32_t *__restrict__ xy, const double *__restrict__ st, int n,
+                                                          int *claim, double *ch4, int pass) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int lr = band_owned_row(G, xy[2 * i]);
+    if (lr < 0) return;
+    const size_t c = (size_t)lr * G.N + xy[2 * i + 1];
+    if (pass == 0) { if (claim[c] == n - 1 - i) ch4[(size_t)(lr - 1) * G.N + xy[2 * i + 1]] = st[i]; }
+    else claim[c] = 0x7fffffff;
+}
+
+// device-side synthetic reset of the band (+ its ghost rows) and of the replicated agents: same distribution as
+// initialize_grid / initialize_agents (daisy_world_rl.py:285-302, 173-179), counter RNG keyed by the GLOBAL cell index,
+// so any banding of the same world draws the same state.
+__global__ void __launch_bounds__(256) k_band_init_random(BandGeom Gp, uint64_t seed, double prop_l, double prop_d, double init_l,
+                                                          double init_d, double *l, double *d, int32_t *agent_xy, double *agent_state, int n) {
+    const size_t total = (size_t)(Gp.R + 2) * Gp.N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Gp.N), y = (int)(i - (size_t)r * Gp.N);
+        int x = Gp.row0 + r - 1;
+        x = x < 0 ? x + Gp.N : (x >= Gp.N ? x - Gp.N : x);
+        const uint64_t gidx = (uint64_t)x * Gp.N + y;
+        d[i] = dw_u01(seed, gidx, 0) < prop_d ? init_d * dw_u01(seed, gidx, 1) : 0.0;
+        l[i] = dw_u01(seed, gidx, 2) < prop_l ? init_l * dw_u01(seed, gidx, 3) : 0.0;
+    }
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) {
+        agent_xy[2 * i] = (int)(dw_u01(seed ^ 0xA5A5A5A5ull, i, 0) * Gp.N);
+        agent_xy[2 * i + 1] = (int)(dw_u01(seed ^ 0xA5A5A5A5ull, i, 1) * Gp.N);
+        agent_state[i] = 1.0;
+    }
+}

@@ -1,0 +1,457 @@
+// C-ABI of the single-giant-grid path (include/daisyworld_b200_tiled.h). Included at the end of dw_api.cu.
+#include "../../include/daisyworld_b200_tiled.h"
+#include "dw_tiled.cuh"
+
+static thread_local std::string g_dwt_create_error;
+
+struct dwt_handle {
+    dw_config cfg{};
+    dw_clock clk{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int N = 0, R = 0, row0 = 0, n = 0, n_ranks = 1, pitch = 0;
+    // packed padded lattice, ping-pong; cur = buffer holding the current state
+    uint32_t *lat[2] = {nullptr, nullptr};
+    CUtensorMap tmap[2];
+    int cur = 0;
+    bool on_lattice = false;     // false: the state lives in the fp64 planes (right after reset)
+    bool have_pre = false;       // a step has run: lat[1-cur] (or the planes) hold its post-graze pre-state
+    bool pre_is_planes = false;
+    double L_last = 0.0;
+    double *pl = nullptr, *pd = nullptr;       // fp64 cover planes [(R+2) x N] (off-lattice reset state)
+    int *claim = nullptr;                      // [(R+2) x N] graze claims, INT_MAX when idle
+    int32_t *agent_xy = nullptr;
+    double *agent_state = nullptr, *act = nullptr, *gain = nullptr, *reward = nullptr;
+    uint8_t *gz = nullptr, *done = nullptr;
+    int8_t *replay = nullptr;
+    size_t replay_cap = 0;
+    int64_t *agents_done_at = nullptr;
+    int64_t done_at = 0;
+    int *stepmax = nullptr;                    // [DW_FUSED_MAX_STEPS, 2]
+    int chunk_j = 0;                           // steps recorded in stepmax since the last dwt_end_chunk
+    unsigned int *slow_count = nullptr;
+    double *scratch = nullptr;                 // [7 x R x N] materialisation buffer (lazy)
+};
+
+static int dwt_fail(dwt_handle *h, int code, const char *what, const char *detail) {
+    std::string m = std::string(what) + ": " + detail;
+    if (h) h->err = m; else g_dwt_create_error = m;
+    return code;
+}
+#define DWT_TRY(h, expr)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) return dwt_fail((h), DW_E_CUDA, #expr, cudaGetErrorString(e__));          \
+    } while (0)
+#define DWT_LAUNCHED(h) DWT_TRY((h), cudaGetLastError())
+
+extern "C" const char *dwt_last_error(const dwt_handle *h) { return h ? h->err.c_str() : g_dwt_create_error.c_str(); }
+
+static BandGeom dwt_geom_lat(const dwt_handle *h) { return BandGeom{h->N, h->R, h->row0, h->pitch, 4}; }
+static BandGeom dwt_geom_planes(const dwt_handle *h) { return BandGeom{h->N, h->R, h->row0, h->N, 0}; }
+
+static DevParams dwt_params(const dwt_handle *h) { return make_params_cfg(h->cfg); }
+
+typedef CUresult (*dwt_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int dwt_make_tmaps(dwt_handle *h) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DWT_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return dwt_fail(h, DW_E_CUDA, "cuTensorMapEncodeTiled", "driver entry point not found");
+    for (int i = 0; i < 2; ++i) {
+        const cuuint64_t dims[2] = {(cuuint64_t)h->pitch, (cuuint64_t)(h->R + 2)};
+        const cuuint64_t strides[1] = {(cuuint64_t)h->pitch * sizeof(uint32_t)};
+        const cuuint32_t box[2] = {DWT_TILE_PITCH, DWT_TILE_ROWS};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = ((dwt_encode_fn)fn)(&h->tmap[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, h->lat[i], dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return dwt_fail(h, DW_E_CUDA, "cuTensorMapEncodeTiled", "encode failed");
+    }
+    return DW_OK;
+}
+
+extern "C" int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int32_t n_ranks, dwt_handle **out) {
+    if (!out) return dwt_fail(nullptr, DW_E_INVALID, "dwt_create", "out is NULL");
+    *out = nullptr;
+    if (!cfg || cfg->batch != 1 || cfg->n_agents < 0) return dwt_fail(nullptr, DW_E_INVALID, "dwt_create", "batch must be 1, n_agents >= 0");
+    const int N = cfg->dim;
+    if (N < 64 || N % 64 || rows < 64 || rows % 64 || rows > N || row0 < 0 || row0 >= N || n_ranks < 1)
+        return dwt_fail(nullptr, DW_E_UNSUPPORTED, "dwt_create", "tiled path needs N % 64 == 0 and rows % 64 == 0 (64 <= rows <= N)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return dwt_fail(nullptr, DW_E_CUDA, "dwt_create", e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return dwt_fail(nullptr, DW_E_INVALID, "dwt_create", "bad device ordinal");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return dwt_fail(nullptr, DW_E_CUDA, "cudaSetDevice", cudaGetErrorString(e));
+    if (!dw_fast_path_cfg_ok(*cfg))
+        return dwt_fail(nullptr, DW_E_UNSUPPORTED, "dwt_create", "tiled path needs D4-symmetric kernels, a zero-centre uniform albedo kernel and g > 0");
+    dwt_handle *h = new dwt_handle();
+    h->cfg = *cfg;
+    h->N = N; h->R = rows; h->row0 = row0; h->n = cfg->n_agents; h->n_ranks = n_ranks; h->pitch = N + 8;
+    const size_t n = h->n ? h->n : 1, padded = (size_t)(rows + 2) * h->pitch, planes = (size_t)(rows + 2) * N;
+    auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess && cudaMemset(*p, 0, bytes) == cudaSuccess; };
+    bool ok = alloc((void **)&h->lat[0], padded * 4) && alloc((void **)&h->lat[1], padded * 4) && alloc((void **)&h->claim, planes * 4) &&
+              alloc((void **)&h->agent_xy, n * 8) && alloc((void **)&h->agent_state, n * 8) && alloc((void **)&h->act, n * 8) &&
+              alloc((void **)&h->gain, n * 8) && alloc((void **)&h->reward, n * 8) && alloc((void **)&h->gz, n) && alloc((void **)&h->done, n) &&
+              alloc((void **)&h->agents_done_at, n * 8) && alloc((void **)&h->stepmax, (size_t)DW_FUSED_MAX_STEPS * 2 * 4) &&
+              alloc((void **)&h->slow_count, 4);
+    if (ok) ok = cudaMemset(h->claim, 0x7f, planes * 4) == cudaSuccess;       // 0x7f7f7f7f: "idle" (> any agent index)
+    if (!ok) {
+        g_dwt_create_error = std::string("dwt_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        dwt_destroy(h);
+        return DW_E_CUDA;
+    }
+    int rc = dwt_make_tmaps(h);
+    if (rc) { g_dwt_create_error = h->err; dwt_destroy(h); return rc; }
+    h->clk.L = 0.75; h->clk.min_L = 0.75; h->clk.max_L = 1.5; h->clk.ramp_period = 512;
+    h->clk.dL = (h->clk.max_L - h->clk.min_L) / 512.0;
+    *out = h;
+    return DW_OK;
+}
+
+extern "C" int dwt_destroy(dwt_handle *h) {
+    if (!h) return DW_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->agent_xy, h->agent_state, h->act, h->gain, h->reward, h->gz,
+                    h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete h;
+    return DW_OK;
+}
+
+extern "C" int dwt_set_config(dwt_handle *h, const dw_config *cfg) {
+    if (!h || !cfg) return DW_E_INVALID;
+    if (cfg->dim != h->N || cfg->n_agents != h->n || cfg->device != h->cfg.device || cfg->batch != 1)
+        return dwt_fail(h, DW_E_INVALID, "dwt_set_config", "shapes/device of a handle are fixed");
+    h->cfg = *cfg;
+    return DW_OK;
+}
+extern "C" int dwt_set_clock(dwt_handle *h, const dw_clock *clk) { if (!h || !clk) return DW_E_INVALID; h->clk = *clk; return DW_OK; }
+extern "C" int dwt_get_clock(dwt_handle *h, dw_clock *clk) { if (!h || !clk) return DW_E_INVALID; *clk = h->clk; return DW_OK; }
+extern "C" int dwt_set_stream(dwt_handle *h, void *s) { if (!h) return DW_E_INVALID; h->stream = (cudaStream_t)s; return DW_OK; }
+extern "C" int dwt_synchronize(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+static int dwt_ensure_planes(dwt_handle *h) {
+    const size_t bytes = (size_t)(h->R + 2) * h->N * sizeof(double);
+    if (!h->pl) DWT_TRY(h, cudaMalloc((void **)&h->pl, bytes));
+    if (!h->pd) DWT_TRY(h, cudaMalloc((void **)&h->pd, bytes));
+    return DW_OK;
+}
+static void dwt_state_reset(dwt_handle *h) {
+    h->on_lattice = false;
+    h->have_pre = false;
+    h->chunk_j = 0;
+}
+
+extern "C" int dwt_upload_covers(dwt_handle *h, const double *light, const double *dark) {
+    if (!h || !light || !dark) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = dwt_ensure_planes(h);
+    if (rc) return rc;
+    const size_t bytes = (size_t)(h->R + 2) * h->N * sizeof(double);
+    DWT_TRY(h, cudaMemcpyAsync(h->pl, light, bytes, cudaMemcpyHostToDevice, h->stream));
+    DWT_TRY(h, cudaMemcpyAsync(h->pd, dark, bytes, cudaMemcpyHostToDevice, h->stream));
+    DWT_TRY(h, cudaMemsetAsync(h->stepmax, 0, (size_t)DW_FUSED_MAX_STEPS * 2 * 4, h->stream));
+    dwt_state_reset(h);
+    return DW_OK;
+}
+
+extern "C" int dwt_upload_agents(dwt_handle *h, const int64_t *agent_indices, const double *agent_states) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t n = h->n;
+    if (!n) return DW_OK;
+    if (agent_indices) {
+        std::vector<int32_t> xy(n * 2);
+        for (size_t i = 0; i < xy.size(); ++i) {
+            int64_t v = agent_indices[i] % h->N;
+            xy[i] = (int32_t)(v < 0 ? v + h->N : v);
+        }
+        DWT_TRY(h, cudaMemcpyAsync(h->agent_xy, xy.data(), xy.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if (agent_states) DWT_TRY(h, cudaMemcpyAsync(h->agent_state, agent_states, n * 8, cudaMemcpyHostToDevice, h->stream));
+    return DW_OK;
+}
+
+extern "C" int dwt_init_random(dwt_handle *h, uint64_t seed, double light_proportion, double dark_proportion, double initial_al,
+                               double initial_ad) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = dwt_ensure_planes(h);
+    if (rc) return rc;
+    k_band_init_random<<<grid_for((size_t)(h->R + 2) * h->N), 256, 0, h->stream>>>(dwt_geom_planes(h), seed, light_proportion, dark_proportion,
+                                                                                  initial_al, initial_ad, h->pl, h->pd, h->agent_xy,
+                                                                                  h->agent_state, h->n);
+    DWT_LAUNCHED(h);
+    DWT_TRY(h, cudaMemsetAsync(h->stepmax, 0, (size_t)DW_FUSED_MAX_STEPS * 2 * 4, h->stream));
+    dwt_state_reset(h);
+    return DW_OK;
+}
+
+static inline int dwt_blocks(int n) { return (n + 255) / 256; }
+
+extern "C" int dwt_decide(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed) {
+    if (!h || policy < 0 || policy > DW_POLICY_RANDOM) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->n) return DW_OK;
+    if (policy == DW_POLICY_REPLAY) {
+        if (!actions) return dwt_fail(h, DW_E_INVALID, "dwt_decide", "REPLAY needs actions[n]");
+        if (h->replay_cap < (size_t)h->n) {
+            if (h->replay) cudaFree(h->replay);
+            h->replay = nullptr;
+            DWT_TRY(h, cudaMalloc((void **)&h->replay, h->n));
+            h->replay_cap = h->n;
+        }
+        DWT_TRY(h, cudaMemcpyAsync(h->replay, actions, h->n, cudaMemcpyHostToDevice, h->stream));
+    }
+    const uint32_t step = (uint32_t)h->clk.step_count;
+    if (h->on_lattice)
+        k_band_decide<LatCells><<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), LatCells{h->lat[h->cur]}, h->agent_xy, h->n, policy,
+                                                                          h->replay, seed, step, h->n_ranks, h->act);
+    else
+        k_band_decide<PlaneCells><<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_planes(h), PlaneCells{h->pl, h->pd}, h->agent_xy, h->n,
+                                                                            policy, h->replay, seed, step, h->n_ranks, h->act);
+    DWT_LAUNCHED(h);
+    return DW_OK;
+}
+
+extern "C" int dwt_move_graze(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->n) return DW_OK;
+    const int nb = dwt_blocks(h->n);
+    const BandGeom G = h->on_lattice ? dwt_geom_lat(h) : dwt_geom_planes(h);
+    k_band_move_claim<<<nb, 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act, h->claim, h->gz);
+    DWT_LAUNCHED(h);
+    if (h->on_lattice)
+        k_band_graze<LatCells><<<nb, 256, 0, h->stream>>>(G, LatCells{h->lat[h->cur]}, h->agent_xy, h->n, h->gz, h->claim, h->gain);
+    else
+        k_band_graze<PlaneCells><<<nb, 256, 0, h->stream>>>(G, PlaneCells{h->pl, h->pd}, h->agent_xy, h->n, h->gz, h->claim, h->gain);
+    DWT_LAUNCHED(h);
+    k_band_claim_reset<<<nb, 256, 0, h->stream>>>(G, h->agent_xy, h->n, h->gz, h->claim);
+    DWT_LAUNCHED(h);
+    return DW_OK;
+}
+
+extern "C" int dwt_finish_agents(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->n) return DW_OK;
+    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(h->agent_state, h->n, h->gain, h->gz, h->reward, h->done, h->agents_done_at);
+    DWT_LAUNCHED(h);
+    return DW_OK;
+}
+
+extern "C" int dwt_stencil(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->chunk_j >= DW_FUSED_MAX_STEPS) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "call dwt_end_chunk at least every 4096 steps");
+    int *smax = h->stepmax + 2 * h->chunk_j;
+    if (!h->on_lattice) {
+        if (!h->pl) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "no state uploaded");
+        // the reset state is off the 0.001 lattice: first step in literal arithmetic, planes -> lattice
+        k_band_first_step<<<grid_for((size_t)h->R * h->N), 256, 0, h->stream>>>(dwt_params(h), h->cfg.S * h->clk.L, dwt_geom_planes(h), h->pl,
+                                                                                 h->pd, dwt_geom_lat(h), h->lat[h->cur], smax);
+        DWT_LAUNCHED(h);
+        h->on_lattice = true;
+        h->pre_is_planes = true;
+    } else {
+        TiledArgs A{};
+        A.P = dwt_params(h);
+        make_fast_coef(h->cfg, A.F);
+        make_step_coef(h->cfg, h->clk.L, A.C);
+        A.out = h->lat[1 - h->cur];
+        A.pitch = h->pitch;
+        A.tiles_x = h->N / DWT_TILE;
+        A.tiles_y = h->R / DWT_TILE;
+        A.stepmax = smax;
+        A.slow_count = h->slow_count;
+        k_tiled_step<<<A.tiles_x * A.tiles_y, 256, 0, h->stream>>>(h->tmap[h->cur], A);
+        DWT_LAUNCHED(h);
+        h->cur = 1 - h->cur;
+        h->pre_is_planes = false;
+    }
+    h->have_pre = true;
+    h->L_last = h->clk.L;
+    h->chunk_j += 1;
+    update_L(h->clk);
+    return DW_OK;
+}
+
+extern "C" int dwt_halo_wrap(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->R != h->N) return dwt_fail(h, DW_E_STATE, "dwt_halo_wrap", "only for a handle that owns the whole torus");
+    if (!h->on_lattice) return DW_OK;
+    k_band_ghost_rows_wrap<<<dwt_blocks(h->N), 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur]);
+    DWT_LAUNCHED(h);
+    return DW_OK;
+}
+
+extern "C" int dwt_ghost_cols(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->on_lattice) return DW_OK;
+    k_band_ghost_cols<<<dwt_blocks(h->R + 2), 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur]);
+    DWT_LAUNCHED(h);
+    return DW_OK;
+}
+
+extern "C" int dwt_get_ptrs(dwt_handle *h, dwt_ptrs *out) {
+    if (!h || !out) return DW_E_INVALID;
+    uint32_t *L = h->lat[h->cur];
+    out->act = h->act;
+    out->gain = h->gain;
+    out->stepmax = h->stepmax;
+    out->send_top = L + (size_t)1 * h->pitch + 4;
+    out->send_bottom = L + (size_t)h->R * h->pitch + 4;
+    out->recv_top = L + 4;
+    out->recv_bottom = L + (size_t)(h->R + 1) * h->pitch + 4;
+    return DW_OK;
+}
+
+extern "C" int dwt_run(dwt_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed) {
+    if (!h || K < 0) return DW_E_INVALID;
+    if (h->R != h->N) return dwt_fail(h, DW_E_STATE, "dwt_run", "only for a handle that owns the whole torus (use the phase calls for bands)");
+    for (int64_t j = 0; j < K; ++j) {
+        int rc = dwt_decide(h, policy, actions ? actions + (size_t)j * h->n : nullptr, seed);
+        if (!rc) rc = dwt_move_graze(h);
+        if (!rc) rc = dwt_finish_agents(h);
+        if (!rc) rc = dwt_stencil(h);
+        if (!rc) rc = dwt_halo_wrap(h);
+        if (!rc) rc = dwt_ghost_cols(h);
+        if (rc) return rc;
+    }
+    return DW_OK;
+}
+
+extern "C" int dwt_end_chunk(dwt_handle *h, int32_t K, int32_t *first_all_done) {
+    if (!h || K < 0 || K > h->chunk_j) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    std::vector<int> m((size_t)2 * (K ? K : 1));
+    if (K) DWT_TRY(h, cudaMemcpyAsync(m.data(), h->stepmax, (size_t)2 * K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaMemsetAsync(h->stepmax, 0, (size_t)2 * h->chunk_j * sizeof(int), h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    int first = -1;
+    for (int j = 0; j < K; ++j) {
+        const bool grid_done = (m[2 * j] > m[2 * j + 1] ? m[2 * j] : m[2 * j + 1]) <= 5;
+        if (!grid_done) h->done_at += 1;
+        else if (first < 0) first = j;
+    }
+    if (first_all_done) *first_all_done = first;
+    h->chunk_j = 0;
+    return DW_OK;
+}
+
+extern "C" int dwt_reset_lifespans(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    h->done_at = 0;
+    if (h->n) DWT_TRY(h, cudaMemsetAsync(h->agents_done_at, 0, (size_t)h->n * 8, h->stream));
+    return DW_OK;
+}
+
+extern "C" int dwt_get_lifespans(dwt_handle *h, int64_t *done_at, int64_t *agents_done_at) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (done_at) *done_at = h->done_at;
+    if (agents_done_at && h->n) DWT_TRY(h, cudaMemcpyAsync(agents_done_at, h->agents_done_at, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dwt_get_agents(dwt_handle *h, int64_t *agent_indices, double *agent_states) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t n = h->n;
+    if (!n) return DW_OK;
+    std::vector<int32_t> xy(n * 2);
+    if (agent_indices) DWT_TRY(h, cudaMemcpyAsync(xy.data(), h->agent_xy, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (agent_states) DWT_TRY(h, cudaMemcpyAsync(agent_states, h->agent_state, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    if (agent_indices) for (size_t i = 0; i < xy.size(); ++i) agent_indices[i] = xy[i];
+    return DW_OK;
+}
+
+extern "C" int dwt_get_reward_done(dwt_handle *h, double *reward, uint8_t *done) {
+    if (!h) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (reward && h->n) DWT_TRY(h, cudaMemcpyAsync(reward, h->reward, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (done && h->n) DWT_TRY(h, cudaMemcpyAsync(done, h->done, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+static int dwt_ensure_scratch(dwt_handle *h) {
+    if (!h->scratch) DWT_TRY(h, cudaMalloc((void **)&h->scratch, (size_t)7 * h->R * h->N * sizeof(double)));
+    return DW_OK;
+}
+
+extern "C" int dwt_get_covers(dwt_handle *h, double *light, double *dark) {
+    if (!h || !light || !dark) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t RN = (size_t)h->R * h->N;
+    if (!h->on_lattice) {
+        if (!h->pl) return dwt_fail(h, DW_E_STATE, "dwt_get_covers", "no state uploaded");
+        DWT_TRY(h, cudaMemcpyAsync(light, h->pl + h->N, RN * 8, cudaMemcpyDeviceToHost, h->stream));
+        DWT_TRY(h, cudaMemcpyAsync(dark, h->pd + h->N, RN * 8, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        int rc = dwt_ensure_scratch(h);
+        if (rc) return rc;
+        k_band_covers<<<grid_for(RN), 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur], h->scratch);
+        DWT_LAUNCHED(h);
+        DWT_TRY(h, cudaMemcpyAsync(light, h->scratch, RN * 8, cudaMemcpyDeviceToHost, h->stream));
+        DWT_TRY(h, cudaMemcpyAsync(dark, h->scratch + RN, RN * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dwt_get_grid(dwt_handle *h, double *grid) {
+    if (!h || !grid) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->have_pre) return dwt_fail(h, DW_E_STATE, "dwt_get_grid", "needs at least one step since the last reset");
+    int rc = dwt_ensure_scratch(h);
+    if (rc) return rc;
+    const size_t RN = (size_t)h->R * h->N;
+    const DevParams P = dwt_params(h);
+    if (h->pre_is_planes)
+        k_band_materialise<PrePlanes><<<grid_for(RN), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, dwt_geom_planes(h), PrePlanes{h->pl, h->pd}, h->scratch);
+    else
+        k_band_materialise<PreLattice><<<grid_for(RN), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, dwt_geom_lat(h), PreLattice{h->lat[1 - h->cur]},
+                                                                            h->scratch);
+    DWT_LAUNCHED(h);
+    if (h->n) {
+        const int nb = dwt_blocks(h->n);
+        const BandGeom G = dwt_geom_lat(h);
+        k_band_stamp_claim<<<nb, 256, 0, h->stream>>>(G, h->agent_xy, h->n, h->claim);
+        k_band_stamp_write<<<nb, 256, 0, h->stream>>>(G, h->agent_xy, h->agent_state, h->n, h->claim, h->scratch + 4 * RN, 0);
+        k_band_stamp_write<<<nb, 256, 0, h->stream>>>(G, h->agent_xy, h->agent_state, h->n, h->claim, h->scratch + 4 * RN, 1);
+        DWT_LAUNCHED(h);
+    }
+    DWT_TRY(h, cudaMemcpyAsync(grid, h->scratch, 7 * RN * 8, cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dwt_debug_slow_count(dwt_handle *h, uint64_t *count) {
+    if (!h || !count) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    unsigned int c = 0;
+    DWT_TRY(h, cudaMemcpyAsync(&c, h->slow_count, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    *count = c;
+    return DW_OK;
+}

@@ -51,6 +51,80 @@ def _ptr(a, ctype):
     return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
 
 
+def set_default_attributes(obj, **kwargs):
+    """Constants and kwargs of RLDaisyWorld.__init__ (reference :15-79); shared with banded.BandedDaisyWorld."""
+    self = obj
+    self.ch = 7
+    self.batch_size = 32                      # ctor kwarg is ignored like the reference (:20)
+    self.kr = query_kwargs("kr", 1, **kwargs)
+    self.neighborhood_mode = query_kwargs("neighborhood_mode", "von_neumann", **kwargs)
+    self.neighborhood = make_neighborhood(self.kr, self.neighborhood_mode)
+    self.dim = kwargs["grid_dimension"] if "grid_dimension" in kwargs else 16
+
+    self.p = 1.00
+    self.g = 0.003265
+    self.S = 1000.0
+    self.sigma = 5.67e-8
+    self.gamma = 0.25
+    self.q = 0.2 * self.S / self.sigma
+    self.use_microclimate = True
+    self.collision_mode = query_kwargs("collision_mode", 0, **kwargs)
+    self.q2 = self.q / 8.0 if self.use_microclimate else 0.0
+    self.Toptim = 295.5
+    self.dt = 1.0
+    self.ddL = 0.0
+    self.agent_gamma = 0.05
+    self.max_L = 1.5
+    self.min_L = 0.75
+    self.initial_L = self.min_L
+    self.ramp_period = kwargs["ramp_period"] if "ramp_period" in kwargs else 512
+    self.ramp_up_down = False
+    self.albedo_bare = 0.5
+    self.albedo_light = 0.75
+    self.albedo_dark = 0.25
+    self.temp_optimal = 295.5
+    self.food_chain_penalty = 0.5
+    self.initial_al = 0.2
+    self.initial_ad = 0.2
+    self.light_proportion = 0.33
+    self.dark_proportion = 0.33
+    self.n_agents = query_kwargs("n_agents", 4, **kwargs)
+
+
+def set_default_kernels(obj):
+    """initialize_neighborhood (reference :265-283): daisy-spread and albedo kernels."""
+    obj.n_daisies = 2
+    obj.daisy_kernel = np.ones((1, 1, 3, 3)) * np.exp(-1)
+    obj.daisy_kernel[:, :, 1, 1] = 1.0
+    obj.daisy_kernel[:, :, 0::2, 0::2] = np.exp(-2)
+    obj.daisy_kernel /= obj.daisy_kernel.sum()
+    obj.local_albedo_kernel = np.zeros((1, 1, 3, 3))
+    obj.local_albedo_kernel[:, :, 1, 1] = 1.0
+    obj.adjacent_albedo_kernel = np.ones((1, 1, 3, 3)) / 8.0
+    obj.adjacent_albedo_kernel[:, :, 1, 1] = 0.0
+
+
+def make_config_struct(obj, batch, dim, n_agents, device):
+    """dw_config from the public attributes of an environment object."""
+    c = DwConfig(batch=int(batch), dim=int(dim), n_agents=int(n_agents), device=int(device),
+                 p=obj.p, g=obj.g, S=obj.S, sigma=obj.sigma, gamma=obj.gamma, q=obj.q, q2=obj.q2,
+                 temp_optimal=obj.temp_optimal, dt=obj.dt, agent_gamma=obj.agent_gamma,
+                 albedo_bare=obj.albedo_bare, albedo_light=obj.albedo_light, albedo_dark=obj.albedo_dark)
+    c.daisy_kernel[:] = [float(v) for v in np.asarray(obj.daisy_kernel, dtype=np.float64).ravel()]
+    c.adjacent_kernel[:] = [float(v) for v in np.asarray(obj.adjacent_albedo_kernel, dtype=np.float64).ravel()]
+    mask = np.asarray(obj.neighborhood, dtype=np.float64)
+    if mask.shape != (3, 3):
+        raise ValueError("get_obs gathers a 3-wide window (reference :257-258): only kr=1 neighbourhoods work")
+    c.obs_mask[:] = [float(v) for v in mask.ravel()]
+    return c
+
+
+def make_clock_struct(obj):
+    return DwClock(L=float(obj.L), dL=float(obj.dL), min_L=float(obj.min_L), max_L=float(obj.max_L),
+                   ddL=float(obj.ddL), step_count=int(obj.step_count), ramp_period=int(obj.ramp_period),
+                   ramp_up_down=int(bool(obj.ramp_up_down)))
+
+
 class _Mirror:
     """Host mirror of one device array with write detection."""
     __slots__ = ("pristine", "handed", "assigned")
@@ -77,41 +151,7 @@ class RLDaisyWorld:
     _DIAG_ATTRS = ("temp", "temp_light", "temp_dark", "temp_effective", "beta", "beta_l", "beta_d", "growth")
 
     def __init__(self, **kwargs):
-        self.ch = 7
-        self.batch_size = 32                      # ctor kwarg is ignored like the reference (:20)
-        self.kr = query_kwargs("kr", 1, **kwargs)
-        self.neighborhood_mode = query_kwargs("neighborhood_mode", "von_neumann", **kwargs)
-        self.neighborhood = make_neighborhood(self.kr, self.neighborhood_mode)
-        self.dim = kwargs["grid_dimension"] if "grid_dimension" in kwargs else 16
-
-        self.p = 1.00
-        self.g = 0.003265
-        self.S = 1000.0
-        self.sigma = 5.67e-8
-        self.gamma = 0.25
-        self.q = 0.2 * self.S / self.sigma
-        self.use_microclimate = True
-        self.collision_mode = query_kwargs("collision_mode", 0, **kwargs)
-        self.q2 = self.q / 8.0 if self.use_microclimate else 0.0
-        self.Toptim = 295.5
-        self.dt = 1.0
-        self.ddL = 0.0
-        self.agent_gamma = 0.05
-        self.max_L = 1.5
-        self.min_L = 0.75
-        self.initial_L = self.min_L
-        self.ramp_period = kwargs["ramp_period"] if "ramp_period" in kwargs else 512
-        self.ramp_up_down = False
-        self.albedo_bare = 0.5
-        self.albedo_light = 0.75
-        self.albedo_dark = 0.25
-        self.temp_optimal = 295.5
-        self.food_chain_penalty = 0.5
-        self.initial_al = 0.2
-        self.initial_ad = 0.2
-        self.light_proportion = 0.33
-        self.dark_proportion = 0.33
-        self.n_agents = query_kwargs("n_agents", 4, **kwargs)
+        set_default_attributes(self, **kwargs)
 
         # additions (not in the reference)
         self.device = int(kwargs.get("device", os.environ.get("LOCAL_RANK", 0)))
@@ -139,17 +179,7 @@ class RLDaisyWorld:
         _lib.check(self._lib, self._h, rc, what)
 
     def _config(self):
-        c = DwConfig(batch=int(self.batch_size), dim=int(self.dim), n_agents=int(self.n_agents), device=self.device,
-                     p=self.p, g=self.g, S=self.S, sigma=self.sigma, gamma=self.gamma, q=self.q, q2=self.q2,
-                     temp_optimal=self.temp_optimal, dt=self.dt, agent_gamma=self.agent_gamma,
-                     albedo_bare=self.albedo_bare, albedo_light=self.albedo_light, albedo_dark=self.albedo_dark)
-        c.daisy_kernel[:] = [float(v) for v in np.asarray(self.daisy_kernel, dtype=np.float64).ravel()]
-        c.adjacent_kernel[:] = [float(v) for v in np.asarray(self.adjacent_albedo_kernel, dtype=np.float64).ravel()]
-        mask = np.asarray(self.neighborhood, dtype=np.float64)
-        if mask.shape != (3, 3):
-            raise ValueError("get_obs gathers a 3-wide window (reference :257-258): only kr=1 neighbourhoods work")
-        c.obs_mask[:] = [float(v) for v in mask.ravel()]
-        return c
+        return make_config_struct(self, self.batch_size, self.dim, self.n_agents, self.device)
 
     def _clock(self):
         return DwClock(L=float(self.L), dL=float(self.dL), min_L=float(self.min_L), max_L=float(self.max_L),
@@ -315,15 +345,7 @@ class RLDaisyWorld:
 
     def initialize_neighborhood(self):
         """reference :265-283"""
-        self.n_daisies = 2
-        self.daisy_kernel = np.ones((1, 1, 3, 3)) * np.exp(-1)
-        self.daisy_kernel[:, :, 1, 1] = 1.0
-        self.daisy_kernel[:, :, 0::2, 0::2] = np.exp(-2)
-        self.daisy_kernel /= self.daisy_kernel.sum()
-        self.local_albedo_kernel = np.zeros((1, 1, 3, 3))
-        self.local_albedo_kernel[:, :, 1, 1] = 1.0
-        self.adjacent_albedo_kernel = np.ones((1, 1, 3, 3)) / 8.0
-        self.adjacent_albedo_kernel[:, :, 1, 1] = 0.0
+        set_default_kernels(self)
 
     def initialize_agents(self):
         """reference :173-179 (one randint draw; states = 1)."""
