@@ -12,6 +12,10 @@ no work is skipped): 1 literal materialising step (the reset state is off the 0.
 host memory, the T-step run, and the download of the lifespan counters, all inside the timed region.
 N > 1: one process per GPU (torchrun), worlds sharded (1000 per rank, weak scaling), no data-path collective;
 one NCCL all-reduce of the 8-double lifespan-statistics vector per bench step, inside the timed region.
+
+The same JSON line carries, under "giant_grid", a second measured workload (not the headline): BASELINE configs[4], one
+16384x16384 toroidal world with 16384 greedy agents, row-banded over the N GPUs (strong scaling; halo rows + two small
+all-reduces per step over NCCL), timed with CUDA events, max over ranks.  --no-extras skips it.
 """
 import argparse
 import ctypes as C
@@ -24,6 +28,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line (NCCL prints its version banner)
 
 import numpy as np  # noqa: E402
 
@@ -193,6 +198,58 @@ def cpu_baseline_sample():
             "env_steps_per_s": WORLDS * steps / dt, "seconds": dt}
 
 
+# ----------------------------------------------------------------------------------------------- giant grid (configs[4])
+GIANT_N = 16384
+GIANT_STEPS = 64
+
+
+def giant_grid_bench(rank, world, local, fp64_peak_tflops):
+    """One 16384^2 world, 16384 greedy agents, row-banded over `world` GPUs. Every rank calls this (collectives inside)."""
+    import torch
+    import torch.distributed as dist
+    from therldaisyworld_b200.banded import BandedDaisyWorld
+    w = BandedDaisyWorld(GIANT_N, GIANT_N, rank=rank, world_size=world, device=local)
+    w.reset_on_device(seed=SEED)
+    w.run(3, "greedy")                                   # literal first step + 2 lattice steps (warm-up)
+    best = None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if world == 1:
+            w.band.run_local(GIANT_STEPS, "greedy")
+            w._pending += GIANT_STEPS
+        else:
+            for _ in range(GIANT_STEPS):
+                w.step("greedy")
+        e1.record()
+        torch.cuda.synchronize()
+        w.end_chunk()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = float(t[0]) if best is None else min(best, float(t[0]))
+    cells = GIANT_N * GIANT_N * GIANT_STEPS
+    value = cells / (best * 1e-3)
+    done_at, ada = w.lifespans()
+    out = {
+        "workload": f"BASELINE configs[4]: single {GIANT_N}x{GIANT_N} toroidal world, {GIANT_N} greedy agents, row-banded over "
+                    f"{world} GPU(s) ({GIANT_N // world} rows each), {GIANT_STEPS} steps after 3 warm-up steps",
+        "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "scaling": "strong", "n_gpus": world,
+        "us_per_step": best * 1e3 / GIANT_STEPS, "env_steps_per_s": GIANT_STEPS / (best * 1e-3),
+        "hbm_gbs_algorithmic_per_gpu": 8.0 * value / world / 1e9,
+        "fp64_roofline_frac": value * FLOP_PER_CELL_UPDATE / 1e12 / (fp64_peak_tflops * world) if fp64_peak_tflops else None,
+        "exchanges_per_step": 0 if world == 1 else "2 all-reduce(SUM, n doubles) + 1 ring halo exchange (2 rows each way)",
+        "literal_recomputations": w.band.slow_count(), "biosphere_alive_steps": done_at,
+    }
+    del w
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- product arm
 def run_product(args):
     import torch
@@ -319,11 +376,18 @@ def run_product(args):
     h2d = light.nbytes + dark.nbytes + agents.nbytes + states.nbytes
     d2h = out_done_at.numel() * 8 + out_agents.numel() * 8
 
+    # measured FP64 FMA peak of this device (the fused kernel's roofline denominator)
+    tf, ms = C.c_double(), C.c_double()
+    chk(lib.dw_debug_fp64_peak(h, 20000, 5, C.byref(tf), C.byref(ms)), "dw_debug_fp64_peak")
+    giant = None
+    if not args.no_extras:
+        try:
+            giant = giant_grid_bench(rank, world, local, tf.value)
+        except Exception as e:                                    # the headline line must survive
+            giant = {"error": repr(e)}
+
     if rank == 0:
         peaks = load_peaks()
-        # measured FP64 FMA peak of this device (the fused kernel's roofline denominator)
-        tf, ms = C.c_double(), C.c_double()
-        chk(lib.dw_debug_fp64_peak(h, 20000, 5, C.byref(tf), C.byref(ms)), "dw_debug_fp64_peak")
         fused_s = prof.fused_ms * 1e-3
         achieved = prof.fused_cell_updates * FLOP_PER_CELL_UPDATE / fused_s / 1e12 if fused_s > 0 else None
         roofline = {
@@ -338,9 +402,11 @@ def run_product(args):
             "kernel_share_of_step": fused_s / t_res if t_res > 0 else None,
             "kernel_cell_updates_per_s": prof.fused_cell_updates / fused_s if fused_s > 0 else None,
             "traffic": load_traffic(),
-            "hbm": {"algorithmic_bytes_per_launch": 8 * WORLDS * N * N * 2, "peak_gbs": peaks.get("hbm_gbs") if peaks else 6650.0,
+            "hbm": {"algorithmic_bytes_per_launch": 8 * WORLDS * N * N * ((T_STEPS - 1 + 15) // 16),
+                    "peak_gbs": peaks.get("hbm_gbs") if peaks else 6650.0,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                    "note": "8 B/cell/launch read+write of the packed lattice: the kernel is not HBM bound"},
+                    "note": "packed lattice, 4 B in + 4 B out per cell per 16-step chunk (L2-resident between chunks): "
+                            "the kernel is not HBM bound; `traffic` is the DRAM bytes per launch from profiles/fused_traffic.json"},
         }
         cpu = cpu_baseline_sample() if world == 1 else None
         line = {
@@ -357,6 +423,7 @@ def run_product(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "giant_grid": giant,
             "check": {"mean_done_at_after_T": mean_life, "expected": float(T_STEPS), "ensemble_stats": stats.tolist(),
                       "wall_s_resident": wall_res},
         }
@@ -371,6 +438,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary giant-grid measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

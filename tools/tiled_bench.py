@@ -23,5 +23,9 @@ def bench(N, n, policy, K=64, reps=3):
           f"HBM {8 * N * N * K / best / 1e-3 / 1e9:.0f} GB/s algorithmic, slow cells {w.band.slow_count()}", flush=True)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                       # profiling target: one size, few steps
+        N = int(sys.argv[1])
+        bench(N, N, "greedy", K=8, reps=1)
+        sys.exit(0)
     for N, n in ((1024, 1024), (4096, 4096), (16384, 16384), (16384, 0)):
         bench(N, n, "greedy")
