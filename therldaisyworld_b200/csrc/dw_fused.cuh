@@ -413,23 +413,36 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ F
 // tie filter are patched afterwards by the literal path, outside the unrolled code.
 // Re-evaluate one 4x4 tile of a 64x64 world cell by cell (generic indexing): cells whose fast result is within the tie
 // filter are recomputed in the oracle's order and patched into nb.  Returns the packed per-species max of the tile.
-__device__ __noinline__ uint32_t dw_fix_tile64(const FusedArgs *A, const StepCoef *C, const uint32_t *cb, uint32_t *nb, int r0, int c0) {
-    uint32_t mx = 0;
-    for (int k = 0; k < 16; ++k) {
-        const int x = r0 + (k >> 2), y = c0 + (k & 3);
-        const int xm = (x + 63) & 63, xp = (x + 1) & 63, ym = (y + 63) & 63, yp = (y + 1) & 63;
-        const uint32_t *q0 = cb + xm * 64, *q1 = cb + x * 64, *q2 = cb + xp * 64;
-        const uint32_t E = q1[ym] + q1[yp] + q0[y] + q2[y];
-        const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
-        unsigned tiemin = 0xffffffffu;
-        uint32_t v = dw_fast_cell(A->F, *C, q1[y], E, S8, &tiemin);
-        if (tiemin < DW_TIE_THRESH) {
-            v = dw_slow_cell(A, C->SL, cb, 64, x, y);
-            nb[x * 64 + y] = v;
+// Rare path, warp-cooperative: for every lane whose 4x4 tile hit the tie filter, lanes 0..15 re-evaluate one cell of that
+// tile each (generic indexing); cells within the filter are recomputed in the oracle's order and patched into nb.
+// Returns the lane's packed per-species max with the flagged tiles' stale fast values replaced by the corrected ones
+// (only the warp-wide max of the return values is meaningful).
+__device__ __noinline__ uint32_t dw_fix_warp64(const FusedArgs *A, const StepCoef *C, const uint32_t *cb, uint32_t *nb, unsigned flagged,
+                                               uint32_t mx, int r0, int c0, int lane) {
+    uint32_t extra = 0;
+    bool mine = false;
+    __syncwarp();
+    while (flagged) {
+        const int L = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const int tr0 = __shfl_sync(0xffffffffu, r0, L), tc0 = __shfl_sync(0xffffffffu, c0, L);
+        if (lane == L) mine = true;
+        if (lane < 16) {
+            const int x = tr0 + (lane >> 2), y = tc0 + (lane & 3);
+            const int xm = (x + 63) & 63, xp = (x + 1) & 63, ym = (y + 63) & 63, yp = (y + 1) & 63;
+            const uint32_t *q0 = cb + xm * 64, *q1 = cb + x * 64, *q2 = cb + xp * 64;
+            const uint32_t E = q1[ym] + q1[yp] + q0[y] + q2[y];
+            const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
+            unsigned tiemin = 0xffffffffu;
+            uint32_t v = dw_fast_cell(A->F, *C, q1[y], E, S8, &tiemin);
+            if (tiemin < DW_TIE_THRESH) {
+                v = dw_slow_cell(A, C->SL, cb, 64, x, y);
+                nb[x * 64 + y] = v;
+            }
+            extra = __vmaxu2(extra, v);
         }
-        mx = __vmaxu2(mx, v);
     }
-    return mx;
+    return __vmaxu2(mine ? 0u : mx, extra);
 }
 
 struct Row6 { uint32_t p[4]; uint32_t hp[4]; };     // 4 packed cells of one row + their horizontal neighbour sums
@@ -513,8 +526,9 @@ __device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, co
     const StepCoef C = A.sc[j];
     unsigned tiemin = 0xffffffffu;
     uint32_t mx = dw_tile_core(A.F, C, RowsWorld64{cb, r0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin);
-    // rare (~2e-4 of tile-steps): some cell of this tile sits on a rounding tie -> redo the tile's ties literally
-    if (tiemin < DW_TIE_THRESH) mx = dw_fix_tile64(&A, &A.sc[j], cb, nb, r0, tx * 4);
+    // rare (~2e-4 of tile-steps): some cell of this tile sits on a rounding tie -> the warp redoes that tile's ties literally
+    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
+    if (flagged) mx = dw_fix_warp64(&A, &A.sc[j], cb, nb, flagged, mx, r0, tx * 4, lane);
     return mx;
 }
 

@@ -249,35 +249,46 @@ struct StoreGlobal {
     }
 };
 
-// rare path: re-evaluate the thread's 16 cells one by one from the staged tile; cells on a rounding tie are recomputed
-// in literal order and patched in the output. Returns the packed max of the tile.
-__device__ __noinline__ uint32_t dwt_fix_tile(const TiledArgs *A, const uint32_t *t, uint32_t *o) {
-    uint32_t mx = 0;
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t *p = t + (k >> 2) * DWT_TILE_PITCH + (k & 3);
-        const uint32_t *q0 = p - DWT_TILE_PITCH, *q2 = p + DWT_TILE_PITCH;
-        const uint32_t E = p[-1] + p[1] + q0[0] + q2[0];
-        const uint32_t S8 = E + q0[-1] + q0[1] + q2[-1] + q2[1];
-        unsigned tiemin = 0xffffffffu;
-        uint32_t v = dw_fast_cell(A->F, A->C, p[0], E, S8, &tiemin);
-        if (tiemin < DW_TIE_THRESH) {
-            double l9[9], d9[9];
+// rare path, warp-cooperative: for every lane whose 4x4 tile hit the tie filter, lanes 0..15 re-evaluate one cell of that
+// tile each from the staged tile; cells on a rounding tie are recomputed in literal order and patched in the output.
+// tile_off / out_off: each lane's offsets of its first cell inside the staged tile / the output lattice.
+__device__ __noinline__ uint32_t dwt_fix_warp(const TiledArgs *A, const uint32_t *tile, unsigned flagged, uint32_t mx, int tile_off,
+                                              long long out_off, int lane) {
+    uint32_t extra = 0;
+    bool mine = false;
+    __syncwarp();
+    while (flagged) {
+        const int L = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const int toff = __shfl_sync(0xffffffffu, tile_off, L);
+        const long long ooff = __shfl_sync(0xffffffffu, out_off, L);
+        if (lane == L) mine = true;
+        if (lane < 16) {
+            const uint32_t *p = tile + toff + (lane >> 2) * DWT_TILE_PITCH + (lane & 3);
+            const uint32_t *q0 = p - DWT_TILE_PITCH, *q2 = p + DWT_TILE_PITCH;
+            const uint32_t E = p[-1] + p[1] + q0[0] + q2[0];
+            const uint32_t S8 = E + q0[-1] + q0[1] + q2[-1] + q2[1];
+            unsigned tiemin = 0xffffffffu;
+            uint32_t v = dw_fast_cell(A->F, A->C, p[0], E, S8, &tiemin);
+            if (tiemin < DW_TIE_THRESH) {
+                double l9[9], d9[9];
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const uint32_t w = p[(a - 1) * DWT_TILE_PITCH + (c - 1)];
-                    l9[a * 3 + c] = dw_milli(w & 0xffffu);
-                    d9[a * 3 + c] = dw_milli(w >> 16);
-                }
-            const LitCell lc = dw_literal_cell(A->P, A->C.SL, l9, d9);
-            v = dw_pack((int)rint(lc.nl * 1000.0), (int)rint(lc.nd * 1000.0));
-            o[(size_t)(k >> 2) * A->pitch + (k & 3)] = v;
-            if (A->slow_count) atomicAdd(A->slow_count, 1u);
+                    for (int c = 0; c < 3; ++c) {
+                        const uint32_t w = p[(a - 1) * DWT_TILE_PITCH + (c - 1)];
+                        l9[a * 3 + c] = dw_milli(w & 0xffffu);
+                        d9[a * 3 + c] = dw_milli(w >> 16);
+                    }
+                const LitCell lc = dw_literal_cell(A->P, A->C.SL, l9, d9);
+                v = dw_pack((int)rint(lc.nl * 1000.0), (int)rint(lc.nd * 1000.0));
+                A->out[ooff + (long long)(lane >> 2) * A->pitch + (lane & 3)] = v;
+                if (A->slow_count) atomicAdd(A->slow_count, 1u);
+            }
+            extra = __vmaxu2(extra, v);
         }
-        mx = __vmaxu2(mx, v);
     }
-    return mx;
+    return __vmaxu2(mine ? 0u : mx, extra);
 }
 
 __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledArgs A) {
@@ -305,11 +316,12 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(ok) : "r"(bar_a) : "memory");
     }
-    const uint32_t *t = tile + (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
-    uint32_t *o = A.out + (size_t)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
+    const int tile_off = (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
+    const long long out_off = (long long)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
     unsigned tiemin = 0xffffffffu;
-    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{t}, StoreGlobal{o, A.pitch}, &tiemin);
-    if (tiemin < DW_TIE_THRESH) mx = dwt_fix_tile(&A, t, o);
+    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off}, StoreGlobal{A.out + out_off, A.pitch}, &tiemin);
+    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
+    if (flagged) mx = dwt_fix_warp(&A, tile, flagged, mx, tile_off, out_off, lane);
     const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
     if (lane == 0) { atomicMax(&smax[0], (int)ml); atomicMax(&smax[1], (int)md); }
     __syncthreads();
