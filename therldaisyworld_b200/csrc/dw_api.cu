@@ -13,7 +13,7 @@
 
 static thread_local std::string g_create_error;
 
-enum PreKind { PRE_NONE = 0, PRE_GRID = 1, PRE_LAT = 2 };
+enum PreKind { PRE_NONE = 0, PRE_GRID = 1, PRE_LAT = 2, PRE_COV = 3 };
 
 struct dw_handle {
     dw_config cfg{};
@@ -27,6 +27,11 @@ struct dw_handle {
     int cur = 0;
     bool grid_valid = false;
     bool ch6_dirty[2] = {false, false};
+    // lean reset state: fp64 cover planes [B,2,N,N] (light, dark), off the 0.001 lattice; the 7-channel grid of such a
+    // state (ch0, initial temperatures) is only materialised when a caller asks for it
+    double *cov = nullptr;
+    bool cov_valid = false;
+    double cov_L = 0.0;                 // luminosity of initialize_grid's temperature fill (dw_init_temperatures)
     // packed lattice representation [B,N,N]
     uint32_t *lat[2] = {nullptr, nullptr};
     int lcur = 0;
@@ -67,7 +72,9 @@ struct dw_handle {
     // checkpoint
     struct Ckpt {
         bool have = false, grid_valid = false, lat_valid = false;
-        double *grid = nullptr;
+        double *grid = nullptr, *cov = nullptr;
+        bool cov_valid = false, have_cov = false;
+        double cov_L = 0;
         uint32_t *lat = nullptr, *lat_pre = nullptr;
         int32_t *agent_xy = nullptr;
         double *agent_state = nullptr;
@@ -157,13 +164,35 @@ static int launch_stamp(dw_handle *h, double *grid, bool counters, unsigned int 
 // make grid[cur] hold the full reference grid of the current state
 static int ensure_grid(dw_handle *h) {
     if (h->grid_valid) return DW_OK;
-    if (!h->lat_valid) return dw_fail(h, DW_E_STATE, "ensure_grid", "no state uploaded");
+    if (!h->lat_valid && !h->cov_valid) return dw_fail(h, DW_E_STATE, "ensure_grid", "no state uploaded");
     int rc = ensure_grid_buffers(h);
     if (rc) return rc;
     const DevParams P = make_params(h);
     const size_t total = (size_t)P.B * h->NN;
     double *out = h->grid[h->cur];
-    if (h->pre == PRE_LAT) {
+    if (h->cov_valid) {
+        // the reset state: covers from the lean planes, ch0 and the UNROUNDED initial temperatures (initialize_grid :304-324)
+        k_cov_to_grid<<<grid_for(total), 256, 0, h->stream>>>(P.B, h->NN, h->cov, out);
+        DW_LAUNCHED(h);
+        k_init_fields<<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->cov_L, out);
+        DW_LAUNCHED(h);
+        h->ch6_dirty[h->cur] = false;
+        h->pre = PRE_GRID;
+        h->pre_grid = out;
+        h->L_last = h->cov_L;
+        h->grid_valid = true;
+        return DW_OK;
+    }
+    if (h->pre == PRE_COV) {
+        // the state is one lean step past the reset: literal forward from the post-graze cover planes
+        SrcCov src{h->cov, h->NN};
+        k_forward<SrcCov><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, src, out, nullptr, nullptr,
+                                                                   h->ch6_dirty[h->cur] ? 1 : 0);
+        DW_LAUNCHED(h);
+        h->ch6_dirty[h->cur] = false;
+        rc = launch_stamp(h, out, false, nullptr, false);
+        if (rc) return rc;
+    } else if (h->pre == PRE_LAT) {
         // full literal forward from the post-graze lattice the last fused step started from: reproduces
         // b' (rounded from UNROUNDED l',d'), the temperatures of that step, and l',d' (== lat[lcur]).
         SrcLattice src{h->lat_pre, h->NN};
@@ -227,12 +256,12 @@ extern "C" int dw_destroy(dw_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->grid[0], h->grid[1], h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
+    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
                     h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->pipe_sync,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {
-        void *cp[] = {c.grid, c.lat, c.lat_pre, c.agent_xy, c.agent_state, c.done_at, c.agents_done_at};
+        void *cp[] = {c.grid, c.cov, c.lat, c.lat_pre, c.agent_xy, c.agent_state, c.done_at, c.agents_done_at};
         for (void *p : cp) if (p) cudaFree(p);
     }
     delete h;
@@ -293,6 +322,7 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
         }
         h->ch6_dirty[h->cur] = dirty;   // cleaned (zeroed) the next time a forward writes this buffer
         h->grid_valid = true;
+        h->cov_valid = false;
         h->lat_valid = false;
         h->pre = PRE_NONE;
         h->obs_valid = false;
@@ -318,17 +348,16 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
 extern "C" int dw_upload_covers(dw_handle *h, const double *light, const double *dark) {
     if (!h || !light || !dark) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    int rc = ensure_grid_buffers(h);
-    if (rc) return rc;
     const size_t B = h->cfg.batch, NN = h->NN;
-    double *g = h->grid[h->cur];
-    DW_CUDA_TRY(h, cudaMemsetAsync(g, 0, B * 7 * NN * sizeof(double), h->stream));
-    DW_CUDA_TRY(h, cudaMemcpy2DAsync(g + NN, 7 * NN * sizeof(double), light, NN * sizeof(double), NN * sizeof(double), B,
+    int rc = dev_alloc(h, &h->cov, B * 2 * NN);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemcpy2DAsync(h->cov, 2 * NN * sizeof(double), light, NN * sizeof(double), NN * sizeof(double), B,
                                      cudaMemcpyHostToDevice, h->stream));
-    DW_CUDA_TRY(h, cudaMemcpy2DAsync(g + 2 * NN, 7 * NN * sizeof(double), dark, NN * sizeof(double), NN * sizeof(double), B,
+    DW_CUDA_TRY(h, cudaMemcpy2DAsync(h->cov + NN, 2 * NN * sizeof(double), dark, NN * sizeof(double), NN * sizeof(double), B,
                                      cudaMemcpyHostToDevice, h->stream));
-    h->ch6_dirty[h->cur] = false;
-    h->grid_valid = true;
+    h->cov_valid = true;
+    h->cov_L = h->clk.L;
+    h->grid_valid = false;
     h->lat_valid = false;
     h->pre = PRE_NONE;
     h->obs_valid = false;
@@ -341,15 +370,15 @@ extern "C" int dw_init_random(dw_handle *h, uint64_t seed, double light_proporti
                               double initial_ad) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    int rc = ensure_grid_buffers(h);
+    int rc = dev_alloc(h, &h->cov, (size_t)h->cfg.batch * 2 * h->NN);
     if (rc) return rc;
     const DevParams P = make_params(h);
     k_init_random<<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, seed, h->world0, light_proportion, dark_proportion,
-                                                                         initial_al, initial_ad, h->grid[h->cur], h->agent_xy,
-                                                                         h->agent_state);
+                                                                         initial_al, initial_ad, h->cov, h->agent_xy, h->agent_state);
     DW_LAUNCHED(h);
-    h->ch6_dirty[h->cur] = false;
-    h->grid_valid = true;
+    h->cov_valid = true;
+    h->cov_L = h->clk.L;
+    h->grid_valid = false;
     h->lat_valid = false;
     h->pre = PRE_NONE;
     h->obs_valid = false;
@@ -360,6 +389,15 @@ extern "C" int dw_init_random(dw_handle *h, uint64_t seed, double light_proporti
 extern "C" int dw_init_temperatures(dw_handle *h) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->cov_valid && !h->grid_valid) {
+        // lean reset state: remember the luminosity; the fields are filled when (if) the 7-channel grid is materialised,
+        // the diagnostics come straight from the cover planes
+        h->cov_L = h->clk.L;
+        h->pre = PRE_COV;
+        h->L_last = h->clk.L;
+        h->obs_valid = false;
+        return DW_OK;
+    }
     if (!h->grid_valid) return dw_fail(h, DW_E_STATE, "dw_init_temperatures", "upload a grid first");
     const DevParams P = make_params(h);
     k_init_fields<<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, h->grid[h->cur]);
@@ -388,11 +426,16 @@ static int stage_action(dw_handle *h, const int64_t *action, size_t count) {
     return DW_OK;
 }
 
-static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, int policy, uint64_t seed) {
+static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, int policy, uint64_t seed, bool on_cov = false) {
     if (h->cfg.n_agents == 0) return DW_OK;
     const DevParams P = make_params(h);
-    k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, h->agent_state, act_dev, ab, am,
-                                                             policy, seed, (uint32_t)h->clk.step_count);
+    const size_t NN = h->NN;
+    if (on_cov)
+        k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->cov, 2 * NN, 0, NN, h->agent_xy, h->agent_state, act_dev, ab, am,
+                                                                 policy, seed, (uint32_t)h->clk.step_count);
+    else
+        k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid[h->cur], 7 * NN, NN, 2 * NN, h->agent_xy, h->agent_state,
+                                                                 act_dev, ab, am, policy, seed, (uint32_t)h->clk.step_count);
     DW_LAUNCHED(h);
     return DW_OK;
 }
@@ -415,6 +458,7 @@ static int launch_forward_tail(dw_handle *h, bool counters, unsigned int *alive_
     int rc = launch_stamp(h, out, counters, alive_slot, true);
     if (rc) return rc;
     h->grid_valid = true;
+    h->cov_valid = false;
     h->lat_valid = false;
     h->obs_valid = false;
     update_L(h->clk);
@@ -433,6 +477,7 @@ extern "C" int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab,
     if (rc) return rc;
     rc = launch_agents(h, h->action_dev, ab, am, DW_POLICY_REPLAY, 0);
     h->lat_valid = false;
+    h->cov_valid = false;
     h->obs_valid = false;
     return rc;
 }
@@ -591,6 +636,9 @@ extern "C" int dw_get_diag(dw_handle *h, int32_t which, double *out) {
     if (h->pre == PRE_GRID) {
         SrcGrid src{h->pre_grid, 7 * h->NN, h->NN};
         k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
+    } else if (h->pre == PRE_COV) {
+        SrcCov src{h->cov, h->NN};
+        k_diag<SrcCov><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
     } else {
         SrcLattice src{h->lat_pre, h->NN};
         k_diag<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
@@ -668,6 +716,14 @@ static int ckpt_save(dw_handle *h, int slot) {
         if (rc) return rc;
         DW_CUDA_TRY(h, cudaMemcpyAsync(c.grid, h->grid[h->cur], B * 7 * NN * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
+    c.have_cov = h->cov_valid || h->pre == PRE_COV;
+    if (c.have_cov) {
+        rc = dev_alloc(h, &c.cov, B * 2 * NN);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(c.cov, h->cov, B * 2 * NN * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    c.cov_valid = h->cov_valid;
+    c.cov_L = h->cov_L;
     if (h->lat_valid) {
         rc = dev_alloc(h, &c.lat, B * NN);
         if (!rc) rc = dev_alloc(h, &c.lat_pre, B * NN);
@@ -690,7 +746,7 @@ static int ckpt_save(dw_handle *h, int slot) {
     c.have = true; c.grid_valid = h->grid_valid; c.lat_valid = h->lat_valid; c.clk = h->clk;
     // a PRE_GRID pre-state lives in the other ping-pong buffer and is not checkpointed: diagnostics of the
     // step before the checkpoint are not restorable, the state itself is.
-    c.pre = (h->pre == PRE_LAT) ? PRE_LAT : PRE_NONE;
+    c.pre = (h->pre == PRE_LAT || h->pre == PRE_COV) ? h->pre : PRE_NONE;
     c.L_last = h->L_last;
     c.ch6_dirty[0] = h->ch6_dirty[0]; c.ch6_dirty[1] = h->ch6_dirty[1];
     return DW_OK;
@@ -705,6 +761,13 @@ static int ckpt_restore(dw_handle *h, int slot) {
         if (rc) return rc;
         DW_CUDA_TRY(h, cudaMemcpyAsync(h->grid[h->cur], c.grid, B * 7 * NN * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
+    if (c.have_cov) {
+        int rc = dev_alloc(h, &h->cov, B * 2 * NN);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->cov, c.cov, B * 2 * NN * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->cov_valid = c.cov_valid;
+    h->cov_L = c.cov_L;
     if (c.lat_valid) {
         DW_CUDA_TRY(h, cudaMemcpyAsync(h->lat[h->lcur], c.lat, B * NN * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
         if (c.pre == PRE_LAT)

@@ -13,6 +13,12 @@ struct SrcGrid {           // fp64 grid[B,7,N,N]
     __device__ __forceinline__ double l(int b, size_t c) const { return g[b * world_stride + NN + c]; }
     __device__ __forceinline__ double d(int b, size_t c) const { return g[b * world_stride + 2 * NN + c]; }
 };
+struct SrcCov {            // fp64 cover planes [B,2,N,N] (light, dark): the lean reset state
+    const double *c;
+    size_t NN;
+    __device__ __forceinline__ double l(int b, size_t k) const { return c[(size_t)b * 2 * NN + k]; }
+    __device__ __forceinline__ double d(int b, size_t k) const { return c[(size_t)b * 2 * NN + NN + k]; }
+};
 struct SrcLattice {        // packed milli-covers [B,N,N]
     const uint32_t *k;
     size_t NN;
@@ -71,6 +77,44 @@ __global__ void __launch_bounds__(256) k_forward(DevParams P, double SL, Src src
             const unsigned m = __activemask();
             const int b0 = __shfl_sync(m, b, 0);
             double ml = rl, md = rd;
+            if (m == 0xffffffffu && __all_sync(m, b == b0)) {
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    ml = fmax(ml, __shfl_xor_sync(m, ml, s));
+                    md = fmax(md, __shfl_xor_sync(m, md, s));
+                }
+                if ((threadIdx.x & 31) == 0) {
+                    dw_atomic_max_pos(world_max + 2 * b, ml);
+                    dw_atomic_max_pos(world_max + 2 * b + 1, md);
+                }
+            } else {
+                dw_atomic_max_pos(world_max + 2 * b, ml);
+                dw_atomic_max_pos(world_max + 2 * b + 1, md);
+            }
+        }
+    }
+}
+
+// Same literal step, but only the new covers are kept, as packed lattice words (the first step of a fused run from the
+// off-lattice reset state: nothing else of the 7-channel grid feeds the next step).
+template <class Src>
+__global__ void __launch_bounds__(256) k_forward_lattice(DevParams P, double SL, Src src, uint32_t *__restrict__ lat_out,
+                                                         unsigned long long *world_max) {
+    const size_t NN = (size_t)P.N * P.N;
+    const size_t total = (size_t)P.B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / NN);
+        const size_t c = i - (size_t)b * NN;
+        const int x = (int)(c / P.N), y = (int)(c - (size_t)x * P.N);
+        double l9[9], d9[9];
+        dw_load9(src, b, P.N, x, y, l9, d9);
+        const LitCell o = dw_literal_cell(P, SL, l9, d9);
+        const double kl = rint(o.nl * 1000.0), kd = rint(o.nd * 1000.0);
+        lat_out[i] = ((uint32_t)(int)kl) | ((uint32_t)(int)kd << 16);
+        if (world_max) {
+            double ml = dw_div1000(kl), md = dw_div1000(kd);
+            const unsigned m = __activemask();
+            const int b0 = __shfl_sync(m, b, 0);
             if (m == 0xffffffffu && __all_sync(m, b == b0)) {
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) {
@@ -161,14 +205,15 @@ __device__ __forceinline__ int dw_greedy_pick(const double (&food)[4], bool gree
 
 // One thread per world, agents strictly in index order (grazing conflicts: lower index eats first).
 // action: device int8 [ab,am] (policy REPLAY/explicit), ignored for other policies.
-__global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *grid, int32_t *agent_xy, double *agent_state,
-                                                     const int8_t *action, int ab, int am, int policy, uint64_t seed,
-                                                     uint32_t step) {
+// covers: base pointer of the cover storage; world w's light / dark planes start at w*world_stride + l_off / d_off
+// (7-channel grid: 7NN, NN, 2NN; lean cover planes: 2NN, 0, NN).
+__global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *covers, size_t world_stride, size_t l_off, size_t d_off,
+                                                     int32_t *agent_xy, double *agent_state, const int8_t *action, int ab, int am,
+                                                     int policy, uint64_t seed, uint32_t step) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
     const int N = P.N, n = P.n_agents;
-    const size_t NN = (size_t)N * N;
-    double *gl = grid + (size_t)b * 7 * NN + NN, *gd = gl + NN;
+    double *gl = covers + (size_t)b * world_stride + l_off, *gd = covers + (size_t)b * world_stride + d_off;
     int32_t *xy = agent_xy + (size_t)b * n * 2;
     double *st = agent_state + (size_t)b * n;
     for (int i = 0; i < n; ++i) st[i] = st[i] - P.agent_gamma;
@@ -233,10 +278,12 @@ __global__ void __launch_bounds__(128) k_stamp_reward(DevParams P, double *grid,
     if (b >= P.B) return;
     const int N = P.N, n = P.n_agents;
     const size_t NN = (size_t)N * N;
-    double *g4 = grid + (size_t)b * 7 * NN + 4 * NN;
-    for (int i = 0; i < n; ++i) {
-        const int x = agent_xy[((size_t)b * n + i) * 2], y = agent_xy[((size_t)b * n + i) * 2 + 1];
-        g4[(size_t)x * N + y] = agent_state[(size_t)b * n + i];
+    if (grid) {                        // lean runs keep no 7-channel grid: the stamp happens when one is materialised
+        double *g4 = grid + (size_t)b * 7 * NN + 4 * NN;
+        for (int i = 0; i < n; ++i) {
+            const int x = agent_xy[((size_t)b * n + i) * 2], y = agent_xy[((size_t)b * n + i) * 2 + 1];
+            g4[(size_t)x * N + y] = agent_state[(size_t)b * n + i];
+        }
     }
     if (n > 0) {
         for (int i = 0; i < n; ++i) {
@@ -294,15 +341,15 @@ __device__ __forceinline__ double dw_u01(uint64_t seed, uint64_t idx, uint32_t s
 }
 
 __global__ void __launch_bounds__(256) k_init_random(DevParams P, uint64_t seed, uint64_t world0, double prop_l, double prop_d,
-                                                     double init_l, double init_d, double *grid, int32_t *agent_xy, double *agent_state) {
+                                                     double init_l, double init_d, double *cov, int32_t *agent_xy, double *agent_state) {
     const size_t NN = (size_t)P.N * P.N, total = (size_t)P.B * NN;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t b = i / NN, c = i - b * NN;
         const uint64_t gidx = (world0 + b) * NN + c;
         const double d = dw_u01(seed, gidx, 0) < prop_d ? init_d * dw_u01(seed, gidx, 1) : 0.0;
         const double l = dw_u01(seed, gidx, 2) < prop_l ? init_l * dw_u01(seed, gidx, 3) : 0.0;
-        double *g = grid + b * 7 * NN + c;
-        g[0] = (P.p - l) - d; g[NN] = l; g[2 * NN] = d; g[3 * NN] = 0; g[4 * NN] = 0; g[5 * NN] = 0; g[6 * NN] = 0;
+        cov[b * 2 * NN + c] = l;
+        cov[b * 2 * NN + NN + c] = d;
     }
     const size_t na = (size_t)P.B * P.n_agents;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na; i += (size_t)gridDim.x * blockDim.x) {
@@ -310,6 +357,17 @@ __global__ void __launch_bounds__(256) k_init_random(DevParams P, uint64_t seed,
         agent_xy[2 * i] = (int)(dw_u01(seed ^ 0xA5A5A5A5ull, gidx, 0) * P.N);
         agent_xy[2 * i + 1] = (int)(dw_u01(seed ^ 0xA5A5A5A5ull, gidx, 1) * P.N);
         agent_state[i] = 1.0;
+    }
+}
+
+// lean cover planes [B,2,N,N] -> 7-channel grid with channels 1,2 set and the rest zero (initialize_grid :304-312)
+__global__ void __launch_bounds__(256) k_cov_to_grid(int B, size_t NN, const double *__restrict__ cov, double *__restrict__ grid) {
+    const size_t total = (size_t)B * NN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / NN, c = i - b * NN;
+        double *g = grid + b * 7 * NN + c;
+        g[0] = 0; g[NN] = cov[b * 2 * NN + c]; g[2 * NN] = cov[b * 2 * NN + NN + c];
+        g[3 * NN] = 0; g[4 * NN] = 0; g[5 * NN] = 0; g[6 * NN] = 0;
     }
 }
 

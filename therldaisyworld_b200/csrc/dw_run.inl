@@ -51,13 +51,19 @@ static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
     s.SL = c.S * L;
 }
 
-// bring the state onto the packed lattice; *converted = false if some cover is not an exact k/1000
-static int grid_to_lattice(dw_handle *h, bool *converted) {
+static int ensure_lattice_buffers(dw_handle *h) {
     const size_t B = h->cfg.batch, NN = h->NN;
     int rc = dev_alloc(h, &h->lat[0], B * NN);
     if (!rc) rc = dev_alloc(h, &h->lat[1], B * NN);
     if (!rc) rc = dev_alloc(h, &h->lat_pre, B * NN);
     if (!rc) rc = dev_alloc(h, &h->slow_count, (size_t)2);
+    return rc;
+}
+
+// bring the state onto the packed lattice; *converted = false if some cover is not an exact k/1000
+static int grid_to_lattice(dw_handle *h, bool *converted) {
+    const size_t B = h->cfg.batch, NN = h->NN;
+    int rc = ensure_lattice_buffers(h);
     if (rc) return rc;
     DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
     k_grid_to_lattice<<<grid_for(B * NN), 256, 0, h->stream>>>((int)B, NN, h->grid[h->cur], h->lat[h->lcur], h->slow_count + 1);
@@ -168,10 +174,43 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
 
 static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive);
 
+// First step of a run from the lean reset state (fp64 cover planes, off the lattice): update_agents on the planes, one
+// literal forward whose new covers go straight onto the packed lattice, reward/done and lifespan counters. No 7-channel
+// grid is touched; the post-graze planes stay behind as the pre-state for lazy materialisation / diagnostics.
+static int lean_first_step(dw_handle *h, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive_slot) {
+    int rc = ensure_lattice_buffers(h);
+    if (rc) return rc;
+    if (policy == DW_POLICY_REPLAY) rc = launch_agents(h, act_dev, h->cfg.batch, h->cfg.n_agents, policy, seed, true);
+    else rc = launch_agents(h, nullptr, 0, 0, policy, seed, true);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->world_max, 0, (size_t)P.B * 2 * sizeof(unsigned long long), h->stream));
+    SrcCov src{h->cov, h->NN};
+    k_forward_lattice<SrcCov><<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, h->lat[h->lcur], h->world_max);
+    DW_LAUNCHED(h);
+    rc = launch_stamp(h, nullptr, true, alive_slot, true);
+    if (rc) return rc;
+    h->pre = PRE_COV;
+    h->L_last = h->clk.L;
+    h->lat_valid = true;
+    h->cov_valid = false;
+    h->grid_valid = false;
+    h->obs_valid = false;
+    update_L(h->clk);
+    return DW_OK;
+}
+
 // K <= 64 steps, fused where the state allows it
 static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed) {
     unsigned int *alive = h->alive;
     const size_t per_step = (size_t)h->cfg.batch * h->cfg.n_agents;
+    if (!h->lat_valid && h->cov_valid) {
+        int rc = lean_first_step(h, policy, act_dev, seed, alive);
+        if (rc) return rc;
+        K -= 1; alive += 1;
+        if (act_dev) act_dev += per_step;
+        if (K == 0) return DW_OK;
+    }
     if (!h->lat_valid) {
         if (!h->grid_valid) return dw_fail(h, DW_E_STATE, "dw_run", "no state uploaded");
         bool ok = false;
