@@ -16,9 +16,13 @@
  *   dwt_move_graze    update_agents (:181-216): pay agent_gamma, move, graze in agent-index order -> gain[n]
  *                     [ranks > 1: all-reduce SUM of gain]
  *   dwt_finish_agents state += gain, clip (:244), reward/done (:486-492), agents_done_at += !done
- *   dwt_stencil       forward (:434-452) on the band -> new covers; update_L (:463-473); per-step species max
- *   dwt_halo_*        ghost rows: toroidal wrap (one rank) or the neighbours' edge rows (caller copies), then
- *                     dwt_ghost_cols
+ *   dwt_stencil       forward (:434-452) on the band -> new covers (ghost columns included); update_L (:463-473);
+ *                     per-step species max. Parts 1 + 2 split it into edge tile rows and interior so that the
+ *                     halo exchange can overlap the interior.
+ *   ghost rows        toroidal wrap (dwt_halo_wrap, one rank) or the neighbours' edge rows (caller copies whole
+ *                     stored rows of N + 8 words).
+ * gain[n] and act[n] are adjacent in memory (gain first): finishing step j can be deferred until the decisions of
+ * step j + 1 exist, so that ONE all-reduce per step carries both (therldaisyworld_b200/banded.py does that).
  *
  * Constraints of the tiled kernels: N % 64 == 0, rows % 64 == 0, N >= 64, D4-symmetric kernels (the defaults).
  */
@@ -34,13 +38,14 @@ extern "C" {
 typedef struct dwt_handle dwt_handle;
 
 /* Device pointers a multi-rank driver needs (valid until the next dwt_stencil for the halo rows, for the life of the
-   handle for the rest). Row pointers address N packed u32 cells (light milli-cover | dark << 16). */
+   handle for the rest). Row pointers address N + 8 packed u32 words (light milli-cover | dark << 16; word 3 and word N + 4
+   are the ghost columns). */
 typedef struct dwt_ptrs {
-    double *act;            /* [n]   action + 1 per agent (0 = not decided here) */
+    double *act;            /* [n]   action + 1 per agent (0 = not decided here); act == gain + n */
     double *gain;           /* [n]   food eaten per agent on this rank */
     int32_t *stepmax;       /* [4096, 2] per-step max milli-cover of (light, dark) over this band */
-    uint32_t *send_top;     /* band row 0          -> the rank above's bottom ghost */
-    uint32_t *send_bottom;  /* band row rows-1     -> the rank below's top ghost */
+    uint32_t *send_top;     /* band row 0 (whole stored row, N + 8 words) -> the rank above's bottom ghost */
+    uint32_t *send_bottom;  /* band row rows-1                            -> the rank below's top ghost */
     uint32_t *recv_top;     /* ghost row above the band */
     uint32_t *recv_bottom;  /* ghost row below the band */
 } dwt_ptrs;
@@ -69,9 +74,8 @@ int dwt_init_random(dwt_handle *h, uint64_t seed, double light_proportion, doubl
 int dwt_decide(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed);
 int dwt_move_graze(dwt_handle *h);
 int dwt_finish_agents(dwt_handle *h);
-int dwt_stencil(dwt_handle *h);
+int dwt_stencil(dwt_handle *h, int32_t part);   /* 0: whole band; 1: edge tile rows, then 2: interior tile rows */
 int dwt_halo_wrap(dwt_handle *h);      /* one rank: ghost rows from the band's own edge rows */
-int dwt_ghost_cols(dwt_handle *h);     /* after the ghost rows are in place */
 int dwt_get_ptrs(dwt_handle *h, dwt_ptrs *out);
 
 /* K whole steps on one rank (rows == N): the phases above back to back on the handle's stream, no host sync. */

@@ -62,6 +62,9 @@ class ThreadComm:
         up, down = (self.rank - 1) % self.world_size, (self.rank + 1) % self.world_size
         sh.slots[self.rank] = (send_top, send_bottom)
         sh.barrier.wait()
+        if send_top.is_cuda:      # bands of one process may exchange on side streams: order them device-wide (test only)
+            import torch
+            torch.cuda.synchronize()
         recv_top.copy_(sh.slots[up][1])
         recv_bottom.copy_(sh.slots[down][0])
         sh.barrier.wait()
@@ -101,8 +104,9 @@ class OracleBand:
         self.N, self.n, self.row0, self.rows, self.n_ranks = N, n_agents, row0, rows, n_ranks
         self.o = OracleDaisyWorld(grid_dimension=N, n_agents=0)
         self.set_params(params)
-        self.act = torch.zeros(n_agents, dtype=torch.float64)
-        self.gain = torch.zeros(n_agents, dtype=torch.float64)
+        self.exch = torch.zeros(2 * n_agents, dtype=torch.float64)      # [gain | act] like the device band
+        self.gain = self.exch[:n_agents]
+        self.act = self.exch[n_agents:]
         self.stepmax = torch.zeros(4096 * 2, dtype=torch.int32)
         self.j = 0
         self.done_at = 0
@@ -144,6 +148,7 @@ class OracleBand:
         return rel + 1 if rel < self.rows else -1
 
     def decide(self, policy, actions_step=None, seed=0):
+        self._absorb_halo()
         N = self.N
         food = self.l + self.d
         for i in range(self.n):
@@ -190,7 +195,7 @@ class OracleBand:
         self.st = np.clip(s, 0.0, 1.0)
         self.ada += (self.st >= 0.1)
 
-    def stencil(self):
+    def stencil(self, part=0):
         from oracle.daisy_numpy import round3
         self.o.L = self.clk.L
         f = self.o.fields(self.l[None], self.d[None])
@@ -208,19 +213,17 @@ class OracleBand:
         self.l[0], self.l[-1] = self.l[-2].copy(), self.l[1].copy()
         self.d[0], self.d[-1] = self.d[-2].copy(), self.d[1].copy()
 
-    def ghost_cols(self):
-        if hasattr(self, "_halo"):
-            # halo tensors carry (light, dark) packed as milli-cover integers like the device rows
+    def _absorb_halo(self):
+        """Unpack the ghost rows received by the last exchange (packed milli-cover words like the device rows)."""
+        if getattr(self, "_halo", None) is not None:
             for name, row in (("recv_top", 0), ("recv_bottom", self.rows + 1)):
                 w = self._halo[name].numpy().astype(np.int64)
                 self.l[row] = (w & 0xffff) / 1000.0
                 self.d[row] = (w >> 16) / 1000.0
+            self._halo = None
 
-    def act_tensor(self):
-        return self.act
-
-    def gain_tensor(self):
-        return self.gain
+    def exch_tensor(self, gain=True, act=True):
+        return self.exch[(0 if gain else self.n):(2 * self.n if act else self.n)]
 
     def stepmax_tensor(self, K):
         return self.stepmax[:2 * K]
@@ -261,4 +264,5 @@ class OracleBand:
         return self.xy.copy(), self.st.copy()
 
     def covers(self):
+        self._absorb_halo()
         return np.stack([self.l[1:-1], self.d[1:-1]])

@@ -46,7 +46,7 @@ SYMBOLS = [
 TILED_SYMBOLS = [
     "dwt_last_error", "dwt_create", "dwt_destroy", "dwt_set_config", "dwt_set_clock", "dwt_get_clock", "dwt_set_stream",
     "dwt_synchronize", "dwt_upload_covers", "dwt_upload_agents", "dwt_init_random", "dwt_decide", "dwt_move_graze",
-    "dwt_finish_agents", "dwt_stencil", "dwt_halo_wrap", "dwt_ghost_cols", "dwt_get_ptrs", "dwt_run", "dwt_end_chunk",
+    "dwt_finish_agents", "dwt_stencil", "dwt_halo_wrap", "dwt_get_ptrs", "dwt_run", "dwt_end_chunk",
     "dwt_reset_lifespans", "dwt_get_lifespans", "dwt_get_agents", "dwt_get_reward_done", "dwt_get_covers", "dwt_get_grid",
     "dwt_debug_slow_count",
 ]
@@ -132,9 +132,8 @@ def load():
         "dwt_decide": (C.c_int, [vp, i32, pi8, u64]),
         "dwt_move_graze": (C.c_int, [vp]),
         "dwt_finish_agents": (C.c_int, [vp]),
-        "dwt_stencil": (C.c_int, [vp]),
+        "dwt_stencil": (C.c_int, [vp, i32]),
         "dwt_halo_wrap": (C.c_int, [vp]),
-        "dwt_ghost_cols": (C.c_int, [vp]),
         "dwt_get_ptrs": (C.c_int, [vp, C.POINTER(DwtPtrs)]),
         "dwt_run": (C.c_int, [vp, i64, i32, pi8, u64]),
         "dwt_end_chunk": (C.c_int, [vp, i32, pi32]),

@@ -7,9 +7,11 @@ grid does not fit in shared memory: rank r owns rows ``[r*N/R, (r+1)*N/R)`` on i
 One env step = the phase sequence of the header, with exactly these exchanges between ranks (``torch.distributed``:
 NCCL over NVLink on GPUs, gloo in the CPU tests -- plumbing only, the data path is the CUDA kernels):
 
-  * greedy / anti-greedy: SUM all-reduce of ``act[n]`` (only the owner band of an agent can see its neighbourhood);
-  * SUM all-reduce of ``gain[n]`` (only the owner band of a cell knows what was eaten there);
-  * after the stencil: the band's first/last row goes to the upper/lower neighbour's ghost row (ring, toroidal);
+  * ONE SUM all-reduce per step over ``[gain(j-1) | act(j)]``: only the owner band of a cell knows what was eaten there,
+    only the owner band of an agent sees its neighbourhood (greedy / anti-greedy).  Finishing step j-1 (state += gain,
+    clip, reward/done) is deferred until the decisions of step j exist, so both vectors travel together;
+  * after the edge tile rows of the stencil: the band's first/last row goes to the upper/lower neighbour's ghost row
+    (ring, toroidal) on a side stream while the interior tile rows are still being computed;
   * per chunk of steps: MAX all-reduce of the per-step cover maxima (lifespan bookkeeping, ``grid_done``).
 
 ``world_size == 1`` needs none of them (``dwt_halo_wrap`` closes the torus locally).
@@ -84,6 +86,7 @@ class DeviceBand:
             raise _lib.DaisyWorldError(f"dwt_create failed (code {rc}): {msg.decode() if msg else ''}")
         self._h = h
         self._views = {}
+        self._side = None
 
     def __del__(self):
         try:
@@ -142,14 +145,26 @@ class DeviceBand:
     def finish_agents(self):
         self._check(self._lib.dwt_finish_agents(self._h), "dwt_finish_agents")
 
-    def stencil(self):
-        self._check(self._lib.dwt_stencil(self._h), "dwt_stencil")
+    def stencil(self, part=0):
+        self._check(self._lib.dwt_stencil(self._h, int(part)), "dwt_stencil")
 
     def halo_wrap(self):
         self._check(self._lib.dwt_halo_wrap(self._h), "dwt_halo_wrap")
 
-    def ghost_cols(self):
-        self._check(self._lib.dwt_ghost_cols(self._h), "dwt_ghost_cols")
+    def stencil_and_exchange(self, comm):
+        """Edge tile rows, then the halo exchange on a side stream overlapped with the interior tile rows."""
+        torch = self._torch
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._edge_done = torch.cuda.Event()
+        self.stencil(1)
+        main = torch.cuda.current_stream(self.device)
+        self._edge_done.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._edge_done)
+            comm.exchange_halos(*self.halo_tensors())
+        self.stencil(2)
+        main.wait_stream(self._side)
 
     def run_local(self, K, policy, actions=None, seed=0):
         """K steps without any exchange (a band that is the whole torus)."""
@@ -179,19 +194,19 @@ class DeviceBand:
             self._views[key] = t
         return t
 
-    def act_tensor(self):
-        return self._view(self._ptrs().act, (max(self.n, 1),), "<f8")[:self.n]
-
-    def gain_tensor(self):
-        return self._view(self._ptrs().gain, (max(self.n, 1),), "<f8")[:self.n]
+    def exch_tensor(self, gain=True, act=True):
+        """The exchange vector [gain[n] | act[n]] (or one half of it) as a torch view."""
+        t = self._view(self._ptrs().gain, (2 * max(self.n, 1),), "<f8")
+        return t[(0 if gain else self.n):(2 * self.n if act else self.n)]
 
     def stepmax_tensor(self, K):
         return self._view(self._ptrs().stepmax, (4096 * 2,), "<i4")[:2 * K]
 
     def halo_tensors(self):
-        """(send_top, send_bottom, recv_top, recv_bottom) rows of the CURRENT lattice buffer, int32 views of N cells."""
+        """(send_top, send_bottom, recv_top, recv_bottom): whole stored rows (N + 8 words, ghost columns included) of the
+        lattice buffer the current step writes, as int32 views."""
         p = self._ptrs()
-        return tuple(self._view(q, (self.N,), "<i4") for q in (p.send_top, p.send_bottom, p.recv_top, p.recv_bottom))
+        return tuple(self._view(q, (self.N + 8,), "<i4") for q in (p.send_top, p.send_bottom, p.recv_top, p.recv_bottom))
 
     # ---- getters
     def reset_lifespans(self):
@@ -261,6 +276,7 @@ class BandedDaisyWorld:
         self.dL = (self.max_L - self.min_L) / self.ramp_period
         self.step_count = 0
         self._pending = 0          # steps recorded since the last end_chunk
+        self._gain_pending = False # multi-rank: gains of the last step not yet summed / applied
         self.first_done_step = None
 
     # ---- reset
@@ -272,6 +288,7 @@ class BandedDaisyWorld:
         self.band.set_clock(make_clock_struct(self))
         self.band.reset_lifespans()
         self._pending = 0
+        self._gain_pending = False
         self.first_done_step = None
 
     def load_state(self, light, dark, agent_indices, agent_states):
@@ -291,22 +308,36 @@ class BandedDaisyWorld:
     def step(self, policy="greedy", actions_step=None, seed=0):
         b, comm = self.band, self.comm
         b.decide(policy, actions_step, seed)
-        if comm is not None and policy in _WORLD_POLICIES and self.n_agents:
-            comm.all_reduce_sum(b.act_tensor())
-        b.move_graze()
-        if comm is not None and self.n_agents:
-            comm.all_reduce_sum(b.gain_tensor())
-        b.finish_agents()
-        b.stencil()
         if comm is None:
+            b.move_graze()
+            b.finish_agents()
+            b.stencil(0)
             b.halo_wrap()
         else:
-            comm.exchange_halos(*b.halo_tensors())
-        b.ghost_cols()
+            need_act = bool(self.n_agents) and policy in _WORLD_POLICIES
+            if self._gain_pending or need_act:
+                comm.all_reduce_sum(b.exch_tensor(gain=self._gain_pending, act=need_act))
+            if self._gain_pending:
+                b.finish_agents()                    # step j-1, before its gz flags are overwritten
+            b.move_graze()
+            self._gain_pending = bool(self.n_agents)
+            if hasattr(b, "stencil_and_exchange"):
+                b.stencil_and_exchange(comm)
+            else:
+                b.stencil(0)
+                comm.exchange_halos(*b.halo_tensors())
         self._pending += 1
+
+    def _flush(self):
+        """Finish the last step's agents (multi-rank: the deferred gain all-reduce)."""
+        if self._gain_pending:
+            self.comm.all_reduce_sum(self.band.exch_tensor(gain=True, act=False))
+            self.band.finish_agents()
+            self._gain_pending = False
 
     def end_chunk(self):
         """Fold the per-step cover maxima of the steps since the last call into the lifespan counter."""
+        self._flush()
         K = self._pending
         if K == 0:
             return
@@ -345,6 +376,7 @@ class BandedDaisyWorld:
         return self.band.lifespans()
 
     def agents(self):
+        self._flush()
         return self.band.agents()
 
     def local_covers(self):
@@ -353,4 +385,5 @@ class BandedDaisyWorld:
 
     def local_grid(self):
         """[7, rows, N]: env.grid[0] restricted to this rank's rows."""
+        self._flush()
         return self.band.grid()

@@ -151,21 +151,19 @@ __global__ void __launch_bounds__(256) k_band_graze(BandGeom G, Cells C, const i
     gain[i] = got;
 }
 
-__global__ void __launch_bounds__(256) k_band_claim_reset(BandGeom G, const int32_t *__restrict__ xy, int n, const uint8_t *__restrict__ gz,
-                                                          int *claim) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !gz[i]) return;
-    const int lr = band_owned_row(G, xy[2 * i]);
-    if (lr >= 0) claim[(size_t)lr * G.N + xy[2 * i + 1]] = 0x7fffffff;
-}
-
-// Phase 4 (replicated, after the gains were summed over ranks): state += gain, clip, reward/done, lifespan counter.
-__global__ void __launch_bounds__(256) k_band_finish(double *st, int n, const double *__restrict__ gain, const uint8_t *__restrict__ gz,
-                                                     double *reward, uint8_t *done, int64_t *agents_done_at) {
+// Phase 4 (replicated, after the gains were summed over ranks): state += gain, clip, reward/done, lifespan counter;
+// also returns the graze claims of this step to "idle".
+__global__ void __launch_bounds__(256) k_band_finish(BandGeom G, const int32_t *__restrict__ xy, int *claim, double *st, int n,
+                                                     const double *__restrict__ gain, const uint8_t *__restrict__ gz, double *reward,
+                                                     uint8_t *done, int64_t *agents_done_at) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = st[i];
-    if (gz[i]) s = s + gain[i];
+    if (gz[i]) {
+        s = s + gain[i];
+        const int lr = band_owned_row(G, xy[2 * i]);
+        if (lr >= 0) claim[(size_t)lr * G.N + xy[2 * i + 1]] = 0x7fffffff;
+    }
     s = dw_clip01(s);
     st[i] = s;
     reward[i] = s;
@@ -174,18 +172,13 @@ __global__ void __launch_bounds__(256) k_band_finish(double *st, int n, const do
 }
 
 // ---- ghost maintenance ---------------------------------------------------------------------------------------------
+// The stencil kernels write the ghost COLUMNS of the rows they produce, so a ghost ROW is a copy of a whole stored row
+// (pitch words): from the band's own edge rows on a single-rank torus, from the neighbours otherwise.
 __global__ void __launch_bounds__(256) k_band_ghost_rows_wrap(BandGeom G, uint32_t *lat) {   // single-rank torus: R == N
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= G.N) return;
-    lat[G.c0 + c] = lat[(size_t)G.R * G.pitch + G.c0 + c];
-    lat[(size_t)(G.R + 1) * G.pitch + G.c0 + c] = lat[(size_t)G.pitch + G.c0 + c];
-}
-__global__ void __launch_bounds__(256) k_band_ghost_cols(BandGeom G, uint32_t *lat) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= G.R + 2) return;
-    uint32_t *row = lat + (size_t)r * G.pitch;
-    row[G.c0 - 1] = row[G.c0 + G.N - 1];
-    row[G.c0 + G.N] = row[G.c0];
+    if (c >= G.pitch) return;
+    lat[c] = lat[(size_t)G.R * G.pitch + c];
+    lat[(size_t)(G.R + 1) * G.pitch + c] = lat[(size_t)G.pitch + c];
 }
 
 // ---- first step: literal forward from the off-lattice fp64 cover planes [(R+2) x N] onto the padded lattice ---------
@@ -208,7 +201,10 @@ __global__ void __launch_bounds__(256) k_band_first_step(DevParams P, double SL,
             }
         const LitCell o = dw_literal_cell(P, SL, l9, d9);
         const uint32_t q = dw_pack((int)rint(o.nl * 1000.0), (int)rint(o.nd * 1000.0));
-        lat_out[(size_t)(r + 1) * Gl.pitch + Gl.c0 + y] = q;
+        uint32_t *orow = lat_out + (size_t)(r + 1) * Gl.pitch;
+        orow[Gl.c0 + y] = q;
+        if (y == 0) orow[Gl.c0 + Gl.N] = q;              // ghost columns of the produced row
+        if (y == Gl.N - 1) orow[Gl.c0 - 1] = q;
         mx = __vmaxu2(mx, q);
     }
     const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
@@ -227,7 +223,9 @@ struct TiledArgs {
     StepCoef C;
     uint32_t *out;          // padded lattice written by this step
     int pitch;
-    int tiles_x, tiles_y;   // tiles per row / per band column
+    int tiles_x;            // tiles per row
+    int tr_first, tr_skip_lo, tr_skip_hi;   // tile rows of this launch: blockIdx -> tr, skipping [tr_skip_lo, tr_skip_hi)
+    int N;
     int *stepmax;           // [2] per-species max of the new band (atomicMax)
     unsigned int *slow_count;
 };
@@ -244,8 +242,13 @@ struct RowsTile72 {
 struct StoreGlobal {
     uint32_t *o;            // first cell of the thread's first output row
     int pitch;
+    int gsel, goff;         // ghost column duty of this thread: 0 none; 1: it holds column 0 (q[0]), 2: column N-1 (q[3]);
+                            // the ghost copy lives goff words from the thread's first cell of the row
     __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
-        *reinterpret_cast<uint4 *>(o + (size_t)i * pitch) = make_uint4(q[0], q[1], q[2], q[3]);
+        uint32_t *r = o + (size_t)i * pitch;
+        *reinterpret_cast<uint4 *>(r) = make_uint4(q[0], q[1], q[2], q[3]);
+        if (gsel == 1) r[goff] = q[0];
+        else if (gsel == 2) r[goff] = q[3];
     }
 };
 
@@ -282,7 +285,11 @@ __device__ __noinline__ uint32_t dwt_fix_warp(const TiledArgs *A, const uint32_t
                     }
                 const LitCell lc = dw_literal_cell(A->P, A->C.SL, l9, d9);
                 v = dw_pack((int)rint(lc.nl * 1000.0), (int)rint(lc.nd * 1000.0));
-                A->out[ooff + (long long)(lane >> 2) * A->pitch + (lane & 3)] = v;
+                const long long oc = ooff + (long long)(lane >> 2) * A->pitch + (lane & 3);
+                A->out[oc] = v;
+                const int col = (int)(oc % A->pitch) - 4;                  // ghost copies of the edge columns
+                if (col == 0) A->out[oc + A->N] = v;
+                if (col == A->N - 1) A->out[oc - A->N] = v;
                 if (A->slow_count) atomicAdd(A->slow_count, 1u);
             }
             extra = __vmaxu2(extra, v);
@@ -297,7 +304,9 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
     __shared__ int smax[2];
     const int tid = threadIdx.x, lane = tid & 31;
     const int tx = tid & 15, r0 = (tid >> 4) * 4;
-    const int tc = blockIdx.x % A.tiles_x, tr = blockIdx.x / A.tiles_x;
+    const int tc = blockIdx.x % A.tiles_x;
+    int tr = A.tr_first + blockIdx.x / A.tiles_x;
+    if (tr >= A.tr_skip_lo) tr += A.tr_skip_hi - A.tr_skip_lo;
     const uint32_t bar_a = dwt_smem_u32(&bar);
     if (tid == 0) {
         smax[0] = 0; smax[1] = 0;
@@ -319,7 +328,9 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
     const int tile_off = (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
     const long long out_off = (long long)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
     unsigned tiemin = 0xffffffffu;
-    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off}, StoreGlobal{A.out + out_off, A.pitch}, &tiemin);
+    const int gsel = (tx == 0 && tc == 0) ? 1 : ((tx == 15 && tc == A.tiles_x - 1) ? 2 : 0);
+    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off},
+                               StoreGlobal{A.out + out_off, A.pitch, gsel, gsel == 1 ? A.N : 3 - A.N}, &tiemin);
     const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
     if (flagged) mx = dwt_fix_warp(&A, tile, flagged, mx, tile_off, out_off, lane);
     const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);

@@ -21,7 +21,9 @@ struct dwt_handle {
     double *pl = nullptr, *pd = nullptr;       // fp64 cover planes [(R+2) x N] (off-lattice reset state)
     int *claim = nullptr;                      // [(R+2) x N] graze claims, INT_MAX when idle
     int32_t *agent_xy = nullptr;
-    double *agent_state = nullptr, *act = nullptr, *gain = nullptr, *reward = nullptr;
+    double *agent_state = nullptr, *exch = nullptr, *reward = nullptr;   // exch: gain[n] then act[n] (one all-reduce covers both)
+    double *act = nullptr, *gain = nullptr;
+    bool step_open = false;      // dwt_stencil(part 1) done, part 2 pending
     uint8_t *gz = nullptr, *done = nullptr;
     int8_t *replay = nullptr;
     size_t replay_cap = 0;
@@ -96,11 +98,13 @@ extern "C" int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int3
     const size_t n = h->n ? h->n : 1, padded = (size_t)(rows + 2) * h->pitch, planes = (size_t)(rows + 2) * N;
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess && cudaMemset(*p, 0, bytes) == cudaSuccess; };
     bool ok = alloc((void **)&h->lat[0], padded * 4) && alloc((void **)&h->lat[1], padded * 4) && alloc((void **)&h->claim, planes * 4) &&
-              alloc((void **)&h->agent_xy, n * 8) && alloc((void **)&h->agent_state, n * 8) && alloc((void **)&h->act, n * 8) &&
-              alloc((void **)&h->gain, n * 8) && alloc((void **)&h->reward, n * 8) && alloc((void **)&h->gz, n) && alloc((void **)&h->done, n) &&
+              alloc((void **)&h->agent_xy, n * 8) && alloc((void **)&h->agent_state, n * 8) && alloc((void **)&h->exch, 2 * n * 8) &&
+              alloc((void **)&h->reward, n * 8) && alloc((void **)&h->gz, n) && alloc((void **)&h->done, n) &&
               alloc((void **)&h->agents_done_at, n * 8) && alloc((void **)&h->stepmax, (size_t)DW_FUSED_MAX_STEPS * 2 * 4) &&
               alloc((void **)&h->slow_count, 4);
     if (ok) ok = cudaMemset(h->claim, 0x7f, planes * 4) == cudaSuccess;       // 0x7f7f7f7f: "idle" (> any agent index)
+    h->gain = h->exch;
+    h->act = h->exch ? h->exch + n : nullptr;
     if (!ok) {
         g_dwt_create_error = std::string("dwt_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         dwt_destroy(h);
@@ -118,7 +122,7 @@ extern "C" int dwt_destroy(dwt_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->agent_xy, h->agent_state, h->act, h->gain, h->reward, h->gz,
+    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->agent_xy, h->agent_state, h->exch, h->reward, h->gz,
                     h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
@@ -240,8 +244,6 @@ extern "C" int dwt_move_graze(dwt_handle *h) {
     else
         k_band_graze<PlaneCells><<<nb, 256, 0, h->stream>>>(G, PlaneCells{h->pl, h->pd}, h->agent_xy, h->n, h->gz, h->claim, h->gain);
     DWT_LAUNCHED(h);
-    k_band_claim_reset<<<nb, 256, 0, h->stream>>>(G, h->agent_xy, h->n, h->gz, h->claim);
-    DWT_LAUNCHED(h);
     return DW_OK;
 }
 
@@ -249,40 +251,60 @@ extern "C" int dwt_finish_agents(dwt_handle *h) {
     if (!h) return DW_E_INVALID;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->n) return DW_OK;
-    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(h->agent_state, h->n, h->gain, h->gz, h->reward, h->done, h->agents_done_at);
+    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), h->agent_xy, h->claim, h->agent_state, h->n, h->gain, h->gz,
+                                                           h->reward, h->done, h->agents_done_at);
     DWT_LAUNCHED(h);
     return DW_OK;
 }
 
-extern "C" int dwt_stencil(dwt_handle *h) {
-    if (!h) return DW_E_INVALID;
+// part 0: the whole band. part 1 / part 2: the two edge tile rows first, then the interior, so that the caller can send
+// the new edge rows to the neighbours while the interior is still being computed.
+extern "C" int dwt_stencil(dwt_handle *h, int32_t part) {
+    if (!h || part < 0 || part > 2) return DW_E_INVALID;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->chunk_j >= DW_FUSED_MAX_STEPS) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "call dwt_end_chunk at least every 4096 steps");
+    if ((part == 2) != h->step_open) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "part 2 must follow part 1");
     int *smax = h->stepmax + 2 * h->chunk_j;
-    if (!h->on_lattice) {
-        if (!h->pl) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "no state uploaded");
-        // the reset state is off the 0.001 lattice: first step in literal arithmetic, planes -> lattice
-        k_band_first_step<<<grid_for((size_t)h->R * h->N), 256, 0, h->stream>>>(dwt_params(h), h->cfg.S * h->clk.L, dwt_geom_planes(h), h->pl,
-                                                                                 h->pd, dwt_geom_lat(h), h->lat[h->cur], smax);
-        DWT_LAUNCHED(h);
-        h->on_lattice = true;
-        h->pre_is_planes = true;
+    const int tiles_y = h->R / DWT_TILE;
+    if (!h->on_lattice || (part == 2 && h->pre_is_planes)) {
+        if (part != 2) {
+            if (!h->pl) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "no state uploaded");
+            // the reset state is off the 0.001 lattice: first step in literal arithmetic, planes -> lattice (not split)
+            k_band_first_step<<<grid_for((size_t)h->R * h->N), 256, 0, h->stream>>>(dwt_params(h), h->cfg.S * h->clk.L, dwt_geom_planes(h),
+                                                                                     h->pl, h->pd, dwt_geom_lat(h), h->lat[h->cur], smax);
+            DWT_LAUNCHED(h);
+            h->on_lattice = true;
+            h->pre_is_planes = true;
+        }
     } else {
         TiledArgs A{};
         A.P = dwt_params(h);
         make_fast_coef(h->cfg, A.F);
         make_step_coef(h->cfg, h->clk.L, A.C);
-        A.out = h->lat[1 - h->cur];
+        if (part != 2) h->cur = 1 - h->cur;            // lat[cur] is the buffer being written from now on
+        A.out = h->lat[h->cur];
         A.pitch = h->pitch;
+        A.N = h->N;
         A.tiles_x = h->N / DWT_TILE;
-        A.tiles_y = h->R / DWT_TILE;
         A.stepmax = smax;
         A.slow_count = h->slow_count;
-        k_tiled_step<<<A.tiles_x * A.tiles_y, 256, 0, h->stream>>>(h->tmap[h->cur], A);
-        DWT_LAUNCHED(h);
-        h->cur = 1 - h->cur;
-        h->pre_is_planes = false;
+        int rows_of_tiles = tiles_y;
+        A.tr_first = 0; A.tr_skip_lo = tiles_y; A.tr_skip_hi = tiles_y;      // part 0: all tile rows
+        if (part == 1) {                                 // tile rows 0 and tiles_y-1
+            rows_of_tiles = tiles_y >= 2 ? 2 : 1;
+            A.tr_skip_lo = 1; A.tr_skip_hi = tiles_y >= 2 ? tiles_y - 1 : 1;
+        } else if (part == 2) {                          // tile rows 1 .. tiles_y-2
+            rows_of_tiles = tiles_y >= 2 ? tiles_y - 2 : 0;
+            A.tr_first = 1;
+        }
+        if (rows_of_tiles > 0) {
+            k_tiled_step<<<A.tiles_x * rows_of_tiles, 256, 0, h->stream>>>(h->tmap[1 - h->cur], A);
+            DWT_LAUNCHED(h);
+        }
+        if (part != 2) h->pre_is_planes = false;
     }
+    if (part == 1) { h->step_open = true; return DW_OK; }
+    h->step_open = false;
     h->have_pre = true;
     h->L_last = h->clk.L;
     h->chunk_j += 1;
@@ -295,16 +317,7 @@ extern "C" int dwt_halo_wrap(dwt_handle *h) {
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->R != h->N) return dwt_fail(h, DW_E_STATE, "dwt_halo_wrap", "only for a handle that owns the whole torus");
     if (!h->on_lattice) return DW_OK;
-    k_band_ghost_rows_wrap<<<dwt_blocks(h->N), 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur]);
-    DWT_LAUNCHED(h);
-    return DW_OK;
-}
-
-extern "C" int dwt_ghost_cols(dwt_handle *h) {
-    if (!h) return DW_E_INVALID;
-    DWT_TRY(h, cudaSetDevice(h->cfg.device));
-    if (!h->on_lattice) return DW_OK;
-    k_band_ghost_cols<<<dwt_blocks(h->R + 2), 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur]);
+    k_band_ghost_rows_wrap<<<dwt_blocks(h->pitch), 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur]);
     DWT_LAUNCHED(h);
     return DW_OK;
 }
@@ -315,10 +328,10 @@ extern "C" int dwt_get_ptrs(dwt_handle *h, dwt_ptrs *out) {
     out->act = h->act;
     out->gain = h->gain;
     out->stepmax = h->stepmax;
-    out->send_top = L + (size_t)1 * h->pitch + 4;
-    out->send_bottom = L + (size_t)h->R * h->pitch + 4;
-    out->recv_top = L + 4;
-    out->recv_bottom = L + (size_t)(h->R + 1) * h->pitch + 4;
+    out->send_top = L + (size_t)1 * h->pitch;
+    out->send_bottom = L + (size_t)h->R * h->pitch;
+    out->recv_top = L;
+    out->recv_bottom = L + (size_t)(h->R + 1) * h->pitch;
     return DW_OK;
 }
 
@@ -329,9 +342,8 @@ extern "C" int dwt_run(dwt_handle *h, int64_t K, int32_t policy, const int8_t *a
         int rc = dwt_decide(h, policy, actions ? actions + (size_t)j * h->n : nullptr, seed);
         if (!rc) rc = dwt_move_graze(h);
         if (!rc) rc = dwt_finish_agents(h);
-        if (!rc) rc = dwt_stencil(h);
+        if (!rc) rc = dwt_stencil(h, 0);
         if (!rc) rc = dwt_halo_wrap(h);
-        if (!rc) rc = dwt_ghost_cols(h);
         if (rc) return rc;
     }
     return DW_OK;
