@@ -60,8 +60,8 @@ struct dw_handle {
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     bool fused_attr_set = false;
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
-    unsigned int *pipe_sync = nullptr;         // [1 + pairs] work queue + per-pair progress of the persistent kernel
-    int pipe_blocks = 0, persist_blocks = 0;   // resident CTAs of the persistent kernels on this device
+    unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
+    int persist_blocks = 0;                    // resident CTAs of the persistent kernel on this device
     // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
     dw_profile prof{};
     bool profiling = false;
@@ -257,7 +257,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->pipe_sync,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {

@@ -23,18 +23,9 @@
 #ifndef DW_CELL_ILP
 #define DW_CELL_ILP 2                    // cells advanced in lockstep by the fast path (1, 2 or 4)
 #endif
-#ifndef DW_TILE_WINDOW
-#define DW_TILE_WINDOW 1                 // 1: rolling 3-row register window over the tile; 0: re-read rows per output row
-#endif
 #define DW_FUSED_MAX_STEPS 4096        // longest launch (coefficient table / alive counters)
 #define DW_FUSED_MAX_AGENTS 1024
 #define DW_FIX_BITS 20                 // fixed-point fraction bits of the rounding trick (ulp of 1.5*2^32)
-#ifndef DW_N64_MIN_BLOCKS
-#define DW_N64_MIN_BLOCKS 4            // resident CTAs per SM the 64x64 kernel is register-budgeted for
-#endif
-#ifndef DW_N64_ROW_UNROLL
-#define DW_N64_ROW_UNROLL 1
-#endif
 #define DW_TIE_EPS 4                   // filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover)
 
 // The fast path works with X' = g^2 * X (X = T_l^4 resp. T_d^4): its fourth root is T' = sqrt(g)*T, so that
@@ -73,11 +64,11 @@ struct FusedArgs {
     unsigned int world0;        // global index of this handle's first world (RANDOM policy counter)
     int K, policy;
     unsigned int *slow_count;   // diagnostics: number of literal recomputations (may be NULL)
-    // persistent pipelined kernel only
+    // persistent kernel only
     int Kc;                     // steps per work item
-    int n_pairs, n_chunks;      // work items = n_pairs * n_chunks, chunk-major
+    int n_pairs, n_chunks;      // work items = n_pairs (worlds) * n_chunks, chunk-major
     unsigned int *queue;        // [1] next work item (zeroed before the launch)
-    unsigned int *pair_done;    // [n_pairs] chunks completed per world pair (zeroed before the launch)
+    unsigned int *pair_done;    // [n_pairs] chunks completed per world (zeroed before the launch)
 };
 
 // ---- fast fourth root ------------------------------------------------------------------------------------
@@ -765,189 +756,6 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
         if (tid == 0) {
             __threadfence();
             atomicExch(A.pair_done + b, (unsigned)(c + 1));
-        }
-    }
-}
-
-// ---- 64x64, persistent + pipelined: 2 worlds per CTA, 8 compute warps + 1 agent warp, dynamic work queue --------------
-// Work item = (pair of worlds, chunk of Kc steps), handed out chunk-major from a global counter, so all worlds of the
-// ensemble advance together and every SM stays full until the end of the launch (no wave quantisation at B=1000).
-// Inside an item the two worlds A,B are software-pipelined: while the 8 compute warps run the stencil of one world,
-// the 9th warp does the lifespan bookkeeping and the (sequential, latency-bound) agent phase of the other one, so the
-// agents never stall the FP64 pipe and there is one __syncthreads per world-step.
-#define DW_PIPE_THREADS 288
-#ifndef DW_PIPE_MIN_BLOCKS
-#define DW_PIPE_MIN_BLOCKS 3
-#endif
-struct PipeSlot {
-    uint32_t *buf[2];
-    AgentSmem S;
-    int *smax;       // [2 parities][2 species]
-    int *last_max;   // [2] max of the last bookkept step
-};
-
-// shared-memory layout of the pipelined kernel: 4 world buffers | 2n agent states | per slot: 3n ints + smax[4] + last_max[2]
-__device__ __forceinline__ PipeSlot dw_pipe_slot(unsigned char *smem_raw, int n, int s) {
-    PipeSlot W;
-    uint32_t *base = reinterpret_cast<uint32_t *>(smem_raw);
-    W.buf[0] = base + (2 * s) * 4096;
-    W.buf[1] = base + (2 * s + 1) * 4096;
-    double *st = reinterpret_cast<double *>(base + 4 * 4096);
-    W.S.st = st + s * n;
-    int *ip = reinterpret_cast<int *>(st + 2 * n) + s * (3 * n + 6);
-    W.S.xy = ip; W.S.act = ip + n; W.S.ada = ip + 2 * n;
-    W.smax = ip + 3 * n; W.last_max = ip + 3 * n + 4;
-    return W;
-}
-
-__device__ __forceinline__ void dw_pipe_bookkeep(const FusedArgs &A, const PipeSlot &W, int jl, int jg, int n, int lane, int &life) {
-    int *sm = W.smax + 2 * (jl & 1);
-    const int m0 = sm[0], m1 = sm[1];
-    __syncwarp();
-    if (lane == 0) {
-        if (max(m0, m1) > 5) { life += 1; atomicAdd(A.alive + jg, 1u); }     // grid_done = max(grid[:,1:3]) <= 0.005
-        W.last_max[0] = m0; W.last_max[1] = m1;
-        sm[0] = 0; sm[1] = 0;
-    }
-    for (int i = lane; i < n; i += 32) W.S.ada[i] += (W.S.st[i] < 0.1) ? 0 : 1;
-    __syncwarp();
-}
-
-// agent-warp side of one pipeline slot (kept out of line: it must not inflate the register budget of the stencil path)
-__device__ __noinline__ int dw_pipe_agent_slot(const FusedArgs *Ap, unsigned char *smem_raw, int s, int jl, int j0, int kc, int w,
-                                               int lane) {
-    const FusedArgs &A = *Ap;
-    const int n = A.P.n_agents;
-    const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
-    int add = 0;
-    if (jl >= 1) dw_pipe_bookkeep(A, W, jl - 1, j0 + jl - 1, n, lane, add);
-    if (jl < kc && n > 0) dw_agents_phase(A, j0 + jl, w, W.buf[jl & 1], W.S, lane);
-    return add;
-}
-
-// load / store of one work item's two worlds (L2 reads: another SM may have written them)
-__device__ __noinline__ void dw_pipe_load(const FusedArgs *Ap, unsigned char *smem_raw, int wA, bool hasB, int tid) {
-    const FusedArgs &A = *Ap;
-    const int n = A.P.n_agents;
-    for (int i = tid; i < 2048; i += DW_PIPE_THREADS) {
-        const int s = i >> 10, k = i & 1023;
-        if (s == 0 || hasB)
-            reinterpret_cast<uint4 *>(dw_pipe_slot(smem_raw, n, s).buf[0])[k] =
-                __ldcg(reinterpret_cast<const uint4 *>(A.lat + (size_t)(wA + s) * 4096) + k);
-    }
-    for (int i = tid; i < 2 * n; i += DW_PIPE_THREADS) {
-        const int s = i >= n, k = i - s * n;
-        if (s == 0 || hasB) {
-            const size_t g = (size_t)(wA + s) * n + k;
-            const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
-            W.S.st[k] = __ldcg(A.agent_state + g);
-            W.S.xy[k] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
-            W.S.ada[k] = 0;
-        }
-    }
-    if (tid < 12) dw_pipe_slot(smem_raw, n, tid / 6).smax[tid % 6] = 0;
-}
-
-__device__ __noinline__ void dw_pipe_store(const FusedArgs *Ap, unsigned char *smem_raw, int wA, bool hasB, int kc, int tid) {
-    const FusedArgs &A = *Ap;
-    const int n = A.P.n_agents;
-    for (int i = tid; i < 2048; i += DW_PIPE_THREADS) {
-        const int s = i >> 10, k = i & 1023;
-        if (s == 0 || hasB)
-            reinterpret_cast<uint4 *>(A.lat + (size_t)(wA + s) * 4096)[k] =
-                reinterpret_cast<const uint4 *>(dw_pipe_slot(smem_raw, n, s).buf[kc & 1])[k];
-    }
-    for (int i = tid; i < 2 * n; i += DW_PIPE_THREADS) {
-        const int s = i >= n, k = i - s * n;
-        if (s == 0 || hasB) {
-            const size_t g = (size_t)(wA + s) * n + k;
-            const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
-            const double r = W.S.st[k];
-            A.agent_state[g] = r;
-            A.agent_xy[2 * g] = W.S.xy[k] & 0xffff;
-            A.agent_xy[2 * g + 1] = W.S.xy[k] >> 16;
-            A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + W.S.ada[k];
-            A.reward[g] = r;
-            A.done[g] = r < 0.1;
-        }
-    }
-    if (n == 0 && tid < 4) {
-        const int s = tid >> 1, ch = tid & 1;
-        if (s == 0 || hasB) {
-            const int m = dw_pipe_slot(smem_raw, n, s).last_max[ch];
-            A.reward[2 * (wA + s) + ch] = m > 0 ? 1.0 : 0.0;
-            A.done[2 * (wA + s) + ch] = m > 0 ? 0 : 1;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(DW_PIPE_THREADS, DW_PIPE_MIN_BLOCKS) k_fused_n64_pipe(const __grid_constant__ FusedArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = A.P.n_agents;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_agent = warp == 8;
-    const int tx = tid & 15, r0 = ((tid >> 4) & 15) * 4;
-    volatile int *s_item = reinterpret_cast<volatile int *>(dw_pipe_slot(smem_raw, n, 1).last_max + 2);   // work item broadcast
-    const int n_items = A.n_pairs * A.n_chunks;
-
-    for (;;) {
-        if (tid == 0) *s_item = (int)atomicAdd(A.queue, 1u);
-        __syncthreads();
-        const int t = *s_item;
-        if (t >= n_items) break;
-        const int c = t / A.n_pairs, p = t - c * A.n_pairs;
-        if (tid == 0) {
-            while (atomicAdd(A.pair_done + p, 0u) < (unsigned)c) __nanosleep(200);
-            __threadfence();
-        }
-        __syncthreads();
-        const int wA = 2 * p;
-        const bool hasB = wA + 1 < A.P.B;
-        const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
-        dw_pipe_load(&A, smem_raw, wA, hasB, tid);
-        __syncthreads();
-
-        int life0 = 0, life1 = 0;
-#pragma unroll 1
-        for (int slot = 0; slot <= 2 * kc; ++slot) {
-            if (!is_agent) {
-                const int s = (slot - 1) & 1, jl = (slot - 1) >> 1, jg = j0 + jl;
-                if (slot >= 1 && (s == 0 || hasB)) {
-                    const PipeSlot W = dw_pipe_slot(smem_raw, n, s);
-                    const uint32_t *cb = W.buf[jl & 1];
-                    uint32_t *nb = W.buf[(jl + 1) & 1];
-                    if (jg == A.K - 1) {        // post-graze state of the launch's last step (lazy materialisation)
-                        uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)(wA + s) * 4096);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) gp[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
-                    }
-                    const uint32_t mx = dw_tile_step64(A, jg, cb, nb, r0, tx, lane);
-                    const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
-                    int *sm = W.smax + 2 * (jl & 1);
-                    if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
-                }
-            } else {
-                const int s = slot & 1, jl = slot >> 1;
-                if (s == 0 || hasB) {
-                    const int add = dw_pipe_agent_slot(&A, smem_raw, s, jl, j0, kc, wA + s, lane);
-                    if (s == 0) life0 += add; else life1 += add;
-                }
-            }
-            __syncthreads();
-        }
-        if (is_agent) {
-            if (hasB) life1 += dw_pipe_agent_slot(&A, smem_raw, 1, kc, j0, kc, wA + 1, lane);   // bookkeeping of B's last step
-            if (lane == 0) {
-                A.done_at[wA] = __ldcg(A.done_at + wA) + life0;
-                if (hasB) A.done_at[wA + 1] = __ldcg(A.done_at + wA + 1) + life1;
-            }
-        }
-        __syncthreads();
-        dw_pipe_store(&A, smem_raw, wA, hasB, kc, tid);
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicExch(A.pair_done + p, (unsigned)(c + 1));
         }
     }
 }

@@ -76,10 +76,6 @@ static int grid_to_lattice(dw_handle *h, bool *converted) {
     return DW_OK;
 }
 
-static size_t pipe_smem_bytes(int n) {
-    return 4 * 4096 * sizeof(uint32_t) + 2 * (size_t)n * sizeof(double) + (6 * (size_t)n + 12 + 4) * sizeof(int);
-}
-
 static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive) {
     if (K > DW_FUSED_MAX_STEPS) return dw_fail(h, DW_E_INVALID, "launch_fused", "K too large");
     FusedArgs A{};
@@ -107,46 +103,36 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     A.seed = seed; A.step0 = (unsigned int)h->clk.step_count; A.world0 = h->world0;
     A.K = K; A.policy = policy;
     A.slow_count = h->slow_count;
-    // kernel selection: 64x64 worlds run the persistent kernel (dynamic work queue); DW_FUSED_IMPL overrides for
-    // experiments: "persist" (default) | "pipe" (2 worlds per CTA + agent warp) | "simple" (one CTA per world) | "generic"
+    // kernel selection: 64x64 worlds with <= 32 agents run the persistent kernel (dynamic work queue); DW_FUSED_IMPL
+    // overrides for experiments: "persist" (default) | "simple" (one CTA per world) | "generic" (any N)
     const char *impl = getenv("DW_FUSED_IMPL");
     const bool n64 = h->cfg.dim == 64 && !(impl && !strcmp(impl, "generic"));
-    const bool pipe = n64 && impl && !strcmp(impl, "pipe") && h->cfg.n_agents <= 256;
-    const bool persist = n64 && !pipe && !(impl && !strcmp(impl, "simple")) && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
+    const bool persist = n64 && !(impl && !strcmp(impl, "simple")) && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
     if (h->profiling) DW_CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
-    if (pipe || persist) {
-        const size_t smem = pipe ? pipe_smem_bytes(h->cfg.n_agents) : 0;      // the persistent kernel's smem is static
-        const int threads = pipe ? DW_PIPE_THREADS : 256;
-        int &blocks = pipe ? h->pipe_blocks : h->persist_blocks;
-        if (!blocks) {
+    if (persist) {
+        if (!h->persist_blocks) {
             int per_sm = 0, sms = 0;
-            if (pipe) {
-                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_pipe, threads, smem));
-            } else {
-                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                    cudaSharedmemCarveoutMaxShared));
-                DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist, threads, smem));
-            }
+            DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                cudaSharedmemCarveoutMaxShared));
+            DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist, 256, 0));
             DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
             if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "persistent kernel does not fit on an SM");
-            blocks = per_sm * sms;
+            h->persist_blocks = per_sm * sms;
         }
-        const char *kc_env = getenv("DW_PIPE_KC");
+        const char *kc_env = getenv("DW_PERSIST_KC");
         A.Kc = kc_env ? atoi(kc_env) : 16;
         if (A.Kc < 1) A.Kc = 1;
-        A.n_pairs = pipe ? (h->cfg.batch + 1) / 2 : h->cfg.batch;
+        A.n_pairs = h->cfg.batch;
         A.n_chunks = (K + A.Kc - 1) / A.Kc;
-        rc = dev_alloc(h, &h->pipe_sync, (size_t)h->cfg.batch + 1);
+        rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
         if (rc) return rc;
-        DW_CUDA_TRY(h, cudaMemsetAsync(h->pipe_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
-        A.queue = h->pipe_sync;
-        A.pair_done = h->pipe_sync + 1;
+        DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
+        A.queue = h->persist_sync;
+        A.pair_done = h->persist_sync + 1;
         A.lat = h->lat[h->lcur];                      // in place
         const long long items = (long long)A.n_pairs * A.n_chunks;
-        const int grid = (int)(items < blocks ? items : blocks);
-        if (pipe) k_fused_n64_pipe<<<grid, threads, smem, h->stream>>>(A);
-        else k_fused_n64_persist<<<grid, threads, smem, h->stream>>>(A);
+        const int grid = (int)(items < h->persist_blocks ? items : h->persist_blocks);
+        k_fused_n64_persist<<<grid, 256, 0, h->stream>>>(A);
     } else {
         const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
         if (smem > 48 * 1024 && !h->fused_attr_set) {
