@@ -87,6 +87,23 @@ int dwt_end_chunk(dwt_handle *h, int32_t K, int32_t *first_all_done);
 int dwt_reset_lifespans(dwt_handle *h);
 int dwt_get_lifespans(dwt_handle *h, int64_t *done_at /*[1]*/, int64_t *agents_done_at /*[n]*/);
 
+/* ---- peer-memory mode: one process per GPU, no collective on the step path -----------------------------------------
+ * Every rank maps every other rank's exchange vector, barrier flags and lattice buffers (CUDA IPC over NVLink/NVSwitch).
+ * The owner band of an agent / the winner of a graze stores its result straight into ALL ranks' exchange vectors
+ * (exactly one writer per entry: nothing to reduce), a band pushes its edge rows into the neighbours' ghost rows, and
+ * ranks meet at device-side flag barriers. dwt_step_p2p is one env step; every rank calls it in lock-step.
+ * Setup: dwt_ipc_export on every rank -> all-gather the blobs (any transport) -> dwt_ipc_attach. */
+#define DWT_IPC_HANDLE_BYTES 64
+#define DWT_PEER_BUFFERS 4          /* lattice buffer 0, lattice buffer 1, exchange vector, barrier flags */
+int dwt_ipc_export(dwt_handle *h, void *handles /* [DWT_PEER_BUFFERS][DWT_IPC_HANDLE_BYTES] */);
+int dwt_ipc_attach(dwt_handle *h, int32_t rank, int32_t n_ranks, const void *all_handles /* [n_ranks][4][64] */);
+/* same-process variant (several bands of one process, tests): raw device pointers [n_ranks][DWT_PEER_BUFFERS] */
+int dwt_get_peer_buffers(dwt_handle *h, void **out /* [DWT_PEER_BUFFERS] */);
+int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, void *const *table);
+int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions /* [n] or NULL */, uint64_t seed);
+int dwt_flush_p2p(dwt_handle *h);                       /* finish the agents of the last step */
+int dwt_peer_status(dwt_handle *h, int32_t *timed_out); /* 1 if a barrier gave up waiting for a peer */
+
 /* getters (synchronise) */
 int dwt_get_agents(dwt_handle *h, int64_t *agent_indices, double *agent_states);
 int dwt_get_reward_done(dwt_handle *h, double *reward, uint8_t *done);          /* [n] */

@@ -45,6 +45,8 @@ class ThreadComm:
         sh = self.sh
         sh.slots[self.rank] = t
         sh.barrier.wait()
+        if t.is_cuda:                # bands of one process may run on different streams: order them device-wide (test only)
+            torch.cuda.synchronize()
         stacked = torch.stack(list(sh.slots))
         out = stacked.sum(0) if op == "sum" else stacked.max(0).values
         sh.barrier.wait()            # everyone has read every slot

@@ -79,6 +79,46 @@ def test_bands_on_one_gpu_match_oracle(bands, policy):
     _compare(worlds, ref, done_at, ada)
 
 
+@pytest.mark.parametrize("bands,policy", [(2, "greedy"), (4, "antigreedy"), (4, "replay"), (2, "none")])
+def test_peer_memory_mode_bands_on_one_gpu(bands, policy):
+    """dwt_step_p2p: owners publish decisions / gains into every band's exchange vector, edge rows are pushed into the
+    neighbours' ghost rows, bands meet at device-side flag barriers. Here the 'peers' are bands of one process on one GPU,
+    each on its own stream (the IPC variant of the same code path runs in tools/banded_nccl_check.py)."""
+    import torch
+    N, n, steps = 256, 200, 30
+    light, dark, ai, st = make_state(N, n, seed=17, clustered=True)
+    ai[n // 2:, 0] = (ai[n // 2:, 0] + N // bands) % N
+    shared = ThreadComm.Shared(bands)
+    worlds = [_world(N, n, rank=r, world_size=bands, comm=ThreadComm(r, bands, shared), mode="p2p") for r in range(bands)]
+    streams = [torch.cuda.Stream() for _ in range(bands)]
+    tables = [w.band.peer_buffers() for w in worlds]
+    for r, w in enumerate(worlds):
+        w.band.set_stream(streams[r].cuda_stream)
+        w.band.attach_peers(r, tables)
+    ref = full_oracle(worlds[0], light, dark, ai, st)
+    acts = np.random.RandomState(4).randint(9, size=(steps, n)) if policy == "replay" else None
+    out = {}
+
+    def go(w):
+        with torch.cuda.stream(streams[w.rank]):
+            w.load_state(light, dark, ai, st)
+            w.run(steps, policy, actions=acts, chunk=8)
+            out[w.rank] = (w.local_covers(), w.agents(), w.lifespans(), w.local_grid(), w.band.peer_timed_out())
+
+    run_threads(worlds, go)
+    _, done_at, ada = ref.run(steps, policy, actions=None if acts is None else acts[:, None, :])
+    assert not any(out[r][4] for r in range(bands)), "a peer barrier timed out"
+    covers = np.concatenate([out[r][0] for r in range(bands)], axis=1)
+    np.testing.assert_array_equal(covers[0], ref.grid[0, 1])
+    np.testing.assert_array_equal(covers[1], ref.grid[0, 2])
+    np.testing.assert_array_equal(np.concatenate([out[r][3] for r in range(bands)], axis=1), ref.grid[0])
+    for r in range(bands):
+        np.testing.assert_array_equal(out[r][1][0], ref.agent_indices[0])
+        np.testing.assert_array_equal(out[r][1][1], ref.agent_states[0, :, 0])
+        assert out[r][2][0] == int(done_at[0])
+        np.testing.assert_array_equal(out[r][2][1], ada[0, :, 0])
+
+
 def test_device_reset_is_banding_invariant_and_fast_path_is_used():
     """dwt_init_random keys the RNG by global cell index: 1 band and 2 bands draw and evolve the same world."""
     N, n, steps = 128, 50, 25

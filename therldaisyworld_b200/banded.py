@@ -15,6 +15,11 @@ NCCL over NVLink on GPUs, gloo in the CPU tests -- plumbing only, the data path 
   * per chunk of steps: MAX all-reduce of the per-step cover maxima (lifespan bookkeeping, ``grid_done``).
 
 ``world_size == 1`` needs none of them (``dwt_halo_wrap`` closes the torus locally).
+
+``mode="p2p"`` (GPUs of one node) takes the collectives off the step path altogether: the ranks map each other's
+exchange vectors, barrier flags and lattice buffers through CUDA IPC once, and a step is ``dwt_step_p2p`` -- the owner of
+an agent / the winner of a graze stores straight into every rank's exchange vector over NVLink, edge rows are pushed
+into the neighbours' ghost rows, ranks meet at device-side flag barriers.  Only the per-chunk MAX all-reduce remains.
 """
 import ctypes as C
 
@@ -166,6 +171,44 @@ class DeviceBand:
         self.stencil(2)
         main.wait_stream(self._side)
 
+    # ---- peer-memory mode
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.dwt_set_stream(self._h, C.c_void_p(int(cuda_stream))), "dwt_set_stream")
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(4 * 64)
+        self._check(self._lib.dwt_ipc_export(self._h, buf), "dwt_ipc_export")
+        return bytes(buf.raw)
+
+    def ipc_attach(self, rank, blobs):
+        blob = b"".join(blobs)
+        self._check(self._lib.dwt_ipc_attach(self._h, int(rank), len(blobs), C.create_string_buffer(blob, len(blob))), "dwt_ipc_attach")
+
+    def peer_buffers(self):
+        out = (C.c_void_p * 4)()
+        self._check(self._lib.dwt_get_peer_buffers(self._h, out), "dwt_get_peer_buffers")
+        return [int(v or 0) for v in out]
+
+    def attach_peers(self, rank, tables):
+        """Same-process peers: tables[r] = peer_buffers() of rank r."""
+        flat = (C.c_void_p * (4 * len(tables)))(*[p for t in tables for p in t])
+        self._check(self._lib.dwt_attach_peers(self._h, int(rank), len(tables), flat), "dwt_attach_peers")
+
+    def step_p2p(self, policy, actions_step=None, seed=0):
+        a = None
+        if policy == "replay":
+            a = np.ascontiguousarray(np.asarray(actions_step).reshape(self.n), dtype=np.int8)
+        self._check(self._lib.dwt_step_p2p(self._h, DW_POLICY[policy], None if a is None else a.ctypes.data_as(C.POINTER(C.c_int8)),
+                                           C.c_uint64(seed)), "dwt_step_p2p")
+
+    def flush_p2p(self):
+        self._check(self._lib.dwt_flush_p2p(self._h), "dwt_flush_p2p")
+
+    def peer_timed_out(self):
+        v = C.c_int32(0)
+        self._check(self._lib.dwt_peer_status(self._h, C.byref(v)), "dwt_peer_status")
+        return bool(v.value)
+
     def run_local(self, K, policy, actions=None, seed=0):
         """K steps without any exchange (a band that is the whole torus)."""
         a = None
@@ -262,7 +305,7 @@ class BandedDaisyWorld:
     oracle-backed stand-in in the CPU tests."""
 
     def __init__(self, grid_dimension, n_agents, rank=0, world_size=1, group=None, device=0, band_factory=None, comm=None,
-                 **kwargs):
+                 mode="nccl", **kwargs):
         set_default_attributes(self, grid_dimension=grid_dimension, n_agents=n_agents, **kwargs)
         set_default_kernels(self)
         self.batch_size = 1
@@ -278,6 +321,12 @@ class BandedDaisyWorld:
         self._pending = 0          # steps recorded since the last end_chunk
         self._gain_pending = False # multi-rank: gains of the last step not yet summed / applied
         self.first_done_step = None
+        self.mode = mode if self.world_size > 1 else "local"
+        if self.mode == "p2p" and comm is None:
+            # one-off exchange of the CUDA IPC handles (any transport would do; torch.distributed is at hand)
+            blobs = [None] * self.world_size
+            self.comm.dist.all_gather_object(blobs, self.band.ipc_export(), group=group)
+            self.band.ipc_attach(self.rank, blobs)
 
     # ---- reset
     def _reset_clock(self):
@@ -307,6 +356,11 @@ class BandedDaisyWorld:
     # ---- stepping
     def step(self, policy="greedy", actions_step=None, seed=0):
         b, comm = self.band, self.comm
+        if self.mode == "p2p":
+            b.step_p2p(policy, actions_step, seed)
+            self._gain_pending = bool(self.n_agents)
+            self._pending += 1
+            return
         b.decide(policy, actions_step, seed)
         if comm is None:
             b.move_graze()
@@ -331,8 +385,11 @@ class BandedDaisyWorld:
     def _flush(self):
         """Finish the last step's agents (multi-rank: the deferred gain all-reduce)."""
         if self._gain_pending:
-            self.comm.all_reduce_sum(self.band.exch_tensor(gain=True, act=False))
-            self.band.finish_agents()
+            if self.mode == "p2p":
+                self.band.flush_p2p()
+            else:
+                self.comm.all_reduce_sum(self.band.exch_tensor(gain=True, act=False))
+                self.band.finish_agents()
             self._gain_pending = False
 
     def end_chunk(self):

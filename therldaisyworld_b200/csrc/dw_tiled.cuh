@@ -73,13 +73,53 @@ __device__ __forceinline__ int band_col(const BandGeom &G, int y) {
     return y < 0 ? y + G.N : (y >= G.N ? y - G.N : y);
 }
 
+// ---- peer-memory mode (one process per GPU, P2P stores over NVLink / NVSwitch, no NCCL on the step path) --------------
+// Every rank maps every other rank's exchange vector, flag array and lattice buffers (CUDA IPC).  The owner of an agent /
+// the winner of a graze stores its result straight into ALL ranks' exchange vectors (exactly one writer per entry, so
+// nothing has to be reduced), a band pushes its edge rows into the neighbours' ghost rows, and ranks meet at flag
+// barriers (k_peer_barrier) instead of collectives.
+#define DWT_MAX_RANKS 8
+struct PeerTable {
+    double *exch[DWT_MAX_RANKS];           // [gain1 | gain0 | act], n doubles each
+    unsigned int *flags[DWT_MAX_RANKS];    // [DWT_MAX_RANKS] barrier epochs, slot r written by rank r
+    int rank, R, on;                       // on == 0: single-process / NCCL mode (local stores only)
+};
+
+// All ranks meet here: every prior write of this rank (to its own or to peer memory) is visible to a peer that has seen
+// the flag. Spins are bounded (~seconds) so that a missing peer produces an error flag instead of a hung GPU.
+__global__ void k_peer_barrier(PeerTable PT, unsigned int epoch, unsigned int *timed_out) {
+    const int p = threadIdx.x;
+    if (p >= PT.R) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(PT.flags[p] + PT.rank), "r"(epoch) : "memory");
+    const unsigned int *mine = PT.flags[PT.rank] + p;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > 8000000000ll) { *timed_out = 1u; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+// a band's first / last stored row (ghost columns included) -> the neighbours' ghost rows
+__global__ void __launch_bounds__(256) k_band_push_halo(const uint32_t *__restrict__ lat, int R, int pitch, uint32_t *up_ghost_bottom,
+                                                        uint32_t *down_ghost_top) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= pitch) return;
+    up_ghost_bottom[c] = lat[(size_t)pitch + c];
+    down_ghost_top[c] = lat[(size_t)R * pitch + c];
+}
+
 // ---- agents --------------------------------------------------------------------------------------------------------
 // Phase 1: the owner band of each agent decides its action from the pre-move state. act[i] = action + 1 for owned
 // agents, 0 otherwise (the caller sums act over ranks). Policies that do not look at the world (replay, none, random)
 // fill every entry on every rank and need no exchange.
 template <class Cells>
 __global__ void __launch_bounds__(256) k_band_decide(BandGeom G, Cells C, const int32_t *__restrict__ xy, int n, int policy,
-                                                     const int8_t *__restrict__ replay, uint64_t seed, uint32_t step, int n_ranks,
+                                                     const int8_t *__restrict__ replay, uint64_t seed, uint32_t step, PeerTable PT,
                                                      double *__restrict__ act) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -97,7 +137,11 @@ __global__ void __launch_bounds__(256) k_band_decide(BandGeom G, Cells C, const 
         const double food[4] = {C.food(row + band_col(G, y - 1)), C.food(rowm + band_col(G, y)), C.food(rowp + band_col(G, y)),
                                 C.food(row + band_col(G, y + 1))};
         out = (double)(dw_greedy_pick(food, policy == DW_POLICY_GREEDY) + 1);
-    }
+        if (PT.on) {                                     // owner publishes the decision to every rank (act = exch + 2n)
+            for (int p = 0; p < PT.R; ++p) PT.exch[p][2 * (size_t)n + i] = out;
+            return;
+        }
+    } else if (PT.on) return;                            // peer-memory mode: the owner rank writes this entry
     act[i] = out;
 }
 
@@ -133,20 +177,26 @@ __global__ void __launch_bounds__(256) k_band_move_claim(BandGeom G, double agen
 // clear the ghost copy (the owner rank does the eating). gain[i] = food eaten by agent i on THIS rank (0 elsewhere).
 template <class Cells>
 __global__ void __launch_bounds__(256) k_band_graze(BandGeom G, Cells C, const int32_t *__restrict__ xy, int n,
-                                                    const uint8_t *__restrict__ gz, const int *__restrict__ claim, double *__restrict__ gain) {
+                                                    const uint8_t *__restrict__ gz, const int *__restrict__ claim, double *__restrict__ gain,
+                                                    PeerTable PT, int gain_off) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double got = 0.0;
+    bool won = false;
     if (gz[i]) {
         const int x = xy[2 * i], y = xy[2 * i + 1];
         const int lr = band_owned_row(G, x);
         bool clear = true;
         if (lr >= 0) {
-            if (claim[(size_t)lr * G.N + y] == i) got = C.food((size_t)lr * G.pitch + G.c0 + y);
+            if (claim[(size_t)lr * G.N + y] == i) { got = C.food((size_t)lr * G.pitch + G.c0 + y); won = true; }
             else clear = false;                          // a lower-index agent eats here; it also does the clearing
         }
         if (clear)
             band_row_images(G, x, [&](int r) { band_col_images(G, y, [&](int cc) { C.zero((size_t)r * G.pitch + cc); }); });
+    }
+    if (PT.on) {                                         // the winner publishes to every rank; the vectors were zeroed by k_band_finish
+        if (won) for (int p = 0; p < PT.R; ++p) PT.exch[p][(size_t)gain_off + i] = got;
+        return;
     }
     gain[i] = got;
 }
@@ -154,13 +204,15 @@ __global__ void __launch_bounds__(256) k_band_graze(BandGeom G, Cells C, const i
 // Phase 4 (replicated, after the gains were summed over ranks): state += gain, clip, reward/done, lifespan counter;
 // also returns the graze claims of this step to "idle".
 __global__ void __launch_bounds__(256) k_band_finish(BandGeom G, const int32_t *__restrict__ xy, int *claim, double *st, int n,
-                                                     const double *__restrict__ gain, const uint8_t *__restrict__ gz, double *reward,
+                                                     double *gain, int zero_gain, const uint8_t *__restrict__ gz, double *reward,
                                                      uint8_t *done, int64_t *agents_done_at) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = st[i];
+    const double g = gain[i];
+    if (zero_gain) gain[i] = 0.0;                        // peer-memory mode: only winners write, so the vector is re-armed here
     if (gz[i]) {
-        s = s + gain[i];
+        s = s + g;
         const int lr = band_owned_row(G, xy[2 * i]);
         if (lr >= 0) claim[(size_t)lr * G.N + xy[2 * i + 1]] = 0x7fffffff;
     }

@@ -21,8 +21,18 @@ struct dwt_handle {
     double *pl = nullptr, *pd = nullptr;       // fp64 cover planes [(R+2) x N] (off-lattice reset state)
     int *claim = nullptr;                      // [(R+2) x N] graze claims, INT_MAX when idle
     int32_t *agent_xy = nullptr;
-    double *agent_state = nullptr, *exch = nullptr, *reward = nullptr;   // exch: gain[n] then act[n] (one all-reduce covers both)
+    // exch = [gain1 | gain0 | act], n doubles each. gain = gain0 and act are adjacent (one all-reduce covers both in NCCL
+    // mode); peer-memory mode alternates between gain0 and gain1 by step parity.
+    double *agent_state = nullptr, *exch = nullptr, *reward = nullptr;
     double *act = nullptr, *gain = nullptr;
+    // peer-memory mode
+    PeerTable pt{};
+    unsigned int *flags = nullptr, *timed_out = nullptr;
+    unsigned int epoch = 0;
+    uint32_t *peer_lat[2][DWT_MAX_RANKS] = {};
+    std::vector<void *> ipc_opened;
+    int gain_parity = 0, pending_parity = 0;
+    bool p2p_gain_pending = false;
     bool step_open = false;      // dwt_stencil(part 1) done, part 2 pending
     uint8_t *gz = nullptr, *done = nullptr;
     int8_t *replay = nullptr;
@@ -98,13 +108,16 @@ extern "C" int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int3
     const size_t n = h->n ? h->n : 1, padded = (size_t)(rows + 2) * h->pitch, planes = (size_t)(rows + 2) * N;
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess && cudaMemset(*p, 0, bytes) == cudaSuccess; };
     bool ok = alloc((void **)&h->lat[0], padded * 4) && alloc((void **)&h->lat[1], padded * 4) && alloc((void **)&h->claim, planes * 4) &&
-              alloc((void **)&h->agent_xy, n * 8) && alloc((void **)&h->agent_state, n * 8) && alloc((void **)&h->exch, 2 * n * 8) &&
+              alloc((void **)&h->agent_xy, n * 8) && alloc((void **)&h->agent_state, n * 8) && alloc((void **)&h->exch, 3 * n * 8) &&
+              alloc((void **)&h->flags, (DWT_MAX_RANKS + 1) * 4) &&
               alloc((void **)&h->reward, n * 8) && alloc((void **)&h->gz, n) && alloc((void **)&h->done, n) &&
               alloc((void **)&h->agents_done_at, n * 8) && alloc((void **)&h->stepmax, (size_t)DW_FUSED_MAX_STEPS * 2 * 4) &&
-              alloc((void **)&h->slow_count, 4);
+              alloc((void **)&h->slow_count, 4) && alloc((void **)&h->replay, n);
+    if (ok) h->replay_cap = n;
     if (ok) ok = cudaMemset(h->claim, 0x7f, planes * 4) == cudaSuccess;       // 0x7f7f7f7f: "idle" (> any agent index)
-    h->gain = h->exch;
-    h->act = h->exch ? h->exch + n : nullptr;
+    h->gain = h->exch ? h->exch + n : nullptr;
+    h->act = h->exch ? h->exch + 2 * n : nullptr;
+    h->timed_out = h->flags ? h->flags + DWT_MAX_RANKS : nullptr;
     if (!ok) {
         g_dwt_create_error = std::string("dwt_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         dwt_destroy(h);
@@ -122,7 +135,8 @@ extern "C" int dwt_destroy(dwt_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->agent_xy, h->agent_state, h->exch, h->reward, h->gz,
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->agent_xy, h->agent_state, h->exch, h->flags, h->reward, h->gz,
                     h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
@@ -223,10 +237,10 @@ extern "C" int dwt_decide(dwt_handle *h, int32_t policy, const int8_t *actions, 
     const uint32_t step = (uint32_t)h->clk.step_count;
     if (h->on_lattice)
         k_band_decide<LatCells><<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), LatCells{h->lat[h->cur]}, h->agent_xy, h->n, policy,
-                                                                          h->replay, seed, step, h->n_ranks, h->act);
+                                                                          h->replay, seed, step, h->pt, h->act);
     else
         k_band_decide<PlaneCells><<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_planes(h), PlaneCells{h->pl, h->pd}, h->agent_xy, h->n,
-                                                                            policy, h->replay, seed, step, h->n_ranks, h->act);
+                                                                            policy, h->replay, seed, step, h->pt, h->act);
     DWT_LAUNCHED(h);
     return DW_OK;
 }
@@ -240,9 +254,11 @@ extern "C" int dwt_move_graze(dwt_handle *h) {
     k_band_move_claim<<<nb, 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act, h->claim, h->gz);
     DWT_LAUNCHED(h);
     if (h->on_lattice)
-        k_band_graze<LatCells><<<nb, 256, 0, h->stream>>>(G, LatCells{h->lat[h->cur]}, h->agent_xy, h->n, h->gz, h->claim, h->gain);
+        k_band_graze<LatCells><<<nb, 256, 0, h->stream>>>(G, LatCells{h->lat[h->cur]}, h->agent_xy, h->n, h->gz, h->claim, h->gain, h->pt,
+                                                           h->gain_parity ? 0 : h->n);
     else
-        k_band_graze<PlaneCells><<<nb, 256, 0, h->stream>>>(G, PlaneCells{h->pl, h->pd}, h->agent_xy, h->n, h->gz, h->claim, h->gain);
+        k_band_graze<PlaneCells><<<nb, 256, 0, h->stream>>>(G, PlaneCells{h->pl, h->pd}, h->agent_xy, h->n, h->gz, h->claim, h->gain, h->pt,
+                                                             h->gain_parity ? 0 : h->n);
     DWT_LAUNCHED(h);
     return DW_OK;
 }
@@ -251,7 +267,8 @@ extern "C" int dwt_finish_agents(dwt_handle *h) {
     if (!h) return DW_E_INVALID;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->n) return DW_OK;
-    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), h->agent_xy, h->claim, h->agent_state, h->n, h->gain, h->gz,
+    double *gain = h->pt.on ? (h->pending_parity ? h->exch : h->exch + h->n) : h->gain;
+    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), h->agent_xy, h->claim, h->agent_state, h->n, gain, h->pt.on, h->gz,
                                                            h->reward, h->done, h->agents_done_at);
     DWT_LAUNCHED(h);
     return DW_OK;
@@ -465,5 +482,147 @@ extern "C" int dwt_debug_slow_count(dwt_handle *h, uint64_t *count) {
     DWT_TRY(h, cudaMemcpyAsync(&c, h->slow_count, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     DWT_TRY(h, cudaStreamSynchronize(h->stream));
     *count = c;
+    return DW_OK;
+}
+
+// ---- peer-memory mode ----------------------------------------------------------------------------------------------------
+enum { DWT_PEER_LAT0 = 0, DWT_PEER_LAT1 = 1, DWT_PEER_EXCH = 2, DWT_PEER_FLAGS = 3 };
+
+extern "C" int dwt_get_peer_buffers(dwt_handle *h, void **out) {
+    if (!h || !out) return DW_E_INVALID;
+    out[DWT_PEER_LAT0] = h->lat[0]; out[DWT_PEER_LAT1] = h->lat[1]; out[DWT_PEER_EXCH] = h->exch; out[DWT_PEER_FLAGS] = h->flags;
+    return DW_OK;
+}
+
+extern "C" int dwt_ipc_export(dwt_handle *h, void *handles) {
+    if (!h || !handles) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    void *bufs[DWT_PEER_BUFFERS];
+    dwt_get_peer_buffers(h, bufs);
+    for (int k = 0; k < DWT_PEER_BUFFERS; ++k) {
+        cudaIpcMemHandle_t m;
+        DWT_TRY(h, cudaIpcGetMemHandle(&m, bufs[k]));
+        static_assert(sizeof(m) == DWT_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+        memcpy((unsigned char *)handles + (size_t)k * DWT_IPC_HANDLE_BYTES, &m, sizeof(m));
+    }
+    return DW_OK;
+}
+
+// table: [n_ranks][DWT_PEER_BUFFERS] device pointers valid in THIS process (own entries may be NULL: the handle's own
+// buffers are used for its rank)
+extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, void *const *table) {
+    if (!h || !table || n_ranks < 2 || n_ranks > DWT_MAX_RANKS || rank < 0 || rank >= n_ranks || n_ranks != h->n_ranks)
+        return dwt_fail(h, DW_E_INVALID, "dwt_attach_peers", "2 <= n_ranks <= 8 ranks, matching dwt_create");
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    void *own[DWT_PEER_BUFFERS];
+    dwt_get_peer_buffers(h, own);
+    PeerTable T{};
+    T.rank = rank; T.R = n_ranks; T.on = 1;
+    for (int r = 0; r < n_ranks; ++r) {
+        void *const *row = table + (size_t)r * DWT_PEER_BUFFERS;
+        auto pick = [&](int k) { return r == rank ? own[k] : row[k]; };
+        if (!pick(DWT_PEER_LAT0) || !pick(DWT_PEER_LAT1) || !pick(DWT_PEER_EXCH) || !pick(DWT_PEER_FLAGS))
+            return dwt_fail(h, DW_E_INVALID, "dwt_attach_peers", "missing peer pointer");
+        h->peer_lat[0][r] = (uint32_t *)pick(DWT_PEER_LAT0);
+        h->peer_lat[1][r] = (uint32_t *)pick(DWT_PEER_LAT1);
+        T.exch[r] = (double *)pick(DWT_PEER_EXCH);
+        T.flags[r] = (unsigned int *)pick(DWT_PEER_FLAGS);
+    }
+    // Force-load every kernel of the step now: with lazy module loading the first launch of a kernel can wait for the
+    // device to drain, which never happens while a peer band of the same process spins in a barrier waiting for us.
+    {
+        cudaFuncAttributes fa;
+        const void *ks[] = {(const void *)k_band_decide<LatCells>, (const void *)k_band_decide<PlaneCells>, (const void *)k_band_move_claim,
+                            (const void *)k_band_graze<LatCells>, (const void *)k_band_graze<PlaneCells>, (const void *)k_band_finish,
+                            (const void *)k_band_first_step, (const void *)k_tiled_step, (const void *)k_band_push_halo,
+                            (const void *)k_peer_barrier, (const void *)k_band_covers, (const void *)k_band_materialise<PreLattice>,
+                            (const void *)k_band_materialise<PrePlanes>, (const void *)k_band_stamp_claim, (const void *)k_band_stamp_write,
+                            (const void *)k_band_ghost_rows_wrap, (const void *)k_band_init_random};
+        for (const void *k : ks) DWT_TRY(h, cudaFuncGetAttributes(&fa, k));
+    }
+    DWT_TRY(h, cudaMemsetAsync(h->flags, 0, (DWT_MAX_RANKS + 1) * 4, h->stream));
+    DWT_TRY(h, cudaMemsetAsync(h->exch, 0, (size_t)3 * (h->n ? h->n : 1) * 8, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    h->pt = T;
+    h->epoch = 0;
+    h->gain_parity = 0;
+    h->p2p_gain_pending = false;
+    return DW_OK;
+}
+
+extern "C" int dwt_ipc_attach(dwt_handle *h, int32_t rank, int32_t n_ranks, const void *all_handles) {
+    if (!h || !all_handles || n_ranks < 2 || n_ranks > DWT_MAX_RANKS || rank < 0 || rank >= n_ranks) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    std::vector<void *> table((size_t)n_ranks * DWT_PEER_BUFFERS, nullptr);
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) continue;
+        for (int k = 0; k < DWT_PEER_BUFFERS; ++k) {
+            cudaIpcMemHandle_t m;
+            memcpy(&m, (const unsigned char *)all_handles + ((size_t)r * DWT_PEER_BUFFERS + k) * DWT_IPC_HANDLE_BYTES, sizeof(m));
+            void *p = nullptr;
+            DWT_TRY(h, cudaIpcOpenMemHandle(&p, m, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(p);
+            table[(size_t)r * DWT_PEER_BUFFERS + k] = p;
+        }
+    }
+    return dwt_attach_peers(h, rank, n_ranks, table.data());
+}
+
+static int dwt_barrier(dwt_handle *h) {
+    h->epoch += 1;
+    k_peer_barrier<<<1, 32, 0, h->stream>>>(h->pt, h->epoch, h->timed_out);
+    DWT_LAUNCHED(h);
+    return DW_OK;
+}
+
+// One env step of a band in peer-memory mode: no collective, no host synchronisation. Every rank must call it the same
+// number of times with the same policy. The agents of the step are finished (state += gain, reward/done) at the start of
+// the next step or by dwt_flush_p2p.
+extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed) {
+    if (!h) return DW_E_INVALID;
+    if (!h->pt.on) return dwt_fail(h, DW_E_STATE, "dwt_step_p2p", "attach the peers first (dwt_ipc_attach / dwt_attach_peers)");
+    int rc = DW_OK;
+    if (h->n) {
+        rc = dwt_decide(h, policy, actions, seed);
+        if (rc) return rc;
+        // decisions that read the world were published by the owner ranks: meet before anyone moves
+        if (policy == DW_POLICY_GREEDY || policy == DW_POLICY_ANTIGREEDY) { rc = dwt_barrier(h); if (rc) return rc; }
+        if (h->p2p_gain_pending) {           // gains of the previous step are complete since its closing barrier
+            rc = dwt_finish_agents(h);
+            if (rc) return rc;
+        }
+        rc = dwt_move_graze(h);
+        if (rc) return rc;
+        h->p2p_gain_pending = true;
+        h->pending_parity = h->gain_parity;
+        h->gain_parity ^= 1;
+    }
+    rc = dwt_stencil(h, 0);
+    if (rc) return rc;
+    const int up = (h->pt.rank + h->pt.R - 1) % h->pt.R, down = (h->pt.rank + 1) % h->pt.R;
+    k_band_push_halo<<<dwt_blocks(h->pitch), 256, 0, h->stream>>>(h->lat[h->cur], h->R, h->pitch,
+                                                                  h->peer_lat[h->cur][up] + (size_t)(h->R + 1) * h->pitch,
+                                                                  h->peer_lat[h->cur][down]);
+    DWT_LAUNCHED(h);
+    return dwt_barrier(h);
+}
+
+extern "C" int dwt_flush_p2p(dwt_handle *h) {
+    if (!h) return DW_E_INVALID;
+    if (h->pt.on && h->p2p_gain_pending) {
+        int rc = dwt_finish_agents(h);
+        if (rc) return rc;
+        h->p2p_gain_pending = false;
+    }
+    return DW_OK;
+}
+
+extern "C" int dwt_peer_status(dwt_handle *h, int32_t *timed_out) {
+    if (!h || !timed_out) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    unsigned int v = 0;
+    DWT_TRY(h, cudaMemcpyAsync(&v, h->timed_out, 4, cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    *timed_out = (int32_t)v;
     return DW_OK;
 }

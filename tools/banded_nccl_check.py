@@ -1,5 +1,6 @@
-"""torchrun --nproc-per-node R tools/banded_nccl_check.py : the row-banded giant world over R GPUs with NCCL.
-(1) parity at N=256*R/2.. against the full-torus C oracle (rank 0 gathers the bands); (2) timing at N=16384."""
+"""torchrun --nproc-per-node R tools/banded_nccl_check.py : the row-banded giant world over R GPUs, in both exchange modes
+("nccl": torch.distributed collectives; "p2p": CUDA-IPC peer memory + device-side flag barriers, no collective per step).
+(1) parity at N = 128 R against the full-torus C oracle (rank 0 gathers the bands); (2) timing at N = 16384."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -22,10 +23,10 @@ def gather_rows(x):
 from band_helpers import full_oracle, make_state
 N, n, steps = 64 * world * 2, 150, 40
 failed = False
-for policy in ("none", "replay", "greedy"):
+for mode, policy in [(m, p) for m in ("nccl", "p2p") for p in ("none", "replay", "greedy")]:
     light, dark, ai, st = make_state(N, n, seed=9, clustered=True)
     ai[n // 2:, 0] = (ai[n // 2:, 0] + N // world) % N
-    w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local)
+    w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local, mode=mode)
     w.load_state(light, dark, ai, st)
     ref = full_oracle(w, light, dark, ai, st) if rank == 0 else None       # before the run: takes the clock from w
     acts = np.random.RandomState(2).randint(9, size=(steps, n)) if policy == "replay" else None
@@ -39,7 +40,7 @@ for policy in ("none", "replay", "greedy"):
                   "state": np.array_equal(w.agents()[1], ref.agent_states[0, :, 0]), "done_at": w.lifespans()[0] == int(done_at[0]),
                   "agents_done_at": np.array_equal(w.lifespans()[1], ada[0, :, 0])}
         ok = all(checks.values())
-        print(f"PARITY N={N} ranks={world} {policy}: {'OK' if ok else 'MISMATCH'} {checks}", flush=True)
+        print(f"PARITY N={N} ranks={world} {mode} {policy}: {'OK' if ok else 'MISMATCH'} {checks} timed_out={w.band.peer_timed_out()}", flush=True)
         if not ok:
             failed = True
             bad = np.argwhere(covers[0] != ref.grid[0, 1])
@@ -54,23 +55,27 @@ if float(flag[0]) > 0:
     dist.destroy_process_group()
     sys.exit(1)
 N, n, K = 16384, 16384, 64
-w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local)
-w.reset_on_device(seed=1)
-w.run(3, "greedy")
-for policy in ("greedy", "none"):
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(K):
-        w.step(policy)
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    w.end_chunk()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms = float(t[0])
-        print(f"TIMING N={N} n={n} ranks={world} {policy}: {ms / K * 1e3:.1f} us/step (wall {wall / K * 1e6:.1f}) -> {N * N * K / ms / 1e-3:.3e} cell-updates/s", flush=True)
+for mode in ("nccl", "p2p"):
+    w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local, mode=mode)
+    w.reset_on_device(seed=1)
+    w.run(3, "greedy")
+    for policy in ("greedy", "none"):
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            w.step(policy)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        w.end_chunk()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ms = float(t[0])
+            print(f"TIMING N={N} n={n} ranks={world} {mode} {policy}: {ms / K * 1e3:.1f} us/step (wall {wall / K * 1e6:.1f}) -> "
+                  f"{N * N * K / ms / 1e-3:.3e} cell-updates/s timed_out={w.band.peer_timed_out()}", flush=True)
+    del w
+    torch.cuda.empty_cache()
 dist.destroy_process_group()
