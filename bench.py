@@ -28,7 +28,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line (NCCL prints its version banner)
+# stdout carries exactly ONE JSON line: keep a private handle to it and point fd 1 at stderr, so that anything a library
+# prints (NCCL writes its version banner to stdout) cannot end up in front of the line.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import numpy as np  # noqa: E402
 
@@ -95,7 +98,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- helpers
@@ -208,7 +211,23 @@ def giant_grid_bench(rank, world, local, fp64_peak_tflops):
     import torch
     import torch.distributed as dist
     from therldaisyworld_b200.banded import BandedDaisyWorld
-    w = BandedDaisyWorld(GIANT_N, GIANT_N, rank=rank, world_size=world, device=local)
+    mode = "local"
+    if world > 1:
+        # peer-memory mode (CUDA IPC + device-side barriers, no collective per step); NCCL mode if the mapping fails anywhere
+        mode = "p2p"
+        try:
+            w = BandedDaisyWorld(GIANT_N, GIANT_N, rank=rank, world_size=world, device=local, mode="p2p")
+            ok = 1.0
+        except Exception:
+            w, ok = None, 0.0
+        flag = torch.tensor([ok], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag[0]) < 1.0:
+            mode = "nccl"
+            del w
+            w = BandedDaisyWorld(GIANT_N, GIANT_N, rank=rank, world_size=world, device=local, mode="nccl")
+    else:
+        w = BandedDaisyWorld(GIANT_N, GIANT_N, rank=rank, world_size=world, device=local)
     w.reset_on_device(seed=SEED)
     w.run(3, "greedy")                                   # literal first step + 2 lattice steps (warm-up)
     best = None
@@ -242,7 +261,12 @@ def giant_grid_bench(rank, world, local, fp64_peak_tflops):
         "us_per_step": best * 1e3 / GIANT_STEPS, "env_steps_per_s": GIANT_STEPS / (best * 1e-3),
         "hbm_gbs_algorithmic_per_gpu": 8.0 * value / world / 1e9,
         "fp64_roofline_frac": value * FLOP_PER_CELL_UPDATE / 1e12 / (fp64_peak_tflops * world) if fp64_peak_tflops else None,
-        "exchanges_per_step": 0 if world == 1 else "2 all-reduce(SUM, n doubles) + 1 ring halo exchange (2 rows each way)",
+        "exchange_mode": mode,
+        "exchanges_per_step": {"local": "none (toroidal wrap on the device)",
+                               "p2p": "owner-publishes P2P stores of decisions/gains into every rank's exchange vector, edge rows pushed "
+                                      "into the neighbours' ghost rows, 2 device-side flag barriers; no collective",
+                               "nccl": "1 all-reduce(SUM, 2n doubles) + 1 ring halo exchange overlapped with the interior tiles"}[mode],
+        "peer_barrier_timed_out": bool(w.band.peer_timed_out()) if mode == "p2p" else None,
         "literal_recomputations": w.band.slow_count(), "biosphere_alive_steps": done_at,
     }
     del w
@@ -427,7 +451,7 @@ def run_product(args):
             "check": {"mean_done_at_after_T": mean_life, "expected": float(T_STEPS), "ensemble_stats": stats.tolist(),
                       "wall_s_resident": wall_res},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
