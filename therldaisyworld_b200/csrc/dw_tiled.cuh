@@ -294,13 +294,8 @@ struct RowsTile72 {
 struct StoreGlobal {
     uint32_t *o;            // first cell of the thread's first output row
     int pitch;
-    int gsel, goff;         // ghost column duty of this thread: 0 none; 1: it holds column 0 (q[0]), 2: column N-1 (q[3]);
-                            // the ghost copy lives goff words from the thread's first cell of the row
     __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
-        uint32_t *r = o + (size_t)i * pitch;
-        *reinterpret_cast<uint4 *>(r) = make_uint4(q[0], q[1], q[2], q[3]);
-        if (gsel == 1) r[goff] = q[0];
-        else if (gsel == 2) r[goff] = q[3];
+        *reinterpret_cast<uint4 *>(o + (size_t)i * pitch) = make_uint4(q[0], q[1], q[2], q[3]);
     }
 };
 
@@ -337,16 +332,13 @@ __device__ __noinline__ uint32_t dwt_fix_warp(const TiledArgs *A, const uint32_t
                     }
                 const LitCell lc = dw_literal_cell(A->P, A->C.SL, l9, d9);
                 v = dw_pack((int)rint(lc.nl * 1000.0), (int)rint(lc.nd * 1000.0));
-                const long long oc = ooff + (long long)(lane >> 2) * A->pitch + (lane & 3);
-                A->out[oc] = v;
-                const int col = (int)(oc % A->pitch) - 4;                  // ghost copies of the edge columns
-                if (col == 0) A->out[oc + A->N] = v;
-                if (col == A->N - 1) A->out[oc - A->N] = v;
+                A->out[ooff + (long long)(lane >> 2) * A->pitch + (lane & 3)] = v;
                 if (A->slow_count) atomicAdd(A->slow_count, 1u);
             }
             extra = __vmaxu2(extra, v);
         }
     }
+    __syncwarp();                                        // patches (made by helper lanes) before the owners re-read their cells
     return __vmaxu2(mine ? 0u : mx, extra);
 }
 
@@ -380,11 +372,19 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
     const int tile_off = (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
     const long long out_off = (long long)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
     unsigned tiemin = 0xffffffffu;
-    const int gsel = (tx == 0 && tc == 0) ? 1 : ((tx == 15 && tc == A.tiles_x - 1) ? 2 : 0);
-    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off},
-                               StoreGlobal{A.out + out_off, A.pitch, gsel, gsel == 1 ? A.N : 3 - A.N}, &tiemin);
+    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off}, StoreGlobal{A.out + out_off, A.pitch}, &tiemin);
     const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
     if (flagged) mx = dwt_fix_warp(&A, tile, flagged, mx, tile_off, out_off, lane);
+    // ghost columns of the produced rows: the two threads of a row group that hold column 0 / N-1 copy their (final) cells
+    if (tx == 0 && tc == 0) {
+        uint32_t *o = A.out + out_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[(size_t)i * A.pitch + A.N] = o[(size_t)i * A.pitch];
+    } else if (tx == 15 && tc == A.tiles_x - 1) {
+        uint32_t *o = A.out + out_off + 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[(size_t)i * A.pitch - A.N] = o[(size_t)i * A.pitch];
+    }
     const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
     if (lane == 0) { atomicMax(&smax[0], (int)ml); atomicMax(&smax[1], (int)md); }
     __syncthreads();
