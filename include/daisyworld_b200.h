@@ -42,8 +42,11 @@ enum {
     DW_POLICY_GREEDY = 1,     /* Greedy(eps=0), argmax branch (daisy/agents/greedy.py:16-30) */
     DW_POLICY_ANTIGREEDY = 2, /* Greedy(greedy=False), argmin branch (greedy.py:27-28) */
     DW_POLICY_REPLAY = 3,     /* actions[K,B,n] supplied by the caller (stochastic policies replayed) */
-    DW_POLICY_RANDOM = 4      /* uniform 0..8 per agent-step from a device counter RNG (throughput runs;
+    DW_POLICY_RANDOM = 4,     /* uniform 0..8 per agent-step from a device counter RNG (throughput runs;
                                  not stream-compatible with numpy's MT19937) */
+    DW_POLICY_EPS_GREEDY = 5  /* Greedy(epsilon=eps) (greedy.py:23-32): ONE coin per step for the whole ensemble (the
+                                 reference draws one np.random.rand() per call): random actions if it lands below eps
+                                 (dw_set_epsilon), greedy otherwise. Counter RNG like DW_POLICY_RANDOM. */
 };
 
 /* dw_get_diag selectors: unrounded side-effect attributes of the last forward
@@ -108,6 +111,8 @@ int dw_get_clock(dw_handle *h, dw_clock *clk);
 /* luminosity the last forward pass used (the L behind env.temp / env.dead_temp, daisy_world_rl.py:403-416) */
 int dw_get_last_L(dw_handle *h, double *L);
 int dw_set_stream(dw_handle *h, void *cuda_stream);
+/* Greedy.epsilon for DW_POLICY_EPS_GREEDY (0 = always greedy, 1 = always random; README's "half-random" is 0.5) */
+int dw_set_epsilon(dw_handle *h, double epsilon);
 
 /* env.grid / env.agent_indices / env.agent_states assignment (any of the pointers may be NULL = keep).
    Host -> device; pinned host memory makes the copy asynchronous. */

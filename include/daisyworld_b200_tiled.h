@@ -58,6 +58,7 @@ int dwt_set_config(dwt_handle *h, const dw_config *cfg);
 int dwt_set_clock(dwt_handle *h, const dw_clock *clk);
 int dwt_get_clock(dwt_handle *h, dw_clock *clk);
 int dwt_set_stream(dwt_handle *h, void *cuda_stream);
+int dwt_set_epsilon(dwt_handle *h, double epsilon);       /* for DW_POLICY_EPS_GREEDY, see dw_set_epsilon */
 int dwt_synchronize(dwt_handle *h);
 
 /* reset(): cover planes of the band INCLUDING its two ghost rows, host fp64 [(rows + 2), N] each (row 0 = world row

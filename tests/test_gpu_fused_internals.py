@@ -90,3 +90,27 @@ def test_division_free_rounding_is_exact_on_device():
     bad = C.c_uint32(123)
     assert env._lib.dw_debug_markstein(env._h, 2000000, C.byref(bad)) == 0
     assert bad.value == 0
+
+
+def test_eps_greedy_limits_and_kernel_consistency():
+    """DW_POLICY_EPS_GREEDY: epsilon 0 is the greedy policy, epsilon 1 the random one (same counter RNG), and for
+    0 < epsilon < 1 the fused kernel and the materialising kernels agree step for step (one coin per step, resolved on
+    the host from (seed, step_count))."""
+    def run(policy, eps, disable=False, N=64, B=6):
+        if disable:
+            os.environ["DW_DISABLE_FUSED"] = "1"
+        try:
+            env = _env(N, B, 4, seed=21)
+            env.set_epsilon(eps)
+            env.reset_lifespans()
+            env.run(120, policy=policy, seed=9)
+            return env.grid.copy(), env.agent_states.copy(), env.agent_indices.copy(), env.lifespans()[1].copy()
+        finally:
+            os.environ.pop("DW_DISABLE_FUSED", None)
+
+    for a, b in ((run("eps_greedy", 0.0), run("greedy", 0.0)), (run("eps_greedy", 1.0), run("random", 0.0)),
+                 (run("eps_greedy", 0.5), run("eps_greedy", 0.5, disable=True))):
+        for u, v in zip(a, b):
+            np.testing.assert_array_equal(u, v)
+    half, greedy, rnd = run("eps_greedy", 0.5), run("greedy", 0.0), run("random", 0.0)
+    assert not np.array_equal(half[2], greedy[2]) and not np.array_equal(half[2], rnd[2])

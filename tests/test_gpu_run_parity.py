@@ -135,3 +135,24 @@ def test_device_side_reset_distribution_and_run():
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
+
+
+def test_ensemble_sharding_is_invisible():
+    """A 48-world ensemble run as one handle or as three 16-world shards with world offsets (the multi-rank layout) gives
+    the same worlds: device reset and device random policy are keyed by the GLOBAL world index."""
+    from therldaisyworld_b200 import RLDaisyWorld
+
+    def make(B, offset):
+        np.random.seed(1)
+        env = RLDaisyWorld(grid_dimension=64)
+        env.batch_size = B
+        env.reset_on_device(seed=5, world_offset=offset)
+        env.reset_lifespans()
+        env.run(150, policy="random", seed=3)
+        return env.grid.copy(), env.agent_states.copy(), env.lifespans()
+
+    whole = make(48, 0)
+    parts = [make(16, off) for off in (0, 16, 32)]
+    np.testing.assert_array_equal(np.concatenate([p[0] for p in parts]), whole[0])
+    np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), whole[1])
+    np.testing.assert_array_equal(np.concatenate([p[2][1] for p in parts]), whole[2][1])

@@ -6,7 +6,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DW_LIB", os.path.join(PKG, "libdaisyworld_b200.so"))   # DW_LIB: kernel-variant experiments
 
-DW_POLICY = {"none": 0, "greedy": 1, "antigreedy": 2, "replay": 3, "random": 4}
+DW_POLICY = {"none": 0, "greedy": 1, "antigreedy": 2, "replay": 3, "random": 4, "eps_greedy": 5}
 DW_DIAG = {"temp": 0, "temp_light": 1, "temp_dark": 2, "temp_effective": 3, "beta": 4, "beta_l": 5, "beta_d": 6,
            "growth": 7}
 
@@ -35,7 +35,7 @@ class DwRunResult(C.Structure):
 # every symbol include/daisyworld_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
-    "dw_set_stream", "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
+    "dw_set_stream", "dw_set_epsilon", "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
     "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
@@ -44,7 +44,7 @@ SYMBOLS = [
 
 # every symbol include/daisyworld_b200_tiled.h declares (single giant grid, row bands)
 TILED_SYMBOLS = [
-    "dwt_last_error", "dwt_create", "dwt_destroy", "dwt_set_config", "dwt_set_clock", "dwt_get_clock", "dwt_set_stream",
+    "dwt_last_error", "dwt_create", "dwt_destroy", "dwt_set_config", "dwt_set_clock", "dwt_get_clock", "dwt_set_stream", "dwt_set_epsilon",
     "dwt_synchronize", "dwt_upload_covers", "dwt_upload_agents", "dwt_init_random", "dwt_decide", "dwt_move_graze",
     "dwt_finish_agents", "dwt_stencil", "dwt_halo_wrap", "dwt_get_ptrs", "dwt_run", "dwt_end_chunk",
     "dwt_reset_lifespans", "dwt_get_lifespans", "dwt_get_agents", "dwt_get_reward_done", "dwt_get_covers", "dwt_get_grid",
@@ -86,6 +86,7 @@ def load():
         "dw_get_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
         "dw_get_last_L": (C.c_int, [vp, pd]),
         "dw_set_stream": (C.c_int, [vp, vp]),
+        "dw_set_epsilon": (C.c_int, [vp, C.c_double]),
         "dw_upload_state": (C.c_int, [vp, pd, pi64, pd]),
         "dw_upload_covers": (C.c_int, [vp, pd, pd]),
         "dw_init_random": (C.c_int, [vp, u64, C.c_double, C.c_double, C.c_double, C.c_double]),
@@ -126,6 +127,7 @@ def load():
         "dwt_set_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
         "dwt_get_clock": (C.c_int, [vp, C.POINTER(DwClock)]),
         "dwt_set_stream": (C.c_int, [vp, vp]),
+        "dwt_set_epsilon": (C.c_int, [vp, C.c_double]),
         "dwt_synchronize": (C.c_int, [vp]),
         "dwt_upload_covers": (C.c_int, [vp, pd, pd]),
         "dwt_upload_agents": (C.c_int, [vp, pi64, pd]),

@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import DwClock, DwtPtrs, DW_POLICY
 from .env import make_clock_struct, make_config_struct, set_default_attributes, set_default_kernels
 
-_WORLD_POLICIES = ("greedy", "antigreedy")      # decisions that read the grid (need the act all-reduce)
+_WORLD_POLICIES = ("greedy", "antigreedy", "eps_greedy")      # decisions that (may) read the grid: need the act exchange
 
 
 def band_rows(N, world_size, rank):
@@ -111,6 +111,9 @@ class DeviceBand:
 
     def set_clock(self, clk):
         self._check(self._lib.dwt_set_clock(self._h, C.byref(clk)), "dwt_set_clock")
+
+    def set_epsilon(self, epsilon):
+        self._check(self._lib.dwt_set_epsilon(self._h, float(epsilon)), "dwt_set_epsilon")
 
     def get_clock(self):
         clk = DwClock()

@@ -58,6 +58,7 @@ struct dw_handle {
     double *fwd_in = nullptr, *fwd_out = nullptr;
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
+    double epsilon = 0.0;                      // Greedy.epsilon of DW_POLICY_EPS_GREEDY
     bool fused_attr_set = false;
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
@@ -298,6 +299,11 @@ extern "C" int dw_set_stream(dw_handle *h, void *s) {
     h->stream = (cudaStream_t)s;
     return DW_OK;
 }
+extern "C" int dw_set_epsilon(dw_handle *h, double epsilon) {
+    if (!h || !(epsilon >= 0.0 && epsilon <= 1.0)) return DW_E_INVALID;
+    h->epsilon = epsilon;
+    return DW_OK;
+}
 extern "C" int dw_synchronize(dw_handle *h) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -430,12 +436,13 @@ static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, in
     if (h->cfg.n_agents == 0) return DW_OK;
     const DevParams P = make_params(h);
     const size_t NN = h->NN;
+    policy = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)h->clk.step_count);
     if (on_cov)
         k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->cov, 2 * NN, 0, NN, h->agent_xy, h->agent_state, act_dev, ab, am,
-                                                                 policy, seed, (uint32_t)h->clk.step_count);
+                                                                 policy, seed, (uint32_t)h->clk.step_count, h->world0);
     else
         k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid[h->cur], 7 * NN, NN, 2 * NN, h->agent_xy, h->agent_state,
-                                                                 act_dev, ab, am, policy, seed, (uint32_t)h->clk.step_count);
+                                                                 act_dev, ab, am, policy, seed, (uint32_t)h->clk.step_count, h->world0);
     DW_LAUNCHED(h);
     return DW_OK;
 }
@@ -505,7 +512,7 @@ extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t 
 extern "C" int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    if (policy == DW_POLICY_REPLAY || policy < 0 || policy > DW_POLICY_RANDOM)
+    if (policy == DW_POLICY_REPLAY || policy < 0 || policy > DW_POLICY_EPS_GREEDY)
         return dw_fail(h, DW_E_INVALID, "dw_step_policy", "use dw_step for explicit actions");
     int rc = ensure_grid(h);
     if (rc) return rc;

@@ -41,6 +41,7 @@ struct StepCoef {        // per-step (luminosity dependent) coefficients
     double x0;           // g^2 * (cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al)
     double xs_l, xs_d;   // g^2 * (q-cL)*a*(al-ab)/1000, g^2 * (q-cL)*a*(ad-ab)/1000   (a = adjacent tap)
     double SL;           // S*L for the literal path
+    int policy, pad_;    // the policy of this step (DW_POLICY_EPS_GREEDY resolved to GREEDY / RANDOM on the host)
 };
 
 struct FusedArgs {
@@ -242,18 +243,19 @@ __device__ __forceinline__ double dw_food(uint32_t pk) { return dw_milli(pk & 0x
 __device__ __forceinline__ void dw_agents_phase(const FusedArgs &A, int j, int b, uint32_t *cb, const AgentSmem &S, int lane) {
     const int N = A.P.N, n = A.P.n_agents;
     // pass 1: decisions from the state the previous step left (= the observation the policy would have seen)
+    const int pol = A.sc[j].policy;
     for (int i = lane; i < n; i += 32) {
         int a;
-        if (A.policy == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + i];
-        else if (A.policy == DW_POLICY_NONE) a = 0;
-        else if (A.policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, i, A.step0 + j) % 9u);
+        if (pol == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + i];
+        else if (pol == DW_POLICY_NONE) a = 0;
+        else if (pol == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, i, A.step0 + j) % 9u);
         else {
             const int x = S.xy[i] & 0xffff, y = S.xy[i] >> 16;
             const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
             const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
             const double food[4] = {dw_food(cb[x * N + ym]), dw_food(cb[xm * N + y]), dw_food(cb[xp * N + y]),
                                     dw_food(cb[x * N + yp])};
-            a = dw_greedy_pick(food, A.policy == DW_POLICY_GREEDY);
+            a = dw_greedy_pick(food, pol == DW_POLICY_GREEDY);
         }
         S.act[i] = a;
     }
@@ -635,13 +637,14 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
         st = sm.st[lane];
         x = sm.xy[lane] & 0xffff;
         y = sm.xy[lane] >> 16;
-        if (A.policy == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + lane];
-        else if (A.policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, lane, A.step0 + j) % 9u);
-        else if (A.policy != DW_POLICY_NONE) {
+        const int pol = A.sc[j].policy;
+        if (pol == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + lane];
+        else if (pol == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, lane, A.step0 + j) % 9u);
+        else if (pol != DW_POLICY_NONE) {
             const int xm = (x + N - 1) & (N - 1), xp = (x + 1) & (N - 1), ym = (y + N - 1) & (N - 1), yp = (y + 1) & (N - 1);
             const uint32_t c0 = cb[x * N + ym], c1 = cb[xm * N + y], c2 = cb[xp * N + y], c3 = cb[x * N + yp];
             const double food[4] = {dw_food(c0), dw_food(c1), dw_food(c2), dw_food(c3)};
-            a = dw_greedy_pick(food, A.policy == DW_POLICY_GREEDY);
+            a = dw_greedy_pick(food, pol == DW_POLICY_GREEDY);
         }
     }
     st = st - A.P.agent_gamma;

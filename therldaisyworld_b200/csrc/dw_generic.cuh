@@ -182,12 +182,19 @@ __global__ void __launch_bounds__(256) k_diag(DevParams P, double SL, Src src, i
 
 // ---- agents (update_agents, daisy_world_rl.py:181-244; Greedy, agents/greedy.py:16-30) -------------
 // counter RNG for DW_POLICY_RANDOM (throughput ensembles only; parity for stochastic policies is by replay)
-__device__ __forceinline__ uint32_t dw_hash_rng(uint64_t seed, uint32_t world, uint32_t agent, uint32_t step) {
+__host__ __device__ __forceinline__ uint32_t dw_hash_rng(uint64_t seed, uint32_t world, uint32_t agent, uint32_t step) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)world * 0x10001ull + agent + 1) + ((uint64_t)step << 32);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
     return (uint32_t)(z >> 32);
+}
+// DW_POLICY_EPS_GREEDY: the policy of one step -- one coin per step for the whole ensemble, like the single
+// np.random.rand() of Greedy.__call__ (agents/greedy.py:23). Resolved on the host (per launch or per step-table entry).
+__host__ __device__ __forceinline__ int dw_resolve_policy(int policy, double epsilon, uint64_t seed, uint32_t step) {
+    if (policy != DW_POLICY_EPS_GREEDY) return policy;
+    const double u = (double)dw_hash_rng(seed ^ 0x5EEDC01D5EEDC01Dull, 0xffffffffu, 0xffffffffu, step) * (1.0 / 4294967296.0);
+    return u < epsilon ? DW_POLICY_RANDOM : DW_POLICY_GREEDY;
 }
 
 // greedy / anti-greedy choice from the four Von Neumann neighbours' l+d (candidates in action order
@@ -209,7 +216,7 @@ __device__ __forceinline__ int dw_greedy_pick(const double (&food)[4], bool gree
 // (7-channel grid: 7NN, NN, 2NN; lean cover planes: 2NN, 0, NN).
 __global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *covers, size_t world_stride, size_t l_off, size_t d_off,
                                                      int32_t *agent_xy, double *agent_state, const int8_t *action, int ab, int am,
-                                                     int policy, uint64_t seed, uint32_t step) {
+                                                     int policy, uint64_t seed, uint32_t step, uint32_t world0) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
     const int N = P.N, n = P.n_agents;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *covers
             const int x = xy[2 * i], y = xy[2 * i + 1];
             if (policy == DW_POLICY_REPLAY) a = action[(size_t)b * am + i];
             else if (policy == DW_POLICY_NONE) a = 0;
-            else if (policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(seed, b, i, step) % 9u);
+            else if (policy == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(seed, world0 + b, i, step) % 9u);
             else {
                 const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
                 const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;

@@ -86,6 +86,8 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     std::vector<StepCoef> table(K);
     for (int j = 0; j < K; ++j) {
         make_step_coef(h->cfg, clk.L, table[j]);
+        table[j].policy = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)(h->clk.step_count + j));
+        table[j].pad_ = 0;
         L_last = clk.L;
         update_L(clk);
     }
@@ -270,7 +272,7 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
 }
 
 static int check_policy(dw_handle *h, int policy, const int8_t *actions) {
-    if (policy < 0 || policy > DW_POLICY_RANDOM) return dw_fail(h, DW_E_INVALID, "policy", "unknown policy");
+    if (policy < 0 || policy > DW_POLICY_EPS_GREEDY) return dw_fail(h, DW_E_INVALID, "policy", "unknown policy");
     if (policy == DW_POLICY_REPLAY && h->cfg.n_agents > 0 && !actions) return dw_fail(h, DW_E_INVALID, "policy", "REPLAY needs actions[K,B,n]");
     return DW_OK;
 }

@@ -39,6 +39,7 @@ struct dwt_handle {
     size_t replay_cap = 0;
     int64_t *agents_done_at = nullptr;
     int64_t done_at = 0;
+    double epsilon = 0.0;                      // Greedy.epsilon of DW_POLICY_EPS_GREEDY
     int *stepmax = nullptr;                    // [DW_FUSED_MAX_STEPS, 2]
     int chunk_j = 0;                           // steps recorded in stepmax since the last dwt_end_chunk
     unsigned int *slow_count = nullptr;
@@ -152,6 +153,11 @@ extern "C" int dwt_set_config(dwt_handle *h, const dw_config *cfg) {
 }
 extern "C" int dwt_set_clock(dwt_handle *h, const dw_clock *clk) { if (!h || !clk) return DW_E_INVALID; h->clk = *clk; return DW_OK; }
 extern "C" int dwt_get_clock(dwt_handle *h, dw_clock *clk) { if (!h || !clk) return DW_E_INVALID; *clk = h->clk; return DW_OK; }
+extern "C" int dwt_set_epsilon(dwt_handle *h, double epsilon) {
+    if (!h || !(epsilon >= 0.0 && epsilon <= 1.0)) return DW_E_INVALID;
+    h->epsilon = epsilon;
+    return DW_OK;
+}
 extern "C" int dwt_set_stream(dwt_handle *h, void *s) { if (!h) return DW_E_INVALID; h->stream = (cudaStream_t)s; return DW_OK; }
 extern "C" int dwt_synchronize(dwt_handle *h) {
     if (!h) return DW_E_INVALID;
@@ -221,9 +227,10 @@ extern "C" int dwt_init_random(dwt_handle *h, uint64_t seed, double light_propor
 static inline int dwt_blocks(int n) { return (n + 255) / 256; }
 
 extern "C" int dwt_decide(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed) {
-    if (!h || policy < 0 || policy > DW_POLICY_RANDOM) return DW_E_INVALID;
+    if (!h || policy < 0 || policy > DW_POLICY_EPS_GREEDY) return DW_E_INVALID;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->n) return DW_OK;
+    policy = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)h->clk.step_count);
     if (policy == DW_POLICY_REPLAY) {
         if (!actions) return dwt_fail(h, DW_E_INVALID, "dwt_decide", "REPLAY needs actions[n]");
         if (h->replay_cap < (size_t)h->n) {
@@ -586,7 +593,8 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
         rc = dwt_decide(h, policy, actions, seed);
         if (rc) return rc;
         // decisions that read the world were published by the owner ranks: meet before anyone moves
-        if (policy == DW_POLICY_GREEDY || policy == DW_POLICY_ANTIGREEDY) { rc = dwt_barrier(h); if (rc) return rc; }
+        const int pol = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)h->clk.step_count);
+        if (pol == DW_POLICY_GREEDY || pol == DW_POLICY_ANTIGREEDY) { rc = dwt_barrier(h); if (rc) return rc; }
         if (h->p2p_gain_pending) {           // gains of the previous step are complete since its closing barrier
             rc = dwt_finish_agents(h);
             if (rc) return rc;

@@ -485,6 +485,11 @@ class RLDaisyWorld:
         self._state_changed()
         return self._collect()
 
+    def set_epsilon(self, epsilon):
+        """Greedy.epsilon (agents/greedy.py:8) for policy="eps_greedy": per step ONE coin for the whole ensemble decides
+        between random and greedy actions, like the reference's single np.random.rand() per call (device counter RNG)."""
+        self._check(self._lib.dw_set_epsilon(self._h, float(epsilon)), "dw_set_epsilon")
+
     def reset_lifespans(self):
         self._check(self._lib.dw_reset_lifespans(self._h), "dw_reset_lifespans")
 
@@ -499,7 +504,8 @@ class RLDaisyWorld:
     def run(self, K, policy="greedy", actions=None, seed=0, stop_all_done=False):
         """K steps on the device with an on-device policy; lifespan counters accumulate (see lifespans()).
 
-        policy: "none" | "greedy" | "antigreedy" | "random" | "replay" (actions[K,B,n(,1)] ints 0..8).
+        policy: "none" | "greedy" | "antigreedy" | "random" | "eps_greedy" (see set_epsilon) | "replay"
+        (actions[K,B,n(,1)] ints 0..8).
         Returns (steps_run, worlds_alive, all_done_hit)."""
         B, N, n = self._shape
         a8 = None
