@@ -44,10 +44,14 @@ enum {
     DW_POLICY_REPLAY = 3,     /* actions[K,B,n] supplied by the caller (stochastic policies replayed) */
     DW_POLICY_RANDOM = 4,     /* uniform 0..8 per agent-step from a device counter RNG (throughput runs;
                                  not stream-compatible with numpy's MT19937) */
-    DW_POLICY_EPS_GREEDY = 5  /* Greedy(epsilon=eps) (greedy.py:23-32): ONE coin per step for the whole ensemble (the
+    DW_POLICY_EPS_GREEDY = 5, /* Greedy(epsilon=eps) (greedy.py:23-32): ONE coin per step for the whole ensemble (the
                                  reference draws one np.random.rand() per call): random actions if it lands below eps
                                  (dw_set_epsilon), greedy otherwise. Counter RNG like DW_POLICY_RANDOM. */
+    DW_POLICY_MLP = 6         /* MLP.get_action (daisy/agents/mlp.py:97-116): 63-16-32-9 ReLU network on the agent's
+                                 masked 7x3x3 observation, argmax of the logits; weights from dw_set_mlp. The
+                                 observation is built on the device from the state the last step started from. */
 };
+#define DW_MLP_PARAMS 1808    /* 63*16 + 16*32 + 32*9, flat layout of MLP.get_parameters (mlp.py:122-147) */
 
 /* dw_get_diag selectors: unrounded side-effect attributes of the last forward
    (daisy_world_rl.py:345-347,373,404,415-419). Each is [B,1,N,N] except growth [B,2,N,N]. */
@@ -113,6 +117,8 @@ int dw_get_last_L(dw_handle *h, double *L);
 int dw_set_stream(dw_handle *h, void *cuda_stream);
 /* Greedy.epsilon for DW_POLICY_EPS_GREEDY (0 = always greedy, 1 = always random; README's "half-random" is 0.5) */
 int dw_set_epsilon(dw_handle *h, double epsilon);
+/* MLP.set_parameters (daisy/agents/mlp.py:130-147) for DW_POLICY_MLP: host double[DW_MLP_PARAMS] */
+int dw_set_mlp(dw_handle *h, const double *parameters, int32_t n_parameters);
 
 /* env.grid / env.agent_indices / env.agent_states assignment (any of the pointers may be NULL = keep).
    Host -> device; pinned host memory makes the copy asynchronous. */

@@ -299,6 +299,33 @@ class OracleGreedy:
         return np.random.randint(9, size=(B, n, 1, 1)).reshape(B, n, 1)
 
 
+class OracleMLP:
+    """NumPy restatement of the MLP policy (reference: daisy/agents/mlp.py:12-147): 63 -> 16 -> 32 -> 9, no biases,
+    relu(x) = x * (x > 0) (:20), action = argmax of the raw logits (:106-116); flat parameter layout of
+    get_parameters / set_parameters (:122-147): the three weight matrices row-major, in order."""
+
+    SHAPES = ((63, 16), (16, 32), (32, 9))
+    N_PARAMS = sum(a * b for a, b in SHAPES)
+
+    def __init__(self, parameters):
+        p = np.asarray(parameters, dtype=np.float64).ravel()
+        assert p.size == self.N_PARAMS
+        self.layers, k = [], 0
+        for a, b in self.SHAPES:
+            self.layers.append(p[k:k + a * b].reshape(a, b))
+            k += a * b
+
+    def logits(self, obs):
+        x = obs.reshape(*obs.shape[:-3], 63)
+        for w in self.layers[:-1]:
+            x = np.matmul(x, w)
+            x = x * (x > 0.0)
+        return np.matmul(x, self.layers[-1])
+
+    def __call__(self, obs):
+        return np.argmax(self.logits(obs), axis=-1, keepdims=True)
+
+
 def lifespan_loop(env, agent, max_steps=100000):
     """The README lifespan metric (notebooks/greedy_longevity_abatement.ipynb cell 2).
 

@@ -59,6 +59,17 @@ def run_case(name, seed, ctor, attrs, policy, steps, ckpts, out_dir, action_shap
         agent.greedy = policy["kind"] != "antigreedy"
         agent.epsilon = {"greedy": 0.0, "antigreedy": 0.0, "random": 1.0, "half_random": 0.5}[policy["kind"]]
 
+    mlp_params = None
+    if policy["kind"] == "mlp":               # the reference's MLP policy (daisy/agents/mlp.py) with its stored trained weights
+        from daisy.agents.mlp import MLP
+        import glob
+        agent = MLP()
+        path = glob.glob(os.path.join(REF_ROOT, "results", "cmaes_exp_002", "*best_agent_gen127.json"))[0]
+        mlp_params = np.array(json.load(open(path))["parameters"], dtype=np.float64)
+        if policy.get("perturb"):             # a second, different network: the stored one plus seeded noise
+            mlp_params = mlp_params + np.random.RandomState(policy["perturb"]).randn(mlp_params.size) * policy.get("std", 0.5)
+        agent.set_parameters(mlp_params)
+
     B, n, N = env.batch_size, env.n_agents, env.dim
     rec = dict(
         init_grid=env.grid.copy(),
@@ -123,6 +134,8 @@ def run_case(name, seed, ctor, attrs, policy, steps, ckpts, out_dir, action_shap
         diag_beta_l=env.beta_l.copy(), diag_beta_d=env.beta_d.copy(), diag_growth=env.growth.copy(),
         done_at=done_at, agents_done_at=agents_done_at,
     )
+    if mlp_params is not None:
+        rec["mlp_params"] = mlp_params
     meta = dict(name=name, seed=seed, ctor=ctor, attrs=attrs, policy=policy, steps=t,
                 to_death=to_death, B=B, n=n, N=N, numpy=np.__version__,
                 final_step_count=int(env.step_count), dL=float(env.dL))
@@ -133,7 +146,16 @@ def run_case(name, seed, ctor, attrs, policy, steps, ckpts, out_dir, action_shap
           f"-> {path} ({os.path.getsize(path)/1024:.0f} KiB)")
 
 
+REF_ROOT = "/root/reference"
+
 CASES = [
+    # next row N1: the reference's MLP policy (63-16-32-9 ReLU, argmax) with the stored trained weights / a perturbed copy
+    dict(name="mlp_n16_b4_200", seed=17, ctor=dict(grid_dimension=16), attrs=dict(batch_size=4),
+         policy=dict(kind="mlp"), steps=200, ckpts=[1, 2, 100]),
+    dict(name="mlp_n64_b2_n6_60", seed=19, ctor=dict(grid_dimension=64, n_agents=6), attrs=dict(batch_size=2),
+         policy=dict(kind="mlp", perturb=2, std=2.0), steps=60, ckpts=[1, 30]),
+    dict(name="mlp_n16_b4_mixed_150", seed=17, ctor=dict(grid_dimension=16), attrs=dict(batch_size=4),
+         policy=dict(kind="mlp", perturb=2, std=2.0), steps=150, ckpts=[1, 75]),
     # BASELINE config 1: default grid, no agents, single world, run to biosphere death (seed 42)
     dict(name="cfg1_n16_b1_noagents_todeath", seed=42, ctor=dict(n_agents=0), attrs=dict(batch_size=1),
          policy=dict(kind="none"), steps=0, ckpts=[1, 2, 100, 300, 440], to_death=True),
@@ -186,6 +208,8 @@ def main():
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
     ap.add_argument("--only", default=None)
     args = ap.parse_args()
+    global REF_ROOT
+    REF_ROOT = args.ref
     sys.path.insert(0, args.ref)
     warnings.filterwarnings("ignore", category=DeprecationWarning)
     os.makedirs(args.out, exist_ok=True)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_DIR, golden_names
-from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy, env_from_golden, neighborhood_mask
+from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy, OracleMLP, env_from_golden, neighborhood_mask
 
 
 def replay(z, env, check_every_step=True):
@@ -68,6 +68,20 @@ def test_oracle_greedy_policy_reproduces_reference_actions(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     env, meta = env_from_golden(z)
     agent = OracleGreedy(epsilon=0.0, greedy=meta["policy"]["kind"] != "antigreedy")
+    obs = env.get_obs(env.agent_indices)
+    for t in range(meta["steps"]):
+        action = agent(obs)
+        np.testing.assert_array_equal(action, z["actions"][t])
+        obs, _, _, _ = env.step(action)
+    np.testing.assert_array_equal(env.grid, z["ckpt_grid"][-1])
+
+
+@pytest.mark.parametrize("name", ["mlp_n16_b4_200", "mlp_n64_b2_n6_60", "mlp_n16_b4_mixed_150"])
+def test_oracle_mlp_policy_reproduces_reference_actions(name):
+    """OracleMLP with the recorded weights, driven by oracle observations, picks the actions the reference MLP picked."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    env, meta = env_from_golden(z)
+    agent = OracleMLP(z["mlp_params"])
     obs = env.get_obs(env.agent_indices)
     for t in range(meta["steps"]):
         action = agent(obs)

@@ -6,7 +6,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DW_LIB", os.path.join(PKG, "libdaisyworld_b200.so"))   # DW_LIB: kernel-variant experiments
 
-DW_POLICY = {"none": 0, "greedy": 1, "antigreedy": 2, "replay": 3, "random": 4, "eps_greedy": 5}
+DW_POLICY = {"none": 0, "greedy": 1, "antigreedy": 2, "replay": 3, "random": 4, "eps_greedy": 5, "mlp": 6}
 DW_DIAG = {"temp": 0, "temp_light": 1, "temp_dark": 2, "temp_effective": 3, "beta": 4, "beta_l": 5, "beta_d": 6,
            "growth": 7}
 
@@ -35,7 +35,7 @@ class DwRunResult(C.Structure):
 # every symbol include/daisyworld_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
-    "dw_set_stream", "dw_set_epsilon", "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
+    "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
     "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
@@ -87,6 +87,7 @@ def load():
         "dw_get_last_L": (C.c_int, [vp, pd]),
         "dw_set_stream": (C.c_int, [vp, vp]),
         "dw_set_epsilon": (C.c_int, [vp, C.c_double]),
+        "dw_set_mlp": (C.c_int, [vp, pd, i32]),
         "dw_upload_state": (C.c_int, [vp, pd, pi64, pd]),
         "dw_upload_covers": (C.c_int, [vp, pd, pd]),
         "dw_init_random": (C.c_int, [vp, u64, C.c_double, C.c_double, C.c_double, C.c_double]),

@@ -59,6 +59,8 @@ struct dw_handle {
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     double epsilon = 0.0;                      // Greedy.epsilon of DW_POLICY_EPS_GREEDY
+    double *mlp_dev = nullptr;                 // [DW_MLP_PARAMS] weights of DW_POLICY_MLP
+    bool mlp_set = false;
     bool fused_attr_set = false;
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
@@ -258,7 +260,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->mlp_dev,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {
@@ -509,14 +511,52 @@ extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t 
     return launch_forward_tail(h, false, nullptr);
 }
 
+extern "C" int dw_set_mlp(dw_handle *h, const double *parameters, int32_t n_parameters) {
+    if (!h || !parameters) return DW_E_INVALID;
+    if (n_parameters != DW_MLP_PARAMS) return dw_fail(h, DW_E_INVALID, "dw_set_mlp", "expected 63*16 + 16*32 + 32*9 = 1808 parameters");
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = dev_alloc(h, &h->mlp_dev, (size_t)DW_MLP_PARAMS);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->mlp_dev, parameters, DW_MLP_PARAMS * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->mlp_set = true;
+    return DW_OK;
+}
+
+static int compute_obs(dw_handle *h);
+
+// DW_POLICY_MLP: actions of every agent for the next step from the current observations -> h->action_dev (int8 [B,n])
+static int mlp_actions(dw_handle *h) {
+    const size_t count = (size_t)h->cfg.batch * h->cfg.n_agents;
+    if (!count) return DW_OK;
+    if (!h->mlp_set) return dw_fail(h, DW_E_STATE, "DW_POLICY_MLP", "call dw_set_mlp first");
+    int rc = compute_obs(h);
+    if (rc) return rc;
+    if (h->action_cap < count) {
+        if (h->action_dev) cudaFree(h->action_dev);
+        h->action_dev = nullptr;
+        DW_CUDA_TRY(h, cudaMalloc((void **)&h->action_dev, count));
+        h->action_cap = count;
+    }
+    k_mlp_act<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->mlp_dev, h->obs, count, h->action_dev);
+    DW_LAUNCHED(h);
+    return DW_OK;
+}
+
 extern "C" int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    if (policy == DW_POLICY_REPLAY || policy < 0 || policy > DW_POLICY_EPS_GREEDY)
+    if (policy == DW_POLICY_REPLAY || policy < 0 || policy > DW_POLICY_MLP)
         return dw_fail(h, DW_E_INVALID, "dw_step_policy", "use dw_step for explicit actions");
-    int rc = ensure_grid(h);
+    int rc = DW_OK;
+    if (policy == DW_POLICY_MLP) {
+        rc = mlp_actions(h);
+        if (rc) return rc;
+    }
+    rc = ensure_grid(h);
     if (rc) return rc;
-    rc = launch_agents(h, nullptr, 0, 0, policy, seed);
+    if (policy == DW_POLICY_MLP) rc = launch_agents(h, h->action_dev, h->cfg.batch, h->cfg.n_agents, DW_POLICY_REPLAY, seed);
+    else rc = launch_agents(h, nullptr, 0, 0, policy, seed);
     if (rc) return rc;
     return launch_forward_tail(h, false, nullptr);
 }
@@ -553,11 +593,25 @@ static int compute_obs(dw_handle *h) {
     if (h->obs_valid) return DW_OK;
     const size_t B = h->cfg.batch, n = h->cfg.n_agents;
     if (n == 0) { h->obs_valid = true; return DW_OK; }
-    int rc = ensure_grid(h);
-    if (rc) return rc;
-    rc = dev_alloc(h, &h->obs, B * n * 63);
+    int rc = dev_alloc(h, &h->obs, B * n * 63);
     if (rc) return rc;
     const DevParams P = make_params(h);
+    if (!h->grid_valid && h->lat_valid && (h->pre == PRE_LAT || h->pre == PRE_COV)) {
+        // after a fused run: re-evaluate only the agents' windows from the state the last step started from instead of
+        // materialising the whole 7-channel grid
+        const double SL = h->cfg.S * h->L_last;
+        if (h->pre == PRE_LAT)
+            k_obs_from_pre<SrcLattice><<<grid_for(B * n * 9), 256, 0, h->stream>>>(P, SL, SrcLattice{h->lat_pre, h->NN}, h->agent_xy,
+                                                                                   h->agent_state, h->obs);
+        else
+            k_obs_from_pre<SrcCov><<<grid_for(B * n * 9), 256, 0, h->stream>>>(P, SL, SrcCov{h->cov, h->NN}, h->agent_xy, h->agent_state,
+                                                                               h->obs);
+        DW_LAUNCHED(h);
+        h->obs_valid = true;
+        return DW_OK;
+    }
+    rc = ensure_grid(h);
+    if (rc) return rc;
     k_obs<<<grid_for(B * n * 63), 256, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, (int)B, (int)n, h->obs);
     DW_LAUNCHED(h);
     h->obs_valid = true;

@@ -336,6 +336,80 @@ __global__ void __launch_bounds__(256) k_obs(DevParams P, const double *__restri
     }
 }
 
+// Observations straight from the state the last forward STARTED from (post-graze lattice / cover planes / grid): the
+// window cells are re-evaluated literally, which reproduces exactly what forward wrote there (b' from the unrounded
+// covers, rounded temperatures, agent stamp: highest index on a cell wins, dead agents included) without materialising
+// the whole 7-channel grid. One thread per (agent, window cell).
+template <class Src>
+__global__ void __launch_bounds__(256) k_obs_from_pre(DevParams P, double SL, Src src, const int32_t *__restrict__ agent_xy,
+                                                      const double *__restrict__ agent_state, double *__restrict__ obs) {
+    const int N = P.N, n = P.n_agents;
+    const size_t total = (size_t)P.B * n * 9;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t ag = i / 9;
+        const int w = (int)(i - ag * 9), b = (int)(ag / n);
+        double *o = obs + ag * 63 + w;
+        const double m = P.mask[w];
+        int x = agent_xy[ag * 2] + w / 3 - 1, y = agent_xy[ag * 2 + 1] + w % 3 - 1;
+        x = x < 0 ? x + N : (x >= N ? x - N : x);
+        y = y < 0 ? y + N : (y >= N ? y - N : y);
+        double l9[9], d9[9];
+        dw_load9(src, b, N, x, y, l9, d9);
+        const LitCell c = dw_literal_cell(P, SL, l9, d9);
+        double ch4 = dw_round3(c.Tl);
+        for (int k = 0; k < n; ++k) {                       // forward :454-459, agents in order: the last one stays
+            const size_t a2 = (size_t)b * n + k;
+            if (agent_xy[a2 * 2] == x && agent_xy[a2 * 2 + 1] == y) ch4 = agent_state[a2];
+        }
+        o[0] = dw_round3(c.nb) * m;
+        o[9] = dw_round3(c.nl) * m;
+        o[18] = dw_round3(c.nd) * m;
+        o[27] = dw_round3(c.T) * m;
+        o[36] = ch4 * m;
+        o[45] = dw_round3(c.Td) * m;
+        o[54] = 0.0 * m;
+    }
+}
+
+// MLP.get_action (daisy/agents/mlp.py:97-116): x(63) -> relu(x W1)(16) -> relu(. W2)(32) -> . W3 (9) -> argmax (first
+// maximum, like np.argmax). One thread per agent; relu(v) = v * (v > 0) as in the reference (:20).
+__global__ void __launch_bounds__(128) k_mlp_act(const double *__restrict__ w, const double *__restrict__ obs, size_t count,
+                                                 int8_t *__restrict__ action) {
+    const size_t a = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (a >= count) return;
+    const double *x = obs + a * 63;
+    const double *w1 = w, *w2 = w + 63 * 16, *w3 = w2 + 16 * 32;
+    double h1[16], h2[32];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) h1[o] = 0.0;
+    for (int k = 0; k < 63; ++k) {
+        const double xk = x[k];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) h1[o] = h1[o] + xk * w1[k * 16 + o];
+    }
+#pragma unroll
+    for (int o = 0; o < 16; ++o) h1[o] = h1[o] * (h1[o] > 0.0 ? 1.0 : 0.0);
+#pragma unroll
+    for (int o = 0; o < 32; ++o) h2[o] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int o = 0; o < 32; ++o) h2[o] = h2[o] + h1[k] * w2[k * 32 + o];
+    }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) h2[o] = h2[o] * (h2[o] > 0.0 ? 1.0 : 0.0);
+    int best = 0;
+    double bv = 0.0;
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s = s + h2[k] * w3[k * 9 + o];
+        if (o == 0 || s > bv) { bv = s; best = o; }
+    }
+    action[a] = (int8_t)best;
+}
+
 // ---- device-side synthetic initial state (throughput ensembles; NOT numpy-stream compatible) -----------------------
 // Same distribution as initialize_grid/initialize_agents (daisy_world_rl.py:285-302,173-179): per cell and species
 // u0,u1 ~ U[0,1): cover = (u0 < proportion) * initial * u1; agents uniform on the grid with state 1.

@@ -93,8 +93,8 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     }
     int rc = dev_alloc(h, &h->sc_dev, (size_t)DW_FUSED_MAX_STEPS);
     if (rc) return rc;
+    // pageable source: cudaMemcpyAsync returns once the data is staged, so the local table may go out of scope
     DW_CUDA_TRY(h, cudaMemcpyAsync(h->sc_dev, table.data(), K * sizeof(StepCoef), cudaMemcpyHostToDevice, h->stream));
-    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));       // table is a local
     A.sc = h->sc_dev;
     A.lat_in = h->lat[h->lcur];
     A.lat_out = h->lat[1 - h->lcur];
@@ -188,9 +188,8 @@ static int lean_first_step(dw_handle *h, int policy, const int8_t *act_dev, uint
     return DW_OK;
 }
 
-// K <= 64 steps, fused where the state allows it
-static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed) {
-    unsigned int *alive = h->alive;
+// K steps, fused where the state allows it
+static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive) {
     const size_t per_step = (size_t)h->cfg.batch * h->cfg.n_agents;
     if (!h->lat_valid && h->cov_valid) {
         int rc = lean_first_step(h, policy, act_dev, seed, alive);
@@ -249,7 +248,20 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
                           unsigned int *alive_last, int *first_all_done = nullptr) {
     if (K < 1 || K > DW_FUSED_MAX_STEPS) return dw_fail(h, DW_E_INVALID, "run_chunk", "1 <= K <= 4096");
     DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, DW_FUSED_MAX_STEPS * sizeof(unsigned int), h->stream));
-    int rc = dw_fused_supported(h) ? run_steps_fused(h, K, policy, act_dev, seed) : run_steps_generic(h, K, policy, act_dev, seed, h->alive);
+    int rc = DW_OK;
+    if (policy == DW_POLICY_MLP) {
+        // the policy runs between steps on the device (observation windows from the last pre-state, then the network);
+        // each step is a one-step launch replaying the device-resident actions
+        for (int j = 0; j < K && !rc; ++j) {
+            rc = mlp_actions(h);
+            if (rc) break;
+            rc = dw_fused_supported(h) ? run_steps_fused(h, 1, DW_POLICY_REPLAY, h->action_dev, seed, h->alive + j)
+                                       : run_steps_generic(h, 1, DW_POLICY_REPLAY, h->action_dev, seed, h->alive + j);
+        }
+    } else {
+        rc = dw_fused_supported(h) ? run_steps_fused(h, K, policy, act_dev, seed, h->alive)
+                                   : run_steps_generic(h, K, policy, act_dev, seed, h->alive);
+    }
     if (rc) return rc;
     std::vector<unsigned int> alive(K);
     DW_CUDA_TRY(h, cudaMemcpyAsync(alive.data(), h->alive, K * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
@@ -272,7 +284,8 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
 }
 
 static int check_policy(dw_handle *h, int policy, const int8_t *actions) {
-    if (policy < 0 || policy > DW_POLICY_EPS_GREEDY) return dw_fail(h, DW_E_INVALID, "policy", "unknown policy");
+    if (policy < 0 || policy > DW_POLICY_MLP) return dw_fail(h, DW_E_INVALID, "policy", "unknown policy");
+    if (policy == DW_POLICY_MLP && h->cfg.n_agents > 0 && !h->mlp_set) return dw_fail(h, DW_E_STATE, "policy", "DW_POLICY_MLP needs dw_set_mlp");
     if (policy == DW_POLICY_REPLAY && h->cfg.n_agents > 0 && !actions) return dw_fail(h, DW_E_INVALID, "policy", "REPLAY needs actions[K,B,n]");
     return DW_OK;
 }

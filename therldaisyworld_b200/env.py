@@ -490,6 +490,21 @@ class RLDaisyWorld:
         between random and greedy actions, like the reference's single np.random.rand() per call (device counter RNG)."""
         self._check(self._lib.dw_set_epsilon(self._h, float(epsilon)), "dw_set_epsilon")
 
+    def observe(self):
+        """Observations of the current state for all agents (what the last step()/run() would have returned). After a
+        fused run only the agents' windows are re-evaluated on the device; the full grid is not materialised."""
+        B, N, n = self._shape
+        obs = np.zeros((B, n, self.ch, 3, 3))
+        self._push()
+        self._check(self._lib.dw_get_obs(self._h, _ptr(obs, C.c_double)), "dw_get_obs")
+        return obs
+
+    def set_mlp(self, parameters):
+        """Weights of the reference's MLP policy (daisy/agents/mlp.py: MLP.get_parameters()) for policy="mlp": the
+        63-16-32-9 ReLU network is evaluated on the device between steps, on observations built on the device."""
+        p = np.ascontiguousarray(np.asarray(parameters, dtype=np.float64).ravel())
+        self._check(self._lib.dw_set_mlp(self._h, _ptr(p, C.c_double), int(p.size)), "dw_set_mlp")
+
     def reset_lifespans(self):
         self._check(self._lib.dw_reset_lifespans(self._h), "dw_reset_lifespans")
 
@@ -504,7 +519,7 @@ class RLDaisyWorld:
     def run(self, K, policy="greedy", actions=None, seed=0, stop_all_done=False):
         """K steps on the device with an on-device policy; lifespan counters accumulate (see lifespans()).
 
-        policy: "none" | "greedy" | "antigreedy" | "random" | "eps_greedy" (see set_epsilon) | "replay"
+        policy: "none" | "greedy" | "antigreedy" | "random" | "eps_greedy" (see set_epsilon) | "mlp" (see set_mlp) | "replay"
         (actions[K,B,n(,1)] ints 0..8).
         Returns (steps_run, worlds_alive, all_done_hit)."""
         B, N, n = self._shape
