@@ -78,4 +78,36 @@ for mode in ("nccl", "p2p"):
                   f"{N * N * K / ms / 1e-3:.3e} cell-updates/s timed_out={w.band.peer_timed_out()}", flush=True)
     del w
     torch.cuda.empty_cache()
+
+# ---- full size: R bands vs ONE band (the whole torus on rank 0's GPU), same device-drawn world, bit equality ----------
+def checksum(cov):          # exact: milli-cover integers
+    k = np.rint(cov * 1000.0).astype(np.int64)
+    w = (np.arange(k.shape[-1], dtype=np.int64) % 977 + 1)
+    return np.array([k[0].sum(), k[1].sum(), (k[0] * w).sum(), (k[1] * w).sum()], dtype=np.int64)
+
+N, n, K = 16384, 16384, 16
+for mode in ("p2p", "nccl"):
+    w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local, mode=mode)
+    w.reset_on_device(seed=2)
+    w.run(K, "greedy", chunk=8)
+    cs = torch.from_numpy(checksum(w.local_covers())).cuda()
+    dist.all_reduce(cs)
+    ai, st = w.agents()
+    life = w.lifespans()
+    del w
+    torch.cuda.empty_cache()
+    if rank == 0:
+        one = BandedDaisyWorld(N, n, device=local)
+        one.reset_on_device(seed=2)
+        one.run(K, "greedy", chunk=8)
+        ref_cs = checksum(one.local_covers())
+        ai1, st1 = one.agents()
+        life1 = one.lifespans()
+        ok = (np.array_equal(cs.cpu().numpy(), ref_cs) and np.array_equal(ai, ai1) and np.array_equal(st, st1)
+              and life[0] == life1[0] and np.array_equal(life[1], life1[1]))
+        print(f"FULLSIZE N={N} n={n} {K} greedy steps, {world} bands ({mode}) vs 1 band: {'IDENTICAL' if ok else 'MISMATCH'} "
+              f"checksums {cs.cpu().numpy().tolist()} vs {ref_cs.tolist()}", flush=True)
+        del one
+        torch.cuda.empty_cache()
+    dist.barrier()
 dist.destroy_process_group()
