@@ -1,6 +1,6 @@
 """Multi-rank lifespan ensembles: worlds are independent, so an ensemble shards contiguously across ranks with NO
-data-path collective.  The only exchanges are (1) a bitwise-AND all-reduce of a 64-bit "every world of my shard was
-grid_done at step j" mask per 64-step segment -- the notebook's loop stops at the first step where ALL worlds are
+data-path collective.  The only exchanges are (1) an AND all-reduce (MIN over 64 bit flags) of the "every world of my
+shard was grid_done at step j" mask per 64-step segment -- the notebook's loop stops at the first step where ALL worlds are
 done (notebooks/greedy_longevity_abatement.ipynb cell 2) -- and (2) one SUM all-reduce of the 8-double lifespan
 statistics vector at the end.  One process per GPU; torch.distributed is only plumbing (NCCL on GPUs, gloo in the
 CPU tests, where an oracle-backed shard stands in for the device).
@@ -62,14 +62,14 @@ class DeviceShard:
 
 
 def _and_reduce(mask, group, dist, device):
+    """Bitwise AND of a 64-bit mask over the ranks. NCCL has no BAND, so the mask travels as 64 {0,1} flags and is
+    reduced with MIN (works on NCCL and gloo alike)."""
     import torch
     if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return mask
-    # int64 carries the 64 mask bits (two's complement); BAND is supported by both gloo and NCCL
-    t = torch.tensor([mask - (1 << 64) if mask >= (1 << 63) else mask], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.BAND, group=group)
-    v = int(t.item())
-    return v + (1 << 64) if v < 0 else v
+    bits = torch.tensor([(mask >> j) & 1 for j in range(64)], dtype=torch.int32, device=device)
+    dist.all_reduce(bits, op=dist.ReduceOp.MIN, group=group)
+    return sum(int(b) << j for j, b in enumerate(bits.tolist()))
 
 
 def simulate_lifespan(shard, policy="greedy", actions=None, seed=0, max_steps=100000, group=None, device="cpu", segment=64):
