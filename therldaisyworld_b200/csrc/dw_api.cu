@@ -43,6 +43,7 @@ struct dw_handle {
     double L_last = 0.0;
 
     int32_t *agent_xy = nullptr;
+    long long *agent_idx64 = nullptr;   // staging of uploaded int64 agent_indices (converted on the device: no host sync)
     double *agent_state = nullptr;
     double *obs = nullptr;
     bool obs_valid = false;
@@ -259,7 +260,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
+    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
                     h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->mlp_dev,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -336,13 +337,13 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
         h->obs_valid = false;
     }
     if (n && agent_indices) {
-        std::vector<int32_t> xy(B * n * 2);
-        for (size_t i = 0; i < xy.size(); ++i) {
-            int64_t v = agent_indices[i] % h->cfg.dim;
-            xy[i] = (int32_t)(v < 0 ? v + h->cfg.dim : v);
-        }
-        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_xy, xy.data(), xy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // xy is a local
+        // int64 -> wrapped int32 on the device: with pinned host memory the whole upload is asynchronous
+        const size_t count = B * n * 2;
+        int rc = dev_alloc(h, &h->agent_idx64, count);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_idx64, agent_indices, count * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+        k_agent_indices_in<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->agent_idx64, count, h->cfg.dim, h->agent_xy);
+        DW_LAUNCHED(h);
         h->obs_valid = false;
     }
     if (n && agent_states) {

@@ -441,6 +441,14 @@ __global__ void __launch_bounds__(256) k_init_random(DevParams P, uint64_t seed,
     }
 }
 
+// env.agent_indices (int64, any integers) -> wrapped int32 positions (the reference wraps with % dim, :208)
+__global__ void __launch_bounds__(256) k_agent_indices_in(const long long *__restrict__ src, size_t count, int N, int32_t *__restrict__ xy) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    long long v = src[i] % N;
+    xy[i] = (int32_t)(v < 0 ? v + N : v);
+}
+
 // lean cover planes [B,2,N,N] -> 7-channel grid with channels 1,2 set and the rest zero (initialize_grid :304-312)
 __global__ void __launch_bounds__(256) k_cov_to_grid(int B, size_t NN, const double *__restrict__ cov, double *__restrict__ grid) {
     const size_t total = (size_t)B * NN;
