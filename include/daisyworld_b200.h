@@ -119,6 +119,17 @@ int dw_set_stream(dw_handle *h, void *cuda_stream);
 int dw_set_epsilon(dw_handle *h, double epsilon);
 /* MLP.set_parameters (daisy/agents/mlp.py:130-147) for DW_POLICY_MLP: host double[DW_MLP_PARAMS] */
 int dw_set_mlp(dw_handle *h, const double *parameters, int32_t n_parameters);
+/* ES fitness rollout, SimpleGaussianES.get_fitness (daisy/evo/sges.py:144-181), for a whole population at once: the batch
+   is n_members contiguous blocks of batch/n_members worlds; in block m the first half of every world's agents acts with
+   members[m], the second half with members[adversary_index] (DW_POLICY_MLP on both).  members: host
+   double[n_members][DW_MLP_PARAMS]. */
+int dw_set_mlp_population(dw_handle *h, const double *members, int32_t n_members, int32_t adversary_index);
+/* Runs the rollout from the uploaded reset state until every member's loop has ended (all its agents done, or
+   max_steps): per step the member's sum_reward += mean(reward[:, :half]) while its loop is alive. */
+int dw_run_population(dw_handle *h, int64_t max_steps, int64_t *steps_run);
+/* fitness[m] = sum_reward / (worlds_per_member * n_agents); member_steps[m] = env.step_count when member m's loop ended;
+   total_steps[B, n] = per-agent (1 - done) counts up to that step (== done_at of get_fitness) */
+int dw_get_population_results(dw_handle *h, double *fitness, int64_t *member_steps, int64_t *total_steps);
 
 /* env.grid / env.agent_indices / env.agent_states assignment (any of the pointers may be NULL = keep).
    Host -> device; pinned host memory makes the copy asynchronous. */

@@ -326,6 +326,26 @@ class OracleMLP:
         return np.argmax(self.logits(obs), axis=-1, keepdims=True)
 
 
+def es_get_fitness(env, agent, adversary, max_steps=768):
+    """NumPy restatement of SimpleGaussianES.get_fitness (reference: daisy/evo/sges.py:144-181): one member (first half of
+    every world's agents) against an adversary (second half) on a freshly reset env; returns (fitness, total_steps,
+    done_at, steps_run)."""
+    obs = env.reset()
+    half = obs.shape[1] // 2
+    all_done = False
+    done_at = np.zeros((*obs.shape[:2], 1), dtype=int)
+    total_steps = np.zeros((*obs.shape[:2], 1), dtype=int)
+    sum_reward = 0.0
+    while not all_done and env.step_count < max_steps:
+        action = np.append(agent(obs[:, :half]), adversary(obs[:, half:]), axis=1)
+        obs, reward, done, info = env.step(action)
+        all_done = (np.ones_like(done).sum() - done.sum()) == 0
+        done_at += (1 - 1 * done)
+        sum_reward += (reward[:, :half]).mean()
+        total_steps += (1 - 1 * done)
+    return sum_reward / (obs.shape[0] * obs.shape[1]), total_steps, done_at, env.step_count
+
+
 def lifespan_loop(env, agent, max_steps=100000):
     """The README lifespan metric (notebooks/greedy_longevity_abatement.ipynb cell 2).
 

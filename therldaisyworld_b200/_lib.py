@@ -35,7 +35,8 @@ class DwRunResult(C.Structure):
 # every symbol include/daisyworld_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
-    "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
+    "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_set_mlp_population", "dw_run_population", "dw_get_population_results",
+    "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_policy", "dw_update_agents",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag",
     "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
@@ -88,6 +89,9 @@ def load():
         "dw_set_stream": (C.c_int, [vp, vp]),
         "dw_set_epsilon": (C.c_int, [vp, C.c_double]),
         "dw_set_mlp": (C.c_int, [vp, pd, i32]),
+        "dw_set_mlp_population": (C.c_int, [vp, pd, i32, i32]),
+        "dw_run_population": (C.c_int, [vp, i64, pi64]),
+        "dw_get_population_results": (C.c_int, [vp, pd, pi64, pi64]),
         "dw_upload_state": (C.c_int, [vp, pd, pi64, pd]),
         "dw_upload_covers": (C.c_int, [vp, pd, pd]),
         "dw_init_random": (C.c_int, [vp, u64, C.c_double, C.c_double, C.c_double, C.c_double]),

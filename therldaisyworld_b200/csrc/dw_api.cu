@@ -60,8 +60,15 @@ struct dw_handle {
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     double epsilon = 0.0;                      // Greedy.epsilon of DW_POLICY_EPS_GREEDY
-    double *mlp_dev = nullptr;                 // [DW_MLP_PARAMS] weights of DW_POLICY_MLP
+    double *mlp_dev = nullptr;                 // [DW_MLP_PARAMS] weights of DW_POLICY_MLP, or [n_members][DW_MLP_PARAMS]
+    size_t mlp_cap = 0;
     bool mlp_set = false;
+    // population mode (ES fitness rollouts): members own contiguous blocks of worlds
+    int pop_members = 0, pop_adversary = 0;
+    double *pop_sum = nullptr;                 // [members] sum_reward
+    int *pop_done = nullptr;                   // [members] loop ended
+    int64_t *pop_steps = nullptr, *pop_frozen = nullptr;   // [members] step count at the end; [B,n] frozen (1-done) counters
+    unsigned int *pop_ndone = nullptr;
     bool fused_attr_set = false;
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
@@ -261,7 +268,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->mlp_dev,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {
@@ -512,15 +519,39 @@ extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t 
     return launch_forward_tail(h, false, nullptr);
 }
 
+static int mlp_upload(dw_handle *h, const double *params, int sets) {
+    const size_t count = (size_t)sets * DW_MLP_PARAMS;
+    if (h->mlp_cap < count) {
+        if (h->mlp_dev) cudaFree(h->mlp_dev);
+        h->mlp_dev = nullptr;
+        DW_CUDA_TRY(h, cudaMalloc((void **)&h->mlp_dev, count * sizeof(double)));
+        h->mlp_cap = count;
+    }
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->mlp_dev, params, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->mlp_set = true;
+    return DW_OK;
+}
+
 extern "C" int dw_set_mlp(dw_handle *h, const double *parameters, int32_t n_parameters) {
     if (!h || !parameters) return DW_E_INVALID;
     if (n_parameters != DW_MLP_PARAMS) return dw_fail(h, DW_E_INVALID, "dw_set_mlp", "expected 63*16 + 16*32 + 32*9 = 1808 parameters");
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    int rc = dev_alloc(h, &h->mlp_dev, (size_t)DW_MLP_PARAMS);
+    int rc = mlp_upload(h, parameters, 1);
     if (rc) return rc;
-    DW_CUDA_TRY(h, cudaMemcpyAsync(h->mlp_dev, parameters, DW_MLP_PARAMS * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->mlp_set = true;
+    h->pop_members = 0;
+    return DW_OK;
+}
+
+extern "C" int dw_set_mlp_population(dw_handle *h, const double *members, int32_t n_members, int32_t adversary_index) {
+    if (!h || !members) return DW_E_INVALID;
+    if (n_members < 1 || adversary_index < 0 || adversary_index >= n_members || h->cfg.batch % n_members)
+        return dw_fail(h, DW_E_INVALID, "dw_set_mlp_population", "batch must split evenly over the members; 0 <= adversary < n_members");
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = mlp_upload(h, members, n_members);
+    if (rc) return rc;
+    h->pop_members = n_members;
+    h->pop_adversary = adversary_index;
     return DW_OK;
 }
 
@@ -539,7 +570,10 @@ static int mlp_actions(dw_handle *h) {
         DW_CUDA_TRY(h, cudaMalloc((void **)&h->action_dev, count));
         h->action_cap = count;
     }
-    k_mlp_act<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->mlp_dev, h->obs, count, h->action_dev);
+    const int n = h->cfg.n_agents;
+    k_mlp_act<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->mlp_dev, h->obs, count, h->action_dev,
+                                                                        h->pop_members ? h->cfg.batch / h->pop_members : 0, n, n / 2,
+                                                                        h->pop_adversary);
     DW_LAUNCHED(h);
     return DW_OK;
 }

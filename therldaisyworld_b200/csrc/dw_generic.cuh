@@ -373,10 +373,17 @@ __global__ void __launch_bounds__(256) k_obs_from_pre(DevParams P, double SL, Sr
 
 // MLP.get_action (daisy/agents/mlp.py:97-116): x(63) -> relu(x W1)(16) -> relu(. W2)(32) -> . W3 (9) -> argmax (first
 // maximum, like np.argmax). One thread per agent; relu(v) = v * (v > 0) as in the reference (:20).
+// Population mode (wpm > 0, ES fitness rollouts, daisy/evo/sges.py:161-168): the worlds come in blocks of wpm per member;
+// the first `half` agents of a world use the member's weights, the rest the adversary's.
 __global__ void __launch_bounds__(128) k_mlp_act(const double *__restrict__ w, const double *__restrict__ obs, size_t count,
-                                                 int8_t *__restrict__ action) {
+                                                 int8_t *__restrict__ action, int wpm, int n, int half, int adversary) {
     const size_t a = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (a >= count) return;
+    if (wpm > 0) {
+        const size_t b = a / n;
+        const int i = (int)(a - b * n);
+        w += (size_t)(i < half ? (int)(b / wpm) : adversary) * (63 * 16 + 16 * 32 + 32 * 9);
+    }
     const double *x = obs + a * 63;
     const double *w1 = w, *w2 = w + 63 * 16, *w3 = w2 + 16 * 32;
     double h1[16], h2[32];
@@ -408,6 +415,40 @@ __global__ void __launch_bounds__(128) k_mlp_act(const double *__restrict__ w, c
         if (o == 0 || s > bv) { bv = s; best = o; }
     }
     action[a] = (int8_t)best;
+}
+
+// One step of the population bookkeeping of get_fitness (sges.py:170-175), one block per member: while the member's loop
+// is alive, sum_reward += mean(reward[:, :half]) over its worlds, the per-agent (1 - done) counters are carried along, and
+// the loop ends after the step in which all of its agents are done.
+__global__ void __launch_bounds__(128) k_pop_accumulate(int wpm, int n, int half, const double *__restrict__ reward,
+                                                        const uint8_t *__restrict__ done, const int64_t *__restrict__ agents_done_at,
+                                                        double *sum_reward, int *member_done, int64_t *member_steps, int64_t *frozen,
+                                                        long long step_count, unsigned int *n_done) {
+    const int m = blockIdx.x;
+    if (member_done[m]) return;
+    __shared__ double s_sum[4];
+    __shared__ int s_alive[4];
+    const size_t base = (size_t)m * wpm * n;
+    double sum = 0.0;
+    int alive = 0;
+    for (int k = threadIdx.x; k < wpm * n; k += blockDim.x) {
+        if (k % n < half) sum += reward[base + k];
+        alive += done[base + k] ? 0 : 1;
+        frozen[base + k] = agents_done_at[base + k];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        alive += __shfl_xor_sync(0xffffffffu, alive, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_alive[threadIdx.x >> 5] = alive; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double tot = ((s_sum[0] + s_sum[1]) + s_sum[2]) + s_sum[3];
+        const int al = s_alive[0] + s_alive[1] + s_alive[2] + s_alive[3];
+        sum_reward[m] += tot / (double)(wpm * half);
+        member_steps[m] = step_count;
+        if (al == 0) { member_done[m] = 1; atomicAdd(n_done, 1u); }
+    }
 }
 
 // ---- device-side synthetic initial state (throughput ensembles; NOT numpy-stream compatible) -----------------------

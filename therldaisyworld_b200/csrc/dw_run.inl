@@ -350,3 +350,62 @@ extern "C" int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *act
     }
     return DW_OK;
 }
+
+// ---- ES fitness rollout of a whole population (daisy/evo/sges.py:144-181) -------------------------------------------
+extern "C" int dw_run_population(dw_handle *h, int64_t max_steps, int64_t *steps_run) {
+    if (!h || max_steps < 0) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->pop_members || !h->mlp_set) return dw_fail(h, DW_E_STATE, "dw_run_population", "call dw_set_mlp_population first");
+    const int P = h->pop_members, n = h->cfg.n_agents, wpm = h->cfg.batch / P;
+    if (n < 2) return dw_fail(h, DW_E_INVALID, "dw_run_population", "needs at least two agents per world (member half + adversary half)");
+    const size_t Bn = (size_t)h->cfg.batch * n;
+    int rc = dev_alloc(h, &h->pop_sum, (size_t)P);
+    if (!rc) rc = dev_alloc(h, &h->pop_done, (size_t)P);
+    if (!rc) rc = dev_alloc(h, &h->pop_steps, (size_t)P);
+    if (!rc) rc = dev_alloc(h, &h->pop_frozen, Bn);
+    if (!rc) rc = dev_alloc(h, &h->pop_ndone, (size_t)1);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->pop_sum, 0, P * sizeof(double), h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->pop_done, 0, P * sizeof(int), h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->pop_steps, 0, P * sizeof(int64_t), h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->pop_frozen, 0, Bn * sizeof(int64_t), h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->pop_ndone, 0, sizeof(unsigned int), h->stream));
+    rc = dw_reset_lifespans(h);
+    if (rc) return rc;
+    int64_t t = 0;
+    while (t < max_steps) {
+        DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, sizeof(unsigned int), h->stream));
+        rc = mlp_actions(h);
+        if (rc) return rc;
+        rc = dw_fused_supported(h) ? run_steps_fused(h, 1, DW_POLICY_REPLAY, h->action_dev, 0, h->alive)
+                                   : run_steps_generic(h, 1, DW_POLICY_REPLAY, h->action_dev, 0, h->alive);
+        if (rc) return rc;
+        t += 1;
+        k_pop_accumulate<<<P, 128, 0, h->stream>>>(wpm, n, n / 2, h->reward, h->done, h->agents_done_at, h->pop_sum, h->pop_done,
+                                                   h->pop_steps, h->pop_frozen, (long long)h->clk.step_count, h->pop_ndone);
+        DW_LAUNCHED(h);
+        if ((t & 7) == 0 || t == max_steps) {            // every member's loop over? (one small read-back per 8 steps)
+            unsigned int nd = 0;
+            DW_CUDA_TRY(h, cudaMemcpyAsync(&nd, h->pop_ndone, sizeof(nd), cudaMemcpyDeviceToHost, h->stream));
+            DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if ((int)nd == P) break;
+        }
+    }
+    if (steps_run) *steps_run = t;
+    return DW_OK;
+}
+
+extern "C" int dw_get_population_results(dw_handle *h, double *fitness, int64_t *member_steps, int64_t *total_steps) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->pop_members || !h->pop_sum) return dw_fail(h, DW_E_STATE, "dw_get_population_results", "no population rollout has run");
+    const int P = h->pop_members, n = h->cfg.n_agents, wpm = h->cfg.batch / P;
+    std::vector<double> sum(P);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(sum.data(), h->pop_sum, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (member_steps) DW_CUDA_TRY(h, cudaMemcpyAsync(member_steps, h->pop_steps, P * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (total_steps)
+        DW_CUDA_TRY(h, cudaMemcpyAsync(total_steps, h->pop_frozen, (size_t)h->cfg.batch * n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (fitness) for (int m = 0; m < P; ++m) fitness[m] = sum[m] / (double)(wpm * n);     // sges.py:179
+    return DW_OK;
+}

@@ -1,0 +1,66 @@
+"""ES fitness rollouts on the device (next-row N2): ``SimpleGaussianES.get_fitness`` (``daisy/evo/sges.py:144-181``) for a
+whole population in one batch.
+
+The reference evaluates its members one after the other (or one per MPI rank, ``sges.py:299-349``): each call resets the
+32-world environment and lets the member's MLP drive the first half of every world's agents against an adversary MLP on
+the second half, summing ``reward[:, :half].mean()`` per step until all agents are done or ``max_steps``.  Here the
+members' environments are laid side by side as ONE batch of ``P x worlds_per_member`` worlds: observations, both networks
+(per-world weights), the step and the fitness bookkeeping all run on the device; the host only draws the reset states.
+
+The resets are drawn from the global NumPy stream in exactly the order the sequential reference loop would draw them
+(member 0's dark, light, agents, then member 1's, ...), so with the same seed the fitness values reproduce the reference's.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import DwRunResult  # noqa: F401  (keeps the binding module loaded)
+from .env import RLDaisyWorld, _ptr
+
+
+def evaluate_population(members, adversary_idx=0, max_steps=768, worlds_per_member=32, env=None, **env_kwargs):
+    """members: [P, 1808] MLP parameter vectors (MLP.get_parameters()). Returns (fitness[P], total_steps[P, W, n, 1],
+    member_steps[P], env). Pass `env` (an RLDaisyWorld of this package) to reuse a handle / non-default constants."""
+    members = np.ascontiguousarray(np.asarray(members, dtype=np.float64))
+    P = members.shape[0]
+    W = int(worlds_per_member)
+    if env is None:
+        state = np.random.get_state()
+        env = RLDaisyWorld(**env_kwargs)               # the constructor's own draws must not disturb the caller's stream
+        np.random.set_state(state)
+    N, n = int(env.dim), int(env.n_agents)
+    B = P * W
+    # the P resets of the sequential reference loop, in its RNG order (daisy_world_rl.py:285-302, 173-179)
+    light = np.empty((B, N, N))
+    dark = np.empty((B, N, N))
+    agents = np.empty((B, n, 2), dtype=np.int64)
+    for m in range(P):
+        dp = np.random.rand(W, 2, N, N)
+        lp = np.random.rand(W, 2, N, N)
+        dark[m * W:(m + 1) * W] = 1.0 * (dp[:, 0] < env.dark_proportion) * env.initial_ad * dp[:, 1]
+        light[m * W:(m + 1) * W] = 1.0 * (lp[:, 0] < env.light_proportion) * env.initial_al * lp[:, 1]
+        agents[m * W:(m + 1) * W] = np.random.randint(N, size=(W, n, 2))
+    states = np.ones((B, n))
+    env.batch_size = B
+    env.L = env.min_L
+    env.dL = (env.max_L - env.min_L) / env.ramp_period
+    env.step_count = 0
+    env._ensure_handle((B, N, n))
+    for mm in env._m.values():
+        mm.invalidate()
+    env._push()
+    lib, h = env._lib, env._h
+    env._check(lib.dw_upload_covers(h, _ptr(light, C.c_double), _ptr(dark, C.c_double)), "dw_upload_covers")
+    env._check(lib.dw_upload_state(h, None, _ptr(agents, C.c_int64), _ptr(states, C.c_double)), "dw_upload_state")
+    env._check(lib.dw_init_temperatures(h), "dw_init_temperatures")
+    env._check(lib.dw_set_mlp_population(h, _ptr(members, C.c_double), P, int(adversary_idx)), "dw_set_mlp_population")
+    steps = C.c_int64(0)
+    env._check(lib.dw_run_population(h, int(max_steps), C.byref(steps)), "dw_run_population")
+    env._state_changed()
+    env._pull_clock()
+    fitness = np.zeros(P)
+    member_steps = np.zeros(P, dtype=np.int64)
+    total_steps = np.zeros((B, n), dtype=np.int64)
+    env._check(lib.dw_get_population_results(h, _ptr(fitness, C.c_double), _ptr(member_steps, C.c_int64), _ptr(total_steps, C.c_int64)),
+               "dw_get_population_results")
+    return fitness, total_steps.reshape(P, W, n, 1), member_steps, env
