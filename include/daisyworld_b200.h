@@ -153,6 +153,11 @@ int dw_init_temperatures(dw_handle *h);
    reward/done -> update_L, all on the device.  action: host int64 [ab,am] (ab<=B, am<=n, values 0..8)
    or NULL for step(None). */
 int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t am);
+/* dw_step followed by everything step() returns, in one call with one synchronisation: obs[B,n,7,3,3], reward and done
+   ([B,n], or [B,2] when n_agents == 0) and the advanced clock. Any output pointer may be NULL. policy < 0: explicit
+   action (or NULL = step(None)); otherwise the action is chosen on the device like dw_step_policy. */
+int dw_step_collect(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed, double *obs,
+                    double *reward, uint8_t *done, dw_clock *clk);
 /* Same step with the action chosen on the device by DW_POLICY_* (Greedy.__call__ fused in). */
 int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed);
 

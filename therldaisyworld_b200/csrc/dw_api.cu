@@ -664,6 +664,25 @@ extern "C" int dw_get_obs(dw_handle *h, double *obs) {
     return DW_OK;
 }
 
+extern "C" int dw_step_collect(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed, double *obs,
+                               double *reward, uint8_t *done, dw_clock *clk) {
+    if (!h) return DW_E_INVALID;
+    int rc = policy < 0 ? dw_step(h, action, ab, am) : dw_step_policy(h, policy, seed);
+    if (rc) return rc;
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents;
+    if (obs && n) {
+        rc = compute_obs(h);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->obs, B * n * 63 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    const size_t count = B * (n ? n : 2);
+    if (reward) DW_CUDA_TRY(h, cudaMemcpyAsync(reward, h->reward, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (done) DW_CUDA_TRY(h, cudaMemcpyAsync(done, h->done, count, cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (clk) *clk = h->clk;
+    return DW_OK;
+}
+
 extern "C" int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t b, int32_t m, double *obs) {
     if (!h || b < 0 || m < 0 || b > h->cfg.batch) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));

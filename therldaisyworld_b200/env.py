@@ -446,31 +446,27 @@ class RLDaisyWorld:
         a = None
         if action is not None and n:
             a = self._action(action)
+        return self._step_collect(a, -1, 0)
+
+    def _step_collect(self, a, policy, seed):
+        """One dw_step_collect call: the step and everything step() returns, one synchronisation."""
+        B, N, n = self._shape
         self._push()
         self._dead_L = self.L
-        if a is None:
-            rc = self._lib.dw_step(self._h, None, 0, 0)
-        else:
-            rc = self._lib.dw_step(self._h, _ptr(a, C.c_int64), a.shape[0], a.shape[1])
-        self._check(rc, "dw_step")
-        self._state_changed()
-        return self._collect()
-
-    def _collect(self):
-        B, N, n = self._shape
         obs = np.zeros((B, n, self.ch, 3, 3))
-        self._check(self._lib.dw_get_obs(self._h, _ptr(obs, C.c_double)), "dw_get_obs")
-        if n:
-            reward = np.empty((B, n, 1))
-            done = np.empty((B, n, 1), dtype=np.uint8)
-        else:
-            reward = np.empty((B, 2))
-            done = np.empty((B, 2), dtype=np.uint8)
-        self._check(self._lib.dw_get_reward_done(self._h, _ptr(reward, C.c_double), _ptr(done, C.c_uint8)),
-                    "dw_get_reward_done")
+        shape = (B, n, 1) if n else (B, 2)
+        reward = np.empty(shape)
+        done = np.empty(shape, dtype=np.uint8)
+        clk = DwClock()
+        rc = self._lib.dw_step_collect(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
+                                       0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), _ptr(obs, C.c_double),
+                                       _ptr(reward, C.c_double), _ptr(done, C.c_uint8), C.byref(clk))
+        self._check(rc, "dw_step_collect")
+        self._state_changed()
+        self.L, self.dL, self.min_L, self.max_L = clk.L, clk.dL, clk.min_L, clk.max_L
+        self.step_count = int(clk.step_count)
         if not n:
             reward = reward.astype(bool)
-        self._pull_clock()
         return obs, reward, done.astype(bool), {}
 
     def __call__(self, grid):
@@ -479,11 +475,7 @@ class RLDaisyWorld:
     # ------------------------------------------------------------------ additions: fused path
     def step_policy(self, policy="greedy", seed=0):
         """One step with the action chosen on the device (Greedy's deterministic branch fused in)."""
-        self._push()
-        self._dead_L = self.L
-        self._check(self._lib.dw_step_policy(self._h, DW_POLICY[policy], C.c_uint64(seed)), "dw_step_policy")
-        self._state_changed()
-        return self._collect()
+        return self._step_collect(None, DW_POLICY[policy], seed)
 
     def set_epsilon(self, epsilon):
         """Greedy.epsilon (agents/greedy.py:8) for policy="eps_greedy": per step ONE coin for the whole ensemble decides
