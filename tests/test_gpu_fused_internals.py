@@ -114,3 +114,17 @@ def test_eps_greedy_limits_and_kernel_consistency():
             np.testing.assert_array_equal(u, v)
     half, greedy, rnd = run("eps_greedy", 0.5), run("greedy", 0.0), run("random", 0.0)
     assert not np.array_equal(half[2], greedy[2]) and not np.array_equal(half[2], rnd[2])
+
+
+def test_fast_path_fuzz_random_physics():
+    """Random albedos, solar constant, growth/death constants, time step, ramps and sizes: the fused kernels must stay
+    identical to the literal materialising kernels (tools/fuzz_fast_path.py runs the same check over hundreds of draws)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_fast_path.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.RandomState(123)
+    for c in range(12):
+        attrs, N, n, ramp, no_micro = fuzz.draw(rng)
+        ok, slow, diff, life = fuzz.run_config(attrs, N, n, ramp, no_micro, seed=1000 + c, B=8, steps=250)
+        assert ok, (c, attrs, N, n, ramp, no_micro, diff)
