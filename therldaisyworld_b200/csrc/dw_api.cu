@@ -562,17 +562,31 @@ static int mlp_actions(dw_handle *h) {
     const size_t count = (size_t)h->cfg.batch * h->cfg.n_agents;
     if (!count) return DW_OK;
     if (!h->mlp_set) return dw_fail(h, DW_E_STATE, "DW_POLICY_MLP", "call dw_set_mlp first");
-    int rc = compute_obs(h);
-    if (rc) return rc;
     if (h->action_cap < count) {
         if (h->action_dev) cudaFree(h->action_dev);
         h->action_dev = nullptr;
         DW_CUDA_TRY(h, cudaMalloc((void **)&h->action_dev, count));
         h->action_cap = count;
     }
-    const int n = h->cfg.n_agents;
-    k_mlp_act<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->mlp_dev, h->obs, count, h->action_dev,
-                                                                        h->pop_members ? h->cfg.batch / h->pop_members : 0, n, n / 2,
+    const int n = h->cfg.n_agents, wpm = h->pop_members ? h->cfg.batch / h->pop_members : 0;
+    if (count <= 65536 && !h->grid_valid && !h->obs_valid && h->lat_valid && (h->pre == PRE_LAT || h->pre == PRE_COV)) {
+        // between fused steps: windows and network in one kernel (one warp per agent: latency-optimal for the launch-bound
+        // ensemble sizes; larger ones are throughput-bound and take the two thread-per-element kernels below)
+        const DevParams P = make_params(h);
+        const double SL = h->cfg.S * h->L_last;
+        const unsigned blocks = (unsigned)((count + 3) / 4);
+        if (h->pre == PRE_LAT)
+            k_obs_mlp<SrcLattice><<<blocks, 128, 0, h->stream>>>(P, SL, SrcLattice{h->lat_pre, h->NN}, h->agent_xy, h->agent_state, h->mlp_dev,
+                                                                  count, h->action_dev, wpm, n / 2, h->pop_adversary);
+        else
+            k_obs_mlp<SrcCov><<<blocks, 128, 0, h->stream>>>(P, SL, SrcCov{h->cov, h->NN}, h->agent_xy, h->agent_state, h->mlp_dev, count,
+                                                              h->action_dev, wpm, n / 2, h->pop_adversary);
+        DW_LAUNCHED(h);
+        return DW_OK;
+    }
+    int rc = compute_obs(h);
+    if (rc) return rc;
+    k_mlp_act<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->mlp_dev, h->obs, count, h->action_dev, wpm, n, n / 2,
                                                                         h->pop_adversary);
     DW_LAUNCHED(h);
     return DW_OK;

@@ -417,6 +417,73 @@ __global__ void __launch_bounds__(128) k_mlp_act(const double *__restrict__ w, c
     action[a] = (int8_t)best;
 }
 
+// Observation window + network in one kernel, one warp per agent (the policy path between one-step launches): lanes 0..8
+// re-evaluate the window cells from the pre-state (as k_obs_from_pre), the 63 inputs go through shared memory, then lanes
+// are output neurons (16, 32, 9) and the argmax is taken by lane 0. Same summation order as k_mlp_act.
+template <class Src>
+__global__ void __launch_bounds__(128) k_obs_mlp(DevParams P, double SL, Src src, const int32_t *__restrict__ agent_xy,
+                                                 const double *__restrict__ agent_state, const double *__restrict__ w, size_t count,
+                                                 int8_t *__restrict__ action, int wpm, int half, int adversary) {
+    __shared__ double s_x[4][64], s_h1[4][16], s_h2[4][32], s_o[4][9];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t a = blockIdx.x * (size_t)(blockDim.x >> 5) + wib;
+    if (a >= count) return;                                   // whole warps leave together
+    const int N = P.N, n = P.n_agents;
+    const int b = (int)(a / n);
+    if (wpm > 0) w += (size_t)((int)(a - (size_t)b * n) < half ? b / wpm : adversary) * (63 * 16 + 16 * 32 + 32 * 9);
+    double *x = s_x[wib];
+    if (lane < 9) {
+        const double m = P.mask[lane];
+        int cx = agent_xy[a * 2] + lane / 3 - 1, cy = agent_xy[a * 2 + 1] + lane % 3 - 1;
+        cx = cx < 0 ? cx + N : (cx >= N ? cx - N : cx);
+        cy = cy < 0 ? cy + N : (cy >= N ? cy - N : cy);
+        double l9[9], d9[9];
+        dw_load9(src, b, N, cx, cy, l9, d9);
+        const LitCell c = dw_literal_cell(P, SL, l9, d9);
+        double ch4 = dw_round3(c.Tl);
+        for (int k = 0; k < n; ++k) {
+            const size_t a2 = (size_t)b * n + k;
+            if (agent_xy[a2 * 2] == cx && agent_xy[a2 * 2 + 1] == cy) ch4 = agent_state[a2];
+        }
+        x[lane] = dw_round3(c.nb) * m;
+        x[9 + lane] = dw_round3(c.nl) * m;
+        x[18 + lane] = dw_round3(c.nd) * m;
+        x[27 + lane] = dw_round3(c.T) * m;
+        x[36 + lane] = ch4 * m;
+        x[45 + lane] = dw_round3(c.Td) * m;
+        x[54 + lane] = 0.0 * m;
+    }
+    __syncwarp();
+    const double *w1 = w, *w2 = w + 63 * 16, *w3 = w2 + 16 * 32;
+    if (lane < 16) {
+        double h = 0.0;
+        for (int k = 0; k < 63; ++k) h = h + x[k] * w1[k * 16 + lane];
+        s_h1[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    {
+        double h = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) h = h + s_h1[wib][k] * w2[k * 32 + lane];
+        s_h2[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    if (lane < 9) {
+        double o = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o = o + s_h2[wib][k] * w3[k * 9 + lane];
+        s_o[wib][lane] = o;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int best = 0;
+        double bv = s_o[wib][0];
+#pragma unroll
+        for (int o = 1; o < 9; ++o) if (s_o[wib][o] > bv) { bv = s_o[wib][o]; best = o; }
+        action[a] = (int8_t)best;
+    }
+}
+
 // One step of the population bookkeeping of get_fitness (sges.py:170-175), one block per member: while the member's loop
 // is alive, sum_reward += mean(reward[:, :half]) over its worlds, the per-agent (1 - done) counters are carried along, and
 // the loop ends after the step in which all of its agents are done.
