@@ -87,8 +87,7 @@ struct PeerTable {
 
 // All ranks meet here: every prior write of this rank (to its own or to peer memory) is visible to a peer that has seen
 // the flag. Spins are bounded (~seconds) so that a missing peer produces an error flag instead of a hung GPU.
-__global__ void k_peer_barrier(PeerTable PT, unsigned int epoch, unsigned int *timed_out) {
-    const int p = threadIdx.x;
+__device__ __forceinline__ void dw_peer_barrier_body(const PeerTable &PT, unsigned int epoch, unsigned int *timed_out, int p) {
     if (p >= PT.R) return;
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(PT.flags[p] + PT.rank), "r"(epoch) : "memory");
@@ -103,26 +102,43 @@ __global__ void k_peer_barrier(PeerTable PT, unsigned int epoch, unsigned int *t
     }
     __threadfence_system();
 }
+__global__ void k_peer_barrier(PeerTable PT, unsigned int epoch, unsigned int *timed_out) {
+    dw_peer_barrier_body(PT, epoch, timed_out, threadIdx.x);
+}
+// Tail of a multi-block kernel that ends in a barrier: every block calls this after its own (peer) stores; the block
+// that arrives last at the ticket counter runs the barrier, so the flag is raised only after ALL blocks' stores.
+__device__ __forceinline__ void dw_last_block_barrier(const PeerTable &PT, unsigned int epoch, unsigned int *timed_out, unsigned int *ticket) {
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *ticket = 0u;                        // re-armed for the next launch (stream order)
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last) dw_peer_barrier_body(PT, epoch, timed_out, threadIdx.x);
+}
 
 // a band's first / last stored row (ghost columns included) -> the neighbours' ghost rows
+// ... and then the closing barrier of the step, raised by the block that finishes last.
 __global__ void __launch_bounds__(256) k_band_push_halo(const uint32_t *__restrict__ lat, int R, int pitch, uint32_t *up_ghost_bottom,
-                                                        uint32_t *down_ghost_top) {
+                                                        uint32_t *down_ghost_top, PeerTable PT, unsigned int epoch, unsigned int *timed_out,
+                                                        unsigned int *ticket) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= pitch) return;
-    up_ghost_bottom[c] = lat[(size_t)pitch + c];
-    down_ghost_top[c] = lat[(size_t)R * pitch + c];
+    if (c < pitch) {
+        up_ghost_bottom[c] = lat[(size_t)pitch + c];
+        down_ghost_top[c] = lat[(size_t)R * pitch + c];
+    }
+    dw_last_block_barrier(PT, epoch, timed_out, ticket);
 }
 
 // ---- agents --------------------------------------------------------------------------------------------------------
-// Phase 1: the owner band of each agent decides its action from the pre-move state. act[i] = action + 1 for owned
-// agents, 0 otherwise (the caller sums act over ranks). Policies that do not look at the world (replay, none, random)
-// fill every entry on every rank and need no exchange.
 template <class Cells>
-__global__ void __launch_bounds__(256) k_band_decide(BandGeom G, Cells C, const int32_t *__restrict__ xy, int n, int policy,
-                                                     const int8_t *__restrict__ replay, uint64_t seed, uint32_t step, PeerTable PT,
-                                                     double *__restrict__ act) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void k_band_decide_one(const BandGeom &G, const Cells &C, const int32_t *__restrict__ xy, int n, int policy,
+                                                  const int8_t *__restrict__ replay, uint64_t seed, uint32_t step, const PeerTable &PT,
+                                                  double *__restrict__ act, int i) {
     const int x = xy[2 * i], y = xy[2 * i + 1];
     const int lr = band_owned_row(G, x);
     double out = 0.0;
@@ -143,6 +159,19 @@ __global__ void __launch_bounds__(256) k_band_decide(BandGeom G, Cells C, const 
         }
     } else if (PT.on) return;                            // peer-memory mode: the owner rank writes this entry
     act[i] = out;
+}
+
+// Phase 1: the owner band of each agent decides its action from the pre-move state. act[i] = action + 1 for owned
+// agents, 0 otherwise (the caller sums act over ranks). Policies that do not look at the world (replay, none, random)
+// fill every entry on every rank and need no exchange.
+template <class Cells>
+__global__ void __launch_bounds__(256) k_band_decide(BandGeom G, Cells C, const int32_t *__restrict__ xy, int n, int policy,
+                                                     const int8_t *__restrict__ replay, uint64_t seed, uint32_t step, PeerTable PT,
+                                                     double *__restrict__ act, unsigned int epoch, unsigned int *timed_out,
+                                                     unsigned int *ticket) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) k_band_decide_one<Cells>(G, C, xy, n, policy, replay, seed, step, PT, act, i);
+    if (epoch) dw_last_block_barrier(PT, epoch, timed_out, ticket);     // peer-memory mode, world-reading policies
 }
 
 // Phase 2 (replicated on every rank): pay agent_gamma, move the living, and file the graze claims of cells this band owns.
@@ -168,6 +197,51 @@ __global__ void __launch_bounds__(256) k_band_move_claim(BandGeom G, double agen
             g = 1;
             const int lr = band_owned_row(G, x);
             if (lr >= 0) atomicMin(claim + (size_t)lr * G.N + y, i);
+        }
+    }
+    gz[i] = g;
+}
+
+// Peer-memory mode: phase 4 of step j-1 and phase 2 of step j in one launch (the finish is deferred until the gains are
+// known to be complete, i.e. after the closing barrier of step j-1). The two steps use different claim arrays (step
+// parity), so returning step j-1's claims to "idle" cannot collide with step j's atomicMin on the same cell.
+__global__ void __launch_bounds__(256) k_band_finish_move_claim(BandGeom G, double agent_gamma, int32_t *xy, double *st, int n,
+                                                                const double *__restrict__ act, int *claim_new, uint8_t *gz, int do_finish,
+                                                                double *gain_prev, int *claim_prev, double *reward, uint8_t *done,
+                                                                int64_t *agents_done_at) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = st[i];
+    int x = xy[2 * i], y = xy[2 * i + 1];
+    if (do_finish) {
+        const double g = gain_prev[i];
+        gain_prev[i] = 0.0;
+        if (gz[i]) {
+            s = s + g;
+            const int lr = band_owned_row(G, x);
+            if (lr >= 0) claim_prev[(size_t)lr * G.N + y] = 0x7fffffff;
+        }
+        s = dw_clip01(s);
+        reward[i] = s;
+        done[i] = s < 0.1;
+        agents_done_at[i] += (s < 0.1) ? 0 : 1;
+    }
+    const int a = (int)act[i] - 1;
+    s = s - agent_gamma;
+    st[i] = s;
+    uint8_t g = 0;
+    if (s > 0.0) {
+        if (a != 8) {
+            const int d = (a & 2) ? 1 : -1;
+            if (((a + 1) & 2) == 0) { y += d; y = y < 0 ? y + G.N : (y >= G.N ? y - G.N : y); }
+            else { x += d; x = x < 0 ? x + G.N : (x >= G.N ? x - G.N : x); }
+            xy[2 * i] = x;
+            xy[2 * i + 1] = y;
+        }
+        if (a > 4) {
+            g = 1;
+            const int lr = band_owned_row(G, x);
+            if (lr >= 0) atomicMin(claim_new + (size_t)lr * G.N + y, i);
         }
     }
     gz[i] = g;

@@ -27,11 +27,13 @@ struct dwt_handle {
     double *act = nullptr, *gain = nullptr;
     // peer-memory mode
     PeerTable pt{};
-    unsigned int *flags = nullptr, *timed_out = nullptr;
+    unsigned int *flags = nullptr, *timed_out = nullptr, *ticket = nullptr;
+    int *claim2 = nullptr;                     // second claim array (claims alternate by step parity in peer-memory mode)
     unsigned int epoch = 0;
     uint32_t *peer_lat[2][DWT_MAX_RANKS] = {};
     std::vector<void *> ipc_opened;
     int gain_parity = 0, pending_parity = 0;
+    unsigned int decide_epoch = 0;             // != 0: the next dwt_decide launch ends in a barrier with this epoch
     bool p2p_gain_pending = false;
     bool step_open = false;      // dwt_stencil(part 1) done, part 2 pending
     uint8_t *gz = nullptr, *done = nullptr;
@@ -110,7 +112,7 @@ extern "C" int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int3
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess && cudaMemset(*p, 0, bytes) == cudaSuccess; };
     bool ok = alloc((void **)&h->lat[0], padded * 4) && alloc((void **)&h->lat[1], padded * 4) && alloc((void **)&h->claim, planes * 4) &&
               alloc((void **)&h->agent_xy, n * 8) && alloc((void **)&h->agent_state, n * 8) && alloc((void **)&h->exch, 3 * n * 8) &&
-              alloc((void **)&h->flags, (DWT_MAX_RANKS + 1) * 4) &&
+              alloc((void **)&h->flags, (DWT_MAX_RANKS + 2) * 4) &&
               alloc((void **)&h->reward, n * 8) && alloc((void **)&h->gz, n) && alloc((void **)&h->done, n) &&
               alloc((void **)&h->agents_done_at, n * 8) && alloc((void **)&h->stepmax, (size_t)DW_FUSED_MAX_STEPS * 2 * 4) &&
               alloc((void **)&h->slow_count, 4) && alloc((void **)&h->replay, n);
@@ -119,6 +121,7 @@ extern "C" int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int3
     h->gain = h->exch ? h->exch + n : nullptr;
     h->act = h->exch ? h->exch + 2 * n : nullptr;
     h->timed_out = h->flags ? h->flags + DWT_MAX_RANKS : nullptr;
+    h->ticket = h->flags ? h->flags + DWT_MAX_RANKS + 1 : nullptr;
     if (!ok) {
         g_dwt_create_error = std::string("dwt_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         dwt_destroy(h);
@@ -137,7 +140,7 @@ extern "C" int dwt_destroy(dwt_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->agent_xy, h->agent_state, h->exch, h->flags, h->reward, h->gz,
+    void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->claim2, h->agent_xy, h->agent_state, h->exch, h->flags, h->reward, h->gz,
                     h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
@@ -244,13 +247,18 @@ extern "C" int dwt_decide(dwt_handle *h, int32_t policy, const int8_t *actions, 
     const uint32_t step = (uint32_t)h->clk.step_count;
     if (h->on_lattice)
         k_band_decide<LatCells><<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), LatCells{h->lat[h->cur]}, h->agent_xy, h->n, policy,
-                                                                          h->replay, seed, step, h->pt, h->act);
+                                                                          h->replay, seed, step, h->pt, h->act, h->decide_epoch, h->timed_out, h->ticket);
     else
         k_band_decide<PlaneCells><<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_planes(h), PlaneCells{h->pl, h->pd}, h->agent_xy, h->n,
-                                                                            policy, h->replay, seed, step, h->pt, h->act);
+                                                                            policy, h->replay, seed, step, h->pt, h->act, h->decide_epoch, h->timed_out, h->ticket);
     DWT_LAUNCHED(h);
     return DW_OK;
 }
+
+// claim array of a step: always the first one outside peer-memory mode, alternating by step parity inside it
+static int *dwt_claim(const dwt_handle *h, int parity) { return (h->pt.on && parity) ? h->claim2 : h->claim; }
+
+static int dwt_graze(dwt_handle *h);
 
 extern "C" int dwt_move_graze(dwt_handle *h) {
     if (!h) return DW_E_INVALID;
@@ -258,14 +266,21 @@ extern "C" int dwt_move_graze(dwt_handle *h) {
     if (!h->n) return DW_OK;
     const int nb = dwt_blocks(h->n);
     const BandGeom G = h->on_lattice ? dwt_geom_lat(h) : dwt_geom_planes(h);
-    k_band_move_claim<<<nb, 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act, h->claim, h->gz);
+    k_band_move_claim<<<nb, 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act,
+                                                 dwt_claim(h, h->gain_parity), h->gz);
     DWT_LAUNCHED(h);
+    return dwt_graze(h);
+}
+
+static int dwt_graze(dwt_handle *h) {
+    const int nb = dwt_blocks(h->n);
+    const BandGeom G = h->on_lattice ? dwt_geom_lat(h) : dwt_geom_planes(h);
     if (h->on_lattice)
-        k_band_graze<LatCells><<<nb, 256, 0, h->stream>>>(G, LatCells{h->lat[h->cur]}, h->agent_xy, h->n, h->gz, h->claim, h->gain, h->pt,
-                                                           h->gain_parity ? 0 : h->n);
+        k_band_graze<LatCells><<<nb, 256, 0, h->stream>>>(G, LatCells{h->lat[h->cur]}, h->agent_xy, h->n, h->gz, dwt_claim(h, h->gain_parity),
+                                                           h->gain, h->pt, h->gain_parity ? 0 : h->n);
     else
-        k_band_graze<PlaneCells><<<nb, 256, 0, h->stream>>>(G, PlaneCells{h->pl, h->pd}, h->agent_xy, h->n, h->gz, h->claim, h->gain, h->pt,
-                                                             h->gain_parity ? 0 : h->n);
+        k_band_graze<PlaneCells><<<nb, 256, 0, h->stream>>>(G, PlaneCells{h->pl, h->pd}, h->agent_xy, h->n, h->gz, dwt_claim(h, h->gain_parity),
+                                                             h->gain, h->pt, h->gain_parity ? 0 : h->n);
     DWT_LAUNCHED(h);
     return DW_OK;
 }
@@ -275,7 +290,8 @@ extern "C" int dwt_finish_agents(dwt_handle *h) {
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (!h->n) return DW_OK;
     double *gain = h->pt.on ? (h->pending_parity ? h->exch : h->exch + h->n) : h->gain;
-    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), h->agent_xy, h->claim, h->agent_state, h->n, gain, h->pt.on, h->gz,
+    k_band_finish<<<dwt_blocks(h->n), 256, 0, h->stream>>>(dwt_geom_lat(h), h->agent_xy, dwt_claim(h, h->pending_parity), h->agent_state, h->n,
+                                                           gain, h->pt.on, h->gz,
                                                            h->reward, h->done, h->agents_done_at);
     DWT_LAUNCHED(h);
     return DW_OK;
@@ -542,12 +558,18 @@ extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, vo
         const void *ks[] = {(const void *)k_band_decide<LatCells>, (const void *)k_band_decide<PlaneCells>, (const void *)k_band_move_claim,
                             (const void *)k_band_graze<LatCells>, (const void *)k_band_graze<PlaneCells>, (const void *)k_band_finish,
                             (const void *)k_band_first_step, (const void *)k_tiled_step, (const void *)k_band_push_halo,
+                            (const void *)k_band_finish_move_claim,
                             (const void *)k_peer_barrier, (const void *)k_band_covers, (const void *)k_band_materialise<PreLattice>,
                             (const void *)k_band_materialise<PrePlanes>, (const void *)k_band_stamp_claim, (const void *)k_band_stamp_write,
                             (const void *)k_band_ghost_rows_wrap, (const void *)k_band_init_random};
         for (const void *k : ks) DWT_TRY(h, cudaFuncGetAttributes(&fa, k));
     }
-    DWT_TRY(h, cudaMemsetAsync(h->flags, 0, (DWT_MAX_RANKS + 1) * 4, h->stream));
+    if (!h->claim2) {
+        const size_t bytes = (size_t)(h->R + 2) * h->N * sizeof(int);
+        DWT_TRY(h, cudaMalloc((void **)&h->claim2, bytes));
+        DWT_TRY(h, cudaMemsetAsync(h->claim2, 0x7f, bytes, h->stream));
+    }
+    DWT_TRY(h, cudaMemsetAsync(h->flags, 0, (DWT_MAX_RANKS + 2) * 4, h->stream));
     DWT_TRY(h, cudaMemsetAsync(h->exch, 0, (size_t)3 * (h->n ? h->n : 1) * 8, h->stream));
     DWT_TRY(h, cudaStreamSynchronize(h->stream));
     h->pt = T;
@@ -575,13 +597,6 @@ extern "C" int dwt_ipc_attach(dwt_handle *h, int32_t rank, int32_t n_ranks, cons
     return dwt_attach_peers(h, rank, n_ranks, table.data());
 }
 
-static int dwt_barrier(dwt_handle *h) {
-    h->epoch += 1;
-    k_peer_barrier<<<1, 32, 0, h->stream>>>(h->pt, h->epoch, h->timed_out);
-    DWT_LAUNCHED(h);
-    return DW_OK;
-}
-
 // One env step of a band in peer-memory mode: no collective, no host synchronisation. Every rank must call it the same
 // number of times with the same policy. The agents of the step are finished (state += gain, reward/done) at the start of
 // the next step or by dwt_flush_p2p.
@@ -589,17 +604,25 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
     if (!h) return DW_E_INVALID;
     if (!h->pt.on) return dwt_fail(h, DW_E_STATE, "dwt_step_p2p", "attach the peers first (dwt_ipc_attach / dwt_attach_peers)");
     int rc = DW_OK;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->n) {
-        rc = dwt_decide(h, policy, actions, seed);
-        if (rc) return rc;
-        // decisions that read the world were published by the owner ranks: meet before anyone moves
+        // decisions that read the world are published by the owner ranks: the decide kernel ends in a barrier (raised by
+        // its last block) so that everyone has every decision before anyone moves
         const int pol = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)h->clk.step_count);
-        if (pol == DW_POLICY_GREEDY || pol == DW_POLICY_ANTIGREEDY) { rc = dwt_barrier(h); if (rc) return rc; }
-        if (h->p2p_gain_pending) {           // gains of the previous step are complete since its closing barrier
-            rc = dwt_finish_agents(h);
-            if (rc) return rc;
-        }
-        rc = dwt_move_graze(h);
+        const bool world_policy = pol == DW_POLICY_GREEDY || pol == DW_POLICY_ANTIGREEDY;
+        h->decide_epoch = world_policy ? ++h->epoch : 0u;
+        rc = dwt_decide(h, policy, actions, seed);
+        h->decide_epoch = 0u;
+        if (rc) return rc;
+        // finish of the previous step (its gains are complete since its closing barrier) + move + claims, one launch
+        const BandGeom G = h->on_lattice ? dwt_geom_lat(h) : dwt_geom_planes(h);
+        double *gain_prev = h->pending_parity ? h->exch : h->exch + h->n;
+        k_band_finish_move_claim<<<dwt_blocks(h->n), 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act,
+                                                                          dwt_claim(h, h->gain_parity), h->gz, h->p2p_gain_pending ? 1 : 0,
+                                                                          gain_prev, dwt_claim(h, h->pending_parity), h->reward, h->done,
+                                                                          h->agents_done_at);
+        DWT_LAUNCHED(h);
+        rc = dwt_graze(h);
         if (rc) return rc;
         h->p2p_gain_pending = true;
         h->pending_parity = h->gain_parity;
@@ -607,12 +630,14 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
     }
     rc = dwt_stencil(h, 0);
     if (rc) return rc;
+    // edge rows into the neighbours' ghost rows, then the closing barrier of the step (same launch)
     const int up = (h->pt.rank + h->pt.R - 1) % h->pt.R, down = (h->pt.rank + 1) % h->pt.R;
+    h->epoch += 1;
     k_band_push_halo<<<dwt_blocks(h->pitch), 256, 0, h->stream>>>(h->lat[h->cur], h->R, h->pitch,
                                                                   h->peer_lat[h->cur][up] + (size_t)(h->R + 1) * h->pitch,
-                                                                  h->peer_lat[h->cur][down]);
+                                                                  h->peer_lat[h->cur][down], h->pt, h->epoch, h->timed_out, h->ticket);
     DWT_LAUNCHED(h);
-    return dwt_barrier(h);
+    return DW_OK;
 }
 
 extern "C" int dwt_flush_p2p(dwt_handle *h) {
