@@ -176,6 +176,12 @@ int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states);
 int dw_get_obs(dw_handle *h, double *obs);                                /* obs of the last step / current state */
 int dw_get_reward_done(dw_handle *h, double *reward, uint8_t *done);      /* [B,n] (or [B,2] when n_agents==0) */
 int dw_get_diag(dw_handle *h, int32_t which, double *out);                /* env.temp, env.beta_l, env.growth ... */
+/* Ensemble statistics of one diagnostic field reduced on the device (what the notebooks compute with env.temp.mean(),
+   notebook_helpers.py:50,145,218): out = {mean, population std, min, max} over all worlds and cells (both channels for
+   DW_DIAG_GROWTH). Nothing but four doubles leaves the device. */
+int dw_get_diag_stats(dw_handle *h, int32_t which, double *out /*[4]*/);
+/* The same for the daisy covers of the current state: out = {mean light, mean dark, max light, max dark}. */
+int dw_get_cover_stats(dw_handle *h, double *out /*[4]*/);
 
 /* K fused steps with an on-device policy and the notebook lifespan counters
    (notebooks/greedy_longevity_abatement.ipynb cell 2): done_at[b] += !grid_done, agents_done_at[b,i] += !done.

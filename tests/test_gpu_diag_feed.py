@@ -1,0 +1,42 @@
+"""Next-row N3 (diagnostics feed): ensemble statistics of the unrounded diagnostic fields and of the covers, reduced on the
+device, against NumPy on the downloaded fields -- after a reset, after single steps and after fused runs."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, product_env_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(env):
+    for name in ("temp", "temp_light", "beta_l", "growth"):
+        s, f = env.diag_stats(name), getattr(env, name)
+        np.testing.assert_allclose([s["mean"], s["min"], s["max"]], [f.mean(), f.min(), f.max()], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(s["std"], f.std(), rtol=1e-9)        # NumPy's own two-pass std vs the shifted one-pass sum
+    c, g = env.cover_stats(), env.grid
+    np.testing.assert_allclose([c["mean_light"], c["mean_dark"], c["max_light"], c["max_dark"]],
+                               [g[:, 1].mean(), g[:, 2].mean(), g[:, 1].max(), g[:, 2].max()], rtol=1e-12)
+
+
+def test_device_statistics_match_numpy_in_every_state():
+    z, meta = load_golden("greedy_n64_b2_120")
+    env = product_env_from_golden(z, meta)
+    env.run(1, policy="greedy")          # lean first step: pre-state = cover planes
+    stats_before = env.cover_stats()     # lattice path (no grid materialised yet)
+    _check(env)
+    assert stats_before == env.cover_stats()
+    env.run(40, policy="greedy")         # fused: pre-state = lattice
+    _check(env)
+    env.step_policy("greedy")            # materialising step: pre-state = grid
+    _check(env)
+    # the reference's global mean temperature of the last forward (notebook_helpers.py:50)
+    np.testing.assert_allclose(env.diag_stats("temp")["mean"], env.temp.mean(), rtol=1e-12)
+
+
+def test_series_helper_records_the_plot_feed():
+    z, meta = load_golden("greedy_n16_b4_todeath")
+    env = product_env_from_golden(z, meta)
+    series = env.run_with_series(96, every=32)
+    assert [s["step"] for s in series] == [32, 64, 96]
+    assert all(200 < s["temp_mean"] < 400 and 0 <= s["light"] <= 1 for s in series)
+    np.testing.assert_allclose(series[-1]["temp_mean"], env.temp.mean(), rtol=1e-12)

@@ -778,6 +778,72 @@ extern "C" int dw_get_diag(dw_handle *h, int32_t which, double *out) {
     return DW_OK;
 }
 
+// unrounded diagnostic field `which` of the last forward into h->scratch (count elements)
+static int diag_to_scratch(dw_handle *h, int32_t which, size_t extra, size_t *count_out) {
+    if (h->pre == PRE_NONE) return dw_fail(h, DW_E_STATE, "dw_get_diag", "no forward pass has run on this state yet");
+    const DevParams P = make_params(h);
+    const size_t total = (size_t)P.B * h->NN, count = total * (which == DW_DIAG_GROWTH ? 2 : 1);
+    int rc = ensure_scratch(h, count + extra);
+    if (rc) return rc;
+    const double SL = h->cfg.S * h->L_last;
+    if (h->pre == PRE_GRID) k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcGrid{h->pre_grid, 7 * h->NN, h->NN}, which, h->scratch);
+    else if (h->pre == PRE_COV) k_diag<SrcCov><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcCov{h->cov, h->NN}, which, h->scratch);
+    else k_diag<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcLattice{h->lat_pre, h->NN}, which, h->scratch);
+    DW_LAUNCHED(h);
+    *count_out = count;
+    return DW_OK;
+}
+
+extern "C" int dw_get_diag_stats(dw_handle *h, int32_t which, double *out) {
+    if (!h || !out || which < 0 || which > DW_DIAG_GROWTH) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int blocks = 148 * 4;
+    size_t count = 0;
+    int rc = diag_to_scratch(h, which, (size_t)blocks * 4 + 4, &count);
+    if (rc) return rc;
+    double *partial = h->scratch + count, *res = partial + (size_t)blocks * 4;
+    k_stats_partial<<<blocks, 256, 0, h->stream>>>(h->scratch, count, partial);
+    k_stats_final<<<1, 256, 0, h->stream>>>(partial, blocks, (double)count, h->scratch, res);
+    DW_LAUNCHED(h);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(out, res, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_cover_stats(dw_handle *h, double *out) {
+    if (!h || !out) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int blocks = 148 * 4;
+    const size_t cells = (size_t)h->cfg.batch * h->NN;
+    int rc = ensure_scratch(h, (size_t)blocks * 4 + 4 + 2 * cells);
+    if (rc) return rc;
+    double *partial = h->scratch, *res = partial + (size_t)blocks * 4;
+    if (h->lat_valid && !h->grid_valid) {
+        k_lattice_cover_partial<<<blocks, 256, 0, h->stream>>>(h->lat[h->lcur], cells, partial);
+        k_cover_final<<<1, 256, 0, h->stream>>>(partial, blocks, (double)cells, res);
+        DW_LAUNCHED(h);
+    } else {
+        // fp64 representations: two passes of the generic reduction over the light / dark planes
+        rc = ensure_grid(h);
+        if (rc) return rc;
+        double *planes = res + 4, tmp[8];
+        for (int c = 0; c < 2; ++c) {
+            DW_CUDA_TRY(h, cudaMemcpy2DAsync(planes, h->NN * sizeof(double), h->grid[h->cur] + (size_t)(1 + c) * h->NN, 7 * h->NN * sizeof(double),
+                                             h->NN * sizeof(double), h->cfg.batch, cudaMemcpyDeviceToDevice, h->stream));
+            k_stats_partial<<<blocks, 256, 0, h->stream>>>(planes, cells, partial);
+            k_stats_final<<<1, 256, 0, h->stream>>>(partial, blocks, (double)cells, planes, res);
+            DW_LAUNCHED(h);
+            DW_CUDA_TRY(h, cudaMemcpyAsync(tmp + 4 * c, res, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        }
+        out[0] = tmp[0]; out[1] = tmp[4]; out[2] = tmp[3]; out[3] = tmp[7];
+        return DW_OK;
+    }
+    DW_CUDA_TRY(h, cudaMemcpyAsync(out, res, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
 // ---- lifespan runs ---------------------------------------------------------------------------------------
 extern "C" int dw_reset_lifespans(dw_handle *h) {
     if (!h) return DW_E_INVALID;

@@ -518,6 +518,76 @@ __global__ void __launch_bounds__(128) k_pop_accumulate(int wpm, int n, int half
     }
 }
 
+// ---- ensemble statistics of a field (deterministic two-stage reduction: per-block partials, then one block) --------------
+// partial[b] = {sum, sum of squares, min, max}
+__device__ __forceinline__ void dw_stats_block_reduce(double s, double q, double mn, double mx, double *out4) {
+    __shared__ double sh[4][8];
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][w] = s; sh[1][w] = q; sh[2][w] = mn; sh[3][w] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { s += sh[0][i]; q += sh[1][i]; mn = fmin(mn, sh[2][i]); mx = fmax(mx, sh[3][i]); }
+        out4[0] = s; out4[1] = q; out4[2] = mn; out4[3] = mx;
+    }
+}
+// sums are taken of (x - x[0]): shifted data keeps the variance free of the E[x^2] - mean^2 cancellation
+__global__ void __launch_bounds__(256) k_stats_partial(const double *__restrict__ x, size_t n, double *__restrict__ partial) {
+    double s = 0.0, q = 0.0, mn = 1e300, mx = -1e300;
+    const double shift = x[0];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = x[i], d = v - shift;
+        s += d; q += d * d; mn = fmin(mn, v); mx = fmax(mx, v);
+    }
+    dw_stats_block_reduce(s, q, mn, mx, partial + 4 * blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_stats_final(const double *__restrict__ partial, int blocks, double count, const double *__restrict__ x,
+                                                     double *__restrict__ out) {
+    double s = 0.0, q = 0.0, mn = 1e300, mx = -1e300;
+    for (int i = threadIdx.x; i < blocks; i += blockDim.x) {
+        s += partial[4 * i]; q += partial[4 * i + 1]; mn = fmin(mn, partial[4 * i + 2]); mx = fmax(mx, partial[4 * i + 3]);
+    }
+    __shared__ double r[4];
+    dw_stats_block_reduce(s, q, mn, mx, r);
+    if (threadIdx.x == 0) {
+        const double dm = r[0] / count, var = r[1] / count - dm * dm;
+        out[0] = x[0] + dm; out[1] = sqrt(var > 0.0 ? var : 0.0); out[2] = r[2]; out[3] = r[3];
+    }
+}
+// covers of the packed lattice: {sum light, sum dark, max light, max dark} in milli units per block (exact integers)
+__global__ void __launch_bounds__(256) k_lattice_cover_partial(const uint32_t *__restrict__ lat, size_t n, double *__restrict__ partial) {
+    unsigned long long sl = 0, sd = 0;
+    unsigned int ml = 0, md = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t w = lat[i];
+        sl += w & 0xffffu; sd += w >> 16; ml = max(ml, w & 0xffffu); md = max(md, w >> 16);
+    }
+    // reuse the generic block reduce: sums in the s/q slots, maxima through the max slot (two passes keep it simple)
+    double o1[4], o2[4];
+    dw_stats_block_reduce((double)sl, (double)sd, 0.0, (double)ml, o1);
+    __syncthreads();
+    dw_stats_block_reduce(0.0, 0.0, 0.0, (double)md, o2);
+    if (threadIdx.x == 0) {
+        partial[4 * blockIdx.x] = o1[0]; partial[4 * blockIdx.x + 1] = o1[1]; partial[4 * blockIdx.x + 2] = o1[3]; partial[4 * blockIdx.x + 3] = o2[3];
+    }
+}
+__global__ void __launch_bounds__(256) k_cover_final(const double *__restrict__ partial, int blocks, double cells, double *__restrict__ out) {
+    double sl = 0.0, sd = 0.0, ml = 0.0, md = 0.0;
+    for (int i = threadIdx.x; i < blocks; i += blockDim.x) {
+        sl += partial[4 * i]; sd += partial[4 * i + 1]; ml = fmax(ml, partial[4 * i + 2]); md = fmax(md, partial[4 * i + 3]);
+    }
+    __shared__ double r1[4], r2[4];
+    dw_stats_block_reduce(sl, sd, 0.0, ml, r1);
+    __syncthreads();
+    dw_stats_block_reduce(0.0, 0.0, 0.0, md, r2);
+    if (threadIdx.x == 0) { out[0] = r1[0] / cells / 1000.0; out[1] = r1[1] / cells / 1000.0; out[2] = r1[3] / 1000.0; out[3] = r2[3] / 1000.0; }
+}
+
 // ---- device-side synthetic initial state (throughput ensembles; NOT numpy-stream compatible) -----------------------
 // Same distribution as initialize_grid/initialize_agents (daisy_world_rl.py:285-302,173-179): per cell and species
 // u0,u1 ~ U[0,1): cover = (u0 < proportion) * initial * u1; agents uniform on the grid with state 1.

@@ -301,6 +301,35 @@ class RLDaisyWorld:
     beta_d = property(lambda self: self._diag("beta_d"))
     growth = property(lambda self: self._diag("growth"))
 
+    def diag_stats(self, name):
+        """{mean, std, min, max} of a diagnostic field (temp, temp_light, ..., growth) over the whole ensemble, reduced on
+        the device: what the notebooks compute with env.temp.mean() (notebook_helpers.py:50,145,218) without the download."""
+        out = np.zeros(4)
+        self._push()
+        self._check(self._lib.dw_get_diag_stats(self._h, DW_DIAG[name], _ptr(out, C.c_double)), "dw_get_diag_stats")
+        return dict(mean=out[0], std=out[1], min=out[2], max=out[3])
+
+    def cover_stats(self):
+        """Mean and max light / dark cover of the current state over the whole ensemble, reduced on the device."""
+        out = np.zeros(4)
+        self._push()
+        self._check(self._lib.dw_get_cover_stats(self._h, _ptr(out, C.c_double)), "dw_get_cover_stats")
+        return dict(mean_light=out[0], mean_dark=out[1], max_light=out[2], max_dark=out[3])
+
+    def run_with_series(self, K, every=16, policy="greedy", seed=0):
+        """K steps in chunks of `every`, recording after each chunk the ensemble diagnostics the reference's plot helpers
+        read per step (notebook_helpers.py:45-57): global mean temperature, covers, luminosity, bare-planet temperature."""
+        series = []
+        done = 0
+        while done < K:
+            k = min(every, K - done)
+            self.run(k, policy=policy, seed=seed)
+            done += k
+            t, c = self.diag_stats("temp"), self.cover_stats()
+            series.append(dict(step=self.step_count, L=self.L, temp_mean=t["mean"], temp_std=t["std"], dead_temp=float(self.dead_temp[0]),
+                               light=c["mean_light"], dark=c["mean_dark"]))
+        return series
+
     @property
     def dead_temp(self):
         """reference :406-407,416 -- bare-planet temperature at the L of the last forward."""
