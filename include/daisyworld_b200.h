@@ -192,6 +192,10 @@ int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint6
 /* Multi-rank variant: run exactly `K` (<=64) steps and return, per step, whether every world of THIS handle
    was grid_done (bit j of *done_mask = step j); the caller ANDs masks across ranks and decides. */
 int dw_run_chunk(dw_handle *h, int32_t K, int32_t policy, const int8_t *actions, uint64_t seed, uint64_t *done_mask);
+/* dw_run that also returns, for every step, the ensemble means the reference's plot helpers read (notebook_helpers.py:
+   45-57): out[K][3] = {global mean of the unrounded temperature of that step's forward (env.temp.mean()), mean light cover,
+   mean dark cover after the step}, reduced inside the fused kernel. 64x64 worlds, n_agents <= 32, K <= 4096. */
+int dw_run_series(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed, double *out);
 int dw_reset_lifespans(dw_handle *h);
 int dw_get_lifespans(dw_handle *h, int64_t *done_at /*[B]*/, int64_t *agents_done_at /*[B,n]*/);
 /* Ensemble statistics of the lifespan counters on the DEVICE, for an NCCL all-reduce by the caller:

@@ -40,3 +40,28 @@ def test_series_helper_records_the_plot_feed():
     assert [s["step"] for s in series] == [32, 64, 96]
     assert all(200 < s["temp_mean"] < 400 and 0 <= s["light"] <= 1 for s in series)
     np.testing.assert_allclose(series[-1]["temp_mean"], env.temp.mean(), rtol=1e-12)
+
+
+def test_in_kernel_series_matches_oracle_per_step():
+    """dw_run_series: the per-step global mean temperature (env.temp.mean() of the reference, notebook_helpers.py:50) and
+    mean covers, reduced inside the fused kernel, against the NumPy oracle stepped with its Greedy restatement."""
+    from oracle.daisy_numpy import OracleGreedy, env_from_golden
+    z, meta = load_golden("greedy_n64_b2_120")
+    env = product_env_from_golden(z, meta)
+    K = 60
+    series = env.run_series(K, policy="greedy")
+    oenv, _ = env_from_golden(z)
+    agent = OracleGreedy()
+    obs = oenv.get_obs(oenv.agent_indices)
+    ref = np.zeros((K, 3))
+    for t in range(K):
+        obs, _, _, _ = oenv.step(agent(obs))
+        ref[t] = [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()]
+    np.testing.assert_allclose(series[:, 0], ref[:, 0], rtol=1e-9)          # north_star tolerance for fp64 fields
+    np.testing.assert_allclose(series[:, 1:], ref[:, 1:], rtol=1e-12)
+    np.testing.assert_array_equal(env.grid, oenv.grid)                      # the run itself is unchanged by the series mode
+    # a second call continues from the lattice state (all steps inside the kernel)
+    s2 = env.run_series(10, policy="greedy")
+    for t in range(10):
+        obs, _, _, _ = oenv.step(agent(obs))
+        np.testing.assert_allclose(s2[t], [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()], rtol=1e-9)

@@ -38,7 +38,7 @@ SYMBOLS = [
     "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_set_mlp_population", "dw_run_population", "dw_get_population_results",
     "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_collect", "dw_step_policy", "dw_update_agents",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
-    "dw_run", "dw_run_chunk", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
+    "dw_run", "dw_run_chunk", "dw_run_series", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
     "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak",
 ]
@@ -113,6 +113,7 @@ def load():
         "dw_get_cover_stats": (C.c_int, [vp, pd]),
         "dw_run": (C.c_int, [vp, i64, i32, pi8, u64, i32, C.POINTER(DwRunResult)]),
         "dw_run_chunk": (C.c_int, [vp, i32, i32, pi8, u64, C.POINTER(u64)]),
+        "dw_run_series": (C.c_int, [vp, i64, i32, pi8, u64, pd]),
         "dw_reset_lifespans": (C.c_int, [vp]),
         "dw_get_lifespans": (C.c_int, [vp, pi64, pi64]),
         "dw_lifespan_stats_device": (C.c_int, [vp, vp]),

@@ -60,6 +60,11 @@ struct dw_handle {
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     double epsilon = 0.0;                      // Greedy.epsilon of DW_POLICY_EPS_GREEDY
+    // series mode of the fused kernel (dw_run_series)
+    bool series_on = false;
+    int64_t series_pos = 0;
+    double *series_T = nullptr;
+    unsigned long long *series_l = nullptr, *series_d = nullptr;
     double *mlp_dev = nullptr;                 // [DW_MLP_PARAMS] weights of DW_POLICY_MLP, or [n_members][DW_MLP_PARAMS]
     size_t mlp_cap = 0;
     bool mlp_set = false;
@@ -268,7 +273,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
+                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &c : h->ck) {

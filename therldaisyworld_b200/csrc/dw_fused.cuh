@@ -36,6 +36,8 @@ struct FastCoef {        // launch-constant coefficients of the fast path (host-
     double xk_l, xk_d;   // g^2 * X_l coefficients of the centre covers: (q2-q)*(al-ab)/1000, (q2-q)*(ad-ab)/1000
     double xdd;          // g^2 * (X_d - X_l) = g^2 * q2*(al-ad)
     double topt;         // sqrt(g) * Topt
+    // series mode: X_T = T^4 (scaled by g^2) = X_l + t0 + tk_l*kl + tk_d*kd, with t0 = -g^2 q2 (Al0 - al), tk = -g^2 q2 (a - ab)/1000
+    double t0, tk_l, tk_d;
 };
 struct StepCoef {        // per-step (luminosity dependent) coefficients
     double x0;           // g^2 * (cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al)
@@ -65,6 +67,10 @@ struct FusedArgs {
     unsigned int world0;        // global index of this handle's first world (RANDOM policy counter)
     int K, policy;
     unsigned int *slow_count;   // diagnostics: number of literal recomputations (may be NULL)
+    // series mode (k_fused_n64_persist<true>): per-step ensemble sums, [K] each: sqrt(g)*T of the step's forward (unrounded),
+    // light and dark milli-cover after the step
+    double *series_T;
+    unsigned long long *series_l, *series_d;
     // persistent kernel only
     int Kc;                     // steps per work item
     int n_pairs, n_chunks;      // work items = n_pairs (worlds) * n_chunks, chunk-major
@@ -152,9 +158,9 @@ __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCo
 
 // Two cells in explicit lockstep: the fp64 chain of one cell is serial (8-cycle dependent latency, measured), so the
 // source interleaves two independent cells statement by statement to give the scheduler ILP without more warps.
-template <int W>
+template <int W, bool DIAG = false>
 __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef &C, const uint32_t (&pc)[W], const uint32_t (&E)[W],
-                                              const uint32_t (&S)[W], unsigned *tiemin, uint32_t (&out)[W]) {
+                                              const uint32_t (&S)[W], unsigned *tiemin, uint32_t (&out)[W], double *tsum = nullptr) {
     double kl[W], kd[W], El[W], Ed[W], Sl[W], Sd[W], Rl[W], Rd[W], rb[W], Xl[W], Xd[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) { kl[i] = dw_half2d<0>(pc[i]); kd[i] = dw_half2d<1>(pc[i]); }
@@ -166,6 +172,10 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
     for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(C.xs_l, Sl[i], __fma_rn(C.xs_d, Sd[i], Xl[i]));
 #pragma unroll
     for (int i = 0; i < W; ++i) Xd[i] = Xl[i] + F.xdd;
+    if (DIAG) {              // series mode: the (unrounded) temperature of the cell itself, sqrt(g)*T, summed per thread
+#pragma unroll
+        for (int i = 0; i < W; ++i) *tsum += dw_root4_fast(__fma_rn(F.tk_l, kl[i], __fma_rn(F.tk_d, kd[i], Xl[i] + F.t0)));
+    }
     // seeds first: the MUFU latency (27 cycles) overlaps the rho arithmetic below
     double s1l[W], s1d[W], y0l[W], y0d[W];
 #pragma unroll
@@ -435,6 +445,7 @@ __device__ __noinline__ uint32_t dw_fix_warp64(const FusedArgs *A, const StepCoe
             extra = __vmaxu2(extra, v);
         }
     }
+    __syncwarp();                                        // patches made by helper lanes are visible to the tile's owner
     return __vmaxu2(mine ? 0u : mx, extra);
 }
 
@@ -473,9 +484,9 @@ struct StoreWorld64 {
 
 // One step of one 4x4 tile (fast path): rows come from `rows`, results go to `store`. Returns the packed per-species
 // max of the 16 new cells; *tiemin drops below DW_TIE_THRESH if some cell needs the literal recomputation.
-template <class Rows, class Store>
+template <class Rows, class Store, bool DIAG = false>
 __device__ __forceinline__ uint32_t dw_tile_core(const FastCoef &F, const StepCoef &C, const Rows &rows, const Store &store,
-                                                 unsigned *tiemin) {
+                                                 unsigned *tiemin, double *tsum = nullptr) {
     uint32_t mx = 0;
     Row6 top = rows.load(-1);
     Row6 mid = rows.load(0);
@@ -498,12 +509,12 @@ __device__ __forceinline__ uint32_t dw_tile_core(const FastCoef &F, const StepCo
             const uint32_t pa[2] = {mid.p[0], mid.p[1]}, ea[2] = {E[0], E[1]}, sa[2] = {S8[0], S8[1]};
             const uint32_t pb[2] = {mid.p[2], mid.p[3]}, eb[2] = {E[2], E[3]}, sb[2] = {S8[2], S8[3]};
             uint32_t qa[2], qb[2];
-            dw_fast_cells<2>(F, C, pa, ea, sa, tiemin, qa);
-            dw_fast_cells<2>(F, C, pb, eb, sb, tiemin, qb);
+            dw_fast_cells<2, DIAG>(F, C, pa, ea, sa, tiemin, qa, tsum);
+            dw_fast_cells<2, DIAG>(F, C, pb, eb, sb, tiemin, qb, tsum);
             q[0] = qa[0]; q[1] = qa[1]; q[2] = qb[0]; q[3] = qb[1];
         }
 #else
-        dw_fast_cells<4>(F, C, mid.p, E, S8, tiemin, q);
+        dw_fast_cells<4, DIAG>(F, C, mid.p, E, S8, tiemin, q, tsum);
 #endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) mx = __vmaxu2(mx, q[c]);
@@ -515,10 +526,12 @@ __device__ __forceinline__ uint32_t dw_tile_core(const FastCoef &F, const StepCo
 }
 
 // One step of one 4x4 tile of a 64x64 world: cb -> nb. Returns the packed per-species max of the tile's new cells.
-__device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, const uint32_t *cb, uint32_t *nb, int r0, int tx, int lane) {
+template <bool DIAG = false>
+__device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, const uint32_t *cb, uint32_t *nb, int r0, int tx, int lane,
+                                                   double *tsum = nullptr) {
     const StepCoef C = A.sc[j];
     unsigned tiemin = 0xffffffffu;
-    uint32_t mx = dw_tile_core(A.F, C, RowsWorld64{cb, r0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin);
+    uint32_t mx = dw_tile_core<RowsWorld64, StoreWorld64, DIAG>(A.F, C, RowsWorld64{cb, r0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin, tsum);
     // rare (~2e-4 of tile-steps): some cell of this tile sits on a rounding tie -> the warp redoes that tile's ties literally
     const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
     if (flagged) mx = dw_fix_warp64(&A, &A.sc[j], cb, nb, flagged, mx, r0, tx * 4, lane);
@@ -674,8 +687,11 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
     }
 }
 
+template <bool DIAG>
 __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(const __grid_constant__ FusedArgs A) {
     __shared__ N64Smem sm;
+    __shared__ double s_tsum;
+    __shared__ unsigned int s_cov[2];
     constexpr int NN = 4096;
     const int n = A.P.n_agents;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -706,6 +722,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             sm.ada[tid] = 0;
         }
         if (tid < 4) sm.smax[tid] = 0;
+        if (DIAG && tid == 0) { s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u; }
         __syncthreads();
 
         int life = 0;
@@ -720,11 +737,32 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
 #pragma unroll
                 for (int k = 0; k < 4; ++k) gp[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
             }
-            const uint32_t mx = dw_tile_step64(A, j, cb, nb, r0, tx, lane);
+            double tsum = 0.0;
+            const uint32_t mx = dw_tile_step64<DIAG>(A, j, cb, nb, r0, tx, lane, &tsum);
             const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
             int *smx = sm.smax + 2 * (jl & 1);
             if (lane == 0) { atomicMax(smx, (int)ml); atomicMax(smx + 1, (int)md); }
+            if (DIAG) {
+                // series mode: warp-shuffle reductions of the temperature sum and of the new covers of this thread's tile
+                unsigned int cl = 0, cd = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(nb + (r0 + i) * 64 + tx * 4);   // own stores (fix-ups: see below)
+                    cl += (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu) + (v.w & 0xffffu);
+                    cd += (v.x >> 16) + (v.y >> 16) + (v.z >> 16) + (v.w >> 16);
+                }
+                for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+                cl = __reduce_add_sync(0xffffffffu, cl);
+                cd = __reduce_add_sync(0xffffffffu, cd);
+                if (lane == 0) { atomicAdd(&s_tsum, tsum); atomicAdd(&s_cov[0], cl); atomicAdd(&s_cov[1], cd); }
+            }
             __syncthreads();
+            if (DIAG && tid == 0) {
+                atomicAdd(A.series_T + j, s_tsum);
+                atomicAdd(A.series_l + j, (unsigned long long)s_cov[0]);
+                atomicAdd(A.series_d + j, (unsigned long long)s_cov[1]);
+                s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u;      // the next adds come after the next step's first barrier
+            }
             if (tid == 0) {
                 // lifespan bookkeeping of step j (notebook cell 2): grid_done = max(grid[:,1:3]) <= 0.005
                 if (max(smx[0], smx[1]) > 5) { life += 1; atomicAdd(A.alive + j, 1u); }

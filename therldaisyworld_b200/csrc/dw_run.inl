@@ -37,6 +37,10 @@ static void make_fast_coef(const dw_config &c, FastCoef &F) {
     F.xk_d = g2 * ((c.q2 - c.q) * cd);
     F.xdd = g2 * (c.q2 * (c.albedo_light - c.albedo_dark));
     F.topt = sqrt(c.g) * c.temp_optimal;
+    const double Al0 = c.albedo_bare * c.p;
+    F.t0 = -g2 * (c.q2 * (Al0 - c.albedo_light));
+    F.tk_l = -g2 * (c.q2 * cl);
+    F.tk_d = -g2 * (c.q2 * cd);
 }
 
 static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
@@ -114,9 +118,11 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     if (persist) {
         if (!h->persist_blocks) {
             int per_sm = 0, sms = 0;
-            DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist, cudaFuncAttributePreferredSharedMemoryCarveout,
+            DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                 cudaSharedmemCarveoutMaxShared));
-            DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist, 256, 0));
+            DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                cudaSharedmemCarveoutMaxShared));
+            DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist<true>, 256, 0));
             DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
             if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "persistent kernel does not fit on an SM");
             h->persist_blocks = per_sm * sms;
@@ -134,7 +140,15 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         A.lat = h->lat[h->lcur];                      // in place
         const long long items = (long long)A.n_pairs * A.n_chunks;
         const int grid = (int)(items < h->persist_blocks ? items : h->persist_blocks);
-        k_fused_n64_persist<<<grid, 256, 0, h->stream>>>(A);
+        if (h->series_on) {
+            A.series_T = h->series_T + h->series_pos;
+            A.series_l = h->series_l + h->series_pos;
+            A.series_d = h->series_d + h->series_pos;
+            k_fused_n64_persist<true><<<grid, 256, 0, h->stream>>>(A);
+            h->series_pos += K;
+        } else {
+            k_fused_n64_persist<false><<<grid, 256, 0, h->stream>>>(A);
+        }
     } else {
         const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
         if (smem > 48 * 1024 && !h->fused_attr_set) {
@@ -407,5 +421,60 @@ extern "C" int dw_get_population_results(dw_handle *h, double *fitness, int64_t 
         DW_CUDA_TRY(h, cudaMemcpyAsync(total_steps, h->pop_frozen, (size_t)h->cfg.batch * n * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (fitness) for (int m = 0; m < P; ++m) fitness[m] = sum[m] / (double)(wpm * n);     // sges.py:179
+    return DW_OK;
+}
+
+// ---- per-step ensemble series from inside the fused kernel ---------------------------------------------------------------
+// K steps with the on-device policy; out[K][3] = per step {global mean of the unrounded temperature of that step's forward
+// (env.temp.mean(), notebook_helpers.py:50), mean light cover, mean dark cover after the step}, reduced in the kernel
+// (warp shuffles -> per-world shared atomics -> one global atomic per world-step). 64x64 worlds with <= 32 agents.
+extern "C" int dw_run_series(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed, double *out) {
+    if (!h || !out || K < 1 || K > DW_FUSED_MAX_STEPS) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.dim != 64 || h->cfg.n_agents > DW_N64_MAX_AGENTS || !dw_fused_supported(h) || policy == DW_POLICY_MLP)
+        return dw_fail(h, DW_E_UNSUPPORTED, "dw_run_series", "series mode runs in the persistent 64x64 kernel (n_agents <= 32, built-in policies)");
+    int rc = dev_alloc(h, &h->series_T, (size_t)DW_FUSED_MAX_STEPS);
+    if (!rc) rc = dev_alloc(h, &h->series_l, (size_t)DW_FUSED_MAX_STEPS);
+    if (!rc) rc = dev_alloc(h, &h->series_d, (size_t)DW_FUSED_MAX_STEPS);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->series_T, 0, K * sizeof(double), h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->series_l, 0, K * sizeof(unsigned long long), h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->series_d, 0, K * sizeof(unsigned long long), h->stream));
+    const double cells = (double)h->cfg.batch * (double)h->NN;
+    int64_t done = 0;
+    if (!h->lat_valid) {
+        // the step that leaves the off-lattice reset state is literal: its statistics come from the lazy diagnostics
+        dw_run_result r;
+        rc = dw_run(h, 1, policy, actions, seed, 0, &r);
+        if (rc) return rc;
+        double t[4], c[4];
+        rc = dw_get_diag_stats(h, DW_DIAG_TEMP, t);
+        if (!rc) rc = dw_get_cover_stats(h, c);
+        if (rc) return rc;
+        out[0] = t[0]; out[1] = c[0]; out[2] = c[1];
+        done = 1;
+        if (actions) actions += (size_t)h->cfg.batch * h->cfg.n_agents;
+    }
+    if (done < K) {
+        h->series_on = true;
+        h->series_pos = 0;
+        dw_run_result r;
+        rc = dw_run(h, K - done, policy, actions, seed, 0, &r);
+        h->series_on = false;
+        if (rc) return rc;
+        const int64_t m = K - done;
+        std::vector<double> T(m);
+        std::vector<unsigned long long> l(m), d(m);
+        DW_CUDA_TRY(h, cudaMemcpyAsync(T.data(), h->series_T, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaMemcpyAsync(l.data(), h->series_l, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaMemcpyAsync(d.data(), h->series_d, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        const double inv_sqrt_g = 1.0 / sqrt(h->cfg.g);
+        for (int64_t j = 0; j < m; ++j) {
+            out[3 * (done + j)] = T[j] * inv_sqrt_g / cells;
+            out[3 * (done + j) + 1] = (double)l[j] / 1000.0 / cells;
+            out[3 * (done + j) + 2] = (double)d[j] / 1000.0 / cells;
+        }
+    }
     return DW_OK;
 }

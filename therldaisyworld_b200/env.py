@@ -316,6 +316,22 @@ class RLDaisyWorld:
         self._check(self._lib.dw_get_cover_stats(self._h, _ptr(out, C.c_double)), "dw_get_cover_stats")
         return dict(mean_light=out[0], mean_dark=out[1], max_light=out[2], max_dark=out[3])
 
+    def run_series(self, K, policy="greedy", actions=None, seed=0):
+        """run() that also returns the per-step ensemble means [K, 3] = (global mean temperature of that step's forward --
+        env.temp.mean() --, mean light cover, mean dark cover), reduced inside the fused kernel (64x64 worlds)."""
+        B, N, n = self._shape
+        a8 = None
+        if policy == "replay":
+            a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
+        out = np.zeros((int(K), 3))
+        self._push()
+        rc = self._lib.dw_run_series(self._h, int(K), DW_POLICY[policy], _ptr(a8, C.c_int8), C.c_uint64(seed), _ptr(out, C.c_double))
+        self._check(rc, "dw_run_series")
+        self._state_changed()
+        self._pull_clock()
+        self._dead_L = None
+        return out
+
     def run_with_series(self, K, every=16, policy="greedy", seed=0):
         """K steps in chunks of `every`, recording after each chunk the ensemble diagnostics the reference's plot helpers
         read per step (notebook_helpers.py:45-57): global mean temperature, covers, luminosity, bare-planet temperature."""
