@@ -24,7 +24,8 @@ def test_fast_root4_relative_error_bound():
     the measured error is ~1e-13."""
     env = _env()
     rng = np.random.RandomState(0)
-    x = np.concatenate([10.0 ** rng.uniform(8, 11.5, size=400000), np.linspace(3e9, 2e10, 100000)])
+    # the kernels take the root of X' = g^2 * T^4 (g = 0.003265: 1e4..2e5; other g shift the range), the literal T^4 is ~1e10
+    x = np.concatenate([10.0 ** rng.uniform(2, 11.5, size=600000), np.linspace(3e9, 2e10, 100000), np.linspace(1e4, 3e5, 100000)])
     y = np.empty_like(x)
     rc = env._lib.dw_debug_root4(env._h, x.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double)), x.size)
     assert rc == 0
