@@ -5,7 +5,7 @@
 // 64x64.  The 3x3 stencils become exact integer sums on the packed words (ALU pipe), and the per-cell physics is
 // a short fp64 sequence ("fast path") that is algebraically equal to the reference formulas but not in the
 // reference's rounding order.  Exactness is restored by a filter: the fast path's result x (in milli-cover
-// units) has a proven error bound far below the filter width; whenever x lies within DW_TIE_EPS of a rounding
+// units) has a proven error bound far below the filter width; whenever x lies within the filter (F.tie_*) of a rounding
 // tie the cell is recomputed by dw_literal_cell() in the oracle's operation order.  Everything else the step
 // needs (agent moves, grazing, greedy argmax, lifespan counters) follows the literal order as well, so a fused
 // run is value-identical to stepping the oracle -- tests/test_gpu_run_parity.py.
@@ -26,7 +26,8 @@
 #define DW_FUSED_MAX_STEPS 4096        // longest launch (coefficient table / alive counters)
 #define DW_FUSED_MAX_AGENTS 1024
 #define DW_FIX_BITS 20                 // fixed-point fraction bits of the rounding trick (ulp of 1.5*2^32)
-#define DW_TIE_EPS 4                   // filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover)
+#define DW_TIE_EPS_MIN 4               // smallest filter half-width in units of 2^-DW_FIX_BITS (3.8e-6 milli-cover); the host widens
+#define DW_TIE_EPS_MAX 256             // it per handle from the physics constants (make_fast_coef, error budget in DESIGN.md section 2)
 
 // The fast path works with X' = g^2 * X (X = T_l^4 resp. T_d^4): its fourth root is T' = sqrt(g)*T, so that
 // beta = 1 - g*(Topt-T)^2 = 1 - (sqrt(g)*Topt - T')^2 is ONE fma.  All X coefficients below carry the factor g^2.
@@ -38,6 +39,9 @@ struct FastCoef {        // launch-constant coefficients of the fast path (host-
     double topt;         // sqrt(g) * Topt
     // series mode: X_T = T^4 (scaled by g^2) = X_l + t0 + tk_l*kl + tk_d*kd, with t0 = -g^2 q2 (Al0 - al), tk = -g^2 q2 (a - ab)/1000
     double t0, tk_l, tk_d;
+    // rounding + tie filter (see DW rounding note below): magic = 1.5*2^32 + 0.5 + eps*2^-FIX, tie_thresh = (2 eps) << (32-FIX)
+    double magic;
+    unsigned int tie_thresh, pad_;
 };
 struct StepCoef {        // per-step (luminosity dependent) coefficients
     double x0;           // g^2 * (cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al)
@@ -125,14 +129,13 @@ __device__ __forceinline__ double dw_half2d(uint32_t p) {
 // Rounding of x (milli units) to the lattice with the tie filter folded into ONE add: f = low word of
 // x + (1.5*2^32 + 0.5 + EPS*2^-FIX) = round((x + 0.5) * 2^FIX) + EPS as a signed fixed-point number.
 //   floor(x + .5) = f >> FIX   unless frac(x + .5) is within EPS*2^-FIX below 1 -- but then the cell is flagged anyway;
-//   tie flag: frac(x + .5) * 2^FIX + EPS (mod 2^FIX) < 2 EPS   <=>   (unsigned)(f << (32-FIX)) < DW_TIE_THRESH.
-#define DW_ROUND_MAGIC (6442450944.0 + 0.5 + (double)DW_TIE_EPS / (double)(1 << DW_FIX_BITS))
+//   tie flag: frac(x + .5) * 2^FIX + EPS (mod 2^FIX) < 2 EPS   <=>   (unsigned)(f << (32-FIX)) < F.tie_thresh.
+// EPS is chosen per handle on the host (F.magic, F.tie_thresh).
 
 // One cell of the fast path. pc: packed centre, E: packed sum of the 4 edge neighbours, S: packed sum of all 8.
-// Returns the packed new cell; *tiemin is lowered below DW_TIE_THRESH when either species sits within the filter of
+// Returns the packed new cell; *tiemin is lowered below F.tie_thresh when either species sits within the filter of
 // a rounding tie (the caller then recomputes the cell in literal order).
 // Straight-line (no branches) so that several cells can be interleaved by the scheduler.
-#define DW_TIE_THRESH ((2u * DW_TIE_EPS) << (32 - DW_FIX_BITS))
 __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCoef &C, uint32_t pc, uint32_t E, uint32_t S,
                                                  unsigned *tiemin) {
     const double kl = dw_u2d(pc & 0xffffu), kd = dw_u2d(pc >> 16);
@@ -149,7 +152,7 @@ __device__ __forceinline__ uint32_t dw_fast_cell(const FastCoef &F, const StepCo
     const double bd = __fma_rn(-dTd, dTd, 1.0);
     const double xl = __fma_rn(Rl, __fma_rn(rb, bl, -F.dtg), kl);             // l + dt*dl in milli units
     const double xd = __fma_rn(Rd, __fma_rn(rb, bd, -F.dtg), kd);
-    const int fl = __double2loint(xl + DW_ROUND_MAGIC), fd = __double2loint(xd + DW_ROUND_MAGIC);
+    const int fl = __double2loint(xl + F.magic), fd = __double2loint(xd + F.magic);
     *tiemin = __vimin3_u32(*tiemin, (unsigned)fl << (32 - DW_FIX_BITS), (unsigned)fd << (32 - DW_FIX_BITS));
     // floor(x + .5) of both species packed as s16x2, clamped to [0,1000] by one VIMNMX.S16x2.RELU
     const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
@@ -212,7 +215,7 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(Rl[i], zl[i], kl[i]); zd[i] = __fma_rn(Rd[i], zd[i], kd[i]); }     // l + dt*dl (milli)
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        const int fl = __double2loint(zl[i] + DW_ROUND_MAGIC), fd = __double2loint(zd[i] + DW_ROUND_MAGIC);
+        const int fl = __double2loint(zl[i] + F.magic), fd = __double2loint(zd[i] + F.magic);
         *tiemin = __vimin3_u32(*tiemin, (unsigned)fl << (32 - DW_FIX_BITS), (unsigned)fd << (32 - DW_FIX_BITS));
         const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
         out[i] = __vimin_s16x2_relu(packed, 1000u | (1000u << 16));
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ F
             if ((pc | S8) != 0u) {          // empty neighbourhood: rho = 0 and the cell stays exactly 0
                 unsigned tiemin = 0xffffffffu;
                 q = dw_fast_cell(A.F, C, pc, E, S8, &tiemin);
-                if (tiemin < DW_TIE_THRESH) q = dw_slow_cell(&A, C.SL, cb, N, x, y);
+                if (tiemin < A.F.tie_thresh) q = dw_slow_cell(&A, C.SL, cb, N, x, y);
             }
             nb[c] = q;
             mx = __vmaxu2(mx, q);
@@ -438,7 +441,7 @@ __device__ __noinline__ uint32_t dw_fix_warp64(const FusedArgs *A, const StepCoe
             const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
             unsigned tiemin = 0xffffffffu;
             uint32_t v = dw_fast_cell(A->F, *C, q1[y], E, S8, &tiemin);
-            if (tiemin < DW_TIE_THRESH) {
+            if (tiemin < A->F.tie_thresh) {
                 v = dw_slow_cell(A, C->SL, cb, 64, x, y);
                 nb[x * 64 + y] = v;
             }
@@ -483,7 +486,7 @@ struct StoreWorld64 {
 };
 
 // One step of one 4x4 tile (fast path): rows come from `rows`, results go to `store`. Returns the packed per-species
-// max of the 16 new cells; *tiemin drops below DW_TIE_THRESH if some cell needs the literal recomputation.
+// max of the 16 new cells; *tiemin drops below F.tie_thresh if some cell needs the literal recomputation.
 template <class Rows, class Store, bool DIAG = false>
 __device__ __forceinline__ uint32_t dw_tile_core(const FastCoef &F, const StepCoef &C, const Rows &rows, const Store &store,
                                                  unsigned *tiemin, double *tsum = nullptr) {
@@ -533,7 +536,7 @@ __device__ __forceinline__ uint32_t dw_tile_step64(const FusedArgs &A, int j, co
     unsigned tiemin = 0xffffffffu;
     uint32_t mx = dw_tile_core<RowsWorld64, StoreWorld64, DIAG>(A.F, C, RowsWorld64{cb, r0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin, tsum);
     // rare (~2e-4 of tile-steps): some cell of this tile sits on a rounding tie -> the warp redoes that tile's ties literally
-    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
+    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < A.F.tie_thresh);
     if (flagged) mx = dw_fix_warp64(&A, &A.sc[j], cb, nb, flagged, mx, r0, tx * 4, lane);
     return mx;
 }

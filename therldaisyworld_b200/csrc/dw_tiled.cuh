@@ -394,7 +394,7 @@ __device__ __noinline__ uint32_t dwt_fix_warp(const TiledArgs *A, const uint32_t
             const uint32_t S8 = E + q0[-1] + q0[1] + q2[-1] + q2[1];
             unsigned tiemin = 0xffffffffu;
             uint32_t v = dw_fast_cell(A->F, A->C, p[0], E, S8, &tiemin);
-            if (tiemin < DW_TIE_THRESH) {
+            if (tiemin < A->F.tie_thresh) {
                 double l9[9], d9[9];
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
     const long long out_off = (long long)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
     unsigned tiemin = 0xffffffffu;
     uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off}, StoreGlobal{A.out + out_off, A.pitch}, &tiemin);
-    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < DW_TIE_THRESH);
+    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < A.F.tie_thresh);
     if (flagged) mx = dwt_fix_warp(&A, tile, flagged, mx, tile_off, out_off, lane);
     // ghost columns of the produced rows: the two threads of a row group that hold column 0 / N-1 copy their (final) cells
     if (tx == 0 && tc == 0) {
