@@ -78,3 +78,12 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert "daisy_oracle" not in text, f
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers must compile as C99 on their own (no C++-isms, no CUDA or torch types)."""
+    src = tmp_path / "use_headers.c"
+    src.write_text('#include "daisyworld_b200.h"\n#include "daisyworld_b200_tiled.h"\n'
+                   "int probe(dw_handle *h, dwt_handle *t) { dw_config c; dw_clock k; dwt_ptrs p; (void)c; (void)k; (void)p;\n"
+                   "  return dw_abi_version() + (h != 0) + (t != 0) + DW_POLICY_MLP + DW_MLP_PARAMS + DWT_PEER_BUFFERS; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
