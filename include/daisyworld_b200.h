@@ -172,6 +172,11 @@ int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t b, int32_t
 
 /* Getters (device -> host, synchronise). */
 int dw_get_grid(dw_handle *h, double *grid);                              /* env.grid */
+/* fp32 export ("fp32 mode" of the fields): env.grid / the observations converted to binary32 on the device, half the
+   device->host bytes. The state itself lives on the exact 0.001 lattice, so this is a rounding of exact fp64 fields:
+   |rel. error| <= 2^-24 = 6e-8, inside the 1e-5 tolerance BASELINE.json states for fp32. */
+int dw_get_grid_f32(dw_handle *h, float *grid);                           /* [B,7,N,N] */
+int dw_get_obs_f32(dw_handle *h, float *obs);                             /* [B,n,7,3,3] */
 int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states);
 int dw_get_obs(dw_handle *h, double *obs);                                /* obs of the last step / current state */
 int dw_get_reward_done(dw_handle *h, double *reward, uint8_t *done);      /* [B,n] (or [B,2] when n_agents==0) */

@@ -65,3 +65,16 @@ def test_in_kernel_series_matches_oracle_per_step():
     for t in range(10):
         obs, _, _, _ = oenv.step(agent(obs))
         np.testing.assert_allclose(s2[t], [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()], rtol=1e-9)
+
+
+def test_fp32_export_within_stated_tolerance():
+    """fp32 mode of the fields: BASELINE.json's tolerance for fp32 is 1e-5 relative; the export is one rounding of the
+    exact fp64 fields, so 6e-8 holds."""
+    z, meta = load_golden("greedy_n64_b2_120")
+    env = product_env_from_golden(z, meta)
+    env.run(30, policy="greedy")
+    g32, o32 = env.grid_f32(), env.observe_f32()
+    assert g32.dtype == np.float32 and o32.dtype == np.float32
+    np.testing.assert_allclose(g32, env.grid, rtol=1e-5, atol=0)
+    np.testing.assert_allclose(g32, env.grid, rtol=6e-8, atol=0)
+    np.testing.assert_allclose(o32, env.observe(), rtol=6e-8, atol=0)

@@ -735,6 +735,35 @@ extern "C" int dw_get_grid(dw_handle *h, double *grid) {
     return DW_OK;
 }
 
+static int export_f32(dw_handle *h, const double *src, size_t count, float *dst) {
+    int rc = ensure_scratch(h, (count + 1) / 2);
+    if (rc) return rc;
+    float *tmp = reinterpret_cast<float *>(h->scratch);
+    k_to_f32<<<grid_for(count), 256, 0, h->stream>>>(src, count, tmp);
+    DW_LAUNCHED(h);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(dst, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_get_grid_f32(dw_handle *h, float *grid) {
+    if (!h || !grid) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    return export_f32(h, h->grid[h->cur], (size_t)h->cfg.batch * 7 * h->NN, grid);
+}
+
+extern "C" int dw_get_obs_f32(dw_handle *h, float *obs) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t count = (size_t)h->cfg.batch * h->cfg.n_agents * 63;
+    int rc = compute_obs(h);
+    if (rc || !count) return rc;
+    if (!obs) return DW_E_INVALID;
+    return export_f32(h, h->obs, count, obs);
+}
+
 extern "C" int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));

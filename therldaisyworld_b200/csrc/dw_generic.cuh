@@ -588,6 +588,10 @@ __global__ void __launch_bounds__(256) k_cover_final(const double *__restrict__ 
     if (threadIdx.x == 0) { out[0] = r1[0] / cells / 1000.0; out[1] = r1[1] / cells / 1000.0; out[2] = r1[3] / 1000.0; out[3] = r2[3] / 1000.0; }
 }
 
+__global__ void __launch_bounds__(256) k_to_f32(const double *__restrict__ x, size_t n, float *__restrict__ y) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = (float)x[i];
+}
+
 // ---- device-side synthetic initial state (throughput ensembles; NOT numpy-stream compatible) -----------------------
 // Same distribution as initialize_grid/initialize_agents (daisy_world_rl.py:285-302,173-179): per cell and species
 // u0,u1 ~ U[0,1): cover = (u0 < proportion) * initial * u1; agents uniform on the grid with state 1.

@@ -536,6 +536,23 @@ class RLDaisyWorld:
         self._check(self._lib.dw_get_obs(self._h, _ptr(obs, C.c_double)), "dw_get_obs")
         return obs
 
+    def grid_f32(self):
+        """env.grid as float32, converted on the device (half the download). The covers are exact lattice values, so this is
+        one rounding of the exact fp64 fields: relative error <= 6e-8 (BASELINE's fp32 tolerance is 1e-5)."""
+        B, N, n = self._shape
+        out = np.empty((B, self.ch, N, N), dtype=np.float32)
+        self._push()
+        self._check(self._lib.dw_get_grid_f32(self._h, _ptr(out, C.c_float)), "dw_get_grid_f32")
+        return out
+
+    def observe_f32(self):
+        """observe() as float32 (what an fp32 policy network consumes), converted on the device."""
+        B, N, n = self._shape
+        out = np.zeros((B, n, self.ch, 3, 3), dtype=np.float32)
+        self._push()
+        self._check(self._lib.dw_get_obs_f32(self._h, _ptr(out, C.c_float)), "dw_get_obs_f32")
+        return out
+
     def set_mlp(self, parameters):
         """Weights of the reference's MLP policy (daisy/agents/mlp.py: MLP.get_parameters()) for policy="mlp": the
         63-16-32-9 ReLU network is evaluated on the device between steps, on observations built on the device."""
