@@ -18,12 +18,48 @@ from ._lib import DwRunResult  # noqa: F401  (keeps the binding module loaded)
 from .env import RLDaisyWorld, _ptr
 
 
-def evaluate_population(members, adversary_idx=0, max_steps=768, worlds_per_member=32, env=None, **env_kwargs):
+def evaluate_population(members, adversary_idx=0, max_steps=768, worlds_per_member=32, env=None, member_range=None, **env_kwargs):
     """members: [P, 1808] MLP parameter vectors (MLP.get_parameters()). Returns (fitness[P], total_steps[P, W, n, 1],
-    member_steps[P], env). Pass `env` (an RLDaisyWorld of this package) to reuse a handle / non-default constants."""
-    members = np.ascontiguousarray(np.asarray(members, dtype=np.float64))
-    P = members.shape[0]
+    member_steps[P], env). Pass `env` (an RLDaisyWorld of this package) to reuse a handle / non-default constants.
+    member_range=(lo, hi): evaluate only those members (the reset draws of all P are still consumed, so every rank of a
+    sharded evaluation sees the stream the sequential reference loop would)."""
+    all_members = np.ascontiguousarray(np.asarray(members, dtype=np.float64))
+    lo, hi = (0, all_members.shape[0]) if member_range is None else member_range
     W = int(worlds_per_member)
+    if member_range is not None and hi <= lo:
+        raise ValueError("empty member range (more ranks than members?)")
+    if member_range is not None:
+        # local population = my members + the adversary (appended when it is not one of mine)
+        idx = list(range(lo, hi))
+        if adversary_idx not in idx:
+            idx.append(adversary_idx)
+        local_adv = idx.index(adversary_idx)
+        fitness, total_steps, member_steps, env = _evaluate(all_members[idx], local_adv, max_steps, W, env, env_kwargs,
+                                                            skip=(lo, all_members.shape[0] - hi), n_eval=hi - lo, draw_index=idx)
+        return fitness[:hi - lo], total_steps[:hi - lo], member_steps[:hi - lo], env
+    return _evaluate(all_members, adversary_idx, max_steps, W, env, env_kwargs)
+
+
+def evaluate_population_sharded(members, adversary_idx=0, max_steps=768, worlds_per_member=32, group=None, device=None, **env_kwargs):
+    """The mantle/arm fan-out of the reference (sges.py:299-349) without MPI: every rank of a torch.distributed group
+    evaluates a contiguous slice of the population on its GPU, then the fitness vector is all-gathered. Returns fitness[P]."""
+    import torch
+    import torch.distributed as dist
+    from .ensemble import shard_range
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    P = np.asarray(members).shape[0]
+    lo, hi = shard_range(P, world, rank)
+    if device is not None:
+        env_kwargs["device"] = device
+    fit, _, _, _ = evaluate_population(members, adversary_idx, max_steps, worlds_per_member, member_range=(lo, hi), **env_kwargs)
+    full = torch.zeros(P, dtype=torch.float64, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    full[lo:hi] = torch.from_numpy(fit)
+    dist.all_reduce(full, group=group)          # disjoint slices: the sum is a gather
+    return full.cpu().numpy()
+
+
+def _evaluate(members, adversary_idx, max_steps, W, env, env_kwargs, skip=(0, 0), n_eval=None, draw_index=None):
+    P = members.shape[0]
     if env is None:
         state = np.random.get_state()
         env = RLDaisyWorld(**env_kwargs)               # the constructor's own draws must not disturb the caller's stream
@@ -34,12 +70,22 @@ def evaluate_population(members, adversary_idx=0, max_steps=768, worlds_per_memb
     light = np.empty((B, N, N))
     dark = np.empty((B, N, N))
     agents = np.empty((B, n, 2), dtype=np.int64)
-    for m in range(P):
+    def draw():
         dp = np.random.rand(W, 2, N, N)
         lp = np.random.rand(W, 2, N, N)
-        dark[m * W:(m + 1) * W] = 1.0 * (dp[:, 0] < env.dark_proportion) * env.initial_ad * dp[:, 1]
-        light[m * W:(m + 1) * W] = 1.0 * (lp[:, 0] < env.light_proportion) * env.initial_al * lp[:, 1]
-        agents[m * W:(m + 1) * W] = np.random.randint(N, size=(W, n, 2))
+        return (1.0 * (dp[:, 0] < env.dark_proportion) * env.initial_ad * dp[:, 1],
+                1.0 * (lp[:, 0] < env.light_proportion) * env.initial_al * lp[:, 1], np.random.randint(N, size=(W, n, 2)))
+
+    n_eval = P if n_eval is None else n_eval
+    for _ in range(skip[0]):                       # members evaluated by lower ranks: consume their draws
+        draw()
+    for m in range(P):
+        if m < n_eval:
+            dark[m * W:(m + 1) * W], light[m * W:(m + 1) * W], agents[m * W:(m + 1) * W] = draw()
+        else:                                      # the appended adversary block is never scored: any valid state will do
+            dark[m * W:(m + 1) * W], light[m * W:(m + 1) * W], agents[m * W:(m + 1) * W] = dark[:W], light[:W], agents[:W]
+    for _ in range(skip[1]):
+        draw()
     states = np.ones((B, n))
     env.batch_size = B
     env.L = env.min_L
