@@ -41,12 +41,13 @@ static void make_fast_coef(const dw_config &c, FastCoef &F) {
     F.t0 = -g2 * (c.q2 * (Al0 - c.albedo_light));
     F.tk_l = -g2 * (c.q2 * cl);
     F.tk_d = -g2 * (c.q2 * cd);
-    // Tie-filter half-width from the error budget: the fast fourth root is good to 5e-12 relative
-    // (asserted in the tests), T stays below ~400 K and within ~150 K of the optimum on anything that still grows, so
-    // |dx| <= 1000 * dt * 2 g |Topt - T| * 400 * 5e-12 milli-cover; the filter is 4x that, never below DW_TIE_EPS_MIN.
+    // Tie-filter half-width from the error budget: the fast fourth root is good to 3e-12 relative
+    // (asserted in the tests; measured maximum 2.2e-12), T stays below 400 K and within max(|Topt-150|, |Topt-400|) of the
+    // optimum, so |dx| <= 1000 * dt * 2 g |Topt - T| * 400 * 3e-12 milli-cover (both extremes at once: conservative);
+    // the filter is 3x that, never below DW_TIE_EPS_MIN.
     const double dT = fmax(fabs(c.temp_optimal - 150.0), fabs(c.temp_optimal - 400.0));
-    const double bound = 1000.0 * fabs(c.dt) * 2.0 * c.g * dT * 400.0 * 5e-12;
-    double eps = ceil(4.0 * bound * (double)(1 << DW_FIX_BITS));
+    const double bound = 1000.0 * fabs(c.dt) * 2.0 * c.g * dT * 400.0 * 3e-12;
+    double eps = ceil(3.0 * bound * (double)(1 << DW_FIX_BITS));
     eps = eps < DW_TIE_EPS_MIN ? DW_TIE_EPS_MIN : (eps > DW_TIE_EPS_MAX ? DW_TIE_EPS_MAX : eps);
     F.magic = 6442450944.0 + 0.5 + eps / (double)(1 << DW_FIX_BITS);
     F.tie_thresh = (2u * (unsigned int)eps) << (32 - DW_FIX_BITS);
