@@ -36,7 +36,11 @@ def test_fast_root4_relative_error_bound():
 
 @pytest.mark.parametrize("N,B,n,policy", [(64, 16, 4, "greedy"), (16, 8, 4, "antigreedy"), (33, 4, 7, "random"),
                                           (5, 3, 2, "greedy"), (2, 2, 1, "greedy"), (1, 2, 1, "none"), (12, 4, 0, "none"),
-                                          (40, 2, 40, "greedy")])
+                                          (40, 2, 40, "greedy"),
+                                          # worlds below 64x64 share a CTA (k_fused_sub64_persist): partial last group,
+                                          # agent count at the shared-memory limit (64 worlds x 4), and over it (generic kernel)
+                                          (8, 70, 4, "greedy"), (8, 130, 3, "random"), (16, 19, 9, "antigreedy"),
+                                          (32, 7, 33, "greedy"), (32, 9, 0, "none"), (8, 5, 5, "greedy")])
 def test_fused_equals_materialising_path(N, B, n, policy):
     """Same inputs through dw_run with the fused kernel and with DW_DISABLE_FUSED=1 (materialising kernels only)."""
     res = []

@@ -77,7 +77,7 @@ struct dw_handle {
     bool fused_attr_set = false;
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
-    int persist_blocks = 0;                    // resident CTAs of the persistent kernel on this device
+    int persist_blocks = 0, sub64_blocks = 0;  // resident CTAs of the persistent kernels on this device
     // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
     dw_profile prof{};
     bool profiling = false;

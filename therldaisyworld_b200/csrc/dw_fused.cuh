@@ -804,6 +804,274 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
     }
 }
 
+// ---- worlds smaller than 64x64 (N = 8, 16, 32): (64/N)^2 worlds per CTA, tiled into one 64x64 "super-grid" -------------------
+// The 256 threads keep the 4x4-cells-per-thread tiling and the fast path of the 64x64 kernel; the W = (64/N)^2 worlds of a
+// CTA sit side by side in the two 64x64 shared-memory buffers (world (wy, wx) at rows wy*N.., columns wx*N..), rows wrap
+// inside a world and the halo columns come from the neighbouring lanes of the world's own N/4-lane group. Work items
+// are (group of W worlds, chunk of Kc steps), same persistent queue as the 64x64 kernel. Agents: all W*n of them live in
+// shared memory (W*n <= DW_SUB64_MAX_AGENTS), warp 0 decides for all, then moves and grazes them 32 at a time in flat
+// (world, index) order, so the per-world sequential semantics are those of dw_agents_phase32.
+#define DW_SUB64_MAX_AGENTS 256
+template <int N>
+struct Sub64Smem {
+    uint32_t buf[2][4096];
+    double st[DW_SUB64_MAX_AGENTS];
+    int xy[DW_SUB64_MAX_AGENTS];        // x | y << 16, world-local
+    int ada[DW_SUB64_MAX_AGENTS];
+    signed char act[DW_SUB64_MAX_AGENTS];
+    int smax[2][(64 / N) * (64 / N)][2];
+    int life[(64 / N) * (64 / N)];
+    int item;
+};
+
+template <int N>
+struct RowsSub64 {
+    const uint32_t *cb;
+    int row_base, lr0, tx, lane;         // first super-grid row of the world, first world-local row of the tile
+    __device__ __forceinline__ Row6 load(int k) const {
+        constexpr int TX = N / 4;
+        const uint4 v = *reinterpret_cast<const uint4 *>(cb + (row_base + ((lr0 + k) & (N - 1))) * 64 + tx * 4);
+        const int base = lane & ~(TX - 1);
+        const uint32_t left = __shfl_sync(0xffffffffu, v.w, base | ((lane - 1) & (TX - 1)));
+        const uint32_t right = __shfl_sync(0xffffffffu, v.x, base | ((lane + 1) & (TX - 1)));
+        return dw_make_row(v, left, right);
+    }
+};
+
+// literal recomputation of one cell of a sub-world (wrap inside the world)
+template <int N>
+__device__ __noinline__ uint32_t dw_slow_cell_sub(const FusedArgs *A, double SL, const uint32_t *cb, int X, int Y) {
+    const int rb = X & ~(N - 1), cbse = Y & ~(N - 1);
+    const int xs[3] = {rb | ((X - 1) & (N - 1)), X, rb | ((X + 1) & (N - 1))};
+    const int ys[3] = {cbse | ((Y - 1) & (N - 1)), Y, cbse | ((Y + 1) & (N - 1))};
+    double l9[9], d9[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t k = cb[xs[a] * 64 + ys[c]];
+            l9[a * 3 + c] = dw_milli(k & 0xffffu);
+            d9[a * 3 + c] = dw_milli(k >> 16);
+        }
+    const LitCell o = dw_literal_cell(A->P, SL, l9, d9);
+    if (A->slow_count) atomicAdd(A->slow_count, 1u);
+    return dw_pack((int)rint(o.nl * 1000.0), (int)rint(o.nd * 1000.0));
+}
+
+// warp-cooperative tie fix-up for sub-worlds; the corrected tile's maxima go straight to its world's slots. Returns true
+// for lanes whose own (stale) tile maximum must not be used.
+template <int N>
+__device__ __noinline__ bool dw_fix_warp_sub(const FusedArgs *A, const StepCoef *C, const uint32_t *cb, uint32_t *nb, unsigned flagged,
+                                             int r0, int c0, int lane, int (*smax)[2]) {
+    bool mine = false;
+    __syncwarp();
+    while (flagged) {
+        const int L = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const int tr0 = __shfl_sync(0xffffffffu, r0, L), tc0 = __shfl_sync(0xffffffffu, c0, L);
+        if (lane == L) mine = true;
+        if (lane < 16) {
+            const int X = tr0 + (lane >> 2), Y = tc0 + (lane & 3);
+            const int rb = X & ~(N - 1), cbse = Y & ~(N - 1);
+            const int xm = rb | ((X - 1) & (N - 1)), xp = rb | ((X + 1) & (N - 1)), ym = cbse | ((Y - 1) & (N - 1)), yp = cbse | ((Y + 1) & (N - 1));
+            const uint32_t *q0 = cb + xm * 64, *q1 = cb + X * 64, *q2 = cb + xp * 64;
+            const uint32_t E = q1[ym] + q1[yp] + q0[Y] + q2[Y];
+            const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
+            unsigned tiemin = 0xffffffffu;
+            uint32_t v = dw_fast_cell(A->F, *C, q1[Y], E, S8, &tiemin);
+            if (tiemin < A->F.tie_thresh) {
+                v = dw_slow_cell_sub<N>(A, C->SL, cb, X, Y);
+                nb[X * 64 + Y] = v;
+            }
+            int *sm = smax[(tr0 / N) * (64 / N) + tc0 / N];
+            atomicMax(sm, (int)(v & 0xffffu));
+            atomicMax(sm + 1, (int)(v >> 16));
+        }
+    }
+    __syncwarp();
+    return mine;
+}
+
+template <int N>
+__device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, int group, uint32_t *cb, Sub64Smem<N> &sm, int lane, int n,
+                                                    int n_act) {
+    constexpr int WX = 64 / N, W = WX * WX;
+    const int pol = A.sc[j].policy;
+    // pass 1: every agent decides from the pre-move state
+    for (int a = lane; a < n_act; a += 32) {
+        const int wl = a / n, i = a - wl * n;
+        const int x = sm.xy[a] & 0xffff, y = sm.xy[a] >> 16;
+        const size_t gw = (size_t)group * W + wl;
+        int act = 0;
+        if (pol == DW_POLICY_REPLAY) act = A.actions[((size_t)j * A.P.B + gw) * n + i];
+        else if (pol == DW_POLICY_RANDOM) act = (int)(dw_hash_rng(A.seed, A.world0 + (uint32_t)gw, i, A.step0 + j) % 9u);
+        else if (pol != DW_POLICY_NONE) {
+            const int r = (wl / WX) * N, c = (wl % WX) * N;
+            const int xm = (x + N - 1) & (N - 1), xp = (x + 1) & (N - 1), ym = (y + N - 1) & (N - 1), yp = (y + 1) & (N - 1);
+            const double food[4] = {dw_food(cb[(r + x) * 64 + c + ym]), dw_food(cb[(r + xm) * 64 + c + y]),
+                                    dw_food(cb[(r + xp) * 64 + c + y]), dw_food(cb[(r + x) * 64 + c + yp])};
+            act = dw_greedy_pick(food, pol == DW_POLICY_GREEDY);
+        }
+        sm.act[a] = (signed char)act;
+    }
+    __syncwarp();
+    // pass 2: move + graze, 32 agents at a time in flat (world, index) order; inside a round MATCH.ANY orders the grazers
+    // of a cell, across rounds the earlier round has already emptied it
+    for (int base = 0; base < n_act; base += 32) {
+        const int a = base + lane;
+        const bool active = a < n_act;
+        double st = 0.0;
+        int x = 0, y = 0, cell = -1 - lane;
+        if (active) {
+            st = sm.st[a] - A.P.agent_gamma;
+            x = sm.xy[a] & 0xffff;
+            y = sm.xy[a] >> 16;
+            const int act = sm.act[a];
+            if (st > 0.0) {
+                if (act != 8) {
+                    const int d = (act & 2) ? 1 : -1;
+                    if (((act + 1) & 2) == 0) y = (y + d) & (N - 1);
+                    else x = (x + d) & (N - 1);
+                }
+                if (act > 4) {
+                    const int wl = a / n;
+                    cell = ((wl / WX) * N + x) * 64 + (wl % WX) * N + y;
+                }
+            }
+        }
+        const bool wants = cell >= 0;
+        const uint32_t pk = wants ? cb[cell] : 0u;
+        const unsigned peers = __match_any_sync(0xffffffffu, cell);
+        __syncwarp();
+        if (wants) {
+            const bool taken = (peers & ((1u << lane) - 1u)) != 0u;
+            st = st + (taken ? (0.0 + 0.0) : dw_food(pk));
+            cb[cell] = 0u;
+        }
+        if (active) {
+            st = dw_clip01(st);
+            sm.st[a] = st;
+            sm.xy[a] = x | (y << 16);
+            sm.ada[a] += (st < 0.1) ? 0 : 1;
+        }
+        __syncwarp();
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(const __grid_constant__ FusedArgs A) {
+    constexpr int WX = 64 / N, W = WX * WX, TX = N / 4;
+    __shared__ Sub64Smem<N> sm;
+    const int n = A.P.n_agents, B = A.P.B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int wl = (ty / TX) * WX + tx / TX;            // this thread's world inside the CTA
+    const int row_base = (ty / TX) * N, lr0 = (ty % TX) * 4, r0 = ty * 4;
+    const int n_items = A.n_pairs * A.n_chunks;        // n_pairs = number of world groups
+
+    for (;;) {
+        if (tid == 0) sm.item = (int)atomicAdd(A.queue, 1u);
+        __syncthreads();
+        const int t = sm.item;
+        if (t >= n_items) break;
+        const int c = t / A.n_pairs, g = t - c * A.n_pairs;
+        if (tid == 0) {
+            while (atomicAdd(A.pair_done + g, 0u) < (unsigned)c) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
+        const int n_worlds = min(W, B - g * W);
+        const int n_act = n_worlds * n;
+        // global [world][N][N] -> super-grid
+        for (int q = tid; q < 1024; q += 256) {
+            const int R = q >> 4, C4 = (q & 15) * 4;
+            const int w = (R / N) * WX + C4 / N;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (w < n_worlds) v = __ldcg(reinterpret_cast<const uint4 *>(A.lat + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)));
+            reinterpret_cast<uint4 *>(sm.buf[0])[q] = v;
+        }
+        for (int a = tid; a < n_act; a += 256) {
+            const size_t ga = (size_t)g * W * n + a;
+            sm.st[a] = __ldcg(A.agent_state + ga);
+            sm.xy[a] = __ldcg(A.agent_xy + 2 * ga) | (__ldcg(A.agent_xy + 2 * ga + 1) << 16);
+            sm.ada[a] = 0;
+        }
+        for (int q = tid; q < 2 * W * 2; q += 256) (&sm.smax[0][0][0])[q] = 0;
+        if (tid < W) sm.life[tid] = 0;
+        __syncthreads();
+
+#pragma unroll 1
+        for (int jl = 0; jl < kc; ++jl) {
+            const int j = j0 + jl;
+            uint32_t *cb = sm.buf[jl & 1], *nb = sm.buf[(jl + 1) & 1];
+            if (warp == 0 && n_act > 0) dw_agents_phase_sub<N>(A, j, g, cb, sm, lane, n, n_act);
+            __syncthreads();
+            if (j == A.K - 1) {                        // post-graze state of the launch's last step (lazy materialisation)
+                for (int q = tid; q < 1024; q += 256) {
+                    const int R = q >> 4, C4 = (q & 15) * 4;
+                    const int w = (R / N) * WX + C4 / N;
+                    if (w < n_worlds)
+                        *reinterpret_cast<uint4 *>(A.lat_pre + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)) =
+                            reinterpret_cast<const uint4 *>(cb)[q];
+                }
+            }
+            const StepCoef C = A.sc[j];
+            unsigned tiemin = 0xffffffffu;
+            const uint32_t mx = dw_tile_core(A.F, C, RowsSub64<N>{cb, row_base, lr0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin);
+            int (*smx)[2] = sm.smax[jl & 1];
+            bool stale = false;
+            const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < A.F.tie_thresh);
+            if (flagged) stale = dw_fix_warp_sub<N>(&A, &A.sc[j], cb, nb, flagged, r0, tx * 4, lane, smx);
+            if (!stale && mx) { atomicMax(&smx[wl][0], (int)(mx & 0xffffu)); atomicMax(&smx[wl][1], (int)(mx >> 16)); }
+            __syncthreads();
+            if (warp == 0) {
+                // lifespan bookkeeping of step j for the CTA's worlds (notebook cell 2): grid_done = max(grid[:,1:3]) <= 0.005
+                unsigned alive = 0;
+                for (int w = lane; w < n_worlds; w += 32) {
+                    const bool up = max(smx[w][0], smx[w][1]) > 5;
+                    if (up) { sm.life[w] += 1; alive += 1; }
+                }
+                alive = __reduce_add_sync(0xffffffffu, alive);
+                if (lane == 0 && alive) atomicAdd(A.alive + j, alive);
+                int (*nx)[2] = sm.smax[(jl + 1) & 1];
+                for (int w = lane; w < W; w += 32) { nx[w][0] = 0; nx[w][1] = 0; }
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < 1024; q += 256) {
+            const int R = q >> 4, C4 = (q & 15) * 4;
+            const int w = (R / N) * WX + C4 / N;
+            if (w < n_worlds)
+                *reinterpret_cast<uint4 *>(A.lat + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)) =
+                    reinterpret_cast<const uint4 *>(sm.buf[kc & 1])[q];
+        }
+        for (int a = tid; a < n_act; a += 256) {
+            const size_t ga = (size_t)g * W * n + a;
+            const double r = sm.st[a];
+            A.agent_state[ga] = r;
+            A.agent_xy[2 * ga] = sm.xy[a] & 0xffff;
+            A.agent_xy[2 * ga + 1] = sm.xy[a] >> 16;
+            A.agents_done_at[ga] = __ldcg(A.agents_done_at + ga) + sm.ada[a];
+            A.reward[ga] = r;
+            A.done[ga] = r < 0.1;
+        }
+        if (tid < n_worlds) {
+            const size_t gw = (size_t)g * W + tid;
+            A.done_at[gw] = __ldcg(A.done_at + gw) + sm.life[tid];
+            if (n == 0) {
+                const int *smx = sm.smax[(kc - 1) & 1][tid];
+                for (int ch = 0; ch < 2; ++ch) { A.reward[2 * gw + ch] = smx[ch] > 0 ? 1.0 : 0.0; A.done[2 * gw + ch] = smx[ch] > 0 ? 0 : 1; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicExch(A.pair_done + g, (unsigned)(c + 1));
+        }
+    }
+}
+
 // fp64 grid channels 1,2 -> packed lattice; flags worlds whose covers are not exactly k/1000
 __global__ void __launch_bounds__(256) k_grid_to_lattice(int B, size_t NN, const double *__restrict__ grid, uint32_t *__restrict__ lat,
                                                          unsigned int *off_lattice) {

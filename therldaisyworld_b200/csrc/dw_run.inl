@@ -125,6 +125,9 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     const char *impl = getenv("DW_FUSED_IMPL");
     const bool n64 = h->cfg.dim == 64 && !(impl && !strcmp(impl, "generic"));
     const bool persist = n64 && !(impl && !strcmp(impl, "simple")) && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
+    const int dimN = h->cfg.dim;
+    const bool sub64 = !(impl && !strcmp(impl, "generic")) && (dimN == 8 || dimN == 16 || dimN == 32) &&
+                       (64 / dimN) * (64 / dimN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
     if (h->profiling) DW_CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
     if (persist) {
         if (!h->persist_blocks) {
@@ -160,6 +163,33 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         } else {
             k_fused_n64_persist<false><<<grid, 256, 0, h->stream>>>(A);
         }
+    } else if (sub64) {
+        // worlds of 8x8, 16x16 or 32x32: (64/N)^2 of them per CTA in the 4x4-tile kernel, same persistent queue
+        const int N = h->cfg.dim, W = (64 / N) * (64 / N);
+        void (*kern)(const FusedArgs) = N == 8 ? k_fused_sub64_persist<8> : (N == 16 ? k_fused_sub64_persist<16> : k_fused_sub64_persist<32>);
+        int &blocks = h->sub64_blocks;
+        if (!blocks) {
+            int per_sm = 0, sms = 0;
+            DW_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+            DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+            if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "sub-64 kernel does not fit on an SM");
+            blocks = per_sm * sms;
+        }
+        const char *kc_env = getenv("DW_PERSIST_KC");
+        A.Kc = kc_env ? atoi(kc_env) : 16;
+        if (A.Kc < 1) A.Kc = 1;
+        A.n_pairs = (h->cfg.batch + W - 1) / W;
+        A.n_chunks = (K + A.Kc - 1) / A.Kc;
+        rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
+        A.queue = h->persist_sync;
+        A.pair_done = h->persist_sync + 1;
+        A.lat = h->lat[h->lcur];                      // in place
+        const long long items = (long long)A.n_pairs * A.n_chunks;
+        const int grid = (int)(items < blocks ? items : blocks);
+        kern<<<grid, 256, 0, h->stream>>>(A);
     } else {
         const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
         if (smem > 48 * 1024 && !h->fused_attr_set) {
