@@ -164,6 +164,22 @@ int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed);
 /* Pieces of step(), exposed because callers use them standalone:
    RLDaisyWorld.update_agents(action) (:181-244) */
 int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab, int32_t am);
+/* collision_mode == 1 (daisy_world_rl.py:220-242, default off): where several agents share a cell after the moves, the
+   reference draws npr.rand(1, n, 1) from the caller's GLOBAL NumPy stream per shared cell, in (world, x, y) scan order.
+   The stream stays with the caller, so update_agents is split around the draws:
+     dw_agents_begin    pay agent_gamma, move, graze (no clip yet); returns the post-move agent_indices [B,n,2] so that the
+                        caller can count the shared cells of every world (integer bookkeeping only) and draw.
+                        policy < 0: explicit action [ab,am] (NULL = step(None)); else DW_POLICY_NONE..EPS_GREEDY on the device.
+     dw_agents_collide  noise [cells, n] (the draws, in order), cell_offsets [B+1] (first draw of each world, [0] = 0):
+                        resolves the collisions on the device (winner = resident with the largest state + 0.01 * noise,
+                        gains food_chain_penalty * np.sum(other residents' states), losers keep theirs like :242) and
+                        clips. Fails with DW_E_INVALID if a world's shared-cell count differs from the device's.
+     dw_step_tail_collect   the rest of step(): forward, stamp, obs, reward/done, update_L; outputs like dw_step_collect.
+   Every other stepping call returns DW_E_STATE between dw_agents_begin and dw_agents_collide. */
+int dw_agents_begin(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed,
+                    int64_t *agent_indices);
+int dw_agents_collide(dw_handle *h, const double *noise, const int32_t *cell_offsets, double food_chain_penalty);
+int dw_step_tail_collect(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk);
 /* RLDaisyWorld.forward(grid) (:434-461) on a caller grid (host in, host out) with the handle's agents/L;
    writes the mutated ch0 back into grid_in like the reference (:381). Does not advance the state. */
 int dw_forward(dw_handle *h, double *grid_in, double *grid_out);

@@ -239,8 +239,28 @@ class OracleDaisyWorld:
                     self.agent_states[bb, nn, 0] += self.grid[bb, 1, x, y] + self.grid[bb, 2, x, y]
                     self.grid[bb, 1:3, x, y] *= 0.0
         if self.collision_mode == 1:
-            raise NotImplementedError("collision_mode==1 (stochastic, default off) is out of scope")
+            self.resolve_collisions()
         self.agent_states = np.clip(self.agent_states, 0.0, 1.0)
+
+    def resolve_collisions(self):
+        """reference :220-242 (next row N4). The reference scans every cell (xx, yy) of every world in row-major order and,
+        where more than one agent sits, draws npr.rand(1, n, 1) from the GLOBAL stream: tie-break noise for all n agents of
+        the world. The resident with the largest state + 0.01 * noise gains food_chain_penalty * (sum of the other
+        residents' states, unclipped, dead agents included); the losers are NOT zeroed (the reference's last statement
+        assigns into a fancy-indexed copy, :242). Only occupied cells can hold residents, so visiting the occupied cells in
+        sorted (xx, yy) order consumes the stream exactly like the full scan."""
+        n = self.agent_states.shape[1]
+        for bb in range(self.agent_indices.shape[0]):
+            cells = sorted({(int(x), int(y)) for x, y in self.agent_indices[bb]})
+            for xx, yy in cells:
+                residents = (self.agent_indices[bb, :, 0] == xx) & (self.agent_indices[bb, :, 1] == yy)
+                if residents.sum() > 1:
+                    noise = np.random.rand(1, n, 1)[0, :, 0]
+                    temp = 1.0 * self.agent_states[bb, :, 0] + 0.01 * noise
+                    winner_value = temp[residents].max()
+                    losers = residents & (temp != winner_value)
+                    eat = np.sum(self.agent_states[bb, :, 0][losers])        # NumPy's summation order (see sum_like_numpy)
+                    self.agent_states[bb, temp == winner_value, 0] += self.food_chain_penalty * eat
 
     def get_obs(self, agent_indices):
         B, n = agent_indices.shape[:2]

@@ -72,6 +72,9 @@ def run_case(name, seed, ctor, attrs, policy, steps, ckpts, out_dir, action_shap
 
     B, n, N = env.batch_size, env.n_agents, env.dim
     rec = dict(
+        # global MT19937 state right after reset(): collision fixtures replay the stream from here (actions drawn with
+        # randint and the collision noise of step() interleave in it)
+        rng_key=rng_state_after_reset[1].copy(), rng_pos=np.int64(rng_state_after_reset[2]),
         init_grid=env.grid.copy(),
         init_agent_indices=env.agent_indices.copy(),
         init_agent_states=env.agent_states.copy(),
@@ -195,6 +198,13 @@ CASES = [
     # step(None) with agents: drift + starvation (A.4-2)
     dict(name="none_n16_b2_n4_40", seed=4, ctor=dict(), attrs=dict(batch_size=2),
          policy=dict(kind="none"), steps=40, ckpts=[1, 18, 19]),
+    # N4 row: collision_mode == 1 (reference :220-242). Crowded small grids so several agents share a cell every few steps.
+    dict(name="collide_randint_n5_b3_n12_120", seed=23, ctor=dict(grid_dimension=5, n_agents=12, collision_mode=1),
+         attrs=dict(batch_size=3), policy=dict(kind="randint"), steps=120, ckpts=[1, 2, 60]),
+    dict(name="collide_greedy_n8_b4_n10_150", seed=29, ctor=dict(grid_dimension=8, n_agents=10, collision_mode=1),
+         attrs=dict(batch_size=4, food_chain_penalty=0.8), policy=dict(kind="greedy"), steps=150, ckpts=[1, 75]),
+    dict(name="collide_randint_n7_b2_n40_60", seed=31, ctor=dict(grid_dimension=7, n_agents=40, collision_mode=1),
+         attrs=dict(batch_size=2, agent_gamma=0.01), policy=dict(kind="randint"), steps=60, ckpts=[1, 30]),
     # ramp_up_down branch (N4 row, cheap to pin): short ramp so dL flips sign
     dict(name="rampupdown_n8_b2_100", seed=6, ctor=dict(grid_dimension=8, ramp_period=32),
          attrs=dict(batch_size=2, ramp_up_down=True, ddL=0.01),

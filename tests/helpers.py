@@ -40,3 +40,20 @@ def product_env_from_golden(z, meta, device=0):
 def golden_action(z, t):
     a = z["actions"][t]
     return None if (a.shape == (1, 1, 1) and a[0, 0, 0] == -1) else a
+
+
+def uses_global_stream(z, meta):
+    """Collision fixtures (N4): step() itself draws from the global np.random stream, interleaved with the policy's draws."""
+    return "rng_key" in z.files and meta["ctor"].get("collision_mode", 0) == 1
+
+
+def restore_stream(z):
+    """Put the global legacy MT19937 stream where the reference had it right after reset()."""
+    np.random.set_state(("MT19937", z["rng_key"], int(z["rng_pos"]), 0, 0.0))
+
+
+def consume_policy_draws(z, meta, t):
+    """Re-draw what the recorded policy drew from the global stream before step t (oracle/gen_golden.py::run_case)."""
+    if meta["policy"]["kind"] == "randint":
+        a = np.random.randint(9, size=(meta["B"], meta["n"], 1))
+        np.testing.assert_array_equal(a, z["actions"][t])

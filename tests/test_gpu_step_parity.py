@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from conftest import golden_names
-from helpers import golden_action, load_golden, product_env_from_golden, apply_attrs
+from helpers import (golden_action, load_golden, product_env_from_golden, apply_attrs, consume_policy_draws, restore_stream,
+                     uses_global_stream)
 
 pytestmark = pytest.mark.gpu
 
@@ -18,14 +19,19 @@ def test_step_replays_reference_trajectory(name):
     env = product_env_from_golden(z, meta)
     np.testing.assert_array_equal(env.get_obs(env.agent_indices), z["init_obs"])
     ck = {int(s): i for i, s in enumerate(z["ckpt_steps"])}
+    stream = uses_global_stream(z, meta)          # collision_mode == 1: step() draws from the global np.random stream
+    if stream:
+        restore_stream(z)
     for t in range(meta["steps"]):
         assert env.L == z["L"][t]
+        if stream:
+            consume_policy_draws(z, meta, t)
         obs, reward, done, info = env.step(golden_action(z, t))
         assert info == {}
         np.testing.assert_array_equal(reward, z["reward"][t])
         np.testing.assert_array_equal(done, z["done"][t])
         assert reward.dtype == z["reward"][t].dtype and done.dtype == np.bool_
-        if (t + 1) in ck or t % 37 == 0:
+        if (t + 1) in ck or t % 37 == 0 or stream:
             np.testing.assert_array_equal(env.agent_indices, z["agent_indices"][t])
             np.testing.assert_array_equal(env.agent_states, z["agent_states"][t])
             np.testing.assert_array_equal(env.grid.sum(axis=(-2, -1)), z["chan_sum"][t])
@@ -180,3 +186,58 @@ def test_update_agents_and_get_obs_standalone():
     np.testing.assert_array_equal(env.agent_states, ref.agent_states)
     pos = np.random.randint(9, size=(5, 6, 2))
     np.testing.assert_array_equal(env.get_obs(pos), ref.get_obs(pos))
+
+
+def test_collisions_match_numpy_oracle_on_crowded_worlds():
+    """collision_mode == 1 beyond the recorded fixtures: crowded worlds (up to 60 agents on 4x4 .. 9x9, so cells with
+    more than eight losers exercise NumPy's unrolled summation order), explicit actions, device policies and step(None);
+    the drop-in and the NumPy oracle consume the same global stream and must agree exactly, stream position included."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy
+    rng = np.random.RandomState(5)
+    for N, B, n, penalty, mode in [(5, 4, 60, 0.5, "randint"), (9, 3, 25, 1.3, "greedy"), (7, 5, 9, 0.5, "none"),
+                                   (8, 2, 33, 0.25, "partial")]:
+        np.random.seed(100 + N)
+        env = RLDaisyWorld(grid_dimension=N, n_agents=n, collision_mode=1)
+        env.batch_size = B
+        env.food_chain_penalty = penalty
+        env.agent_gamma = 0.02
+        env.reset()
+        ref = OracleDaisyWorld(grid_dimension=N, n_agents=n, collision_mode=1)
+        ref.batch_size, ref.food_chain_penalty, ref.agent_gamma = B, penalty, 0.02
+        ref.reset()
+        ref.grid, ref.agent_indices, ref.agent_states = env.grid.copy(), env.agent_indices.copy(), env.agent_states.copy()
+        greedy = OracleGreedy(epsilon=0.0, greedy=True)
+        obs_ref = ref.get_obs(ref.agent_indices)
+        for t in range(40):
+            if mode == "randint":
+                action = rng.randint(9, size=(B, n, 1))
+            elif mode == "partial":
+                action = rng.randint(9, size=(B - 1, n - 3, 1))
+            elif mode == "greedy":
+                action = greedy(obs_ref)
+            else:
+                action = None
+            state = np.random.get_state()
+            if mode == "greedy" and t % 2:
+                o1, r1, d1, _ = env.step_policy("greedy")          # decision on the device
+            else:
+                o1, r1, d1, _ = env.step(action)
+            after_env = np.random.get_state()
+            np.random.set_state(state)
+            obs_ref, r2, d2, _ = ref.step(action)
+            after_ref = np.random.get_state()
+            assert after_env[2] == after_ref[2] and np.array_equal(after_env[1], after_ref[1])
+            np.testing.assert_array_equal(env.agent_indices, ref.agent_indices)
+            np.testing.assert_array_equal(env.agent_states, ref.agent_states)
+            np.testing.assert_array_equal(o1, obs_ref)
+            np.testing.assert_array_equal(r1, r2)
+            np.testing.assert_array_equal(d1, d2)
+        np.testing.assert_array_equal(env.grid, ref.grid)
+
+
+def test_collision_mode_multi_step_runs_are_refused():
+    from therldaisyworld_b200 import RLDaisyWorld
+    env = RLDaisyWorld(grid_dimension=8, collision_mode=1)
+    with pytest.raises(NotImplementedError):
+        env.run(4, policy="greedy")

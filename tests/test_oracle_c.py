@@ -10,7 +10,8 @@ from oracle.daisy_c import COracleWorld
 from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy, env_from_golden, lifespan_loop
 
 
-@pytest.mark.parametrize("name", golden_names())
+# collision_mode == 1 (collide_*) is restated in the NumPy oracle only: its RNG is NumPy's global stream
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("collide_")])
 def test_c_oracle_replays_reference_trajectory(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     env, meta = env_from_golden(z)

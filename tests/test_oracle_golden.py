@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_DIR, golden_names
+from helpers import consume_policy_draws, restore_stream, uses_global_stream
 from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy, OracleMLP, env_from_golden, neighborhood_mask
 
 
@@ -20,7 +21,12 @@ def replay(z, env, check_every_step=True):
     B, n = meta["B"], meta["n"]
     done_at = np.zeros((B,), dtype=np.int64)
     agents_done_at = np.zeros((B, n, 1), dtype=np.int64)
+    stream = uses_global_stream(z, meta)
+    if stream:
+        restore_stream(z)
     for t in range(T):
+        if stream:
+            consume_policy_draws(z, meta, t)
         a = z["actions"][t]
         action = None if (a.shape == (1, 1, 1) and a[0, 0, 0] == -1) else a
         assert env.L == z["L"][t]

@@ -75,6 +75,7 @@ struct dw_handle {
     int64_t *pop_steps = nullptr, *pop_frozen = nullptr;   // [members] step count at the end; [B,n] frozen (1-done) counters
     unsigned int *pop_ndone = nullptr;
     bool fused_attr_set = false;
+    bool agents_open = false;                  // between dw_agents_begin and dw_agents_collide the agent states are unclipped
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
     int persist_blocks = 0, sub64_blocks = 0;  // resident CTAs of the persistent kernels on this device
@@ -330,6 +331,7 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t B = h->cfg.batch, n = h->cfg.n_agents, NN = h->NN;
+    if (agent_states) h->agents_open = false;      // a fresh agent state supersedes a pending collision pass
     if (grid) {
         int rc = ensure_grid_buffers(h);
         if (rc) return rc;
@@ -447,7 +449,8 @@ static int stage_action(dw_handle *h, const int64_t *action, size_t count) {
     return DW_OK;
 }
 
-static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, int policy, uint64_t seed, bool on_cov = false) {
+static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, int policy, uint64_t seed, bool on_cov = false,
+                         bool clip = true) {
     if (h->cfg.n_agents == 0) return DW_OK;
     const DevParams P = make_params(h);
     const size_t NN = h->NN;
@@ -457,7 +460,8 @@ static int launch_agents(dw_handle *h, const int8_t *act_dev, int ab, int am, in
                                                                  policy, seed, (uint32_t)h->clk.step_count, h->world0);
     else
         k_agents_grid<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid[h->cur], 7 * NN, NN, 2 * NN, h->agent_xy, h->agent_state,
-                                                                 act_dev, ab, am, policy, seed, (uint32_t)h->clk.step_count, h->world0);
+                                                                 act_dev, ab, am, policy, seed, (uint32_t)h->clk.step_count, h->world0,
+                                                                 clip ? 1 : 0);
     DW_LAUNCHED(h);
     return DW_OK;
 }
@@ -493,6 +497,7 @@ extern "C" int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab,
     if (h->cfg.n_agents == 0) return DW_OK;
     if (!action || ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents)
         return dw_fail(h, DW_E_INVALID, "dw_update_agents", "action must be [ab<=B, am<=n]");
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_update_agents", "dw_agents_begin not closed by dw_agents_collide");
     int rc = ensure_grid(h);
     if (rc) return rc;
     rc = stage_action(h, action, (size_t)ab * am);
@@ -504,9 +509,86 @@ extern "C" int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab,
     return rc;
 }
 
+// ---- collision_mode == 1 (daisy_world_rl.py:220-242): update_agents in two calls around the caller's RNG draws ----
+extern "C" int dw_agents_begin(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed,
+                               int64_t *agent_indices) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_agents_begin", "previous dw_agents_begin not closed by dw_agents_collide");
+    if (h->cfg.n_agents == 0) return DW_OK;
+    if (policy > DW_POLICY_EPS_GREEDY || policy == DW_POLICY_REPLAY)
+        return dw_fail(h, DW_E_INVALID, "dw_agents_begin", "policy must be < 0 (explicit action / NULL) or a device policy without network");
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    if (policy < 0) {
+        if (action) {
+            if (ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents)
+                return dw_fail(h, DW_E_INVALID, "dw_agents_begin", "action must be [ab<=B, am<=n]");
+            rc = stage_action(h, action, (size_t)ab * am);
+            if (rc) return rc;
+            rc = launch_agents(h, h->action_dev, ab, am, DW_POLICY_REPLAY, 0, false, false);
+        } else {
+            rc = launch_agents(h, nullptr, 0, 0, DW_POLICY_NONE, 0, false, false);
+        }
+    } else {
+        rc = launch_agents(h, nullptr, 0, 0, policy, seed, false, false);
+    }
+    if (rc) return rc;
+    h->agents_open = true;
+    h->lat_valid = false;
+    h->cov_valid = false;
+    h->obs_valid = false;
+    return dw_get_agents(h, agent_indices, nullptr);
+}
+
+extern "C" int dw_agents_collide(dw_handle *h, const double *noise, const int32_t *cell_offsets, double food_chain_penalty) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t B = h->cfg.batch, n = h->cfg.n_agents;
+    if (n == 0) return DW_OK;
+    if (!h->agents_open) return dw_fail(h, DW_E_STATE, "dw_agents_collide", "no dw_agents_begin pending");
+    if (!cell_offsets) return dw_fail(h, DW_E_INVALID, "dw_agents_collide", "cell_offsets [B+1] required");
+    const size_t cells = (size_t)cell_offsets[B];
+    if (cell_offsets[0] != 0 || (cells && !noise)) return dw_fail(h, DW_E_INVALID, "dw_agents_collide", "cell_offsets must start at 0; noise [cells, n]");
+    for (size_t b = 0; b < B; ++b)
+        if (cell_offsets[b + 1] < cell_offsets[b]) return dw_fail(h, DW_E_INVALID, "dw_agents_collide", "cell_offsets must not decrease");
+    // scratch: [losers B*n | noise cells*n | offsets (B+1 int32)]
+    int rc = ensure_scratch(h, B * n + cells * n + (B + 2) / 2 + 1);
+    if (!rc) rc = dev_alloc(h, &h->slow_count, (size_t)2);
+    if (rc) return rc;
+    double *los = h->scratch, *noise_dev = h->scratch + B * n;
+    int32_t *off_dev = reinterpret_cast<int32_t *>(noise_dev + cells * n);
+    if (cells) DW_CUDA_TRY(h, cudaMemcpyAsync(noise_dev, noise, cells * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaMemcpyAsync(off_dev, cell_offsets, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
+    const DevParams P = make_params(h);
+    k_collide<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->agent_xy, h->agent_state, noise_dev, off_dev, food_chain_penalty, los,
+                                                        h->slow_count + 1);
+    DW_LAUNCHED(h);
+    unsigned int bad = 0;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(&bad, h->slow_count + 1, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));       // also keeps the pageable noise / offsets alive until they are read
+    h->agents_open = false;
+    if (bad) return dw_fail(h, DW_E_INVALID, "dw_agents_collide", "shared-cell counts differ from the positions on the device");
+    return DW_OK;
+}
+
+static int collect_step_outputs(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk);
+
+extern "C" int dw_step_tail_collect(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_step_tail_collect", "dw_agents_begin not closed by dw_agents_collide");
+    int rc = ensure_grid(h);
+    if (!rc) rc = launch_forward_tail(h, false, nullptr);
+    if (rc) return rc;
+    return collect_step_outputs(h, obs, reward, done, clk);
+}
+
 extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t am) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_step", "dw_agents_begin not closed by dw_agents_collide");
     int rc = ensure_grid(h);
     if (rc) return rc;
     if (h->cfg.n_agents > 0) {
@@ -602,6 +684,7 @@ extern "C" int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed) {
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (policy == DW_POLICY_REPLAY || policy < 0 || policy > DW_POLICY_MLP)
         return dw_fail(h, DW_E_INVALID, "dw_step_policy", "use dw_step for explicit actions");
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_step_policy", "dw_agents_begin not closed by dw_agents_collide");
     int rc = DW_OK;
     if (policy == DW_POLICY_MLP) {
         rc = mlp_actions(h);
@@ -688,6 +771,11 @@ extern "C" int dw_step_collect(dw_handle *h, const int64_t *action, int32_t ab, 
     if (!h) return DW_E_INVALID;
     int rc = policy < 0 ? dw_step(h, action, ab, am) : dw_step_policy(h, policy, seed);
     if (rc) return rc;
+    return collect_step_outputs(h, obs, reward, done, clk);
+}
+
+static int collect_step_outputs(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk) {
+    int rc = DW_OK;
     const size_t B = h->cfg.batch, n = h->cfg.n_agents;
     if (obs && n) {
         rc = compute_obs(h);

@@ -216,7 +216,7 @@ __device__ __forceinline__ int dw_greedy_pick(const double (&food)[4], bool gree
 // (7-channel grid: 7NN, NN, 2NN; lean cover planes: 2NN, 0, NN).
 __global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *covers, size_t world_stride, size_t l_off, size_t d_off,
                                                      int32_t *agent_xy, double *agent_state, const int8_t *action, int ab, int am,
-                                                     int policy, uint64_t seed, uint32_t step, uint32_t world0) {
+                                                     int policy, uint64_t seed, uint32_t step, uint32_t world0, int clip = 1) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
     const int N = P.N, n = P.n_agents;
@@ -272,6 +272,83 @@ __global__ void __launch_bounds__(128) k_agents_grid(DevParams P, double *covers
             xy[2 * i + 1] = y;
         }
     }
+    if (clip)                          // collision_mode == 1 resolves collisions on the unclipped states first (k_collide)
+        for (int i = 0; i < n; ++i) st[i] = dw_clip01(st[i]);
+}
+
+// ---- collision_mode == 1 (daisy_world_rl.py:220-242) ----
+// np.sum of m contiguous doubles as NumPy adds them (0 + pairwise sum: fewer than 8 sequentially, up to 128 with 8
+// interleaved accumulators, larger blocks split in halves rounded down to a multiple of 8).
+__device__ double dw_numpy_pairwise(const double *a, int m) {
+    if (m < 8) {
+        double r = 0.0;
+        for (int i = 0; i < m; ++i) r = r + a[i];
+        return r;
+    }
+    if (m <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        int i = 8;
+        for (; i < m - (m % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = r[k] + a[i + k];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < m; ++i) res = res + a[i];
+        return res;
+    }
+    int m2 = m / 2;
+    m2 -= m2 % 8;
+    return dw_numpy_pairwise(a, m2) + dw_numpy_pairwise(a + m2, m - m2);
+}
+
+// One thread per world, after k_agents_grid(clip = 0). The reference scans the cells of a world in row-major order and,
+// where more than one agent sits, draws npr.rand(1, n, 1): noise[k, 0..n) is the k-th such draw of the whole batch,
+// cell_off[b] the index of world b's first one (the host front counts the shared cells from the post-move positions and
+// draws from the caller's global stream in that order). Per shared cell: temp = 1.0 * state + 0.01 * noise for all n
+// agents, winner value = max over the residents, eat = np.sum of the states of the residents whose temp differs from
+// it (unclipped, dead agents included), every agent whose temp EQUALS the winner value gains penalty * eat; the losers
+// keep their state (the reference's zeroing assigns into a copy, :242). Then the clip of :244.
+// mismatch counts worlds whose number of shared cells differs from the host's.
+__global__ void __launch_bounds__(128) k_collide(DevParams P, const int32_t *agent_xy, double *agent_state, const double *noise,
+                                                 const int32_t *cell_off, double penalty, double *losers_scratch, unsigned int *mismatch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const int N = P.N, n = P.n_agents;
+    const int32_t *xy = agent_xy + (size_t)b * n * 2;
+    double *st = agent_state + (size_t)b * n;
+    double *los = losers_scratch + (size_t)b * n;
+    int k = cell_off[b];
+    const int kend = cell_off[b + 1];
+    int last = -1;
+    for (;;) {
+        int key = 0x7fffffff;
+        for (int i = 0; i < n; ++i) {
+            const int c = xy[2 * i] * N + xy[2 * i + 1];
+            if (c > last && c < key) key = c;
+        }
+        if (key == 0x7fffffff) break;
+        last = key;
+        int residents = 0;
+        for (int i = 0; i < n; ++i) residents += (xy[2 * i] * N + xy[2 * i + 1] == key) ? 1 : 0;
+        if (residents < 2) continue;
+        if (k >= kend) { k += 1; continue; }          // more shared cells than the host counted: reported below
+        const double *nz = noise + (size_t)k * n;
+        k += 1;
+        double winner = 0.0;
+        bool first = true;
+        for (int i = 0; i < n; ++i)
+            if (xy[2 * i] * N + xy[2 * i + 1] == key) {
+                const double t = 1.0 * st[i] + 0.01 * nz[i];
+                winner = first ? t : fmax(winner, t);
+                first = false;
+            }
+        int m = 0;
+        for (int i = 0; i < n; ++i)
+            if (xy[2 * i] * N + xy[2 * i + 1] == key && (1.0 * st[i] + 0.01 * nz[i]) != winner) los[m++] = st[i];
+        const double eat = 0.0 + dw_numpy_pairwise(los, m);
+        for (int i = 0; i < n; ++i)
+            if ((1.0 * st[i] + 0.01 * nz[i]) == winner) st[i] = st[i] + penalty * eat;
+    }
+    if (k != kend) atomicAdd(mismatch, 1u);
     for (int i = 0; i < n; ++i) st[i] = dw_clip01(st[i]);
 }
 

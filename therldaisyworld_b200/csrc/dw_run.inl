@@ -339,6 +339,7 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
 }
 
 static int check_policy(dw_handle *h, int policy, const int8_t *actions) {
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_run", "dw_agents_begin not closed by dw_agents_collide");
     if (policy < 0 || policy > DW_POLICY_MLP) return dw_fail(h, DW_E_INVALID, "policy", "unknown policy");
     if (policy == DW_POLICY_MLP && h->cfg.n_agents > 0 && !h->mlp_set) return dw_fail(h, DW_E_STATE, "policy", "DW_POLICY_MLP needs dw_set_mlp");
     if (policy == DW_POLICY_REPLAY && h->cfg.n_agents > 0 && !actions) return dw_fail(h, DW_E_INVALID, "policy", "REPLAY needs actions[K,B,n]");

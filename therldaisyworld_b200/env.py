@@ -320,6 +320,9 @@ class RLDaisyWorld:
         """run() that also returns the per-step ensemble means [K, 3] = (global mean temperature of that step's forward --
         env.temp.mean() --, mean light cover, mean dark cover), reduced inside the fused kernel (64x64 worlds)."""
         B, N, n = self._shape
+        if self.collision_mode == 1 and n:
+            raise NotImplementedError("collision_mode == 1 draws from the caller's NumPy stream every step: use step() / "
+                                      "step_policy(); multi-step device runs are for collision_mode == 0")
         a8 = None
         if policy == "replay":
             a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
@@ -432,14 +435,37 @@ class RLDaisyWorld:
         return self.get_obs(self.agent_indices)
 
     def update_agents(self, action):
-        """reference :181-244 (collision_mode 0)."""
-        if self.collision_mode == 1:
-            raise NotImplementedError("collision_mode == 1 (stochastic, default off) is not implemented on the device")
+        """reference :181-244."""
         a = self._action(action)
         self._push()
         if self._shape[2]:
-            self._check(self._lib.dw_update_agents(self._h, _ptr(a, C.c_int64), a.shape[0], a.shape[1]), "dw_update_agents")
+            if self.collision_mode == 1:
+                self._update_agents_colliding(a, -1, 0)
+            else:
+                self._check(self._lib.dw_update_agents(self._h, _ptr(a, C.c_int64), a.shape[0], a.shape[1]), "dw_update_agents")
         self._state_changed()
+
+    def _update_agents_colliding(self, a, policy, seed):
+        """update_agents with collision_mode == 1 (reference :220-242). The device moves and grazes the agents and hands
+        back their positions; this side only counts, per world, the cells holding more than one agent and draws the
+        reference's npr.rand(1, n, 1) per such cell from the GLOBAL stream in the reference's (world, x, y) scan order
+        (consecutive draws of n doubles = one draw of [cells, n]); the device then resolves the collisions and clips."""
+        B, N, n = self._shape
+        pos = np.empty((B, n, 2), dtype=np.int64)
+        rc = self._lib.dw_agents_begin(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
+                                       0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), _ptr(pos, C.c_int64))
+        self._check(rc, "dw_agents_begin")
+        key = np.sort(pos[:, :, 0] * N + pos[:, :, 1], axis=1)                 # [B, n]
+        same = key[:, 1:] == key[:, :-1]
+        # a shared cell = a run of equal keys: count the runs' first repeats
+        first_repeat = same & ~np.concatenate([np.zeros((B, 1), dtype=bool), same[:, :-1]], axis=1)
+        offsets = np.zeros(B + 1, dtype=np.int32)
+        np.cumsum(first_repeat.sum(axis=1), out=offsets[1:])
+        cells = int(offsets[-1])
+        noise = np.ascontiguousarray(np.random.rand(cells, n)) if cells else None
+        rc = self._lib.dw_agents_collide(self._h, None if noise is None else _ptr(noise, C.c_double),
+                                         offsets.ctypes.data_as(C.POINTER(C.c_int32)), float(self.food_chain_penalty))
+        self._check(rc, "dw_agents_collide")
 
     def _action(self, action):
         a = np.asarray(action)
@@ -485,8 +511,6 @@ class RLDaisyWorld:
 
     def step(self, action=None):
         """reference :475-497"""
-        if self.collision_mode == 1:
-            raise NotImplementedError("collision_mode == 1 (stochastic, default off) is not implemented on the device")
         B, N, n = self._shape
         a = None
         if action is not None and n:
@@ -503,10 +527,18 @@ class RLDaisyWorld:
         reward = np.empty(shape)
         done = np.empty(shape, dtype=np.uint8)
         clk = DwClock()
-        rc = self._lib.dw_step_collect(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
-                                       0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), _ptr(obs, C.c_double),
-                                       _ptr(reward, C.c_double), _ptr(done, C.c_uint8), C.byref(clk))
-        self._check(rc, "dw_step_collect")
+        if self.collision_mode == 1 and n:
+            if policy == DW_POLICY["mlp"]:
+                raise NotImplementedError("collision_mode == 1 with the device MLP policy: pass the MLP's actions to step()")
+            self._update_agents_colliding(a, policy, seed)
+            rc = self._lib.dw_step_tail_collect(self._h, _ptr(obs, C.c_double), _ptr(reward, C.c_double), _ptr(done, C.c_uint8),
+                                                C.byref(clk))
+            self._check(rc, "dw_step_tail_collect")
+        else:
+            rc = self._lib.dw_step_collect(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
+                                           0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), _ptr(obs, C.c_double),
+                                           _ptr(reward, C.c_double), _ptr(done, C.c_uint8), C.byref(clk))
+            self._check(rc, "dw_step_collect")
         self._state_changed()
         self.L, self.dL, self.min_L, self.max_L = clk.L, clk.dL, clk.min_L, clk.max_L
         self.step_count = int(clk.step_count)
@@ -577,6 +609,9 @@ class RLDaisyWorld:
         (actions[K,B,n(,1)] ints 0..8).
         Returns (steps_run, worlds_alive, all_done_hit)."""
         B, N, n = self._shape
+        if self.collision_mode == 1 and n:
+            raise NotImplementedError("collision_mode == 1 draws from the caller's NumPy stream every step: use step() / "
+                                      "step_policy(); multi-step device runs are for collision_mode == 0")
         a8 = None
         if policy == "replay":
             a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
