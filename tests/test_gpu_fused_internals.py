@@ -40,7 +40,10 @@ def test_fast_root4_relative_error_bound():
                                           # worlds below 64x64 share a CTA (k_fused_sub64_persist): partial last group,
                                           # agent count at the shared-memory limit (64 worlds x 4), and over it (generic kernel)
                                           (8, 70, 4, "greedy"), (8, 130, 3, "random"), (16, 19, 9, "antigreedy"),
-                                          (32, 7, 33, "greedy"), (32, 9, 0, "none"), (8, 5, 5, "greedy")])
+                                          (32, 7, 33, "greedy"), (32, 9, 0, "none"), (8, 5, 5, "greedy"),
+                                          # other multiples of 4 run the 4x4-tile kernel with a host-chosen block size (k_fused_tile4)
+                                          (20, 9, 3, "antigreedy"), (96, 3, 5, "greedy"), (128, 2, 6, "random"), (156, 1, 4, "greedy"),
+                                          (32, 3, 70, "greedy")])
 def test_fused_equals_materialising_path(N, B, n, policy):
     """Same inputs through dw_run with the fused kernel and with DW_DISABLE_FUSED=1 (materialising kernels only)."""
     res = []

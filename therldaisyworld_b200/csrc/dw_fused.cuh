@@ -809,8 +809,9 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
 // CTA sit side by side in the two 64x64 shared-memory buffers (world (wy, wx) at rows wy*N.., columns wx*N..), rows wrap
 // inside a world and the halo columns come from the neighbouring lanes of the world's own N/4-lane group. Work items
 // are (group of W worlds, chunk of Kc steps), same persistent queue as the 64x64 kernel. Agents: all W*n of them live in
-// shared memory (W*n <= DW_SUB64_MAX_AGENTS), warp 0 decides for all, then moves and grazes them 32 at a time in flat
-// (world, index) order, so the per-world sequential semantics are those of dw_agents_phase32.
+// shared memory (W*n <= DW_SUB64_MAX_AGENTS); each warp takes the agents of W/8 whole worlds (worlds are independent),
+// decides for all of them, then moves and grazes them 32 at a time in flat (world, index) order, so the per-world
+// sequential semantics are those of dw_agents_phase32.
 #define DW_SUB64_MAX_AGENTS 256
 template <int N>
 struct Sub64Smem {
@@ -892,13 +893,15 @@ __device__ __noinline__ bool dw_fix_warp_sub(const FusedArgs *A, const StepCoef 
     return mine;
 }
 
+// Called by every warp that owns worlds: the agents [a_lo, a_hi) (flat (world, index) order) of whole worlds. Worlds are
+// independent, so the warps of a CTA run their agent phases concurrently.
 template <int N>
 __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, int group, uint32_t *cb, Sub64Smem<N> &sm, int lane, int n,
-                                                    int n_act) {
+                                                    int a_lo, int n_act) {
     constexpr int WX = 64 / N, W = WX * WX;
     const int pol = A.sc[j].policy;
     // pass 1: every agent decides from the pre-move state
-    for (int a = lane; a < n_act; a += 32) {
+    for (int a = a_lo + lane; a < n_act; a += 32) {
         const int wl = a / n, i = a - wl * n;
         const int x = sm.xy[a] & 0xffff, y = sm.xy[a] >> 16;
         const size_t gw = (size_t)group * W + wl;
@@ -917,7 +920,7 @@ __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, i
     __syncwarp();
     // pass 2: move + graze, 32 agents at a time in flat (world, index) order; inside a round MATCH.ANY orders the grazers
     // of a cell, across rounds the earlier round has already emptied it
-    for (int base = 0; base < n_act; base += 32) {
+    for (int base = a_lo; base < n_act; base += 32) {
         const int a = base + lane;
         const bool active = a < n_act;
         double st = 0.0;
@@ -1005,7 +1008,11 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
         for (int jl = 0; jl < kc; ++jl) {
             const int j = j0 + jl;
             uint32_t *cb = sm.buf[jl & 1], *nb = sm.buf[(jl + 1) & 1];
-            if (warp == 0 && n_act > 0) dw_agents_phase_sub<N>(A, j, g, cb, sm, lane, n, n_act);
+            {   // warp k moves the agents of worlds [k * WPW, (k + 1) * WPW) of the group
+                constexpr int WPW = (W + 7) / 8;
+                const int w_lo = warp * WPW, w_hi = min(w_lo + WPW, n_worlds);
+                if (w_lo < w_hi && n > 0) dw_agents_phase_sub<N>(A, j, g, cb, sm, lane, n, w_lo * n, w_hi * n);
+            }
             __syncthreads();
             if (j == A.K - 1) {                        // post-graze state of the launch's last step (lazy materialisation)
                 for (int q = tid; q < 1024; q += 256) {
@@ -1068,6 +1075,148 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
         if (tid == 0) {
             __threadfence();
             atomicExch(A.pair_done + g, (unsigned)(c + 1));
+        }
+    }
+}
+
+// ---- any N that is a multiple of 4 (and fits in shared memory): one CTA per world, 4x4 tiles dealt round-robin to the threads ----
+// Same fast path and tile core as the 64x64 kernel; the halo columns come from shared memory instead of SHFL (the lanes
+// of a warp do not line up with a world row), the rows wrap by compare. The host picks the block size from the tile count
+// and the shared-memory footprint (launch_fused). dynamic smem: 2*N*N u32 | n doubles | 3n ints | 4 ints.
+struct RowsTile4 {
+    const uint32_t *cb;
+    int N, r0, c0, cl, cr;              // first row / column of the tile, wrapped left and right halo columns
+    __device__ __forceinline__ Row6 load(int k) const {
+        int r = r0 + k;
+        r = r < 0 ? r + N : (r >= N ? r - N : r);
+        const uint32_t *row = cb + r * N;
+        const uint4 v = *reinterpret_cast<const uint4 *>(row + c0);
+        return dw_make_row(v, row[cl], row[cr]);
+    }
+};
+struct StoreTile4 {
+    uint32_t *nb;
+    int N, r0, c0;
+    __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
+        *reinterpret_cast<uint4 *>(nb + (r0 + i) * N + c0) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+};
+
+// warp-cooperative tie fix-up, generic N (see dw_fix_warp64)
+__device__ __noinline__ uint32_t dw_fix_warp_tile4(const FusedArgs *A, const StepCoef *C, const uint32_t *cb, uint32_t *nb, unsigned flagged,
+                                                   uint32_t mx, int r0, int c0, int lane, int N) {
+    uint32_t extra = 0;
+    bool mine = false;
+    __syncwarp();
+    while (flagged) {
+        const int L = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const int tr0 = __shfl_sync(0xffffffffu, r0, L), tc0 = __shfl_sync(0xffffffffu, c0, L);
+        if (lane == L) mine = true;
+        if (lane < 16) {
+            const int x = tr0 + (lane >> 2), y = tc0 + (lane & 3);
+            const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1, ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+            const uint32_t *q0 = cb + xm * N, *q1 = cb + x * N, *q2 = cb + xp * N;
+            const uint32_t E = q1[ym] + q1[yp] + q0[y] + q2[y];
+            const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
+            unsigned tiemin = 0xffffffffu;
+            uint32_t v = dw_fast_cell(A->F, *C, q1[y], E, S8, &tiemin);
+            if (tiemin < A->F.tie_thresh) {
+                v = dw_slow_cell(A, C->SL, cb, N, x, y);
+                nb[x * N + y] = v;
+            }
+            extra = __vmaxu2(extra, v);
+        }
+    }
+    __syncwarp();
+    return __vmaxu2(mine ? 0u : mx, extra);
+}
+
+__global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__ FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.P.N, n = A.P.n_agents, NN = N * N, T = N >> 2, TT = T * T;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    uint32_t *buf0 = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *buf1 = buf0 + NN;
+    AgentSmem S;
+    S.st = reinterpret_cast<double *>(buf1 + NN);
+    S.xy = reinterpret_cast<int *>(S.st + n);
+    S.act = S.xy + n;
+    S.ada = S.act + n;
+    int *s_max = S.ada + n;
+
+    {
+        const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat_in + (size_t)b * NN);
+        for (int c = tid; c < NN / 4; c += nthr) reinterpret_cast<uint4 *>(buf0)[c] = gin[c];
+    }
+    for (int i = tid; i < n; i += nthr) {
+        S.st[i] = A.agent_state[(size_t)b * n + i];
+        S.xy[i] = A.agent_xy[((size_t)b * n + i) * 2] | (A.agent_xy[((size_t)b * n + i) * 2 + 1] << 16);
+        S.ada[i] = 0;
+    }
+    if (tid < 4) s_max[tid] = 0;
+    __syncthreads();
+
+    uint32_t *cb = buf0, *nb = buf1;
+    int life = 0;
+    const int rounds = (TT + nthr - 1) / nthr;
+    for (int j = 0; j < A.K; ++j) {
+        if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane);
+        __syncthreads();
+        if (j == A.K - 1) {
+            uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
+            for (int c = tid; c < NN / 4; c += nthr) gp[c] = reinterpret_cast<const uint4 *>(cb)[c];
+        }
+        const StepCoef C = A.sc[j];
+        uint32_t mx = 0;
+        for (int r = 0; r < rounds; ++r) {                      // uniform trip count: the fix-up below is warp-collective
+            const int tile = tid + r * nthr;
+            const bool active = tile < TT;
+            const int ty = tile / T, tx = tile - ty * T;
+            const int r0 = ty * 4, c0 = tx * 4;
+            unsigned tiemin = 0xffffffffu;
+            uint32_t m = 0;
+            if (active)
+                m = dw_tile_core(A.F, C, RowsTile4{cb, N, r0, c0, c0 == 0 ? N - 1 : c0 - 1, c0 + 4 == N ? 0 : c0 + 4},
+                                 StoreTile4{nb, N, r0, c0}, &tiemin);
+            const unsigned flagged = __ballot_sync(0xffffffffu, active && tiemin < A.F.tie_thresh);
+            if (flagged) m = dw_fix_warp_tile4(&A, &A.sc[j], cb, nb, flagged, m, r0, c0, lane, N);
+            mx = __vmaxu2(mx, m);
+        }
+        const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+        int *sm = s_max + 2 * (j & 1);
+        if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+        __syncthreads();
+        if (warp == 0) {
+            const bool grid_done = max(sm[0], sm[1]) <= 5;
+            if (lane == 0) {
+                if (!grid_done) { life += 1; atomicAdd(A.alive + j, 1u); }
+                s_max[2 * ((j + 1) & 1)] = 0;
+                s_max[2 * ((j + 1) & 1) + 1] = 0;
+            }
+            for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;
+        }
+        uint32_t *t = cb; cb = nb; nb = t;
+    }
+    __syncthreads();
+    {
+        uint4 *gout = reinterpret_cast<uint4 *>(A.lat_out + (size_t)b * NN);
+        for (int c = tid; c < NN / 4; c += nthr) gout[c] = reinterpret_cast<const uint4 *>(cb)[c];
+    }
+    for (int i = tid; i < n; i += nthr) {
+        A.agent_state[(size_t)b * n + i] = S.st[i];
+        A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
+        A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
+        A.agents_done_at[(size_t)b * n + i] += S.ada[i];
+        const double r = S.st[i];
+        A.reward[(size_t)b * n + i] = r;
+        A.done[(size_t)b * n + i] = r < 0.1;
+    }
+    if (tid == 0) {
+        A.done_at[b] += life;
+        if (n == 0) {
+            const int *sm = s_max + 2 * ((A.K - 1) & 1);
+            for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
         }
     }
 }

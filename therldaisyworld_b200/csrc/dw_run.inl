@@ -196,8 +196,29 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
             DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->fused_attr_set = true;
         }
+        const bool tile4 = !n64 && dimN % 4 == 0 && dimN >= 12 && !(impl && !strcmp(impl, "generic"));
         if (n64) k_fused_n64<<<h->cfg.batch, 256, smem, h->stream>>>(A);
-        else k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+        else if (tile4) {
+            // 4x4 tiles dealt round-robin to the threads: pick the block size that keeps the most useful warps resident
+            // (64 registers per thread: at most 1024 threads per SM; CTAs per SM bounded by the shared-memory footprint)
+            if (!h->tile4_threads) {
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_tile4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                const int TT = (dimN / 4) * (dimN / 4);
+                const int cps_max = (int)std::min<size_t>(16, (227 * 1024) / (smem + 1024));
+                double best = -1.0;
+                for (int cps = 1; cps <= std::max(1, cps_max); ++cps) {
+                    const int cap = (1024 / cps) & ~31;                       // threads per CTA that still fit cps CTAs in the register file
+                    if (cap < 32) break;
+                    const int rounds = (TT + cap - 1) / cap;
+                    const int threads = std::min(cap, (((TT + rounds - 1) / rounds) + 31) & ~31);
+                    const double useful = (double)TT / ((double)rounds * threads) * std::min(1024, cps * threads);
+                    if (useful > best) { best = useful; h->tile4_threads = threads; }
+                }
+            }
+            const char *tenv = getenv("DW_TILE4_THREADS");
+            const int threads = tenv ? atoi(tenv) : h->tile4_threads;
+            k_fused_tile4<<<h->cfg.batch, threads, smem, h->stream>>>(A);
+        } else k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
         h->lcur = 1 - h->lcur;
     }
     DW_LAUNCHED(h);
