@@ -6,21 +6,24 @@ import torch
 from therldaisyworld_b200 import RLDaisyWorld
 from therldaisyworld_b200.ensemble import DeviceShard, simulate_lifespan
 
-def run(B, policy, albedo=None, max_steps=100000):
+def run(B, policy, albedo=None, max_steps=100000, epsilon=None):
     np.random.seed(0)
     env = RLDaisyWorld(grid_dimension=64)
     env.batch_size = B
     if albedo:
         env.albedo_light, env.albedo_dark = albedo
+    label = policy if epsilon is None else f"eps={epsilon}"
     t0 = time.perf_counter()
     env.reset_on_device(seed=13)
+    if epsilon is not None:                       # Greedy(epsilon): one coin per step for the whole ensemble (greedy.py:23)
+        env.set_epsilon(epsilon)
     env.synchronize()
     t1 = time.perf_counter()
     out = simulate_lifespan(DeviceShard(env), policy=policy, seed=7, device="cuda", max_steps=max_steps)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     steps = out["steps"]
-    print(f"B={B} {policy:10s} albedo={albedo}: reset {t1 - t0:.2f}s, {steps} steps in {t2 - t1:.2f}s -> "
+    print(f"B={B} {label:10s} albedo={albedo}: reset {t1 - t0:.2f}s, {steps} steps in {t2 - t1:.2f}s -> "
           f"{B * 4096 * steps / (t2 - t1):.3e} cell-updates/s wall; biosphere {out['biosphere_lifespan_mean']:.2f}+-{out['biosphere_lifespan_sem']:.3f} "
           f"agents {out['agent_lifespan_mean']:.2f}+-{out['agent_lifespan_sem']:.3f}; mem {torch.cuda.mem_get_info()[0] / 2**30:.1f} GiB free", flush=True)
 
@@ -29,3 +32,4 @@ if __name__ == "__main__":
     for albedo in (None, (0.5, 0.5)):
         for policy in ("greedy", "antigreedy", "random"):
             run(B, policy, albedo)
+        run(B, "eps_greedy", albedo, epsilon=0.5)     # SURVEY 8(d) cfg 3: the half-random condition
