@@ -77,6 +77,11 @@ struct dw_handle {
     bool fused_attr_set = false;
     bool agents_open = false;                  // between dw_agents_begin and dw_agents_collide the agent states are unclipped
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
+    std::vector<dw_clock> sc_clk;              // clock before each step of the table on the device (+ the one after the last)
+    int sc_policy = -1;                        // what the cached table was built for (launch_fused)
+    uint64_t sc_seed = 0;
+    double sc_eps = 0.0;
+    dw_config sc_cfg{};
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
     int persist_blocks = 0, sub64_blocks = 0;  // resident CTAs of the persistent kernels on this device
     int tile4_threads = 0;                     // block size chosen for k_fused_tile4 (world side a multiple of 4)
@@ -314,6 +319,7 @@ extern "C" int dw_get_last_L(dw_handle *h, double *L) {
 extern "C" int dw_set_stream(dw_handle *h, void *s) {
     if (!h) return DW_E_INVALID;
     h->stream = (cudaStream_t)s;
+    h->sc_clk.clear();                         // the cached coefficient table was uploaded in the old stream's order
     return DW_OK;
 }
 extern "C" int dw_set_epsilon(dw_handle *h, double epsilon) {

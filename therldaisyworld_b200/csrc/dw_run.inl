@@ -91,26 +91,48 @@ static int grid_to_lattice(dw_handle *h, bool *converted) {
     return DW_OK;
 }
 
+static bool same_clock(const dw_clock &a, const dw_clock &b) {
+    return a.L == b.L && a.dL == b.dL && a.min_L == b.min_L && a.max_L == b.max_L && a.ddL == b.ddL && a.step_count == b.step_count &&
+           a.ramp_period == b.ramp_period && a.ramp_up_down == b.ramp_up_down;
+}
+
 static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive) {
     if (K > DW_FUSED_MAX_STEPS) return dw_fail(h, DW_E_INVALID, "launch_fused", "K too large");
     FusedArgs A{};
     A.P = make_params(h);
     make_fast_coef(h->cfg, A.F);
-    dw_clock clk = h->clk;
-    double L_last = clk.L;
-    std::vector<StepCoef> table(K);
-    for (int j = 0; j < K; ++j) {
-        make_step_coef(h->cfg, clk.L, table[j]);
-        table[j].policy = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)(h->clk.step_count + j));
-        table[j].pad_ = 0;
-        L_last = clk.L;
-        update_L(clk);
-    }
+    // Per-step coefficient table (luminosity coefficients + resolved policy). Callers that advance one step per launch (the
+    // MLP policy, the ES population rollout) would rebuild and re-upload it every step: the table is built with look-ahead
+    // and kept on the device while the clock, the constants and the policy stay on the same track.
     int rc = dev_alloc(h, &h->sc_dev, (size_t)DW_FUSED_MAX_STEPS);
     if (rc) return rc;
-    // pageable source: cudaMemcpyAsync returns once the data is staged, so the local table may go out of scope
-    DW_CUDA_TRY(h, cudaMemcpyAsync(h->sc_dev, table.data(), K * sizeof(StepCoef), cudaMemcpyHostToDevice, h->stream));
-    A.sc = h->sc_dev;
+    long long off = -1;
+    if (!h->sc_clk.empty() && policy == h->sc_policy && seed == h->sc_seed && h->epsilon == h->sc_eps &&
+        !memcmp(&h->cfg, &h->sc_cfg, sizeof(dw_config))) {
+        const long long j = h->clk.step_count - h->sc_clk[0].step_count;
+        if (j >= 0 && j + K <= (long long)h->sc_clk.size() - 1 && same_clock(h->sc_clk[j], h->clk)) off = j;
+    }
+    if (off < 0) {
+        const int build = K >= 64 ? K : 512;
+        std::vector<StepCoef> table(build);
+        h->sc_clk.assign(build + 1, h->clk);
+        dw_clock c = h->clk;
+        for (int j = 0; j < build; ++j) {
+            h->sc_clk[j] = c;
+            make_step_coef(h->cfg, c.L, table[j]);
+            table[j].policy = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)(h->clk.step_count + j));
+            table[j].pad_ = 0;
+            update_L(c);
+        }
+        h->sc_clk[build] = c;
+        h->sc_policy = policy; h->sc_seed = seed; h->sc_eps = h->epsilon; h->sc_cfg = h->cfg;
+        // pageable source: cudaMemcpyAsync returns once the data is staged, so the local table may go out of scope
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->sc_dev, table.data(), build * sizeof(StepCoef), cudaMemcpyHostToDevice, h->stream));
+        off = 0;
+    }
+    const double L_last = h->sc_clk[off + K - 1].L;
+    const dw_clock clk = h->sc_clk[off + K];
+    A.sc = h->sc_dev + off;
     A.lat_in = h->lat[h->lcur];
     A.lat_out = h->lat[1 - h->lcur];
     A.lat_pre = h->lat_pre;
