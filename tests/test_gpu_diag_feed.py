@@ -67,6 +67,22 @@ def test_in_kernel_series_matches_oracle_per_step():
         np.testing.assert_allclose(s2[t], [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()], rtol=1e-9)
 
 
+def test_series_for_other_world_sizes_matches_oracle_per_step():
+    """run_series on a shape outside the in-kernel series mode (16x16): same per-step means, sampled between one-step launches."""
+    from oracle.daisy_numpy import OracleGreedy, env_from_golden
+    z, meta = load_golden("greedy_n16_b4_todeath")
+    env = product_env_from_golden(z, meta)
+    K = 40
+    series = env.run_series(K, policy="greedy")
+    oenv, _ = env_from_golden(z)
+    agent = OracleGreedy()
+    obs = oenv.get_obs(oenv.agent_indices)
+    for t in range(K):
+        obs, _, _, _ = oenv.step(agent(obs))
+        np.testing.assert_allclose(series[t], [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()], rtol=1e-9)
+    np.testing.assert_array_equal(env.grid, oenv.grid)
+
+
 def test_fp32_export_within_stated_tolerance():
     """fp32 mode of the fields: BASELINE.json's tolerance for fp32 is 1e-5 relative; the export is one rounding of the
     exact fp64 fields, so 6e-8 holds."""

@@ -75,6 +75,8 @@ struct dw_handle {
     int64_t *pop_steps = nullptr, *pop_frozen = nullptr;   // [members] step count at the end; [B,n] frozen (1-done) counters
     unsigned int *pop_ndone = nullptr;
     bool fused_attr_set = false;
+    unsigned char *pin = nullptr;              // pinned host staging of the single-step path: [action | obs | reward | done]
+    size_t pin_cap = 0;
     bool agents_open = false;                  // between dw_agents_begin and dw_agents_collide the agent states are unclipped
     StepCoef *sc_dev = nullptr;                // per-step coefficient table of a fused launch
     std::vector<dw_clock> sc_clk;              // clock before each step of the table on the device (+ the one after the last)
@@ -283,6 +285,7 @@ extern "C" int dw_destroy(dw_handle *h) {
                     h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->pin) cudaFreeHost(h->pin);
     for (auto &c : h->ck) {
         void *cp[] = {c.grid, c.cov, c.lat, c.lat_pre, c.agent_xy, c.agent_state, c.done_at, c.agents_done_at};
         for (void *p : cp) if (p) cudaFree(p);
@@ -439,12 +442,37 @@ extern "C" int dw_init_temperatures(dw_handle *h) {
     return DW_OK;
 }
 
+// Small transfers of the single-step path go through pinned staging memory: a pageable cudaMemcpyAsync blocks the host for
+// every copy, a pinned one is enqueued and the step ends with ONE synchronisation. Layout: [action count bytes | outputs].
+#define DW_PIN_ACTION_MAX (64 * 1024)
+#define DW_PIN_OUT_MAX (512 * 1024)
+static int ensure_pinned(dw_handle *h) {
+    if (h->pin) return DW_OK;
+    DW_CUDA_TRY(h, cudaMallocHost((void **)&h->pin, DW_PIN_ACTION_MAX + DW_PIN_OUT_MAX));
+    h->pin_cap = DW_PIN_ACTION_MAX + DW_PIN_OUT_MAX;
+    return DW_OK;
+}
+
 static int stage_action(dw_handle *h, const int64_t *action, size_t count) {
     if (h->action_cap < count) {
         if (h->action_dev) cudaFree(h->action_dev);
         h->action_dev = nullptr;
         DW_CUDA_TRY(h, cudaMalloc((void **)&h->action_dev, count));
         h->action_cap = count;
+    }
+    if (count <= DW_PIN_ACTION_MAX) {
+        // every earlier use of the staging area was followed by a synchronisation of this stream or is ordered before this
+        // copy on it; the action bytes are read by the copy engine before the kernels that follow can touch anything else
+        int rc = ensure_pinned(h);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // cheap when idle: the previous upload from this area has been consumed
+        int8_t *a8 = reinterpret_cast<int8_t *>(h->pin);
+        for (size_t i = 0; i < count; ++i) {
+            if (action[i] < 0 || action[i] > 8) return dw_fail(h, DW_E_INVALID, "action", "values must be in 0..8");
+            a8[i] = (int8_t)action[i];
+        }
+        DW_CUDA_TRY(h, cudaMemcpyAsync(h->action_dev, a8, count, cudaMemcpyHostToDevice, h->stream));
+        return DW_OK;
     }
     std::vector<int8_t> a8(count);
     for (size_t i = 0; i < count; ++i) {
@@ -784,15 +812,32 @@ extern "C" int dw_step_collect(dw_handle *h, const int64_t *action, int32_t ab, 
 static int collect_step_outputs(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk) {
     int rc = DW_OK;
     const size_t B = h->cfg.batch, n = h->cfg.n_agents;
-    if (obs && n) {
+    const bool want_obs = obs && n;
+    if (want_obs) {
         rc = compute_obs(h);
         if (rc) return rc;
-        DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->obs, B * n * 63 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     const size_t count = B * (n ? n : 2);
-    if (reward) DW_CUDA_TRY(h, cudaMemcpyAsync(reward, h->reward, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (done) DW_CUDA_TRY(h, cudaMemcpyAsync(done, h->done, count, cudaMemcpyDeviceToHost, h->stream));
-    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t obs_bytes = want_obs ? B * n * 63 * sizeof(double) : 0, rew_bytes = reward ? count * sizeof(double) : 0,
+                 done_bytes = done ? count : 0;
+    if (obs_bytes + rew_bytes + done_bytes <= DW_PIN_OUT_MAX) {
+        // small batches (the reference's default 32 worlds): three enqueued copies into pinned staging, one synchronisation
+        rc = ensure_pinned(h);
+        if (rc) return rc;
+        unsigned char *po = h->pin + DW_PIN_ACTION_MAX, *pr = po + obs_bytes, *pd = pr + rew_bytes;
+        if (obs_bytes) DW_CUDA_TRY(h, cudaMemcpyAsync(po, h->obs, obs_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (rew_bytes) DW_CUDA_TRY(h, cudaMemcpyAsync(pr, h->reward, rew_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (done_bytes) DW_CUDA_TRY(h, cudaMemcpyAsync(pd, h->done, done_bytes, cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (obs_bytes) memcpy(obs, po, obs_bytes);
+        if (rew_bytes) memcpy(reward, pr, rew_bytes);
+        if (done_bytes) memcpy(done, pd, done_bytes);
+    } else {
+        if (want_obs) DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->obs, obs_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (reward) DW_CUDA_TRY(h, cudaMemcpyAsync(reward, h->reward, rew_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (done) DW_CUDA_TRY(h, cudaMemcpyAsync(done, h->done, done_bytes, cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     if (clk) *clk = h->clk;
     return DW_OK;
 }

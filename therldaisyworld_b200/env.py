@@ -318,7 +318,8 @@ class RLDaisyWorld:
 
     def run_series(self, K, policy="greedy", actions=None, seed=0):
         """run() that also returns the per-step ensemble means [K, 3] = (global mean temperature of that step's forward --
-        env.temp.mean() --, mean light cover, mean dark cover), reduced inside the fused kernel (64x64 worlds)."""
+        env.temp.mean() --, mean light cover, mean dark cover): reduced inside the fused kernel for 64x64 worlds with at most 32
+        agents, sampled between one-step launches for every other shape."""
         B, N, n = self._shape
         if self.collision_mode == 1 and n:
             raise NotImplementedError("collision_mode == 1 draws from the caller's NumPy stream every step: use step() / "
@@ -327,6 +328,13 @@ class RLDaisyWorld:
         if policy == "replay":
             a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
         out = np.zeros((int(K), 3))
+        if N != 64 or n > 32 or policy == "mlp":
+            # other shapes: one fused step per sample, the same three means from the device-side reductions
+            for t in range(int(K)):
+                self.run(1, policy=policy, actions=None if a8 is None else a8[t:t + 1], seed=seed)
+                c = self.cover_stats()
+                out[t] = (self.diag_stats("temp")["mean"], c["mean_light"], c["mean_dark"])
+            return out
         self._push()
         rc = self._lib.dw_run_series(self._h, int(K), DW_POLICY[policy], _ptr(a8, C.c_int8), C.c_uint64(seed), _ptr(out, C.c_double))
         self._check(rc, "dw_run_series")
