@@ -241,3 +241,28 @@ def test_collision_mode_multi_step_runs_are_refused():
     env = RLDaisyWorld(grid_dimension=8, collision_mode=1)
     with pytest.raises(NotImplementedError):
         env.run(4, policy="greedy")
+
+
+def test_collision_abi_state_machine_and_count_check():
+    """Between dw_agents_begin and dw_agents_collide every other stepping call is refused (DW_E_STATE = -4), and a draw
+    count that does not match the positions on the device fails the call (DW_E_INVALID = -1) instead of mis-assigning noise."""
+    import ctypes as C
+    from therldaisyworld_b200 import RLDaisyWorld
+    np.random.seed(3)
+    env = RLDaisyWorld(grid_dimension=4, n_agents=20, collision_mode=1)      # 20 agents on 16 cells: shared cells guaranteed
+    env.batch_size = 2
+    env.reset()
+    env._push()
+    lib, h = env._lib, env._h
+    pos = np.empty((2, 20, 2), dtype=np.int64)
+    assert lib.dw_agents_begin(h, None, 0, 0, -1, C.c_uint64(0), pos.ctypes.data_as(C.POINTER(C.c_int64))) == 0
+    assert lib.dw_step_policy(h, 1, C.c_uint64(0)) == -4
+    assert lib.dw_step(h, None, 0, 0) == -4
+    assert lib.dw_agents_begin(h, None, 0, 0, -1, C.c_uint64(0), pos.ctypes.data_as(C.POINTER(C.c_int64))) == -4
+    off = np.zeros(3, dtype=np.int32)                                         # claims "no shared cells"
+    assert lib.dw_agents_collide(h, None, off.ctypes.data_as(C.POINTER(C.c_int32)), 0.5) == -1
+    assert b"shared-cell counts" in lib.dw_last_error(h)
+    # the failed call closed the pass; a regular step works again
+    env._state_changed()
+    obs, reward, done, _ = env.step(np.zeros((2, 20, 1), dtype=np.int64))
+    assert obs.shape == (2, 20, 7, 3, 3)
