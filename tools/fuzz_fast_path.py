@@ -1,13 +1,13 @@
 """Randomised stress test of the lattice fast path + tie filter: random physics constants, the fused kernels against the
 literal materialising kernels (DW_DISABLE_FUSED=1) on the same worlds. Any mismatch = a fast-path result further from the
-literal value than the tie filter assumes. Usage: python tools/fuzz_fast_path.py [n_configs] [seed]"""
+literal value than the tie filter assumes. Usage: python tools/fuzz_fast_path.py [n_configs] [seed] [sizes, e.g. 8,16,32,48,96,128]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from therldaisyworld_b200 import RLDaisyWorld
 
 
-def draw(rng):
+def draw(rng, sizes=(64, 64, 16, 33, 96)):
     a = dict(albedo_bare=rng.uniform(0.3, 0.7), S=rng.uniform(700, 1300), g=10 ** rng.uniform(-3, -2), gamma=rng.uniform(0.05, 0.45),
              dt=rng.choice([0.25, 0.5, 1.0]), temp_optimal=rng.uniform(280, 310), agent_gamma=rng.uniform(0.01, 0.1),
              min_L=rng.uniform(0.5, 0.9), initial_al=rng.uniform(0.05, 0.6), initial_ad=rng.uniform(0.05, 0.6),
@@ -15,7 +15,7 @@ def draw(rng):
     a["albedo_light"] = a["albedo_bare"] + rng.uniform(0.0, 0.3)
     a["albedo_dark"] = a["albedo_bare"] - rng.uniform(0.0, 0.3)
     a["max_L"] = a["min_L"] + rng.uniform(0.3, 1.2)
-    return a, int(rng.choice([64, 64, 16, 33, 96])), int(rng.choice([0, 1, 4, 9])), int(rng.choice([64, 128, 512])), bool(rng.rand() < 0.2)
+    return a, int(rng.choice(list(sizes))), int(rng.choice([0, 1, 4, 9])), int(rng.choice([64, 128, 512])), bool(rng.rand() < 0.2)
 
 
 def run_config(attrs, N, n, ramp, no_micro, seed, B=24, steps=400, policy="greedy"):
@@ -49,9 +49,10 @@ def run_config(attrs, N, n, ramp, no_micro, seed, B=24, steps=400, policy="greed
 if __name__ == "__main__":
     n_cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    sizes = tuple(int(v) for v in sys.argv[3].split(",")) if len(sys.argv) > 3 else (64, 64, 16, 33, 96)
     bad = 0
     for c in range(n_cfg):
-        attrs, N, n, ramp, no_micro = draw(rng)
+        attrs, N, n, ramp, no_micro = draw(rng, sizes)
         ok, slow, diff, life = run_config(attrs, N, n, ramp, no_micro, seed=c)
         cells = 24 * N * N * 400
         print(f"cfg {c}: N={N} n={n} ramp={ramp} micro={not no_micro} mean life {life:.0f}: {'OK' if ok else 'MISMATCH'} diff_cells={diff} "
