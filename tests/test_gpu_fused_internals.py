@@ -135,3 +135,53 @@ def test_fast_path_fuzz_random_physics():
         attrs, N, n, ramp, no_micro = fuzz.draw(rng)
         ok, slow, diff, life = fuzz.run_config(attrs, N, n, ramp, no_micro, seed=1000 + c, B=8, steps=250)
         assert ok, (c, attrs, N, n, ramp, no_micro, diff)
+
+
+def test_screened_forward_equals_literal_forward():
+    """The materialising kernels evaluate every cell with the fast fourth root and FMAs and keep the result only where no
+    rounded channel sits within the error bound of a rounding tie (dw_screened_cell); DW_LITERAL_ONLY=1 forces the literal
+    evaluation everywhere. Both must give the same seven channels on random off-lattice states, on lattice states, with
+    random physics, and on inputs outside the range the bound assumes (covers beyond [0, 1], dead-hot planets, NaN)."""
+    import importlib.util
+    from therldaisyworld_b200 import RLDaisyWorld
+    spec = importlib.util.spec_from_file_location("fuzz", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_fast_path.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.RandomState(2024)
+    cells = 0
+    for case in range(24):
+        N, B = int(rng.choice([5, 16, 33, 64])), 6
+        np.random.seed(case)
+        env = RLDaisyWorld(grid_dimension=N, n_agents=2)
+        env.batch_size = B
+        if case % 3:
+            attrs, _, _, _, no_micro = fuzz.draw(rng)
+            for k, v in attrs.items():
+                setattr(env, k, v)
+            env.q = 0.2 * env.S / env.sigma
+            env.set_use_microclimate(not no_micro)
+        env.reset()
+        env.L = float(rng.uniform(env.min_L, env.max_L))
+        g = env.grid.copy()
+        mode = case % 4
+        if mode == 0:      # arbitrary off-lattice covers
+            g[:, 1], g[:, 2] = rng.rand(B, N, N) * 0.7, rng.rand(B, N, N) * 0.3
+        elif mode == 1:    # lattice covers, sparse
+            g[:, 1] = np.round(rng.rand(B, N, N) * (rng.rand(B, N, N) < 0.4), 3)
+            g[:, 2] = np.round(rng.rand(B, N, N) * 0.5 * (rng.rand(B, N, N) < 0.4), 3)
+        elif mode == 2:    # out-of-range inputs: covers beyond [0, 1], negative, one NaN
+            g[:, 1], g[:, 2] = rng.randn(B, N, N), rng.rand(B, N, N) * 3
+            g[0, 1, 0, 0] = np.nan
+        else:              # a reset state as is
+            pass
+        outs = []
+        for literal in (False, True):
+            if literal:
+                os.environ["DW_LITERAL_ONLY"] = "1"
+            try:
+                outs.append(env.forward(g.copy()))
+            finally:
+                os.environ.pop("DW_LITERAL_ONLY", None)
+        np.testing.assert_array_equal(outs[0], outs[1])
+        cells += B * N * N
+    assert cells > 100000

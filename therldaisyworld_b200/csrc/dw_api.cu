@@ -127,6 +127,20 @@ static DevParams make_params_cfg(const dw_config &c) {
     P.temp_optimal = c.temp_optimal; P.dt = c.dt; P.agent_gamma = c.agent_gamma;
     P.ab = c.albedo_bare; P.al = c.albedo_light; P.ad = c.albedo_dark;
     for (int i = 0; i < 9; ++i) { P.w[i] = c.daisy_kernel[i]; P.adj[i] = c.adjacent_kernel[i]; P.mask[i] = c.obs_mask[i]; }
+    // Screened forward (dw_screened_cell): the fast evaluation differs from the literal one by the fast fourth root
+    // (3e-12 relative, asserted in the tests) plus a few ulp. With T <= 400 K and |Topt - T| <= max(|Topt - 150|, |Topt - 400|)
+    // (the kernel checks the range) and densities in [0, 1]: |d(1000 l')| <= 1000 dt 2 g |Topt - T| T 3e-12, b' twice that,
+    // |d(1000 T)| <= 1000 * 400 * 3e-12. Filters are 4x the bounds.
+    P.adj_sum = 0.0;
+    for (int i = 0; i < 9; ++i) P.adj_sum += c.adjacent_kernel[i];
+    const double dT = fmax(fabs(c.temp_optimal - 150.0), fabs(c.temp_optimal - 400.0));
+    const double bound = 1000.0 * fabs(c.dt) * 2.0 * fabs(c.g) * dT * 400.0 * 3e-12;
+    P.eps_c = fmax(4.0 * bound, 4e-6);
+    P.eps_b = 2.0 * P.eps_c;
+    P.eps_T = 4.0 * 1000.0 * 400.0 * 3e-12;
+    P.xlo = 150.0 * 150.0 * 150.0 * 150.0;
+    P.xhi = 400.0 * 400.0 * 400.0 * 400.0;
+    P.screen = (P.eps_c < 0.05 && c.sigma > 0.0 && !getenv("DW_LITERAL_ONLY")) ? 1 : 0;   // NaN bounds fail the comparison too
     return P;
 }
 static DevParams make_params(const dw_handle *h) { return make_params_cfg(h->cfg); }

@@ -82,30 +82,6 @@ struct FusedArgs {
     unsigned int *pair_done;    // [n_pairs] chunks completed per world (zeroed before the launch)
 };
 
-// ---- fast fourth root ------------------------------------------------------------------------------------
-__device__ __forceinline__ double dw_rsqrt_approx(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-}
-__device__ __forceinline__ double dw_rcp_approx(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-}
-// X^(1/4) for X in the physical range (1e8..1e11): two MUFU.RSQ64H seeds (s1 ~ X^-1/2, y0 = rsqrt(s1) ~ X^1/4), then
-// one Newton step on y^4 = X with 1/(4 y0^3) approximated by s1*s1*y0/4.  Relative error <= ~2e-12 (measured in
-// tests/test_gpu_fused_internals.py), 6 fp64-pipe ops.
-__device__ __forceinline__ double dw_root4_fast(double X) {
-    const double s1 = dw_rsqrt_approx(X);
-    const double y0 = dw_rsqrt_approx(s1);                    // X^(1/4) (1+d), |d| < 2^-21
-    const double z = y0 * y0;
-    const double res = __fma_rn(-z, z, X);                    // X - y0^4
-    const double a = s1 * s1;
-    const double b3 = a * y0;                                 // ~ 1/y0^3
-    return __fma_rn(res * b3, 0.25, y0);
-}
-
 __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
     return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
 }

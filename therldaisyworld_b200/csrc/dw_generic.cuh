@@ -26,6 +26,68 @@ struct SrcLattice {        // packed milli-covers [B,N,N]
     __device__ __forceinline__ double d(int b, size_t c) const { return dw_milli(k[b * NN + c] >> 16); }
 };
 
+__device__ __forceinline__ void dw_atomic_max_pos(unsigned long long *addr, double v);
+// Per-world views: the world's base pointers are formed once per cell, the nine taps are small offsets from them.
+struct ViewF64 {
+    const double *pl, *pd;
+    __device__ __forceinline__ double l(int k) const { return pl[k]; }
+    __device__ __forceinline__ double d(int k) const { return pd[k]; }
+};
+struct ViewLat {
+    const uint32_t *pk;
+    __device__ __forceinline__ double l(int k) const { return dw_milli(pk[k] & 0xffffu); }
+    __device__ __forceinline__ double d(int k) const { return dw_milli(pk[k] >> 16); }
+};
+__device__ __forceinline__ ViewF64 dw_view(const SrcGrid &s, unsigned b) {
+    const double *w = s.g + (size_t)b * s.world_stride + s.NN;
+    return ViewF64{w, w + s.NN};
+}
+__device__ __forceinline__ ViewF64 dw_view(const SrcCov &s, unsigned b) {
+    const double *w = s.c + (size_t)b * 2 * s.NN;
+    return ViewF64{w, w + s.NN};
+}
+__device__ __forceinline__ ViewLat dw_view(const SrcLattice &s, unsigned b) { return ViewLat{s.k + (size_t)b * s.NN}; }
+template <class View>
+__device__ __forceinline__ void dw_load9v(const View &v, int N, int x, int y, double (&l9)[9], double (&d9)[9]) {
+    const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+    const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+    const int rs[3] = {xm * N, x * N, xp * N}, ys[3] = {ym, y, yp};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            l9[a * 3 + c] = v.l(rs[a] + ys[c]);
+            d9[a * 3 + c] = v.d(rs[a] + ys[c]);
+        }
+}
+
+// (world, cell) of a grid-stride loop over B*N*N cells, advanced without 64-bit divisions
+struct CellWalk {
+    unsigned b, c, sb, sc, NN;
+    __device__ __forceinline__ CellWalk(size_t i0, size_t stride, unsigned nn) : NN(nn) {
+        b = (unsigned)(i0 / nn); c = (unsigned)(i0 - (size_t)b * nn);
+        sb = (unsigned)(stride / nn); sc = (unsigned)(stride - (size_t)sb * nn);
+    }
+    __device__ __forceinline__ void next() {
+        c += sc; b += sb;
+        if (c >= NN) { c -= NN; b += 1; }
+    }
+};
+
+// per-world maxima of the new covers (k = 1000 * cover, integer valued) into world_max [B,2] (bit patterns of the doubles)
+__device__ __forceinline__ void dw_world_max_update(unsigned long long *world_max, unsigned b, double kl, double kd) {
+    const unsigned m = __activemask();
+    const unsigned b0 = __shfl_sync(m, b, 0);
+    int il = (int)kl, id = (int)kd;
+    if (m == 0xffffffffu && __all_sync(m, b == b0)) {          // whole warp in one world: two REDUX instead of 32 atomics
+        il = __reduce_max_sync(m, il);
+        id = __reduce_max_sync(m, id);
+        if ((threadIdx.x & 31) != 0) return;
+    }
+    dw_atomic_max_pos(world_max + 2 * b, dw_div1000((double)il));
+    dw_atomic_max_pos(world_max + 2 * b + 1, dw_div1000((double)id));
+}
+
 template <class Src>
 __device__ __forceinline__ void dw_load9(const Src &src, int b, int N, int x, int y, double (&l9)[9], double (&d9)[9]) {
     const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
@@ -53,45 +115,31 @@ __device__ __forceinline__ void dw_atomic_max_pos(unsigned long long *addr, doub
 template <class Src>
 __global__ void __launch_bounds__(256) k_forward(DevParams P, double SL, Src src, double *__restrict__ out,
                                                  double *writeback_b0, unsigned long long *world_max, int zero6) {
-    const size_t NN = (size_t)P.N * P.N;
-    const size_t total = (size_t)P.B * NN;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / NN);
-        const size_t c = i - (size_t)b * NN;
-        const int x = (int)(c / P.N), y = (int)(c - (size_t)x * P.N);
+    const unsigned NN = (unsigned)P.N * (unsigned)P.N;
+    const size_t total = (size_t)P.B * NN, stride = (size_t)gridDim.x * blockDim.x;
+    const double SLs = SL / P.sigma;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    CellWalk w(i, stride, NN);
+    for (; i < total; i += stride, w.next()) {
+        const int x = (int)(w.c / (unsigned)P.N), y = (int)(w.c - (unsigned)x * (unsigned)P.N);
         double l9[9], d9[9];
-        dw_load9(src, b, P.N, x, y, l9, d9);
-        const LitCell o = dw_literal_cell(P, SL, l9, d9);
-        double *ob = out + (size_t)b * 7 * NN + c;
-        const double rl = dw_round3(o.nl), rd = dw_round3(o.nd);
-        ob[0] = dw_round3(o.nb);
-        ob[NN] = rl;
-        ob[2 * NN] = rd;
-        ob[3 * NN] = dw_round3(o.T);
-        ob[4 * NN] = dw_round3(o.Tl);
-        ob[5 * NN] = dw_round3(o.Td);
-        if (zero6) ob[6 * NN] = 0.0;
-        if (writeback_b0) writeback_b0[(size_t)b * 7 * NN + c] = o.b0;
-        if (world_max) {
-            // warp-level pre-reduction when the whole warp sits in one world
-            const unsigned m = __activemask();
-            const int b0 = __shfl_sync(m, b, 0);
-            double ml = rl, md = rd;
-            if (m == 0xffffffffu && __all_sync(m, b == b0)) {
+        dw_load9v(dw_view(src, w.b), P.N, x, y, l9, d9);
+        ScrCell o;
+        double v[6];
+        if (P.screen && dw_screened_cell(P, SLs, l9, d9, o)) {
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) {
-                    ml = fmax(ml, __shfl_xor_sync(m, ml, s));
-                    md = fmax(md, __shfl_xor_sync(m, md, s));
-                }
-                if ((threadIdx.x & 31) == 0) {
-                    dw_atomic_max_pos(world_max + 2 * b, ml);
-                    dw_atomic_max_pos(world_max + 2 * b + 1, md);
-                }
-            } else {
-                dw_atomic_max_pos(world_max + 2 * b, ml);
-                dw_atomic_max_pos(world_max + 2 * b + 1, md);
-            }
+            for (int q = 0; q < 6; ++q) v[q] = dw_div1000(o.k[q]);            // |k| <= 2e6 inside the screened range
+        } else {
+            dw_literal_rounded(P, SL, l9, d9, o);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) v[q] = dw_k2v(o.k[q]);
         }
+        double *ob = out + (size_t)w.b * 7 * NN + w.c;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ob[(size_t)q * NN] = v[q];
+        if (zero6) ob[(size_t)6 * NN] = 0.0;
+        if (writeback_b0) writeback_b0[(size_t)w.b * 7 * NN + w.c] = o.b0;
+        if (world_max) dw_world_max_update(world_max, w.b, o.k[1], o.k[2]);
     }
 }
 
@@ -100,36 +148,19 @@ __global__ void __launch_bounds__(256) k_forward(DevParams P, double SL, Src src
 template <class Src>
 __global__ void __launch_bounds__(256) k_forward_lattice(DevParams P, double SL, Src src, uint32_t *__restrict__ lat_out,
                                                          unsigned long long *world_max) {
-    const size_t NN = (size_t)P.N * P.N;
-    const size_t total = (size_t)P.B * NN;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / NN);
-        const size_t c = i - (size_t)b * NN;
-        const int x = (int)(c / P.N), y = (int)(c - (size_t)x * P.N);
+    const unsigned NN = (unsigned)P.N * (unsigned)P.N;
+    const size_t total = (size_t)P.B * NN, stride = (size_t)gridDim.x * blockDim.x;
+    const double SLs = SL / P.sigma;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    CellWalk w(i, stride, NN);
+    for (; i < total; i += stride, w.next()) {
+        const int x = (int)(w.c / (unsigned)P.N), y = (int)(w.c - (unsigned)x * (unsigned)P.N);
         double l9[9], d9[9];
-        dw_load9(src, b, P.N, x, y, l9, d9);
-        const LitCell o = dw_literal_cell(P, SL, l9, d9);
-        const double kl = rint(o.nl * 1000.0), kd = rint(o.nd * 1000.0);
-        lat_out[i] = ((uint32_t)(int)kl) | ((uint32_t)(int)kd << 16);
-        if (world_max) {
-            double ml = dw_div1000(kl), md = dw_div1000(kd);
-            const unsigned m = __activemask();
-            const int b0 = __shfl_sync(m, b, 0);
-            if (m == 0xffffffffu && __all_sync(m, b == b0)) {
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) {
-                    ml = fmax(ml, __shfl_xor_sync(m, ml, s));
-                    md = fmax(md, __shfl_xor_sync(m, md, s));
-                }
-                if ((threadIdx.x & 31) == 0) {
-                    dw_atomic_max_pos(world_max + 2 * b, ml);
-                    dw_atomic_max_pos(world_max + 2 * b + 1, md);
-                }
-            } else {
-                dw_atomic_max_pos(world_max + 2 * b, ml);
-                dw_atomic_max_pos(world_max + 2 * b + 1, md);
-            }
-        }
+        dw_load9v(dw_view(src, w.b), P.N, x, y, l9, d9);
+        ScrCell o;
+        if (!(P.screen && dw_screened_cell(P, SLs, l9, d9, o))) dw_literal_rounded(P, SL, l9, d9, o);
+        lat_out[i] = ((uint32_t)(int)o.k[1]) | ((uint32_t)(int)o.k[2] << 16);
+        if (world_max) dw_world_max_update(world_max, w.b, o.k[1], o.k[2]);
     }
 }
 
