@@ -151,6 +151,13 @@ static inline int grid_for(size_t total, int block = 256) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// forward launches: two cells per thread when the world side is even (aligned 16-byte accesses), else one
+template <class Src>
+static void launch_forward(dw_handle *h, const DevParams &P, double SL, Src src, double *out, double *writeback_b0,
+                           unsigned long long *world_max, int zero6);
+template <class Src>
+static void launch_forward_lattice(dw_handle *h, const DevParams &P, double SL, Src src, uint32_t *lat_out, unsigned long long *world_max);
+
 static void update_L(dw_clock &c) {   // daisy_world_rl.py:463-473
     c.step_count += 1;
     if (c.ramp_up_down && c.ramp_period != 0 && c.step_count % c.ramp_period == 0) {
@@ -201,6 +208,24 @@ static int launch_stamp(dw_handle *h, double *grid, bool counters, unsigned int 
 }
 
 // make grid[cur] hold the full reference grid of the current state
+template <class Src>
+static void launch_forward(dw_handle *h, const DevParams &P, double SL, Src src, double *out, double *writeback_b0,
+                           unsigned long long *world_max, int zero6) {
+    const size_t total = (size_t)P.B * h->NN;
+    if ((P.N & 1) == 0 && !getenv("DW_FORWARD_X1"))
+        k_forward_x2<Src><<<grid_for(total / 2), 256, 0, h->stream>>>(P, SL, src, out, writeback_b0, world_max, zero6);
+    else
+        k_forward<Src><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, out, writeback_b0, world_max, zero6);
+}
+template <class Src>
+static void launch_forward_lattice(dw_handle *h, const DevParams &P, double SL, Src src, uint32_t *lat_out, unsigned long long *world_max) {
+    const size_t total = (size_t)P.B * h->NN;
+    if ((P.N & 1) == 0 && !getenv("DW_FORWARD_X1"))
+        k_forward_lattice_x2<Src><<<grid_for(total / 2), 256, 0, h->stream>>>(P, SL, src, lat_out, world_max);
+    else
+        k_forward_lattice<Src><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, lat_out, world_max);
+}
+
 static int ensure_grid(dw_handle *h) {
     if (h->grid_valid) return DW_OK;
     if (!h->lat_valid && !h->cov_valid) return dw_fail(h, DW_E_STATE, "ensure_grid", "no state uploaded");
@@ -225,8 +250,7 @@ static int ensure_grid(dw_handle *h) {
     if (h->pre == PRE_COV) {
         // the state is one lean step past the reset: literal forward from the post-graze cover planes
         SrcCov src{h->cov, h->NN};
-        k_forward<SrcCov><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, src, out, nullptr, nullptr,
-                                                                   h->ch6_dirty[h->cur] ? 1 : 0);
+        launch_forward(h, P, h->cfg.S * h->L_last, src, out, nullptr, nullptr, h->ch6_dirty[h->cur] ? 1 : 0);
         DW_LAUNCHED(h);
         h->ch6_dirty[h->cur] = false;
         rc = launch_stamp(h, out, false, nullptr, false);
@@ -235,8 +259,7 @@ static int ensure_grid(dw_handle *h) {
         // full literal forward from the post-graze lattice the last fused step started from: reproduces
         // b' (rounded from UNROUNDED l',d'), the temperatures of that step, and l',d' (== lat[lcur]).
         SrcLattice src{h->lat_pre, h->NN};
-        k_forward<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, src, out, nullptr, nullptr,
-                                                                       h->ch6_dirty[h->cur] ? 1 : 0);
+        launch_forward(h, P, h->cfg.S * h->L_last, src, out, nullptr, nullptr, h->ch6_dirty[h->cur] ? 1 : 0);
         DW_LAUNCHED(h);
         h->ch6_dirty[h->cur] = false;
         rc = launch_stamp(h, out, false, nullptr, false);
@@ -522,8 +545,7 @@ static int launch_forward_tail(dw_handle *h, bool counters, unsigned int *alive_
     double *in = h->grid[h->cur], *out = h->grid[1 - h->cur];
     DW_CUDA_TRY(h, cudaMemsetAsync(h->world_max, 0, (size_t)P.B * 2 * sizeof(unsigned long long), h->stream));
     SrcGrid src{in, 7 * h->NN, h->NN};
-    k_forward<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, out, in, h->world_max,
-                                                                h->ch6_dirty[1 - h->cur] ? 1 : 0);
+    launch_forward(h, P, h->cfg.S * h->clk.L, src, out, in, h->world_max, h->ch6_dirty[1 - h->cur] ? 1 : 0);
     DW_LAUNCHED(h);
     h->ch6_dirty[1 - h->cur] = false;
     h->pre = PRE_GRID;
@@ -757,8 +779,7 @@ extern "C" int dw_forward(dw_handle *h, double *grid_in, double *grid_out) {
     const DevParams P = make_params(h);
     DW_CUDA_TRY(h, cudaMemcpyAsync(h->fwd_in, grid_in, G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     SrcGrid src{h->fwd_in, 7 * h->NN, h->NN};
-    k_forward<SrcGrid><<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, h->fwd_out, h->fwd_in,
-                                                                            nullptr, 1);
+    launch_forward(h, P, h->cfg.S * h->clk.L, src, h->fwd_out, h->fwd_in, nullptr, 1);
     DW_LAUNCHED(h);
     rc = launch_stamp(h, h->fwd_out, false, nullptr, false);
     if (rc) return rc;

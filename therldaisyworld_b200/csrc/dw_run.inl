@@ -272,7 +272,7 @@ static int lean_first_step(dw_handle *h, int policy, const int8_t *act_dev, uint
     const DevParams P = make_params(h);
     DW_CUDA_TRY(h, cudaMemsetAsync(h->world_max, 0, (size_t)P.B * 2 * sizeof(unsigned long long), h->stream));
     SrcCov src{h->cov, h->NN};
-    k_forward_lattice<SrcCov><<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, h->lat[h->lcur], h->world_max);
+    launch_forward_lattice(h, P, h->cfg.S * h->clk.L, src, h->lat[h->lcur], h->world_max);
     DW_LAUNCHED(h);
     rc = launch_stamp(h, nullptr, true, alive_slot, true);
     if (rc) return rc;
