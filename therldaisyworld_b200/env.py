@@ -530,7 +530,7 @@ class RLDaisyWorld:
         B, N, n = self._shape
         self._push()
         self._dead_L = self.L
-        obs = np.zeros((B, n, self.ch, 3, 3))
+        obs = np.empty((B, n, self.ch, 3, 3))
         shape = (B, n, 1) if n else (B, 2)
         reward = np.empty(shape)
         done = np.empty(shape, dtype=np.uint8)
