@@ -241,6 +241,10 @@ int dw_get_profile(dw_handle *h, dw_profile *out);
    path landed within the tie filter; and the fast fourth root evaluated on the device (host in, host out). */
 int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset);
 int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n);
+/* test hook of the screened materialising kernels: over a host grid [B,7,N,N] (channels 1,2 read) at the handle's clock,
+   out[0..2] = largest |screened - literal| * 1000 of the unrounded new covers, bare fraction and temperatures over the
+   cells inside the screened range, out[3..5] = the tie-filter half-widths they must stay below */
+int dw_debug_screen_error(dw_handle *h, const double *grid, double *out);
 /* number of integers k in [-kmax,kmax] for which the division-free k/1000 used by the kernels differs from the IEEE
    quotient (must be 0) */
 int dw_debug_markstein(dw_handle *h, uint32_t kmax, uint32_t *bad);

@@ -185,3 +185,43 @@ def test_screened_forward_equals_literal_forward():
         np.testing.assert_array_equal(outs[0], outs[1])
         cells += B * N * N
     assert cells > 100000
+
+
+def test_screened_evaluation_stays_inside_its_tie_filters():
+    """The error budget of dw_screened_cell, measured: over random off-lattice and lattice states, default and random
+    physics, the largest |screened - literal| of every unrounded channel (units of 0.001) must stay at least 3x below the
+    tie-filter half-width derived on the host (make_params_cfg) -- the margin the exactness argument relies on."""
+    import importlib.util
+    from therldaisyworld_b200 import RLDaisyWorld
+    spec = importlib.util.spec_from_file_location("fuzz", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_fast_path.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.RandomState(77)
+    worst = np.zeros(3)
+    for case in range(30):
+        N, B = 64, 16
+        np.random.seed(case)
+        env = RLDaisyWorld(grid_dimension=N, n_agents=0)
+        env.batch_size = B
+        if case % 2:
+            attrs, _, _, _, no_micro = fuzz.draw(rng)
+            for k, v in attrs.items():
+                setattr(env, k, v)
+            env.q = 0.2 * env.S / env.sigma
+            env.set_use_microclimate(not no_micro)
+        env.reset()
+        env.L = float(rng.uniform(env.min_L, env.max_L))
+        g = env.grid.copy()
+        if case % 3 == 0:
+            g[:, 1], g[:, 2] = rng.rand(B, N, N) * 0.7, rng.rand(B, N, N) * 0.3
+        elif case % 3 == 1:
+            g[:, 1] = np.round(rng.rand(B, N, N) * (rng.rand(B, N, N) < 0.5), 3)
+            g[:, 2] = np.round(rng.rand(B, N, N) * (1 - g[:, 1]) * (rng.rand(B, N, N) < 0.5), 3)
+        env._push()
+        out = np.zeros(6)
+        rc = env._lib.dw_debug_screen_error(env._h, np.ascontiguousarray(g).ctypes.data_as(C.POINTER(C.c_double)),
+                                            out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        assert (out[:3] * 3.0 < out[3:]).all(), (case, out)
+        worst = np.maximum(worst, out[:3] / out[3:])
+    print("largest measured error / filter half-width (covers, bare, temperatures):", worst)

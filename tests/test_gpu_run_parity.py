@@ -137,22 +137,24 @@ def test_device_side_reset_distribution_and_run():
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
 
 
-def test_ensemble_sharding_is_invisible():
-    """A 48-world ensemble run as one handle or as three 16-world shards with world offsets (the multi-rank layout) gives
-    the same worlds: device reset and device random policy are keyed by the GLOBAL world index."""
+@pytest.mark.parametrize("N,sizes", [(64, (16, 16, 16)), (8, (70, 37, 100)), (16, (19, 30, 5)), (32, (7, 2, 9)), (96, (3, 2, 4))])
+def test_ensemble_sharding_is_invisible(N, sizes):
+    """An ensemble run as one handle or as three shards with world offsets (the multi-rank layout) gives the same worlds:
+    device reset and device random policy are keyed by the GLOBAL world index. For worlds below 64x64 the shards also
+    regroup the worlds that share a CTA (k_fused_sub64_persist), which must not matter either."""
     from therldaisyworld_b200 import RLDaisyWorld
 
     def make(B, offset):
         np.random.seed(1)
-        env = RLDaisyWorld(grid_dimension=64)
+        env = RLDaisyWorld(grid_dimension=N)
         env.batch_size = B
         env.reset_on_device(seed=5, world_offset=offset)
         env.reset_lifespans()
         env.run(150, policy="random", seed=3)
         return env.grid.copy(), env.agent_states.copy(), env.lifespans()
 
-    whole = make(48, 0)
-    parts = [make(16, off) for off in (0, 16, 32)]
+    whole = make(sum(sizes), 0)
+    parts = [make(b, int(off)) for b, off in zip(sizes, np.cumsum((0,) + sizes[:-1]))]
     np.testing.assert_array_equal(np.concatenate([p[0] for p in parts]), whole[0])
     np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), whole[1])
     np.testing.assert_array_equal(np.concatenate([p[2][1] for p in parts]), whole[2][1])

@@ -41,7 +41,7 @@ SYMBOLS = [
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_grid_f32", "dw_get_obs_f32", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
     "dw_run", "dw_run_chunk", "dw_run_series", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
-    "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak",
+    "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak", "dw_debug_screen_error",
 ]
 
 # every symbol include/daisyworld_b200_tiled.h declares (single giant grid, row bands)
@@ -129,6 +129,7 @@ def load():
         "dw_set_world_offset": (C.c_int, [vp, C.c_uint32]),
         "dw_debug_slow_count": (C.c_int, [vp, C.POINTER(u64), i32]),
         "dw_debug_root4": (C.c_int, [vp, pd, pd, i32]),
+        "dw_debug_screen_error": (C.c_int, [vp, pd, pd]),
         "dw_debug_markstein": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "dw_debug_fp64_peak": (C.c_int, [vp, i32, i32, pd, pd]),
     }

@@ -877,6 +877,29 @@ static int collect_step_outputs(dw_handle *h, double *obs, double *reward, uint8
     return DW_OK;
 }
 
+// test hook: see k_debug_screen_error. grid: host [B,7,N,N] (only channels 1,2 are read); out[6] = measured maxima
+// {covers, bare, temperatures} and the filter half-widths {eps_c, eps_b, eps_T} they must stay below.
+extern "C" int dw_debug_screen_error(dw_handle *h, const double *grid, double *out) {
+    if (!h || !grid || !out) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t G = (size_t)h->cfg.batch * 7 * h->NN;
+    int rc = dev_alloc(h, &h->fwd_in, G);
+    if (!rc) rc = dev_alloc(h, &h->slow_count, (size_t)2);
+    if (!rc) rc = ensure_scratch(h, 4);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(h->fwd_in, grid, G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(h->scratch);
+    DW_CUDA_TRY(h, cudaMemsetAsync(acc, 0, 3 * sizeof(unsigned long long), h->stream));
+    SrcGrid src{h->fwd_in, 7 * h->NN, h->NN};
+    k_debug_screen_error<SrcGrid><<<grid_for((size_t)P.B * h->NN), 256, 0, h->stream>>>(P, h->cfg.S * h->clk.L, src, acc);
+    DW_LAUNCHED(h);
+    DW_CUDA_TRY(h, cudaMemcpyAsync(out, acc, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    out[3] = P.eps_c; out[4] = P.eps_b; out[5] = P.eps_T;
+    return DW_OK;
+}
+
 extern "C" int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t b, int32_t m, double *obs) {
     if (!h || b < 0 || m < 0 || b > h->cfg.batch) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));

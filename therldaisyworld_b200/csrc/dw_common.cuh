@@ -144,7 +144,7 @@ __device__ __forceinline__ bool dw_screen_round(double x, double eps, double &k)
     return 0.5 - fabs(s - k) > eps;
 }
 __device__ __forceinline__ bool dw_screened_cell(const DevParams &P, double SLs /* S L / sigma */, const double (&l9)[9],
-                                                 const double (&d9)[9], ScrCell &o) {
+                                                 const double (&d9)[9], ScrCell &o, double *raw = nullptr) {
     double rl = P.w[0] * l9[0], rd = P.w[0] * d9[0], sl = P.adj[0] * l9[0], sd = P.adj[0] * d9[0];
 #pragma unroll
     for (int k = 1; k < 9; ++k) {
@@ -167,6 +167,7 @@ __device__ __forceinline__ bool dw_screened_cell(const DevParams &P, double SLs 
     const double nl = dw_clip01(__fma_rn(P.dt, rl * __fma_rn(rb, bl, -P.gamma), l));
     const double nd = dw_clip01(__fma_rn(P.dt, rd * __fma_rn(rb, bd, -P.gamma), d));
     const double nb = (P.p - nl) - nd;
+    if (raw) { raw[0] = nb; raw[1] = nl; raw[2] = nd; raw[3] = T; raw[4] = Tl; raw[5] = Td; }   // dw_debug_screen_error
     bool ok = XT > P.xlo && XT < P.xhi && Xl > P.xlo && Xl < P.xhi && Xd > P.xlo && Xd < P.xhi;
     ok = ok && rl >= 0.0 && rl <= 1.000001 && rd >= 0.0 && rd <= 1.000001 && fabs(rb) <= 1.000001 && fabs(nb) <= 2000.0;
     ok = dw_screen_round(nb, P.eps_b, o.k[0]) && ok;

@@ -260,6 +260,33 @@ __global__ void __launch_bounds__(256, 3) k_forward_lattice_x2(DevParams P, doub
     }
 }
 
+// Test hook: largest deviation (in units of 0.001, the rounding grid) between the screened evaluation and the literal one
+// over the cells the screen ACCEPTS its range for, per channel group {covers, bare fraction, temperatures}; the tie filters
+// P.eps_c / eps_b / eps_T must stay well above these. out: 3 u64 holding the bit patterns of non-negative doubles.
+template <class Src>
+__global__ void __launch_bounds__(256) k_debug_screen_error(DevParams P, double SL, Src src, unsigned long long *out) {
+    const unsigned NN = (unsigned)P.N * (unsigned)P.N;
+    const size_t total = (size_t)P.B * NN, stride = (size_t)gridDim.x * blockDim.x;
+    const double SLs = SL / P.sigma;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    CellWalk w(i, stride, NN);
+    for (; i < total; i += stride, w.next()) {
+        const int x = (int)(w.c / (unsigned)P.N), y = (int)(w.c - (unsigned)x * (unsigned)P.N);
+        double l9[9], d9[9], raw[6];
+        dw_load9v(dw_view(src, w.b), P.N, x, y, l9, d9);
+        ScrCell o;
+        dw_screened_cell(P, SLs, l9, d9, o, raw);
+        const bool in_range = raw[3] > 150.0 && raw[3] < 400.0 && raw[4] > 150.0 && raw[4] < 400.0 && raw[5] > 150.0 && raw[5] < 400.0;
+        if (!in_range) continue;
+        const LitCell c = dw_literal_cell(P, SL, l9, d9);
+        const double ec = fmax(fabs(raw[1] - c.nl), fabs(raw[2] - c.nd)) * 1000.0, eb = fabs(raw[0] - c.nb) * 1000.0;
+        const double eT = fmax(fabs(raw[3] - c.T), fmax(fabs(raw[4] - c.Tl), fabs(raw[5] - c.Td))) * 1000.0;
+        dw_atomic_max_pos(out, ec);
+        dw_atomic_max_pos(out + 1, eb);
+        dw_atomic_max_pos(out + 2, eT);
+    }
+}
+
 // ---- initial temperatures (initialize_grid, daisy_world_rl.py:304-324): ch0 and ch3..5, UNROUNDED ----
 __global__ void __launch_bounds__(256) k_init_fields(DevParams P, double SL, double *grid) {
     const size_t NN = (size_t)P.N * P.N;
