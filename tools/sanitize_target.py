@@ -1,4 +1,4 @@
-"""compute-sanitizer target: a few steps through every fused kernel (sub-64, 64x64 persistent / simple, multiple-of-4 tile,
+"""Quick end-to-end target (also usable under a sanitizer where one is available): a few steps through every fused kernel (sub-64, 64x64 persistent / simple, multiple-of-4 tile,
 one-cell-per-thread), the materialising step, the collision pass and the MLP policy, at sizes a sanitizer run finishes quickly."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
