@@ -45,11 +45,13 @@ def test_fast_root4_relative_error_bound():
                                           (20, 9, 3, "antigreedy"), (96, 3, 5, "greedy"), (128, 2, 6, "random"), (156, 1, 4, "greedy"),
                                           (32, 3, 70, "greedy")])
 def test_fused_equals_materialising_path(N, B, n, policy):
-    """Same inputs through dw_run with the fused kernel and with DW_DISABLE_FUSED=1 (materialising kernels only)."""
+    """Same inputs through dw_run with the fused kernel and with DW_DISABLE_FUSED=1 DW_LITERAL_ONLY=1 (materialising
+    kernels in literal arithmetic only: the ground truth)."""
     res = []
     for disable in (False, True):
         if disable:
             os.environ["DW_DISABLE_FUSED"] = "1"
+            os.environ["DW_LITERAL_ONLY"] = "1"
         else:
             os.environ.pop("DW_DISABLE_FUSED", None)
         try:
@@ -64,6 +66,7 @@ def test_fused_equals_materialising_path(N, B, n, policy):
                         env.L, env.step_count, env.temp.copy(), count.value))
         finally:
             os.environ.pop("DW_DISABLE_FUSED", None)
+            os.environ.pop("DW_LITERAL_ONLY", None)
     a, b = res
     for u, v in zip(a[:4], b[:4]):
         np.testing.assert_array_equal(u, v)

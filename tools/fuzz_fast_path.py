@@ -1,5 +1,5 @@
 """Randomised stress test of the lattice fast path + tie filter: random physics constants, the fused kernels against the
-literal materialising kernels (DW_DISABLE_FUSED=1) on the same worlds. Any mismatch = a fast-path result further from the
+literal materialising kernels (DW_DISABLE_FUSED=1 DW_LITERAL_ONLY=1) on the same worlds. Any mismatch = a fast-path result further from the
 literal value than the tie filter assumes. Usage: python tools/fuzz_fast_path.py [n_configs] [seed] [sizes, e.g. 8,16,32,48,96,128]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,10 +21,12 @@ def draw(rng, sizes=(64, 64, 16, 33, 96)):
 def run_config(attrs, N, n, ramp, no_micro, seed, B=24, steps=400, policy="greedy"):
     out = []
     for disable in (False, True):
-        if disable:
+        if disable:                                  # the ground truth: materialising kernels, literal arithmetic only
             os.environ["DW_DISABLE_FUSED"] = "1"
+            os.environ["DW_LITERAL_ONLY"] = "1"
         else:
             os.environ.pop("DW_DISABLE_FUSED", None)
+            os.environ.pop("DW_LITERAL_ONLY", None)
         try:
             np.random.seed(seed)
             env = RLDaisyWorld(grid_dimension=N, n_agents=n, ramp_period=ramp)
@@ -41,6 +43,7 @@ def run_config(attrs, N, n, ramp, no_micro, seed, B=24, steps=400, policy="greed
             out.append((env.grid[:, 1:3].copy(), env.agent_states.copy(), env.lifespans()[0].copy(), cnt.value))
         finally:
             os.environ.pop("DW_DISABLE_FUSED", None)
+            os.environ.pop("DW_LITERAL_ONLY", None)
     (g0, s0, l0, slow), (g1, s1, l1, _) = out
     ok = np.array_equal(g0, g1) and np.array_equal(s0, s1) and np.array_equal(l0, l1)
     return ok, slow, int((g0 != g1).sum()), float(l0.mean())
