@@ -104,6 +104,22 @@ def set_default_kernels(obj):
     obj.adjacent_albedo_kernel[:, :, 1, 1] = 0.0
 
 
+def shared_cell_offsets(agent_indices, N):
+    """collision_mode == 1 bookkeeping (reference :220-242): the reference draws one npr.rand(1, n, 1) per cell that holds
+    more than one agent, world after world. Returns int32 offsets [B+1]: offsets[b] = number of such cells in worlds < b
+    (so offsets[-1] draws are needed in total). Integer work on the post-move positions only."""
+    pos = np.asarray(agent_indices)
+    B, n = pos.shape[:2]
+    offsets = np.zeros(B + 1, dtype=np.int32)
+    if n > 1:
+        key = np.sort(pos[:, :, 0] * N + pos[:, :, 1], axis=1)                 # [B, n]
+        same = key[:, 1:] == key[:, :-1]
+        # a shared cell = a run of equal keys: count the runs' first repeats
+        first_repeat = same & ~np.concatenate([np.zeros((B, 1), dtype=bool), same[:, :-1]], axis=1)
+        np.cumsum(first_repeat.sum(axis=1), out=offsets[1:])
+    return offsets
+
+
 def make_config_struct(obj, batch, dim, n_agents, device):
     """dw_config from the public attributes of an environment object."""
     c = DwConfig(batch=int(batch), dim=int(dim), n_agents=int(n_agents), device=int(device),
@@ -463,12 +479,7 @@ class RLDaisyWorld:
         rc = self._lib.dw_agents_begin(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
                                        0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), _ptr(pos, C.c_int64))
         self._check(rc, "dw_agents_begin")
-        key = np.sort(pos[:, :, 0] * N + pos[:, :, 1], axis=1)                 # [B, n]
-        same = key[:, 1:] == key[:, :-1]
-        # a shared cell = a run of equal keys: count the runs' first repeats
-        first_repeat = same & ~np.concatenate([np.zeros((B, 1), dtype=bool), same[:, :-1]], axis=1)
-        offsets = np.zeros(B + 1, dtype=np.int32)
-        np.cumsum(first_repeat.sum(axis=1), out=offsets[1:])
+        offsets = shared_cell_offsets(pos, N)
         cells = int(offsets[-1])
         noise = np.ascontiguousarray(np.random.rand(cells, n)) if cells else None
         rc = self._lib.dw_agents_collide(self._h, None if noise is None else _ptr(noise, C.c_double),
