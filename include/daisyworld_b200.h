@@ -180,6 +180,9 @@ int dw_agents_begin(dw_handle *h, const int64_t *action, int32_t ab, int32_t am,
                     int64_t *agent_indices);
 int dw_agents_collide(dw_handle *h, const double *noise, const int32_t *cell_offsets, double food_chain_penalty);
 int dw_step_tail_collect(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk);
+/* same tail for multi-step loops with collisions: advances the lifespan counters of dw_run (notebook cell 2) instead of
+   collecting the observation; *worlds_alive = worlds with max(grid[:,1:3]) > 0.005 after the step */
+int dw_step_tail_counted(dw_handle *h, int64_t *worlds_alive);
 /* RLDaisyWorld.forward(grid) (:434-461) on a caller grid (host in, host out) with the handle's agents/L;
    writes the mutated ch0 back into grid_in like the reference (:381). Does not advance the state. */
 int dw_forward(dw_handle *h, double *grid_in, double *grid_out);

@@ -57,3 +57,5 @@ def consume_policy_draws(z, meta, t):
     if meta["policy"]["kind"] == "randint":
         a = np.random.randint(9, size=(meta["B"], meta["n"], 1))
         np.testing.assert_array_equal(a, z["actions"][t])
+    elif meta["policy"]["kind"] in ("greedy", "antigreedy"):
+        np.random.rand()             # Greedy.__call__ flips its epsilon coin on every call (daisy/agents/greedy.py:23)

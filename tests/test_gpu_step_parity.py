@@ -236,11 +236,28 @@ def test_collisions_match_numpy_oracle_on_crowded_worlds():
         np.testing.assert_array_equal(env.grid, ref.grid)
 
 
-def test_collision_mode_multi_step_runs_are_refused():
-    from therldaisyworld_b200 import RLDaisyWorld
-    env = RLDaisyWorld(grid_dimension=8, collision_mode=1)
+def test_run_with_collisions_reproduces_reference_lifespans():
+    """env.run() with collision_mode == 1: the loop is driven from the host (the noise is the caller's NumPy stream), the
+    decisions, moves, collisions, forward and lifespan counters stay on the device. Against the trajectory recorded from the
+    live reference with its Greedy policy. (The reference's Greedy also flips one epsilon coin per call from the same stream,
+    which the device policy does not; in this fixture no collision is decided by the noise -- the oracle replay reproduces it
+    with either alignment -- so the recorded states are the expected ones here as well.)"""
+    z, meta = load_golden("collide_greedy_n8_b4_n10_150")
+    env = product_env_from_golden(z, meta)
+    env.reset_lifespans()
+    restore_stream(z)
+    steps, alive, hit = env.run(meta["steps"], policy="greedy")
+    assert steps == meta["steps"]
+    done_at, agents_done_at = env.lifespans()
+    np.testing.assert_array_equal(done_at, z["done_at"])
+    np.testing.assert_array_equal(agents_done_at, z["agents_done_at"])
+    np.testing.assert_array_equal(env.agent_indices, z["agent_indices"][-1])
+    np.testing.assert_array_equal(env.agent_states, z["agent_states"][-1])
+    np.testing.assert_array_equal(env.grid, z["ckpt_grid"][-1])
+    assert env.L == z["L"][meta["steps"]] and env.step_count == meta["final_step_count"]
+    # the in-kernel series mode has no collision pass
     with pytest.raises(NotImplementedError):
-        env.run(4, policy="greedy")
+        env.run_series(4, policy="greedy")
 
 
 def test_collision_abi_state_machine_and_count_check():

@@ -37,7 +37,7 @@ SYMBOLS = [
     "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
     "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_set_mlp_population", "dw_run_population", "dw_get_population_results",
     "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_collect", "dw_step_policy", "dw_update_agents",
-    "dw_agents_begin", "dw_agents_collide", "dw_step_tail_collect",
+    "dw_agents_begin", "dw_agents_collide", "dw_step_tail_collect", "dw_step_tail_counted",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_grid_f32", "dw_get_obs_f32", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
     "dw_run", "dw_run_chunk", "dw_run_series", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
@@ -106,6 +106,7 @@ def load():
         "dw_agents_begin": (C.c_int, [vp, pi64, i32, i32, i32, u64, pi64]),
         "dw_agents_collide": (C.c_int, [vp, pd, C.POINTER(C.c_int32), C.c_double]),
         "dw_step_tail_collect": (C.c_int, [vp, pd, pd, pu8, C.POINTER(DwClock)]),
+        "dw_step_tail_counted": (C.c_int, [vp, C.POINTER(C.c_int64)]),
         "dw_forward": (C.c_int, [vp, pd, pd]),
         "dw_get_obs_at": (C.c_int, [vp, pi64, i32, i32, pd]),
         "dw_get_grid": (C.c_int, [vp, pd]),

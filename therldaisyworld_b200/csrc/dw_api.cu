@@ -656,6 +656,24 @@ extern "C" int dw_step_tail_collect(dw_handle *h, double *obs, double *reward, u
     return collect_step_outputs(h, obs, reward, done, clk);
 }
 
+// The rest of step() after dw_agents_collide with the notebook's lifespan counters (done_at, agents_done_at) advanced like
+// dw_run does; *worlds_alive = worlds with max(grid[:,1:3]) > 0.005 after this step. Synchronises.
+extern "C" int dw_step_tail_counted(dw_handle *h, int64_t *worlds_alive) {
+    if (!h) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_step_tail_counted", "dw_agents_begin not closed by dw_agents_collide");
+    int rc = ensure_grid(h);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, sizeof(unsigned int), h->stream));
+    rc = launch_forward_tail(h, true, h->alive);
+    if (rc) return rc;
+    unsigned int alive = 0;
+    DW_CUDA_TRY(h, cudaMemcpyAsync(&alive, h->alive, sizeof(alive), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (worlds_alive) *worlds_alive = alive;
+    return DW_OK;
+}
+
 extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t am) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));

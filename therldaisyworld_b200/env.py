@@ -628,14 +628,13 @@ class RLDaisyWorld:
         (actions[K,B,n(,1)] ints 0..8).
         Returns (steps_run, worlds_alive, all_done_hit)."""
         B, N, n = self._shape
-        if self.collision_mode == 1 and n:
-            raise NotImplementedError("collision_mode == 1 draws from the caller's NumPy stream every step: use step() / "
-                                      "step_policy(); multi-step device runs are for collision_mode == 0")
         a8 = None
         if policy == "replay":
             a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
             if a8.shape[0] < K:
                 raise ValueError("replay needs at least K action frames")
+        if self.collision_mode == 1 and n:
+            return self._run_colliding(int(K), policy, a8, seed, stop_all_done)
         self._push()
         res = DwRunResult()
         rc = self._lib.dw_run(self._h, int(K), DW_POLICY[policy], _ptr(a8, C.c_int8), C.c_uint64(seed),
@@ -645,6 +644,30 @@ class RLDaisyWorld:
         self._pull_clock()
         self._dead_L = None
         return int(res.steps_run), int(res.worlds_alive), bool(res.all_done_hit)
+
+    def _run_colliding(self, K, policy, a8, seed, stop_all_done):
+        """run() with collision_mode == 1: the collision noise comes from the caller's NumPy stream every step (reference
+        :220-242), so the loop is driven from here, one materialising step at a time; policy decisions, moves, grazing,
+        collisions, forward and the lifespan counters stay on the device."""
+        if policy == "mlp":
+            raise NotImplementedError("collision_mode == 1 with the device MLP policy: pass the MLP's actions (policy='replay')")
+        steps, alive, hit = 0, self._shape[0], False
+        count = C.c_int64(0)
+        self._push()                 # once: inside the loop the clock lives on the device (a push would rewind it)
+        for t in range(K):
+            if a8 is None:
+                self._update_agents_colliding(None, DW_POLICY[policy], seed)
+            else:
+                self._update_agents_colliding(np.ascontiguousarray(a8[t], dtype=np.int64), -1, seed)
+            self._check(self._lib.dw_step_tail_counted(self._h, C.byref(count)), "dw_step_tail_counted")
+            steps, alive = steps + 1, int(count.value)
+            if stop_all_done and alive == 0:
+                hit = True
+                break
+        self._state_changed()
+        self._pull_clock()
+        self._dead_L = None
+        return steps, alive, hit
 
     def simulate_lifespan(self, policy="greedy", actions=None, seed=0, max_steps=100000):
         """The notebook's simulate_lifespan (greedy_longevity_abatement.ipynb cell 2) after a reset():
