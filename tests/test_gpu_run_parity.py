@@ -158,3 +158,35 @@ def test_ensemble_sharding_is_invisible(N, sizes):
     np.testing.assert_array_equal(np.concatenate([p[0] for p in parts]), whole[0])
     np.testing.assert_array_equal(np.concatenate([p[1] for p in parts]), whole[1])
     np.testing.assert_array_equal(np.concatenate([p[2][1] for p in parts]), whole[2][1])
+
+
+@pytest.mark.parametrize("N,n,policy", [(8, 4, "greedy"), (16, 9, "antigreedy"), (32, 4, "random"), (64, 4, "greedy"), (96, 5, "greedy"),
+                                        (33, 3, "greedy"), (128, 6, "random")])
+def test_torus_translation_invariance(N, n, policy):
+    """A size-independent property of the path: the world is a torus and nothing in the step depends on absolute
+    coordinates, so shifting the initial covers and agents by (sx, sy) must shift the whole run by (sx, sy) -- through
+    every fused kernel (several worlds per CTA, 64x64, 4x4 tiles, one cell per thread) and the materialising steps.
+    Exercises every wrap-around (rows, halo columns, agents crossing the seam) without the oracle."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    B, sx, sy = 5, N - 3, 5 % N
+    np.random.seed(N)
+    a = RLDaisyWorld(grid_dimension=N, n_agents=n)
+    a.batch_size = B
+    a.reset()
+    b = RLDaisyWorld(grid_dimension=N, n_agents=n)
+    b.batch_size = B
+    b.reset()
+    g0, ai0, st0 = a.grid.copy(), a.agent_indices.copy(), a.agent_states.copy()
+    b.grid = np.roll(g0, (sx, sy), axis=(2, 3))
+    b.agent_indices = (ai0 + np.array([sx, sy])) % N
+    b.agent_states = st0.copy()
+    for env in (a, b):
+        env.reset_lifespans()
+        env.run(1, policy=policy, seed=4)          # literal first step from the off-lattice reset state
+        env.run(90, policy=policy, seed=4)         # fused
+        env.step_policy(policy, seed=4)            # materialising
+    np.testing.assert_array_equal(np.roll(a.grid, (sx, sy), axis=(2, 3)), b.grid)
+    np.testing.assert_array_equal((a.agent_indices + np.array([sx, sy])) % N, b.agent_indices)
+    np.testing.assert_array_equal(a.agent_states, b.agent_states)
+    np.testing.assert_array_equal(a.lifespans()[0], b.lifespans()[0])
+    np.testing.assert_array_equal(a.lifespans()[1], b.lifespans()[1])
