@@ -67,7 +67,7 @@ def run_case(name, seed, ctor, attrs, policy, steps, ckpts, out_dir, action_shap
         path = glob.glob(os.path.join(REF_ROOT, "results", "cmaes_exp_002", "*best_agent_gen127.json"))[0]
         mlp_params = np.array(json.load(open(path))["parameters"], dtype=np.float64)
         if policy.get("perturb"):             # a second, different network: the stored one plus seeded noise
-            mlp_params = mlp_params + np.random.RandomState(policy["perturb"]).randn(mlp_params.size) * policy.get("std", 0.5)
+            mlp_params = mlp_params * policy.get("scale", 1.0) + np.random.RandomState(policy["perturb"]).randn(mlp_params.size) * policy.get("std", 0.5)
         agent.set_parameters(mlp_params)
 
     B, n, N = env.batch_size, env.n_agents, env.dim
@@ -205,11 +205,32 @@ CASES = [
          attrs=dict(batch_size=4, food_chain_penalty=0.8), policy=dict(kind="greedy"), steps=150, ckpts=[1, 75]),
     dict(name="collide_randint_n7_b2_n40_60", seed=31, ctor=dict(grid_dimension=7, n_agents=40, collision_mode=1),
          attrs=dict(batch_size=2, agent_gamma=0.01), policy=dict(kind="randint"), steps=60, ckpts=[1, 30]),
+    # A15: non-default observation masks (daisy/nn/functional.py:51-103). Greedy reads only the four edge cells, the MLP all 63
+    # inputs, so with "moore" the corner cells decide actions
+    dict(name="mlp_moore_n16_b3_100", seed=37, ctor=dict(grid_dimension=16, neighborhood_mode="moore"), attrs=dict(batch_size=3),
+         policy=dict(kind="mlp", perturb=23, std=2.0), steps=100, ckpts=[1, 2, 50]),
+    dict(name="greedy_moore_n64_b2_n6_60", seed=39, ctor=dict(grid_dimension=64, n_agents=6, neighborhood_mode="moore"),
+         attrs=dict(batch_size=2), policy=dict(kind="greedy"), steps=60, ckpts=[1, 30]),
+    dict(name="mlp_circular_n16_b2_60", seed=37, ctor=dict(grid_dimension=16, neighborhood_mode="circular"), attrs=dict(batch_size=2),
+         policy=dict(kind="mlp", perturb=23, std=2.0, scale=0.3), steps=60, ckpts=[1, 30]),
     # ramp_up_down branch (N4 row, cheap to pin): short ramp so dL flips sign
     dict(name="rampupdown_n8_b2_100", seed=6, ctor=dict(grid_dimension=8, ramp_period=32),
          attrs=dict(batch_size=2, ramp_up_down=True, ddL=0.01),
          policy=dict(kind="greedy"), steps=100, ckpts=[1, 32, 33, 64]),
 ]
+
+
+def record_masks(out_dir):
+    """make_neighborhood of the live reference (daisy/nn/functional.py:51-103) for every mode and radius 1..3."""
+    from daisy.nn.functional import make_neighborhood
+    rec = {}
+    for kr in (1, 2, 3):
+        for mode in ("moore", "von_neumann", "circular", "nonsense"):
+            rec[f"{mode}_{kr}"] = make_neighborhood(radius=kr, mode=mode)
+    rec["default"] = make_neighborhood()
+    path = os.path.join(out_dir, "ref_masks.npz")
+    np.savez_compressed(path, **rec)
+    print(f"masks -> {path}")
 
 
 def main():
@@ -223,6 +244,8 @@ def main():
     sys.path.insert(0, args.ref)
     warnings.filterwarnings("ignore", category=DeprecationWarning)
     os.makedirs(args.out, exist_ok=True)
+    if not args.only or args.only == "masks":
+        record_masks(args.out)
     for case in CASES:
         if args.only and args.only not in case["name"]:
             continue

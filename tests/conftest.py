@@ -15,8 +15,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """Trajectory fixtures of oracle/gen_golden.py (big_*: full-size summaries, es_*: ES fitness values have their own tests)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("big_", "es_")))
+    """Trajectory fixtures of oracle/gen_golden.py (big_*: full-size summaries, es_*: ES fitness values, ref_*: other recordings have their own tests)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("big_", "es_", "ref_")))
 
 
 @pytest.fixture(scope="session")

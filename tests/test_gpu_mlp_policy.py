@@ -8,7 +8,8 @@ from helpers import load_golden, product_env_from_golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["mlp_n16_b4_200", "mlp_n64_b2_n6_60", "mlp_n16_b4_mixed_150"]
+# mlp_moore_* / mlp_circular_*: row A15, non-default observation masks applied on the device
+CASES = ["mlp_n16_b4_200", "mlp_n64_b2_n6_60", "mlp_n16_b4_mixed_150", "mlp_moore_n16_b3_100", "mlp_circular_n16_b2_60"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -33,7 +34,7 @@ def test_fused_run_with_device_mlp_matches_reference(name):
     assert env.L == z["L"][K] and env.step_count == meta["final_step_count"]
 
 
-@pytest.mark.parametrize("name", ["mlp_n16_b4_mixed_150"])
+@pytest.mark.parametrize("name", ["mlp_n16_b4_mixed_150", "mlp_moore_n16_b3_100"])
 def test_single_steps_with_device_mlp_match_reference(name):
     z, meta = load_golden(name)
     env = product_env_from_golden(z, meta)

@@ -82,7 +82,8 @@ def test_oracle_greedy_policy_reproduces_reference_actions(name):
     np.testing.assert_array_equal(env.grid, z["ckpt_grid"][-1])
 
 
-@pytest.mark.parametrize("name", ["mlp_n16_b4_200", "mlp_n64_b2_n6_60", "mlp_n16_b4_mixed_150"])
+@pytest.mark.parametrize("name", ["mlp_n16_b4_200", "mlp_n64_b2_n6_60", "mlp_n16_b4_mixed_150", "mlp_moore_n16_b3_100",
+                                  "mlp_circular_n16_b2_60"])
 def test_oracle_mlp_policy_reproduces_reference_actions(name):
     """OracleMLP with the recorded weights, driven by oracle observations, picks the actions the reference MLP picked."""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
@@ -129,3 +130,18 @@ def test_neighborhood_masks():
             assert m.shape == (2 * kr + 1, 2 * kr + 1)
             assert m[kr, kr] == 1.0
             assert m[0, 0] == (1.0 if mode == "moore" else 0.0)
+
+
+def test_neighborhood_masks_equal_the_reference_recording():
+    """A15: the oracle's and the PRODUCT's make_neighborhood against masks recorded from the live reference
+    (daisy/nn/functional.py:51-103; oracle/gen_golden.py::record_masks), every mode, radius 1..3."""
+    from therldaisyworld_b200.env import make_neighborhood
+    z = np.load(os.path.join(GOLDEN_DIR, "ref_masks.npz"))
+    for kr in (1, 2, 3):
+        for mode in ("moore", "von_neumann", "circular", "nonsense"):
+            want = z[f"{mode}_{kr}"]
+            np.testing.assert_array_equal(neighborhood_mask(kr, mode), want)
+            got = make_neighborhood(kr, mode)
+            assert got.dtype == want.dtype and got.shape == want.shape
+            np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(make_neighborhood(), z["default"])
