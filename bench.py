@@ -254,6 +254,10 @@ def giant_grid_bench(rank, world, local, fp64_peak_tflops):
     cells = GIANT_N * GIANT_N * GIANT_STEPS
     value = cells / (best * 1e-3)
     done_at, ada = w.lifespans()
+    # state checksums after the 3 + 2 x GIANT_STEPS steps: exact integers, independent of the banding -> equal at N = 1/2/4/8
+    cover_cs = w.cover_checksum()
+    ai, st = w.agents()
+    agent_cs = [int((ai[:, 0].astype(np.int64) * 16411 + ai[:, 1]).sum()), float(np.sum(st)), int(np.sum(ada))]
     out = {
         "workload": f"BASELINE configs[4]: single {GIANT_N}x{GIANT_N} toroidal world, {GIANT_N} greedy agents, row-banded over "
                     f"{world} GPU(s) ({GIANT_N // world} rows each), {GIANT_STEPS} steps after 3 warm-up steps",
@@ -268,6 +272,9 @@ def giant_grid_bench(rank, world, local, fp64_peak_tflops):
                                "nccl": "1 all-reduce(SUM, 2n doubles) + 1 ring halo exchange overlapped with the interior tiles"}[mode],
         "peer_barrier_timed_out": bool(w.band.peer_timed_out()) if mode == "p2p" else None,
         "literal_recomputations": w.band.slow_count(), "biosphere_alive_steps": done_at,
+        "state_checksum": {"steps": 3 + 2 * GIANT_STEPS, "covers": cover_cs, "agents": agent_cs,
+                           "what": "covers: dwt_cover_checksum summed over the bands (sum kl, sum kd, position-weighted sums, mod 2^64); "
+                                   "agents: [sum(x * 16411 + y), sum(state), sum(agents_done_at)] -- identical for every number of bands"},
     }
     del w
     torch.cuda.empty_cache()
@@ -452,6 +459,18 @@ def run_product(args):
         except Exception as e:                                    # the headline line must survive
             giant = {"error": repr(e)}
 
+    dropin = None
+    if rank == 0 and not args.no_extras:
+        # the path every reference caller uses: ONE env.step() per step through the Python drop-in (lattice-resident state,
+        # K = 1 launch of the fused kernel, one packed device->host copy). Secondary record, not the headline.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from dropin_bench import measure
+            dropin = measure(WORLDS, N, N_AGENTS, iters=200, warm=20, device=local)
+            dropin["what"] = ("single env.step() calls through the drop-in class at the bench's ensemble shape: host Greedy policy "
+                              "(obs download + action upload every step), device policy with / without the observation download")
+        except Exception as e:
+            dropin = {"error": repr(e)}
     if rank == 0:
         peaks = load_peaks()
         fused_s = prof.fused_ms * 1e-3
@@ -460,6 +479,9 @@ def run_product(args):
             "bound": "fp64_fma", "kernel": "k_fused (SMEM-resident lattice kernel)",
             "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
             "frac": (achieved / tf.value) if achieved else None,
+            # second denominator: the nominal FP64 FMA rate, 148 SMs x 64 DFMA/clk x 2 flop x 1.965 GHz (max SM clock)
+            "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12,
+            "frac_nominal": (achieved / (148 * 64 * 2 * 1.965e9 / 1e12)) if achieved else None,
             "peak_source": "measured live: dw_debug_fp64_peak (dependent DFMA chains, full occupancy); MEASURED_PEAKS.json "
                            "has no FP64 entry",
             "flop_per_cell_update": FLOP_PER_CELL_UPDATE,
@@ -492,6 +514,7 @@ def run_product(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "giant_grid": giant,
+            "dropin_step": dropin,
             "check": {"mean_done_at_after_T": mean_life, "mean_done_at_after_T_e2e": mean_life_e2e, "expected": float(T_STEPS),
                       "ensemble_stats": stats.tolist(),
                       "wall_s_resident": wall_res},

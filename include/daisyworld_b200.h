@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DW_ABI_VERSION 1
+#define DW_ABI_VERSION 2
 
 enum {
     DW_OK = 0,
@@ -150,14 +150,28 @@ int dw_init_random(dw_handle *h, uint64_t seed, double light_proportion, double 
 int dw_init_temperatures(dw_handle *h);
 
 /* RLDaisyWorld.step(action) (daisy_world_rl.py:475-497): update_agents -> forward -> get_obs ->
-   reward/done -> update_L, all on the device.  action: host int64 [ab,am] (ab<=B, am<=n, values 0..8)
-   or NULL for step(None). */
+   reward/done -> update_L, all on the device.  action: host int64 [ab,am] (ab<=B, am<=n) or NULL for step(None).
+   The state stays where the fused kernels keep it (packed 0.001 lattice, or the lean cover planes right after a reset)
+   whenever the fast path covers the physics: one K = 1 launch of the fused kernel; the fp64 grid[B,7,N,N], the
+   diagnostics and the observation windows are rebuilt on demand from the state the step started from. Partial actions
+   (ab < B or am < n) and non-D4-symmetric kernels run the materialising kernels (64 B per cell). */
 int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t am);
 /* dw_step followed by everything step() returns, in one call with one synchronisation: obs[B,n,7,3,3], reward and done
    ([B,n], or [B,2] when n_agents == 0) and the advanced clock. Any output pointer may be NULL. policy < 0: explicit
    action (or NULL = step(None)); otherwise the action is chosen on the device like dw_step_policy. */
 int dw_step_collect(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed, double *obs,
                     double *reward, uint8_t *done, dw_clock *clk);
+/* The same step with ALL of its return values brought to the host by one copy: `out` receives the device's output block
+   [reward f64 B*m | done u8 B*m, padded to a multiple of 8 | obs f64 B*n*63] (m = n, or 2 when n_agents == 0); byte offsets
+   from dw_step_out_layout: layout[4] = {reward, done, obs, total bytes}. want_obs == 0 stops after the reward/done part
+   (device policies do not need the observation on the host: at B = 1000, n = 4 it is 2 MB of the 2.04 MB). With `out`
+   from dw_host_alloc (page-locked) the copy is a single DMA at PCIe rate. action values: ANY integer, read like the
+   reference does (a == 8 stays, else a % 4 moves, a > 4 grazes; daisy_world_rl.py:190-212). */
+int dw_step_out_layout(dw_handle *h, int64_t *layout /*[4]*/);
+int dw_step_packed(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed,
+                   int32_t want_obs, void *out, dw_clock *clk);
+int dw_host_alloc(uint64_t bytes, void **out);
+int dw_host_free(void *p);
 /* Same step with the action chosen on the device by DW_POLICY_* (Greedy.__call__ fused in). */
 int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed);
 
@@ -243,6 +257,10 @@ int dw_get_profile(dw_handle *h, dw_profile *out);
 /* Diagnostics of the fused path (tests / profiling): number of cells recomputed in literal order because the fast
    path landed within the tie filter; and the fast fourth root evaluated on the device (host in, host out). */
 int dw_debug_slow_count(dw_handle *h, uint64_t *count, int32_t reset);
+/* where the live state currently resides: flags[4] = {fp64 grid[B,7,N,N] valid, packed lattice valid, lean reset planes
+   valid, kind of the recorded pre-state (0 none, 1 grid, 2 lattice, 3 cover planes)}. Tests use it to check that step()
+   stays lattice-resident. */
+int dw_debug_state(dw_handle *h, int32_t *flags /*[4]*/);
 int dw_debug_root4(dw_handle *h, const double *x, double *y, int32_t n);
 /* test hook of the screened materialising kernels: over a host grid [B,7,N,N] (channels 1,2 read) at the handle's clock,
    out[0..2] = largest |screened - literal| * 1000 of the unrounded new covers, bare fraction and temperatures over the

@@ -112,6 +112,11 @@ int dwt_get_covers(dwt_handle *h, double *light, double *dark);                 
 /* env.grid of the band: [7, rows, N] (channels as in the reference; ch4 carries the agent stamp), materialised by a
    literal forward from the post-graze state the last step started from. Needs at least one step. */
 int dwt_get_grid(dwt_handle *h, double *grid);
+/* Position-weighted checksum of the band's own cells, computed on the device with exact integer arithmetic (mod 2^64):
+   out[4] = {sum kl, sum kd, sum kl*w, sum kd*w} over the milli-covers k = 1000 * cover, w = (global_row * 131 + column)
+   % 977 + 1. Additive over bands: the sum over the ranks of a banded world equals the checksum of the same world on one
+   GPU (bench.py prints it so that the 1/2/4/8-GPU runs can be compared; the reference quantity is env.grid[0, 1:3]). */
+int dwt_cover_checksum(dwt_handle *h, uint64_t *out /*[4]*/);
 int dwt_debug_slow_count(dwt_handle *h, uint64_t *count);
 
 #ifdef __cplusplus

@@ -255,9 +255,10 @@ def test_run_with_collisions_reproduces_reference_lifespans():
     np.testing.assert_array_equal(env.agent_states, z["agent_states"][-1])
     np.testing.assert_array_equal(env.grid, z["ckpt_grid"][-1])
     assert env.L == z["L"][meta["steps"]] and env.step_count == meta["final_step_count"]
-    # the in-kernel series mode has no collision pass
-    with pytest.raises(NotImplementedError):
-        env.run_series(4, policy="greedy")
+    # the in-kernel series mode has no collision pass: run_series samples between host-driven steps instead
+    out = env.run_series(3, policy="greedy")
+    assert out.shape == (3, 3)
+    np.testing.assert_allclose(out[-1], [env.temp.mean(), env.grid[:, 1].mean(), env.grid[:, 2].mean()], rtol=1e-12)
 
 
 def test_collision_abi_state_machine_and_count_check():
@@ -283,3 +284,130 @@ def test_collision_abi_state_machine_and_count_check():
     env._state_changed()
     obs, reward, done, _ = env.step(np.zeros((2, 20, 1), dtype=np.int64))
     assert obs.shape == (2, 20, 7, 3, 3)
+
+
+def _window_obs(grid, pos, mask):
+    """get_obs (daisy_world_rl.py:246-263) by plain indexing: 3x3 windows centred on pos, wrapped, masked."""
+    B, m = pos.shape[:2]
+    N = grid.shape[-1]
+    out = np.zeros((B, m, 7, 3, 3))
+    for b in range(B):
+        for i in range(m):
+            xs, ys = (pos[b, i, 0] + np.arange(-1, 2)) % N, (pos[b, i, 1] + np.arange(-1, 2)) % N
+            out[b, i] = grid[b][:, xs][:, :, ys] * mask
+    return out
+
+
+def test_step_stays_lattice_resident_and_rebuilds_on_demand():
+    """step() keeps the state on the packed lattice (no [B,7,N,N] materialisation); env.grid / diagnostics / get_obs are
+    rebuilt lazily and change nothing; every value still equals the C oracle's."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_c import COracleWorld
+    rng = np.random.RandomState(11)
+    for N, B, n in [(64, 5, 4), (16, 7, 3), (20, 3, 5), (9, 2, 2)]:
+        np.random.seed(N)
+        env = RLDaisyWorld(grid_dimension=N, n_agents=n)
+        env.batch_size = B
+        obs0 = env.reset()
+        assert env.residency() == dict(grid=False, lattice=False, cover_planes=True, pre=3), "reset() must stay lean"
+        ref = COracleWorld(env)                                  # reads env.grid: materialises it once
+        np.testing.assert_array_equal(obs0, ref.get_obs())
+        for t in range(12):
+            a = rng.randint(9, size=(B, n, 1))
+            o1, r1, d1, _ = env.step(a)
+            o2, r2, d2, _ = ref.step(a)
+            res = env.residency()
+            assert res["lattice"] and not res["grid"], f"step {t} materialised the grid: {res}"
+            np.testing.assert_array_equal(o1, o2)
+            np.testing.assert_array_equal(r1, r2)
+            np.testing.assert_array_equal(d1, d2)
+            if t in (0, 5, 11):
+                np.testing.assert_array_equal(env.grid, ref.grid)
+                assert env.residency()["lattice"], "reading env.grid must not drop the lattice"
+            if t in (1, 6):                                      # get_obs at caller-supplied positions, still lean
+                pos = rng.randint(N, size=(B, 2, 2))
+                got = env.get_obs(pos)
+                assert not env.residency()["grid"]
+                np.testing.assert_array_equal(got, _window_obs(ref.grid, pos, env.neighborhood))
+        o1, r1, d1, _ = env.step_policy("greedy", want_obs=False)
+        ref.run(1, "greedy")
+        assert o1 is None
+        np.testing.assert_array_equal(r1[..., 0], np.clip(ref.agent_states.reshape(B, n), 0, None))
+        np.testing.assert_array_equal(env.observe(), ref.get_obs())
+        np.testing.assert_array_equal(env.grid, ref.grid)
+
+
+def test_step_returns_fresh_arrays_from_the_pinned_pool():
+    """The outputs come from page-locked blocks that are recycled only after the caller dropped them: arrays of earlier steps
+    must never change, also when more than the pool's limit are kept alive."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    np.random.seed(2)
+    env = RLDaisyWorld(grid_dimension=16)
+    env.batch_size = 6
+    env.reset()
+    kept, copies = [], []
+    for t in range(40):
+        out = env.step(np.random.randint(9, size=(6, 4, 1)))
+        kept.append(out[:3])
+        copies.append([x.copy() for x in out[:3]])
+        if t % 3 == 0:
+            kept.pop(0), copies.pop(0)                      # some are dropped: their blocks go back to the pool
+    for got, want in zip(kept, copies):
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+    assert out[2].dtype == np.bool_ and out[0].flags.writeable
+
+
+def test_any_integer_action_is_read_like_the_reference():
+    """daisy_world_rl.py:190-212 accepts any integer: a == 8 stays, a % 4 moves (Python modulo), a > 4 grazes."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_numpy import OracleDaisyWorld
+    np.random.seed(8)
+    env = RLDaisyWorld(grid_dimension=8, n_agents=6)
+    env.batch_size = 4
+    env.reset()
+    ref = OracleDaisyWorld(grid_dimension=8, n_agents=6)
+    ref.batch_size = 4
+    ref.reset()
+    ref.grid, ref.agent_indices, ref.agent_states = env.grid.copy(), env.agent_indices.copy(), env.agent_states.copy()
+    rng = np.random.RandomState(1)
+    for t in range(30):
+        a = rng.randint(-9, 26, size=(4, 6, 1))
+        o1, r1, d1, _ = env.step(a)
+        o2, r2, d2, _ = ref.step(a)
+        np.testing.assert_array_equal(env.agent_indices, ref.agent_indices)
+        np.testing.assert_array_equal(env.agent_states, ref.agent_states)
+        np.testing.assert_array_equal(o1, o2)
+    np.testing.assert_array_equal(env.grid, ref.grid)
+    acts = rng.randint(-9, 26, size=(10, 4, 6))
+    env.run(10, policy="replay", actions=acts)
+    for t in range(10):
+        ref.step(acts[t][..., None])
+    np.testing.assert_array_equal(env.grid, ref.grid)
+    np.testing.assert_array_equal(env.agent_states, ref.agent_states)
+
+
+def test_forward_leaves_the_live_state_alone():
+    """env.forward(grid) is side-effect-free on the state (reference :434-461) also when the state is lattice-resident; its
+    diagnostics are served until the state advances."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_c import COracleWorld
+    np.random.seed(4)
+    env = RLDaisyWorld(grid_dimension=16)
+    env.batch_size = 3
+    env.reset()
+    ref = COracleWorld(env)
+    env.run(9, policy="greedy")
+    ref.run(9, "greedy")
+    assert env.residency()["grid"] is False
+    g = np.random.RandomState(0).rand(3, 7, 16, 16) * 0.3
+    out = env.forward(g.copy())
+    wd = COracleWorld(env, grid=g.copy(), agent_indices=ref.agent_indices, agent_states=ref.agent_states)
+    np.testing.assert_array_equal(env.temp, wd.forward_diag()[:, 0:1])
+    np.testing.assert_array_equal(env.grid, ref.grid)                      # still there, still right
+    a = np.full((3, 4, 1), 7)
+    o1, _, _, _ = env.step(a)
+    o2, _, _, _ = ref.step(a)
+    np.testing.assert_array_equal(o1, o2)
+    np.testing.assert_array_equal(env.grid, ref.grid)
+    assert out.shape == g.shape

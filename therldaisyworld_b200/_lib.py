@@ -36,11 +36,11 @@ class DwRunResult(C.Structure):
 SYMBOLS = [
     "dw_abi_version", "dw_last_error", "dw_create", "dw_destroy", "dw_set_config", "dw_set_clock", "dw_get_clock", "dw_get_last_L",
     "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_set_mlp_population", "dw_run_population", "dw_get_population_results",
-    "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_collect", "dw_step_policy", "dw_update_agents",
+    "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_collect", "dw_step_out_layout", "dw_step_packed", "dw_host_alloc", "dw_host_free", "dw_step_policy", "dw_update_agents",
     "dw_agents_begin", "dw_agents_collide", "dw_step_tail_collect", "dw_step_tail_counted",
     "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_grid_f32", "dw_get_obs_f32", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
     "dw_run", "dw_run_chunk", "dw_run_series", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
-    "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count",
+    "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count", "dw_debug_state",
     "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak", "dw_debug_screen_error",
 ]
 
@@ -50,7 +50,7 @@ TILED_SYMBOLS = [
     "dwt_synchronize", "dwt_upload_covers", "dwt_upload_agents", "dwt_init_random", "dwt_decide", "dwt_move_graze",
     "dwt_finish_agents", "dwt_stencil", "dwt_halo_wrap", "dwt_get_ptrs", "dwt_run", "dwt_end_chunk",
     "dwt_reset_lifespans", "dwt_get_lifespans", "dwt_get_agents", "dwt_get_reward_done", "dwt_get_covers", "dwt_get_grid",
-    "dwt_debug_slow_count", "dwt_ipc_export", "dwt_ipc_attach", "dwt_get_peer_buffers", "dwt_attach_peers", "dwt_step_p2p",
+    "dwt_debug_slow_count", "dwt_cover_checksum", "dwt_ipc_export", "dwt_ipc_attach", "dwt_get_peer_buffers", "dwt_attach_peers", "dwt_step_p2p",
     "dwt_flush_p2p", "dwt_peer_status",
 ]
 
@@ -102,6 +102,10 @@ def load():
         "dw_step": (C.c_int, [vp, pi64, i32, i32]),
         "dw_step_policy": (C.c_int, [vp, i32, u64]),
         "dw_step_collect": (C.c_int, [vp, pi64, i32, i32, i32, u64, pd, pd, pu8, C.POINTER(DwClock)]),
+        "dw_step_out_layout": (C.c_int, [vp, pi64]),
+        "dw_step_packed": (C.c_int, [vp, pi64, i32, i32, i32, u64, i32, vp, C.POINTER(DwClock)]),
+        "dw_host_alloc": (C.c_int, [u64, C.POINTER(vp)]),
+        "dw_host_free": (C.c_int, [vp]),
         "dw_update_agents": (C.c_int, [vp, pi64, i32, i32]),
         "dw_agents_begin": (C.c_int, [vp, pi64, i32, i32, i32, u64, pi64]),
         "dw_agents_collide": (C.c_int, [vp, pd, C.POINTER(C.c_int32), C.c_double]),
@@ -129,6 +133,7 @@ def load():
         "dw_synchronize": (C.c_int, [vp]),
         "dw_set_world_offset": (C.c_int, [vp, C.c_uint32]),
         "dw_debug_slow_count": (C.c_int, [vp, C.POINTER(u64), i32]),
+        "dw_debug_state": (C.c_int, [vp, C.POINTER(C.c_int32)]),
         "dw_debug_root4": (C.c_int, [vp, pd, pd, i32]),
         "dw_debug_screen_error": (C.c_int, [vp, pd, pd]),
         "dw_debug_markstein": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
@@ -164,6 +169,7 @@ def load():
         "dwt_get_covers": (C.c_int, [vp, pd, pd]),
         "dwt_get_grid": (C.c_int, [vp, pd]),
         "dwt_debug_slow_count": (C.c_int, [vp, C.POINTER(u64)]),
+        "dwt_cover_checksum": (C.c_int, [vp, C.POINTER(u64)]),
         "dwt_ipc_export": (C.c_int, [vp, vp]),
         "dwt_ipc_attach": (C.c_int, [vp, i32, i32, vp]),
         "dwt_get_peer_buffers": (C.c_int, [vp, C.POINTER(vp)]),
@@ -178,7 +184,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.dw_abi_version() != 1:
+    if lib.dw_abi_version() != 2:
         raise DaisyWorldError("ABI version mismatch between _lib.py and libdaisyworld_b200.so")
     _lib = lib
     return lib

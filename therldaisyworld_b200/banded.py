@@ -207,6 +207,11 @@ class DeviceBand:
     def flush_p2p(self):
         self._check(self._lib.dwt_flush_p2p(self._h), "dwt_flush_p2p")
 
+    def cover_checksum(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self._lib.dwt_cover_checksum(self._h, out), "dwt_cover_checksum")
+        return [int(v) for v in out]
+
     def peer_timed_out(self):
         v = C.c_int32(0)
         self._check(self._lib.dwt_peer_status(self._h, C.byref(v)), "dwt_peer_status")
@@ -385,11 +390,20 @@ class BandedDaisyWorld:
                 comm.exchange_halos(*b.halo_tensors())
         self._pending += 1
 
+    def _check_peers(self):
+        """Peer-memory mode: a device-side flag barrier gives up after a bounded spin (csrc/dw_tiled.cuh, ~4 s or
+        DW_PEER_TIMEOUT_MS) and the step then continues on stale ghost rows / exchange vectors. Every point where results
+        leave the device goes through here, so a stalled peer raises instead of yielding silently wrong grids and lifespans."""
+        if self.mode == "p2p" and self.band.peer_timed_out():
+            raise _lib.DaisyWorldError(f"rank {self.rank}: a peer-memory barrier timed out (a peer rank stalled or died); the state of "
+                                  "this world is not trustworthy -- reset() before continuing")
+
     def _flush(self):
         """Finish the last step's agents (multi-rank: the deferred gain all-reduce)."""
         if self._gain_pending:
             if self.mode == "p2p":
                 self.band.flush_p2p()
+                self._check_peers()
             else:
                 self.comm.all_reduce_sum(self.band.exch_tensor(gain=True, act=False))
                 self.band.finish_agents()
@@ -404,6 +418,7 @@ class BandedDaisyWorld:
         if self.comm is not None:
             self.comm.all_reduce_max(self.band.stepmax_tensor(K))
         first = self.band.end_chunk(K)
+        self._check_peers()
         if first >= 0 and self.first_done_step is None:
             self.first_done_step = self.step_count + first + 1      # 1-based count of steps at which grid_done first held
         self.step_count += K
@@ -438,6 +453,19 @@ class BandedDaisyWorld:
     def agents(self):
         self._flush()
         return self.band.agents()
+
+    def cover_checksum(self):
+        """Exact position-weighted checksum of the WHOLE world's covers (this rank's part summed over the ranks mod 2^64):
+        identical for every banding of the same world (dwt_cover_checksum)."""
+        self._flush()
+        cs = self.band.cover_checksum()
+        if self.comm is not None and hasattr(self.comm, "dist"):
+            # int64 all-reduce wraps mod 2^64 like the device sums; the four words travel as signed values
+            import torch
+            t = torch.tensor([c - (1 << 64) if c >= (1 << 63) else c for c in cs], dtype=torch.int64, device=f"cuda:{self.device}")
+            self.comm.dist.all_reduce(t, group=self.comm.group)
+            cs = [int(v) & ((1 << 64) - 1) for v in t.tolist()]
+        return cs
 
     def local_covers(self):
         """[2, rows, N]: light and dark cover of this rank's band."""

@@ -45,10 +45,20 @@ struct dw_handle {
     int32_t *agent_xy = nullptr;
     long long *agent_idx64 = nullptr;   // staging of uploaded int64 agent_indices (converted on the device: no host sync)
     double *agent_state = nullptr;
+    // step outputs in ONE device block, layout [reward f64 B*m | done u8 B*m (padded to 8) | obs f64 B*n*63], m = n or 2
+    // when n_agents == 0: dw_step_packed brings all of step()'s return values to the host with a single copy. The
+    // observation part is allocated on first use (ensembles that never ask for observations keep the block small).
+    unsigned char *out_block = nullptr;
+    bool out_full = false;
     double *obs = nullptr;
     bool obs_valid = false;
     double *reward = nullptr;
     uint8_t *done = nullptr;
+    bool count_life = true;                    // fused / lean launches add their steps to the lifespan counters (dw_run); step() does not
+    // diagnostics of a standalone dw_forward(grid) call (env.forward refreshes env.temp/beta/growth as a side effect)
+    // live in their own slot: the pre-state of the LIVE state is not touched (the reference's forward leaves the env alone)
+    bool fwd_diag = false;
+    double fwd_L = 0.0;
     unsigned long long *world_max = nullptr;   // [B,2]
     int64_t *done_at = nullptr, *agents_done_at = nullptr;
     unsigned int *alive = nullptr;             // [64] per-step alive-world counters of a chunk
@@ -107,7 +117,7 @@ struct dw_handle {
         dw_clock clk{};
         PreKind pre = PRE_NONE;
         double L_last = 0;
-        bool ch6_dirty[2] = {false, false};
+        bool ch6_dirty_saved = false;   // of the buffer the checkpointed grid was copied from
     } ck[2];   // slot 0: dw_checkpoint_save/restore (caller), slot 1: dw_run's chunk rewind
 };
 
@@ -194,6 +204,37 @@ static int ensure_scratch(dw_handle *h, size_t count) {
     DW_CUDA_TRY(h, cudaMalloc((void **)&h->scratch, count * sizeof(double)));
     h->scratch_cap = count;
     return DW_OK;
+}
+
+static size_t out_m(const dw_handle *h) { return (size_t)h->cfg.batch * (h->cfg.n_agents ? h->cfg.n_agents : 2); }
+static size_t out_done_off(const dw_handle *h) { return out_m(h) * sizeof(double); }
+static size_t out_obs_off(const dw_handle *h) { return out_done_off(h) + ((out_m(h) + 7) & ~(size_t)7); }
+static size_t out_total(const dw_handle *h) { return out_obs_off(h) + (size_t)h->cfg.batch * h->cfg.n_agents * 63 * sizeof(double); }
+
+static int ensure_out_block(dw_handle *h, bool with_obs) {
+    if (h->out_block && (h->out_full || !with_obs)) return DW_OK;
+    const size_t bytes = with_obs ? out_total(h) : out_obs_off(h);
+    unsigned char *blk = nullptr;
+    DW_CUDA_TRY(h, cudaMalloc((void **)&blk, bytes ? bytes : 8));
+    DW_CUDA_TRY(h, cudaMemsetAsync(blk, 0, bytes ? bytes : 8, h->stream));
+    if (h->out_block) {            // growing: keep reward / done of the last step
+        DW_CUDA_TRY(h, cudaMemcpyAsync(blk, h->out_block, out_obs_off(h), cudaMemcpyDeviceToDevice, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->out_block);
+    }
+    h->out_block = blk;
+    h->out_full = with_obs;
+    h->reward = reinterpret_cast<double *>(blk);
+    h->done = blk + out_done_off(h);
+    h->obs = with_obs ? reinterpret_cast<double *>(blk + out_obs_off(h)) : nullptr;
+    h->obs_valid = false;
+    return DW_OK;
+}
+
+// every operation that advances or replaces the live state ends the validity of what was derived from the old one
+static void state_changed(dw_handle *h) {
+    h->obs_valid = false;
+    h->fwd_diag = false;
 }
 
 // ---- lazy conversions between the two state representations -----------------------------------------
@@ -301,8 +342,7 @@ extern "C" int dw_create(const dw_config *cfg, dw_handle **out) {
     const size_t B = cfg->batch, n = cfg->n_agents;
     rc = dev_alloc(h, &h->agent_xy, B * n * 2);
     if (!rc) rc = dev_alloc(h, &h->agent_state, B * n);
-    if (!rc) rc = dev_alloc(h, &h->reward, B * (n ? n : 2));
-    if (!rc) rc = dev_alloc(h, &h->done, B * (n ? n : 2));
+    if (!rc) rc = ensure_out_block(h, false);
     if (!rc) rc = dev_alloc(h, &h->world_max, B * 2);
     if (!rc) rc = dev_alloc(h, &h->done_at, B);
     if (!rc) rc = dev_alloc(h, &h->agents_done_at, B * n);
@@ -318,8 +358,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->obs, h->reward,
-                    h->done, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
+    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
@@ -353,7 +392,7 @@ extern "C" int dw_get_clock(dw_handle *h, dw_clock *clk) {
 }
 extern "C" int dw_get_last_L(dw_handle *h, double *L) {
     if (!h || !L) return DW_E_INVALID;
-    *L = h->L_last;
+    *L = h->fwd_diag ? h->fwd_L : h->L_last;
     return DW_OK;
 }
 extern "C" int dw_set_stream(dw_handle *h, void *s) {
@@ -395,7 +434,7 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
         h->cov_valid = false;
         h->lat_valid = false;
         h->pre = PRE_NONE;
-        h->obs_valid = false;
+        state_changed(h);
     }
     if (n && agent_indices) {
         // int64 -> wrapped int32 on the device: with pinned host memory the whole upload is asynchronous
@@ -405,11 +444,11 @@ extern "C" int dw_upload_state(dw_handle *h, const double *grid, const int64_t *
         DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_idx64, agent_indices, count * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
         k_agent_indices_in<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->agent_idx64, count, h->cfg.dim, h->agent_xy);
         DW_LAUNCHED(h);
-        h->obs_valid = false;
+        state_changed(h);
     }
     if (n && agent_states) {
         DW_CUDA_TRY(h, cudaMemcpyAsync(h->agent_state, agent_states, B * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        h->obs_valid = false;
+        state_changed(h);
     }
     return DW_OK;
 }
@@ -430,7 +469,7 @@ extern "C" int dw_upload_covers(dw_handle *h, const double *light, const double 
     h->grid_valid = false;
     h->lat_valid = false;
     h->pre = PRE_NONE;
-    h->obs_valid = false;
+    state_changed(h);
     return DW_OK;
 }
 
@@ -451,7 +490,7 @@ extern "C" int dw_init_random(dw_handle *h, uint64_t seed, double light_proporti
     h->grid_valid = false;
     h->lat_valid = false;
     h->pre = PRE_NONE;
-    h->obs_valid = false;
+    state_changed(h);
     return DW_OK;
 }
 
@@ -465,7 +504,7 @@ extern "C" int dw_init_temperatures(dw_handle *h) {
         h->cov_L = h->clk.L;
         h->pre = PRE_COV;
         h->L_last = h->clk.L;
-        h->obs_valid = false;
+        state_changed(h);
         return DW_OK;
     }
     if (!h->grid_valid) return dw_fail(h, DW_E_STATE, "dw_init_temperatures", "upload a grid first");
@@ -475,7 +514,7 @@ extern "C" int dw_init_temperatures(dw_handle *h) {
     h->pre = PRE_GRID;
     h->pre_grid = h->grid[h->cur];
     h->L_last = h->clk.L;
-    h->obs_valid = false;
+    state_changed(h);
     return DW_OK;
 }
 
@@ -488,6 +527,16 @@ static int ensure_pinned(dw_handle *h) {
     DW_CUDA_TRY(h, cudaMallocHost((void **)&h->pin, DW_PIN_ACTION_MAX + DW_PIN_OUT_MAX));
     h->pin_cap = DW_PIN_ACTION_MAX + DW_PIN_OUT_MAX;
     return DW_OK;
+}
+
+// The reference accepts ANY integer action (daisy_world_rl.py:190-212): `a == 8` stays, otherwise `a % 4` (Python modulo:
+// non-negative for negative a) picks the move, and `a > 4` grazes. The kernels decode an int8 code c with the same three
+// tests (c == 8, c & 3, c > 4), so a maps to: 0..8 itself; a > 8 -> 12 + a % 4 (move a % 4 and graze); a < 0 -> a mod 4
+// (move, no graze).
+static inline int8_t canonical_action(int64_t a) {
+    if (a >= 0 && a <= 8) return (int8_t)a;
+    if (a > 8) return (int8_t)(12 + (a & 3));
+    return (int8_t)(((a % 4) + 4) % 4);
 }
 
 static int stage_action(dw_handle *h, const int64_t *action, size_t count) {
@@ -504,18 +553,12 @@ static int stage_action(dw_handle *h, const int64_t *action, size_t count) {
         if (rc) return rc;
         DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // cheap when idle: the previous upload from this area has been consumed
         int8_t *a8 = reinterpret_cast<int8_t *>(h->pin);
-        for (size_t i = 0; i < count; ++i) {
-            if (action[i] < 0 || action[i] > 8) return dw_fail(h, DW_E_INVALID, "action", "values must be in 0..8");
-            a8[i] = (int8_t)action[i];
-        }
+        for (size_t i = 0; i < count; ++i) a8[i] = canonical_action(action[i]);
         DW_CUDA_TRY(h, cudaMemcpyAsync(h->action_dev, a8, count, cudaMemcpyHostToDevice, h->stream));
         return DW_OK;
     }
     std::vector<int8_t> a8(count);
-    for (size_t i = 0; i < count; ++i) {
-        if (action[i] < 0 || action[i] > 8) return dw_fail(h, DW_E_INVALID, "action", "values must be in 0..8");
-        a8[i] = (int8_t)action[i];
-    }
+    for (size_t i = 0; i < count; ++i) a8[i] = canonical_action(action[i]);
     DW_CUDA_TRY(h, cudaMemcpyAsync(h->action_dev, a8.data(), count, cudaMemcpyHostToDevice, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DW_OK;
@@ -557,7 +600,7 @@ static int launch_forward_tail(dw_handle *h, bool counters, unsigned int *alive_
     h->grid_valid = true;
     h->cov_valid = false;
     h->lat_valid = false;
-    h->obs_valid = false;
+    state_changed(h);
     update_L(h->clk);
     return DW_OK;
 }
@@ -576,9 +619,28 @@ extern "C" int dw_update_agents(dw_handle *h, const int64_t *action, int32_t ab,
     rc = launch_agents(h, h->action_dev, ab, am, DW_POLICY_REPLAY, 0);
     h->lat_valid = false;
     h->cov_valid = false;
-    h->obs_valid = false;
+    state_changed(h);
     return rc;
 }
+
+static int mlp_actions(dw_handle *h);
+static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, uint64_t seed, unsigned int *alive);
+static bool dw_fused_supported(const dw_handle *h);
+
+// step() keeps the state where the fused kernels keep it (packed lattice / lean reset planes) whenever the physics is one
+// the fast path covers: one K = 1 launch of the fused kernel instead of materialising the fp64 [B,7,N,N] grid (64 B per
+// cell). env.grid, diagnostics and observations are rebuilt on demand from the pre-state the step started from.
+// Partial actions (ab < B or am < n) and exotic kernels take the materialising path. DW_STEP_MATERIALISE=1 forces it.
+static bool lean_step_ok(const dw_handle *h, const int64_t *action, int32_t ab, int32_t am) {
+    if (!dw_fused_supported(h) || getenv("DW_STEP_MATERIALISE")) return false;
+    if (h->cfg.n_agents > 0 && action && (ab != h->cfg.batch || am != h->cfg.n_agents)) return false;
+    return h->lat_valid || h->cov_valid || h->grid_valid;
+}
+struct CountLifeGuard {
+    dw_handle *h; bool old;
+    CountLifeGuard(dw_handle *h_, bool v) : h(h_), old(h_->count_life) { h->count_life = v; }
+    ~CountLifeGuard() { h->count_life = old; }
+};
 
 // ---- collision_mode == 1 (daisy_world_rl.py:220-242): update_agents in two calls around the caller's RNG draws ----
 extern "C" int dw_agents_begin(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed,
@@ -587,11 +649,18 @@ extern "C" int dw_agents_begin(dw_handle *h, const int64_t *action, int32_t ab, 
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_agents_begin", "previous dw_agents_begin not closed by dw_agents_collide");
     if (h->cfg.n_agents == 0) return DW_OK;
-    if (policy > DW_POLICY_EPS_GREEDY || policy == DW_POLICY_REPLAY)
-        return dw_fail(h, DW_E_INVALID, "dw_agents_begin", "policy must be < 0 (explicit action / NULL) or a device policy without network");
-    int rc = ensure_grid(h);
+    if (policy > DW_POLICY_MLP || policy == DW_POLICY_REPLAY)
+        return dw_fail(h, DW_E_INVALID, "dw_agents_begin", "policy must be < 0 (explicit action / NULL) or a device policy");
+    int rc = DW_OK;
+    if (policy == DW_POLICY_MLP) {                 // network actions from the observation of the current state, then replayed
+        rc = mlp_actions(h);
+        if (rc) return rc;
+    }
+    rc = ensure_grid(h);
     if (rc) return rc;
-    if (policy < 0) {
+    if (policy == DW_POLICY_MLP) {
+        rc = launch_agents(h, h->action_dev, h->cfg.batch, h->cfg.n_agents, DW_POLICY_REPLAY, 0, false, false);
+    } else if (policy < 0) {
         if (action) {
             if (ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents)
                 return dw_fail(h, DW_E_INVALID, "dw_agents_begin", "action must be [ab<=B, am<=n]");
@@ -608,7 +677,7 @@ extern "C" int dw_agents_begin(dw_handle *h, const int64_t *action, int32_t ab, 
     h->agents_open = true;
     h->lat_valid = false;
     h->cov_valid = false;
-    h->obs_valid = false;
+    state_changed(h);
     return dw_get_agents(h, agent_indices, nullptr);
 }
 
@@ -678,12 +747,22 @@ extern "C" int dw_step(dw_handle *h, const int64_t *action, int32_t ab, int32_t 
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_step", "dw_agents_begin not closed by dw_agents_collide");
-    int rc = ensure_grid(h);
+    const bool agents = h->cfg.n_agents > 0;
+    if (agents && action && (ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents))
+        return dw_fail(h, DW_E_INVALID, "dw_step", "action must be [ab<=B, am<=n]");
+    int rc = DW_OK;
+    if (lean_step_ok(h, action, ab, am)) {
+        if (agents && action) {
+            rc = stage_action(h, action, (size_t)ab * am);
+            if (rc) return rc;
+        }
+        CountLifeGuard guard(h, false);
+        return run_steps_fused(h, 1, (agents && action) ? DW_POLICY_REPLAY : DW_POLICY_NONE, h->action_dev, 0, h->alive);
+    }
+    rc = ensure_grid(h);
     if (rc) return rc;
-    if (h->cfg.n_agents > 0) {
+    if (agents) {
         if (action) {
-            if (ab < 0 || am < 0 || ab > h->cfg.batch || am > h->cfg.n_agents)
-                return dw_fail(h, DW_E_INVALID, "dw_step", "action must be [ab<=B, am<=n]");
             rc = stage_action(h, action, (size_t)ab * am);
             if (rc) return rc;
             rc = launch_agents(h, h->action_dev, ab, am, DW_POLICY_REPLAY, 0);
@@ -775,9 +854,14 @@ extern "C" int dw_step_policy(dw_handle *h, int32_t policy, uint64_t seed) {
         return dw_fail(h, DW_E_INVALID, "dw_step_policy", "use dw_step for explicit actions");
     if (h->agents_open) return dw_fail(h, DW_E_STATE, "dw_step_policy", "dw_agents_begin not closed by dw_agents_collide");
     int rc = DW_OK;
-    if (policy == DW_POLICY_MLP) {
+    if (policy == DW_POLICY_MLP && h->cfg.n_agents > 0) {
         rc = mlp_actions(h);
         if (rc) return rc;
+    }
+    if (lean_step_ok(h, nullptr, 0, 0)) {
+        CountLifeGuard guard(h, false);
+        if (policy == DW_POLICY_MLP) return run_steps_fused(h, 1, h->cfg.n_agents ? DW_POLICY_REPLAY : DW_POLICY_NONE, h->action_dev, seed, h->alive);
+        return run_steps_fused(h, 1, policy, nullptr, seed, h->alive);
     }
     rc = ensure_grid(h);
     if (rc) return rc;
@@ -801,10 +885,10 @@ extern "C" int dw_forward(dw_handle *h, double *grid_in, double *grid_out) {
     DW_LAUNCHED(h);
     rc = launch_stamp(h, h->fwd_out, false, nullptr, false);
     if (rc) return rc;
-    // the reference's forward() refreshes env.temp/beta/growth as a side effect
-    h->pre = PRE_GRID;
-    h->pre_grid = h->fwd_in;
-    h->L_last = h->clk.L;
+    // the reference's forward() refreshes env.temp/beta/growth as a side effect: the diagnostics are served from this call's
+    // input until the live state advances; the live state's own pre-state is left alone
+    h->fwd_diag = true;
+    h->fwd_L = h->clk.L;
     DW_CUDA_TRY(h, cudaMemcpyAsync(grid_out, h->fwd_out, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     // ch0 of the argument is mutated in place by the reference (:381)
     for (int b = 0; b < h->cfg.batch; ++b)
@@ -814,29 +898,46 @@ extern "C" int dw_forward(dw_handle *h, double *grid_in, double *grid_out) {
     return DW_OK;
 }
 
+// observation windows at `pos` [nb,m,2] (device) without a materialised grid, when the state allows it (lean_obs_ok)
+static bool lean_obs_ok(const dw_handle *h) {
+    if (h->grid_valid) return false;
+    return h->cov_valid || (h->lat_valid && (h->pre == PRE_LAT || h->pre == PRE_COV));
+}
+static int launch_lean_obs(dw_handle *h, const int32_t *pos, int nb, int m, double *out) {
+    const DevParams P = make_params(h);
+    const int g = grid_for((size_t)nb * m * 9);
+    if (h->cov_valid) {
+        // the state right after reset(): initialize_grid's unrounded fields at the reset luminosity, no agent stamp
+        k_obs_from_pre<SrcCov><<<g, 256, 0, h->stream>>>(P, h->cfg.S * h->cov_L, SrcCov{h->cov, h->NN}, pos, nb, m, h->agent_xy,
+                                                         h->agent_state, out, 1);
+    } else if (h->pre == PRE_LAT) {
+        k_obs_from_pre<SrcLattice><<<g, 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, SrcLattice{h->lat_pre, h->NN}, pos, nb, m,
+                                                             h->agent_xy, h->agent_state, out, 0);
+    } else {
+        k_obs_from_pre<SrcCov><<<g, 256, 0, h->stream>>>(P, h->cfg.S * h->L_last, SrcCov{h->cov, h->NN}, pos, nb, m, h->agent_xy,
+                                                         h->agent_state, out, 0);
+    }
+    DW_LAUNCHED(h);
+    return DW_OK;
+}
+
 static int compute_obs(dw_handle *h) {
     if (h->obs_valid) return DW_OK;
     const size_t B = h->cfg.batch, n = h->cfg.n_agents;
     if (n == 0) { h->obs_valid = true; return DW_OK; }
-    int rc = dev_alloc(h, &h->obs, B * n * 63);
+    int rc = ensure_out_block(h, true);
     if (rc) return rc;
-    const DevParams P = make_params(h);
-    if (!h->grid_valid && h->lat_valid && (h->pre == PRE_LAT || h->pre == PRE_COV)) {
-        // after a fused run: re-evaluate only the agents' windows from the state the last step started from instead of
-        // materialising the whole 7-channel grid
-        const double SL = h->cfg.S * h->L_last;
-        if (h->pre == PRE_LAT)
-            k_obs_from_pre<SrcLattice><<<grid_for(B * n * 9), 256, 0, h->stream>>>(P, SL, SrcLattice{h->lat_pre, h->NN}, h->agent_xy,
-                                                                                   h->agent_state, h->obs);
-        else
-            k_obs_from_pre<SrcCov><<<grid_for(B * n * 9), 256, 0, h->stream>>>(P, SL, SrcCov{h->cov, h->NN}, h->agent_xy, h->agent_state,
-                                                                               h->obs);
-        DW_LAUNCHED(h);
+    if (lean_obs_ok(h)) {
+        // lean state: re-evaluate only the agents' windows from the state the last step started from (or from the reset
+        // planes) instead of materialising the whole 7-channel grid
+        rc = launch_lean_obs(h, h->agent_xy, (int)B, (int)n, h->obs);
+        if (rc) return rc;
         h->obs_valid = true;
         return DW_OK;
     }
     rc = ensure_grid(h);
     if (rc) return rc;
+    const DevParams P = make_params(h);
     k_obs<<<grid_for(B * n * 63), 256, 0, h->stream>>>(P, h->grid[h->cur], h->agent_xy, (int)B, (int)n, h->obs);
     DW_LAUNCHED(h);
     h->obs_valid = true;
@@ -860,6 +961,46 @@ extern "C" int dw_step_collect(dw_handle *h, const int64_t *action, int32_t ab, 
     int rc = policy < 0 ? dw_step(h, action, ab, am) : dw_step_policy(h, policy, seed);
     if (rc) return rc;
     return collect_step_outputs(h, obs, reward, done, clk);
+}
+
+// ---- packed step: everything step() returns in ONE device->host copy ------------------------------------------------------
+extern "C" int dw_step_out_layout(dw_handle *h, int64_t *layout) {
+    if (!h || !layout) return DW_E_INVALID;
+    layout[0] = 0;
+    layout[1] = (int64_t)out_done_off(h);
+    layout[2] = (int64_t)out_obs_off(h);
+    layout[3] = (int64_t)out_total(h);
+    return DW_OK;
+}
+
+extern "C" int dw_step_packed(dw_handle *h, const int64_t *action, int32_t ab, int32_t am, int32_t policy, uint64_t seed,
+                              int32_t want_obs, void *out, dw_clock *clk) {
+    if (!h || !out) return DW_E_INVALID;
+    int rc = policy < 0 ? dw_step(h, action, ab, am) : dw_step_policy(h, policy, seed);
+    if (rc) return rc;
+    const bool obs = want_obs && h->cfg.n_agents > 0;
+    if (obs) {
+        rc = compute_obs(h);
+        if (rc) return rc;
+    }
+    DW_CUDA_TRY(h, cudaMemcpyAsync(out, h->out_block, obs ? out_total(h) : out_obs_off(h), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (clk) *clk = h->clk;
+    return DW_OK;
+}
+
+// Page-locked host memory for the packed outputs: a device->host copy into it is one DMA at PCIe rate with no staging
+// copy (pageable destinations are staged by the driver at a fraction of that).
+extern "C" int dw_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return DW_E_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 8);
+    if (e != cudaSuccess) return dw_fail(nullptr, DW_E_CUDA, "dw_host_alloc", cudaGetErrorString(e));
+    return DW_OK;
+}
+extern "C" int dw_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+    return DW_OK;
 }
 
 static int collect_step_outputs(dw_handle *h, double *obs, double *reward, uint8_t *done, dw_clock *clk) {
@@ -924,7 +1065,8 @@ extern "C" int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t
     const size_t count = (size_t)b * m * 63;
     if (!count) return DW_OK;
     if (!agent_indices || !obs) return DW_E_INVALID;
-    int rc = ensure_grid(h);
+    const bool lean = lean_obs_ok(h);          // e.g. reset()'s get_obs: windows from the lean planes, no [B,7,N,N] grid
+    int rc = lean ? DW_OK : ensure_grid(h);
     if (rc) return rc;
     rc = ensure_scratch(h, count + (size_t)b * m);   // obs + positions (int32 pairs fit in one double each)
     if (rc) return rc;
@@ -932,9 +1074,14 @@ extern "C" int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t
     for (size_t i = 0; i < xy.size(); ++i) xy[i] = (int32_t)agent_indices[i];
     int32_t *pos = (int32_t *)(h->scratch + count);
     DW_CUDA_TRY(h, cudaMemcpyAsync(pos, xy.data(), xy.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    const DevParams P = make_params(h);
-    k_obs<<<grid_for(count), 256, 0, h->stream>>>(P, h->grid[h->cur], pos, b, m, h->scratch);
-    DW_LAUNCHED(h);
+    if (lean) {
+        rc = launch_lean_obs(h, pos, b, m, h->scratch);
+        if (rc) return rc;
+    } else {
+        const DevParams P = make_params(h);
+        k_obs<<<grid_for(count), 256, 0, h->stream>>>(P, h->grid[h->cur], pos, b, m, h->scratch);
+        DW_LAUNCHED(h);
+    }
     DW_CUDA_TRY(h, cudaMemcpyAsync(obs, h->scratch, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DW_OK;
@@ -1003,26 +1150,14 @@ extern "C" int dw_get_reward_done(dw_handle *h, double *reward, uint8_t *done) {
     return DW_OK;
 }
 
+static int diag_to_scratch(dw_handle *h, int32_t which, size_t extra, size_t *count_out);
+
 extern "C" int dw_get_diag(dw_handle *h, int32_t which, double *out) {
     if (!h || !out || which < 0 || which > DW_DIAG_GROWTH) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    if (h->pre == PRE_NONE) return dw_fail(h, DW_E_STATE, "dw_get_diag", "no forward pass has run on this state yet");
-    const DevParams P = make_params(h);
-    const size_t total = (size_t)P.B * h->NN, count = total * (which == DW_DIAG_GROWTH ? 2 : 1);
-    int rc = ensure_scratch(h, count);
+    size_t count = 0;
+    int rc = diag_to_scratch(h, which, 0, &count);
     if (rc) return rc;
-    const double SL = h->cfg.S * h->L_last;
-    if (h->pre == PRE_GRID) {
-        SrcGrid src{h->pre_grid, 7 * h->NN, h->NN};
-        k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
-    } else if (h->pre == PRE_COV) {
-        SrcCov src{h->cov, h->NN};
-        k_diag<SrcCov><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
-    } else {
-        SrcLattice src{h->lat_pre, h->NN};
-        k_diag<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, SL, src, which, h->scratch);
-    }
-    DW_LAUNCHED(h);
     DW_CUDA_TRY(h, cudaMemcpyAsync(out, h->scratch, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return DW_OK;
@@ -1030,13 +1165,15 @@ extern "C" int dw_get_diag(dw_handle *h, int32_t which, double *out) {
 
 // unrounded diagnostic field `which` of the last forward into h->scratch (count elements)
 static int diag_to_scratch(dw_handle *h, int32_t which, size_t extra, size_t *count_out) {
-    if (h->pre == PRE_NONE) return dw_fail(h, DW_E_STATE, "dw_get_diag", "no forward pass has run on this state yet");
+    if (h->pre == PRE_NONE && !h->fwd_diag) return dw_fail(h, DW_E_STATE, "dw_get_diag", "no forward pass has run on this state yet");
     const DevParams P = make_params(h);
     const size_t total = (size_t)P.B * h->NN, count = total * (which == DW_DIAG_GROWTH ? 2 : 1);
     int rc = ensure_scratch(h, count + extra);
     if (rc) return rc;
-    const double SL = h->cfg.S * h->L_last;
-    if (h->pre == PRE_GRID) k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcGrid{h->pre_grid, 7 * h->NN, h->NN}, which, h->scratch);
+    const double SL = h->cfg.S * (h->fwd_diag ? h->fwd_L : h->L_last);
+    if (h->fwd_diag)       // the last forward was a standalone forward(grid) call: its input is the diagnostics' source
+        k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcGrid{h->fwd_in, 7 * h->NN, h->NN}, which, h->scratch);
+    else if (h->pre == PRE_GRID) k_diag<SrcGrid><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcGrid{h->pre_grid, 7 * h->NN, h->NN}, which, h->scratch);
     else if (h->pre == PRE_COV) k_diag<SrcCov><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcCov{h->cov, h->NN}, which, h->scratch);
     else k_diag<SrcLattice><<<grid_for(total), 256, 0, h->stream>>>(P, SL, SrcLattice{h->lat_pre, h->NN}, which, h->scratch);
     DW_LAUNCHED(h);
@@ -1193,7 +1330,7 @@ static int ckpt_save(dw_handle *h, int slot) {
     // step before the checkpoint are not restorable, the state itself is.
     c.pre = (h->pre == PRE_LAT || h->pre == PRE_COV) ? h->pre : PRE_NONE;
     c.L_last = h->L_last;
-    c.ch6_dirty[0] = h->ch6_dirty[0]; c.ch6_dirty[1] = h->ch6_dirty[1];
+    c.ch6_dirty_saved = h->ch6_dirty[h->cur];
     return DW_OK;
 }
 
@@ -1225,8 +1362,8 @@ static int ckpt_restore(dw_handle *h, int slot) {
     }
     DW_CUDA_TRY(h, cudaMemcpyAsync(h->done_at, c.done_at, B * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
     h->grid_valid = c.grid_valid; h->lat_valid = c.lat_valid; h->clk = c.clk; h->pre = c.pre; h->L_last = c.L_last;
-    h->ch6_dirty[0] = c.ch6_dirty[0]; h->ch6_dirty[1] = c.ch6_dirty[1];
-    h->obs_valid = false;
+    if (c.grid_valid) h->ch6_dirty[h->cur] = c.ch6_dirty_saved;   // the flags describe physical buffers: `cur` may have flipped since the save
+    state_changed(h);
     return DW_OK;
 }
 
@@ -1309,6 +1446,12 @@ extern "C" int dw_debug_fp64_peak(dw_handle *h, int32_t iters, int32_t reps, dou
 extern "C" int dw_set_world_offset(dw_handle *h, uint32_t world0) {
     if (!h) return DW_E_INVALID;
     h->world0 = world0;
+    return DW_OK;
+}
+
+extern "C" int dw_debug_state(dw_handle *h, int32_t *flags) {
+    if (!h || !flags) return DW_E_INVALID;
+    flags[0] = h->grid_valid; flags[1] = h->lat_valid; flags[2] = h->cov_valid; flags[3] = (int32_t)h->pre;
     return DW_OK;
 }
 

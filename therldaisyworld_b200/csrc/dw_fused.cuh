@@ -70,6 +70,7 @@ struct FusedArgs {
     unsigned int step0;         // env.step_count at launch (RANDOM policy counter)
     unsigned int world0;        // global index of this handle's first world (RANDOM policy counter)
     int K, policy;
+    int count_life, pad2_;      // 1: add this launch's steps to the lifespan counters done_at / agents_done_at (dw_run); 0: step()
     unsigned int *slow_count;   // diagnostics: number of literal recomputations (may be NULL)
     // series mode (k_fused_n64_persist<true>): per-step ensemble sums, [K] each: sqrt(g)*T of the step's forward (unrounded),
     // light and dark milli-cover after the step
@@ -373,13 +374,13 @@ __global__ void __launch_bounds__(256) k_fused_generic(const __grid_constant__ F
         A.agent_state[(size_t)b * n + i] = S.st[i];
         A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
         A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
-        A.agents_done_at[(size_t)b * n + i] += S.ada[i];
+        if (A.count_life) A.agents_done_at[(size_t)b * n + i] += S.ada[i];
         const double r = S.st[i];
         A.reward[(size_t)b * n + i] = r;
         A.done[(size_t)b * n + i] = r < 0.1;
     }
     if (tid == 0) {
-        A.done_at[b] += life;
+        if (A.count_life) A.done_at[b] += life;
         if (n == 0) {
             const int *sm = s_max + 2 * ((A.K - 1) & 1);
             for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
@@ -585,13 +586,13 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64(const __gr
         A.agent_state[(size_t)b * n + i] = S.st[i];
         A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
         A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
-        A.agents_done_at[(size_t)b * n + i] += S.ada[i];
+        if (A.count_life) A.agents_done_at[(size_t)b * n + i] += S.ada[i];
         const double r = S.st[i];
         A.reward[(size_t)b * n + i] = r;
         A.done[(size_t)b * n + i] = r < 0.1;
     }
     if (tid == 0) {
-        A.done_at[b] += life;
+        if (A.count_life) A.done_at[b] += life;
         if (n == 0) {
             const int *sm = s_max + 2 * ((A.K - 1) & 1);
             for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
@@ -761,12 +762,12 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             A.agent_state[g] = r;
             A.agent_xy[2 * g] = sm.xy[tid] & 0xffff;
             A.agent_xy[2 * g + 1] = sm.xy[tid] >> 16;
-            A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + sm.ada[tid];
+            if (A.count_life) A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + sm.ada[tid];
             A.reward[g] = r;
             A.done[g] = r < 0.1;
         }
         if (tid == 0) {
-            A.done_at[b] = __ldcg(A.done_at + b) + life;
+            if (A.count_life) A.done_at[b] = __ldcg(A.done_at + b) + life;
             if (n == 0) {
                 const int *smx = sm.smax + 2 * ((kc - 1) & 1);
                 for (int ch = 0; ch < 2; ++ch) { A.reward[2 * b + ch] = smx[ch] > 0 ? 1.0 : 0.0; A.done[2 * b + ch] = smx[ch] > 0 ? 0 : 1; }
@@ -1035,13 +1036,13 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
             A.agent_state[ga] = r;
             A.agent_xy[2 * ga] = sm.xy[a] & 0xffff;
             A.agent_xy[2 * ga + 1] = sm.xy[a] >> 16;
-            A.agents_done_at[ga] = __ldcg(A.agents_done_at + ga) + sm.ada[a];
+            if (A.count_life) A.agents_done_at[ga] = __ldcg(A.agents_done_at + ga) + sm.ada[a];
             A.reward[ga] = r;
             A.done[ga] = r < 0.1;
         }
         if (tid < n_worlds) {
             const size_t gw = (size_t)g * W + tid;
-            A.done_at[gw] = __ldcg(A.done_at + gw) + sm.life[tid];
+            if (A.count_life) A.done_at[gw] = __ldcg(A.done_at + gw) + sm.life[tid];
             if (n == 0) {
                 const int *smx = sm.smax[(kc - 1) & 1][tid];
                 for (int ch = 0; ch < 2; ++ch) { A.reward[2 * gw + ch] = smx[ch] > 0 ? 1.0 : 0.0; A.done[2 * gw + ch] = smx[ch] > 0 ? 0 : 1; }
@@ -1183,13 +1184,13 @@ __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__
         A.agent_state[(size_t)b * n + i] = S.st[i];
         A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
         A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
-        A.agents_done_at[(size_t)b * n + i] += S.ada[i];
+        if (A.count_life) A.agents_done_at[(size_t)b * n + i] += S.ada[i];
         const double r = S.st[i];
         A.reward[(size_t)b * n + i] = r;
         A.done[(size_t)b * n + i] = r < 0.1;
     }
     if (tid == 0) {
-        A.done_at[b] += life;
+        if (A.count_life) A.done_at[b] += life;
         if (n == 0) {
             const int *sm = s_max + 2 * ((A.K - 1) & 1);
             for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }

@@ -570,22 +570,32 @@ __global__ void __launch_bounds__(256) k_obs(DevParams P, const double *__restri
 // Observations straight from the state the last forward STARTED from (post-graze lattice / cover planes / grid): the
 // window cells are re-evaluated literally, which reproduces exactly what forward wrote there (b' from the unrounded
 // covers, rounded temperatures, agent stamp: highest index on a cell wins, dead agents included) without materialising
-// the whole 7-channel grid. One thread per (agent, window cell).
+// the whole 7-channel grid. One thread per (agent, window cell). pos: [nb,m,2] window centres (the agents' own positions
+// for step()'s observation, caller-supplied ones for get_obs(agent_indices)); world of window (b, i) is b.
+// init != 0: the state right after reset() instead -- src holds the initial covers themselves and the window shows
+// initialize_grid's UNROUNDED fields (ch0 = p-l-d, covers, T, T_light, T_dark; no agent stamp; daisy_world_rl.py:304-324).
 template <class Src>
-__global__ void __launch_bounds__(256) k_obs_from_pre(DevParams P, double SL, Src src, const int32_t *__restrict__ agent_xy,
-                                                      const double *__restrict__ agent_state, double *__restrict__ obs) {
+__global__ void __launch_bounds__(256) k_obs_from_pre(DevParams P, double SL, Src src, const int32_t *__restrict__ pos, int nb, int m,
+                                                      const int32_t *__restrict__ agent_xy, const double *__restrict__ agent_state,
+                                                      double *__restrict__ obs, int init) {
     const int N = P.N, n = P.n_agents;
-    const size_t total = (size_t)P.B * n * 9;
+    const size_t total = (size_t)nb * m * 9;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t ag = i / 9;
-        const int w = (int)(i - ag * 9), b = (int)(ag / n);
+        const int w = (int)(i - ag * 9), b = (int)(ag / m);
         double *o = obs + ag * 63 + w;
-        const double m = P.mask[w];
-        int x = agent_xy[ag * 2] + w / 3 - 1, y = agent_xy[ag * 2 + 1] + w % 3 - 1;
-        x = x < 0 ? x + N : (x >= N ? x - N : x);
-        y = y < 0 ? y + N : (y >= N ? y - N : y);
+        const double mk = P.mask[w];
+        int x = pos[ag * 2] + w / 3 - 1, y = pos[ag * 2 + 1] + w % 3 - 1;
+        x = ((x % N) + N) % N;
+        y = ((y % N) + N) % N;
         double l9[9], d9[9];
         dw_load9(src, b, N, x, y, l9, d9);
+        if (init) {
+            const LitCell c = dw_literal_cell(P, SL, l9, d9);
+            o[0] = c.b0 * mk; o[9] = l9[4] * mk; o[18] = d9[4] * mk; o[27] = c.T * mk; o[36] = c.Tl * mk; o[45] = c.Td * mk;
+            o[54] = 0.0 * mk;
+            continue;
+        }
         ScrCell c;                                          // what forward stored there: screened, literal next to ties
         if (!(P.screen && dw_screened_cell(P, SL / P.sigma, l9, d9, c))) dw_literal_rounded(P, SL, l9, d9, c);
         double ch4 = dw_k2v(c.k[4]);
@@ -593,13 +603,13 @@ __global__ void __launch_bounds__(256) k_obs_from_pre(DevParams P, double SL, Sr
             const size_t a2 = (size_t)b * n + k;
             if (agent_xy[a2 * 2] == x && agent_xy[a2 * 2 + 1] == y) ch4 = agent_state[a2];
         }
-        o[0] = dw_k2v(c.k[0]) * m;
-        o[9] = dw_k2v(c.k[1]) * m;
-        o[18] = dw_k2v(c.k[2]) * m;
-        o[27] = dw_k2v(c.k[3]) * m;
-        o[36] = ch4 * m;
-        o[45] = dw_k2v(c.k[5]) * m;
-        o[54] = 0.0 * m;
+        o[0] = dw_k2v(c.k[0]) * mk;
+        o[9] = dw_k2v(c.k[1]) * mk;
+        o[18] = dw_k2v(c.k[2]) * mk;
+        o[27] = dw_k2v(c.k[3]) * mk;
+        o[36] = ch4 * mk;
+        o[45] = dw_k2v(c.k[5]) * mk;
+        o[54] = 0.0 * mk;
     }
 }
 

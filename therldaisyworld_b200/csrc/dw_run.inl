@@ -141,6 +141,7 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     A.reward = h->reward; A.done = h->done;
     A.seed = seed; A.step0 = (unsigned int)h->clk.step_count; A.world0 = h->world0;
     A.K = K; A.policy = policy;
+    A.count_life = h->count_life ? 1 : 0;
     A.slow_count = h->slow_count;
     // kernel selection: 64x64 worlds with <= 32 agents run the persistent kernel (dynamic work queue); DW_FUSED_IMPL
     // overrides for experiments: "persist" (default) | "simple" (one CTA per world) | "generic" (any N)
@@ -214,8 +215,9 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         kern<<<grid, 256, 0, h->stream>>>(A);
     } else {
         const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
-        if (smem > 48 * 1024 && !h->fused_attr_set) {
+        if (smem > 48 * 1024 && !h->fused_attr_set) {      // both one-CTA-per-world fallbacks (64x64 with > 817 agents needs it too)
             DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->fused_attr_set = true;
         }
         const bool tile4 = !n64 && dimN % 4 == 0 && dimN >= 12 && !(impl && !strcmp(impl, "generic"));
@@ -253,7 +255,7 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     h->grid_valid = false;
     h->pre = PRE_LAT;
     h->L_last = L_last;
-    h->obs_valid = false;
+    state_changed(h);
     h->clk = clk;
     return DW_OK;
 }
@@ -274,14 +276,14 @@ static int lean_first_step(dw_handle *h, int policy, const int8_t *act_dev, uint
     SrcCov src{h->cov, h->NN};
     launch_forward_lattice(h, P, h->cfg.S * h->clk.L, src, h->lat[h->lcur], h->world_max);
     DW_LAUNCHED(h);
-    rc = launch_stamp(h, nullptr, true, alive_slot, true);
+    rc = launch_stamp(h, nullptr, h->count_life, alive_slot, true);
     if (rc) return rc;
     h->pre = PRE_COV;
     h->L_last = h->clk.L;
     h->lat_valid = true;
     h->cov_valid = false;
     h->grid_valid = false;
-    h->obs_valid = false;
+    state_changed(h);
     update_L(h->clk);
     return DW_OK;
 }
@@ -336,7 +338,7 @@ static int run_steps_generic(dw_handle *h, int K, int policy, const int8_t *act_
         if (policy == DW_POLICY_REPLAY) rc = launch_agents(h, act_dev + (size_t)j * per_step, h->cfg.batch, h->cfg.n_agents, policy, seed);
         else rc = launch_agents(h, nullptr, 0, 0, policy, seed);
         if (rc) return rc;
-        rc = launch_forward_tail(h, true, alive + j);
+        rc = launch_forward_tail(h, h->count_life, alive + j);
         if (rc) return rc;
     }
     return DW_OK;

@@ -83,6 +83,8 @@ struct PeerTable {
     double *exch[DWT_MAX_RANKS];           // [gain1 | gain0 | act], n doubles each
     unsigned int *flags[DWT_MAX_RANKS];    // [DWT_MAX_RANKS] barrier epochs, slot r written by rank r
     int rank, R, on;                       // on == 0: single-process / NCCL mode (local stores only)
+    int pad_;
+    long long timeout_clocks;              // bound of a barrier spin (default 8e9 ~ 4 s; DW_PEER_TIMEOUT_MS); <= 0: default
 };
 
 // All ranks meet here: every prior write of this rank (to its own or to peer memory) is visible to a peer that has seen
@@ -92,12 +94,12 @@ __device__ __forceinline__ void dw_peer_barrier_body(const PeerTable &PT, unsign
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(PT.flags[p] + PT.rank), "r"(epoch) : "memory");
     const unsigned int *mine = PT.flags[PT.rank] + p;
-    const long long t0 = clock64();
+    const long long t0 = clock64(), limit = PT.timeout_clocks > 0 ? PT.timeout_clocks : 8000000000ll;
     for (;;) {
         unsigned int v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
         if ((int)(v - epoch) >= 0) break;
-        if (clock64() - t0 > 8000000000ll) { *timed_out = 1u; break; }
+        if (clock64() - t0 > limit) { *timed_out = 1u; break; }
         __nanosleep(100);
     }
     __threadfence_system();
@@ -523,6 +525,24 @@ __global__ void __launch_bounds__(256) k_band_covers(BandGeom G, const uint32_t 
         const uint32_t w = lat[(size_t)(r + 1) * G.pitch + G.c0 + y];
         out[i] = dw_milli(w & 0xffffu);
         out[RN + i] = dw_milli(w >> 16);
+    }
+}
+// Position-weighted checksum of the band's own cells (exact integer arithmetic on the milli-covers, wraps mod 2^64):
+// out[0..3] += {sum kl, sum kd, sum kl * w, sum kd * w}, w = (global_row * 131 + column) % 977 + 1. Additive over bands,
+// so the sum over the ranks of a banded world equals the checksum of the same world held as one band.
+__global__ void __launch_bounds__(256) k_band_checksum(BandGeom G, const uint32_t *__restrict__ lat, unsigned long long *out) {
+    const size_t RN = (size_t)G.R * G.N;
+    unsigned long long a[4] = {0, 0, 0, 0};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < RN; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / G.N), y = (int)(i - (size_t)r * G.N);
+        const uint32_t w = lat[(size_t)(r + 1) * G.pitch + G.c0 + y];
+        const unsigned long long wt = (unsigned long long)((((long long)(G.row0 + r) % G.N) * 131 + y) % 977 + 1);
+        a[0] += w & 0xffffu; a[1] += w >> 16; a[2] += (w & 0xffffu) * wt; a[3] += (w >> 16) * wt;
+    }
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long v = a[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, v);
     }
 }
 // agent stamp of ch4 (forward :454-459): the highest agent index on a cell wins. claim holds INT_MAX outside a stamp.

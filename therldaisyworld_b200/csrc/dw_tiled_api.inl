@@ -46,6 +46,7 @@ struct dwt_handle {
     int chunk_j = 0;                           // steps recorded in stepmax since the last dwt_end_chunk
     unsigned int *slow_count = nullptr;
     double *scratch = nullptr;                 // [7 x R x N] materialisation buffer (lazy)
+    unsigned long long *csum = nullptr;        // [4] dwt_cover_checksum accumulator (lazy)
 };
 
 static int dwt_fail(dwt_handle *h, int code, const char *what, const char *detail) {
@@ -141,7 +142,7 @@ extern "C" int dwt_destroy(dwt_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->claim2, h->agent_xy, h->agent_state, h->exch, h->flags, h->reward, h->gz,
-                    h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch};
+                    h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch, h->csum};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
     return DW_OK;
@@ -498,6 +499,20 @@ extern "C" int dwt_get_grid(dwt_handle *h, double *grid) {
     return DW_OK;
 }
 
+extern "C" int dwt_cover_checksum(dwt_handle *h, uint64_t *out) {
+    if (!h || !out) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->on_lattice) return dwt_fail(h, DW_E_STATE, "dwt_cover_checksum", "the state is off the lattice until the first step has run");
+    if (!h->csum) DWT_TRY(h, cudaMalloc((void **)&h->csum, 4 * sizeof(unsigned long long)));
+    unsigned long long *acc = h->csum;
+    DWT_TRY(h, cudaMemsetAsync(acc, 0, 4 * sizeof(unsigned long long), h->stream));
+    k_band_checksum<<<148 * 8, 256, 0, h->stream>>>(dwt_geom_lat(h), h->lat[h->cur], acc);
+    DWT_LAUNCHED(h);
+    DWT_TRY(h, cudaMemcpyAsync(out, acc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    DWT_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
 extern "C" int dwt_debug_slow_count(dwt_handle *h, uint64_t *count) {
     if (!h || !count) return DW_E_INVALID;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
@@ -541,6 +556,8 @@ extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, vo
     dwt_get_peer_buffers(h, own);
     PeerTable T{};
     T.rank = rank; T.R = n_ranks; T.on = 1;
+    T.timeout_clocks = 0;
+    if (const char *ms = getenv("DW_PEER_TIMEOUT_MS")) T.timeout_clocks = (long long)(atof(ms) * 1.9e6);   // ~1.9 GHz SM clock
     for (int r = 0; r < n_ranks; ++r) {
         void *const *row = table + (size_t)r * DWT_PEER_BUFFERS;
         auto pick = [&](int k) { return r == rank ? own[k] : row[k]; };

@@ -17,6 +17,7 @@ policy and the notebook's lifespan counters.
 import ctypes as C
 import json
 import os
+import weakref
 
 import numpy as np
 import numpy.random as npr
@@ -45,6 +46,13 @@ def make_neighborhood(radius=1, mode="moore"):
     out = np.zeros((2 * radius + 1, 2 * radius + 1))
     out[rr <= radius] = 1.0
     return out
+
+
+def canonical_actions8(actions):
+    """int8 action codes for the device from ANY integers, read like the reference reads them (daisy_world_rl.py:190-212:
+    a == 8 stays, else a % 4 moves (Python modulo), a > 4 grazes): 0..8 as they are, a > 8 -> 12 + a % 4, a < 0 -> a % 4."""
+    a = np.asarray(actions).astype(np.int64, copy=False)
+    return np.where((a >= 0) & (a <= 8), a, np.where(a > 8, 12 + a % 4, a % 4)).astype(np.int8)
 
 
 def _ptr(a, ctype):
@@ -141,6 +149,54 @@ def make_clock_struct(obj):
                    ramp_up_down=int(bool(obj.ramp_up_down)))
 
 
+class _PinnedPool:
+    """Page-locked host blocks for the packed outputs of step() (dw_step_packed): the device->host copy is then one DMA at
+    PCIe rate straight into the arrays the caller receives. step() must return FRESH arrays like the reference, so a block
+    goes back to the pool only when every array carved from it has been garbage-collected (weakref.finalize on the ctypes
+    buffer that is their common base). Callers that keep every observation would pin memory without bound: beyond
+    MAX_LIVE blocks in flight the outputs fall back to ordinary (pageable) memory."""
+    MAX_LIVE = 16
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._free = {}         # nbytes -> [address]
+        self._live = 0
+
+    def take(self, nbytes):
+        """A writable ctypes byte buffer of nbytes in page-locked memory, or None when too many are still referenced."""
+        free = self._free.setdefault(nbytes, [])
+        if free:
+            addr = free.pop()
+        else:
+            if self._live >= self.MAX_LIVE:
+                return None
+            p = C.c_void_p()
+            if self._lib.dw_host_alloc(C.c_uint64(nbytes), C.byref(p)) != 0 or not p.value:
+                return None
+            addr = p.value
+        self._live += 1
+        buf = (C.c_ubyte * nbytes).from_address(addr)
+        fin = weakref.finalize(buf, self._give_back, nbytes, addr)
+        fin.atexit = False
+        return buf
+
+    def _give_back(self, nbytes, addr):
+        self._live -= 1
+        self._free.setdefault(nbytes, []).append(addr)
+
+    def drain(self):
+        for lst in self._free.values():
+            for addr in lst:
+                self._lib.dw_host_free(C.c_void_p(addr))
+        self._free = {}
+
+
+# attributes whose assignment has to reach the device before the next device operation (dw_set_config / dw_set_clock)
+_CFG_ATTRS = frozenset(("p", "g", "S", "sigma", "gamma", "q", "q2", "temp_optimal", "dt", "agent_gamma", "albedo_bare", "albedo_light",
+                        "albedo_dark", "daisy_kernel", "adjacent_albedo_kernel", "neighborhood"))
+_CLK_ATTRS = frozenset(("L", "dL", "min_L", "max_L", "ddL", "step_count", "ramp_period", "ramp_up_down"))
+
+
 class _Mirror:
     """Host mirror of one device array with write detection."""
     __slots__ = ("pristine", "handed", "assigned")
@@ -166,7 +222,18 @@ class _Mirror:
 class RLDaisyWorld:
     _DIAG_ATTRS = ("temp", "temp_light", "temp_dark", "temp_effective", "beta", "beta_l", "beta_d", "growth")
 
+    def __setattr__(self, name, value):
+        # the constants and the luminosity clock are plain mutable attributes like the reference's; assigning one marks the
+        # device copy stale (pushed by the next device operation) instead of re-sending everything on every step
+        if name in _CFG_ATTRS:
+            self.__dict__["_cfg_dirty"] = True
+        elif name in _CLK_ATTRS:
+            self.__dict__["_clk_dirty"] = True
+        object.__setattr__(self, name, value)
+
     def __init__(self, **kwargs):
+        self._cfg_dirty = self._clk_dirty = True
+        self._arr_sig = None
         set_default_attributes(self, **kwargs)
 
         # additions (not in the reference)
@@ -177,6 +244,8 @@ class RLDaisyWorld:
         self._m = {"grid": _Mirror(), "agent_indices": _Mirror(), "agent_states": _Mirror()}
         self._diag_cache = {}
         self._dead_L = None
+        self._pool = _PinnedPool(self._lib)
+        self._layout = None
 
         self.initialize_neighborhood()
         self.initialize_agents()
@@ -188,6 +257,8 @@ class RLDaisyWorld:
             if getattr(self, "_h", None):
                 self._lib.dw_destroy(self._h)
                 self._h = None
+            if getattr(self, "_pool", None):
+                self._pool.drain()
         except Exception:
             pass
 
@@ -202,11 +273,14 @@ class RLDaisyWorld:
                        ddL=float(self.ddL), step_count=int(self.step_count), ramp_period=int(self.ramp_period),
                        ramp_up_down=int(bool(self.ramp_up_down)))
 
+    def _adopt_clock(self, clk):
+        """Mirror the clock the device has advanced (no dirty mark: host and device agree)."""
+        self.__dict__.update(L=clk.L, dL=clk.dL, min_L=clk.min_L, max_L=clk.max_L, step_count=int(clk.step_count))
+
     def _pull_clock(self):
         clk = DwClock()
         self._check(self._lib.dw_get_clock(self._h, C.byref(clk)), "dw_get_clock")
-        self.L, self.dL, self.min_L, self.max_L = clk.L, clk.dL, clk.min_L, clk.max_L
-        self.step_count = int(clk.step_count)
+        self._adopt_clock(clk)
 
     def _ensure_handle(self, shape):
         """(Re)create the device handle when batch_size / dim / n_agents changed (they are re-read at reset())."""
@@ -226,6 +300,9 @@ class RLDaisyWorld:
             raise _lib.DaisyWorldError(f"dw_create failed (code {rc}): {msg.decode() if msg else ''}")
         self._h = h
         self._shape = shape
+        self._cfg_dirty = self._clk_dirty = True
+        self._layout = None
+        self._pool.drain()
         for m in self._m.values():
             m.invalidate()
 
@@ -234,11 +311,19 @@ class RLDaisyWorld:
         if self._h is None:
             raise _lib.DaisyWorldError("environment has no device state; call reset()")
         B, N, n = self._shape
-        cfg = self._config()
-        cfg.batch, cfg.dim, cfg.n_agents = B, N, n      # shapes of live state only change at reset()
-        self._check(self._lib.dw_set_config(self._h, C.byref(cfg)), "dw_set_config")
-        clk = self._clock()
-        self._check(self._lib.dw_set_clock(self._h, C.byref(clk)), "dw_set_clock")
+        # in-place edits of the small kernel arrays (env.daisy_kernel[...] = x) bypass __setattr__: compare their bytes
+        sig = (np.asarray(self.daisy_kernel).tobytes(), np.asarray(self.adjacent_albedo_kernel).tobytes(),
+               np.asarray(self.neighborhood).tobytes())
+        if self._cfg_dirty or sig != self._arr_sig:
+            cfg = self._config()
+            cfg.batch, cfg.dim, cfg.n_agents = B, N, n      # shapes of live state only change at reset()
+            self._check(self._lib.dw_set_config(self._h, C.byref(cfg)), "dw_set_config")
+            self._cfg_dirty = False
+            self._arr_sig = sig
+        if self._clk_dirty:
+            clk = self._clock()
+            self._check(self._lib.dw_set_clock(self._h, C.byref(clk)), "dw_set_clock")
+            self._clk_dirty = False
         g = ai = st = None
         if self._m["grid"].dirty():
             g = np.ascontiguousarray(self._m["grid"].handed, dtype=np.float64)
@@ -337,14 +422,12 @@ class RLDaisyWorld:
         env.temp.mean() --, mean light cover, mean dark cover): reduced inside the fused kernel for 64x64 worlds with at most 32
         agents, sampled between one-step launches for every other shape."""
         B, N, n = self._shape
-        if self.collision_mode == 1 and n:
-            raise NotImplementedError("collision_mode == 1 draws from the caller's NumPy stream every step: use step() / "
-                                      "step_policy(); multi-step device runs are for collision_mode == 0")
+        colliding = self.collision_mode == 1 and n      # noise from the caller's NumPy stream every step: host-driven loop
         a8 = None
         if policy == "replay":
-            a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
+            a8 = np.ascontiguousarray(canonical_actions8(np.asarray(actions).reshape(-1, B, n)[:K]))
         out = np.zeros((int(K), 3))
-        if N != 64 or n > 32 or policy == "mlp":
+        if N != 64 or n > 32 or policy == "mlp" or colliding:
             # other shapes: one fused step per sample, the same three means from the device-side reductions
             for t in range(int(K)):
                 self.run(1, policy=policy, actions=None if a8 is None else a8[t:t + 1], seed=seed)
@@ -536,42 +619,65 @@ class RLDaisyWorld:
             a = self._action(action)
         return self._step_collect(a, -1, 0)
 
-    def _step_collect(self, a, policy, seed):
-        """One dw_step_collect call: the step and everything step() returns, one synchronisation."""
+    def _out_views(self, want_obs):
+        """A fresh block for dw_step_packed and the arrays step() returns carved out of it (layout: dw_step_out_layout)."""
+        B, N, n = self._shape
+        if self._layout is None:
+            lay = (C.c_int64 * 4)()
+            self._check(self._lib.dw_step_out_layout(self._h, lay), "dw_step_out_layout")
+            self._layout = tuple(int(v) for v in lay)
+        r_off, d_off, o_off, total = self._layout
+        nbytes = total if (want_obs and n) else o_off
+        buf = self._pool.take(nbytes)
+        if buf is None:                              # many earlier outputs still referenced: ordinary memory
+            buf = np.empty(nbytes, dtype=np.uint8)
+            ptr = buf.ctypes.data_as(C.c_void_p)
+        else:
+            ptr = C.cast(buf, C.c_void_p)
+        m = n if n else 2
+        reward = np.frombuffer(buf, dtype=np.float64, count=B * m, offset=r_off).reshape((B, n, 1) if n else (B, 2))
+        done = np.frombuffer(buf, dtype=np.uint8, count=B * m, offset=d_off).reshape(reward.shape).view(np.bool_)
+        obs = None
+        if want_obs:
+            obs = (np.frombuffer(buf, dtype=np.float64, count=B * n * 63, offset=o_off) if n else np.empty(0)).reshape(B, n, self.ch, 3, 3)
+        return ptr, obs, reward, done
+
+    def _step_collect(self, a, policy, seed, want_obs=True):
+        """One step and everything step() returns: one C call, one device->host copy, one synchronisation."""
         B, N, n = self._shape
         self._push()
         self._dead_L = self.L
-        obs = np.empty((B, n, self.ch, 3, 3))
-        shape = (B, n, 1) if n else (B, 2)
-        reward = np.empty(shape)
-        done = np.empty(shape, dtype=np.uint8)
         clk = DwClock()
         if self.collision_mode == 1 and n:
-            if policy == DW_POLICY["mlp"]:
-                raise NotImplementedError("collision_mode == 1 with the device MLP policy: pass the MLP's actions to step()")
+            obs = np.empty((B, n, self.ch, 3, 3))
+            reward = np.empty((B, n, 1))
+            done = np.empty((B, n, 1), dtype=np.uint8)
             self._update_agents_colliding(a, policy, seed)
             rc = self._lib.dw_step_tail_collect(self._h, _ptr(obs, C.c_double), _ptr(reward, C.c_double), _ptr(done, C.c_uint8),
                                                 C.byref(clk))
             self._check(rc, "dw_step_tail_collect")
+            done = done.astype(bool)
         else:
-            rc = self._lib.dw_step_collect(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
-                                           0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), _ptr(obs, C.c_double),
-                                           _ptr(reward, C.c_double), _ptr(done, C.c_uint8), C.byref(clk))
-            self._check(rc, "dw_step_collect")
+            ptr, obs, reward, done = self._out_views(want_obs)
+            rc = self._lib.dw_step_packed(self._h, None if a is None else _ptr(a, C.c_int64), 0 if a is None else a.shape[0],
+                                          0 if a is None else a.shape[1], int(policy), C.c_uint64(seed), int(bool(want_obs)), ptr,
+                                          C.byref(clk))
+            self._check(rc, "dw_step_packed")
         self._state_changed()
-        self.L, self.dL, self.min_L, self.max_L = clk.L, clk.dL, clk.min_L, clk.max_L
-        self.step_count = int(clk.step_count)
+        self._adopt_clock(clk)
         if not n:
             reward = reward.astype(bool)
-        return obs, reward, done.astype(bool), {}
+        return obs, reward, done, {}
 
     def __call__(self, grid):
         pass
 
     # ------------------------------------------------------------------ additions: fused path
-    def step_policy(self, policy="greedy", seed=0):
-        """One step with the action chosen on the device (Greedy's deterministic branch fused in)."""
-        return self._step_collect(None, DW_POLICY[policy], seed)
+    def step_policy(self, policy="greedy", seed=0, want_obs=True):
+        """One step with the action chosen on the device (Greedy's deterministic branch, or the MLP of set_mlp, fused in).
+        want_obs=False returns None for the observation and leaves it on the device (the policy reads it there; observe()
+        fetches it later): the step's device->host traffic drops from 504 to 9 bytes per agent."""
+        return self._step_collect(None, DW_POLICY[policy], seed, want_obs=want_obs)
 
     def set_epsilon(self, epsilon):
         """Greedy.epsilon (agents/greedy.py:8) for policy="eps_greedy": per step ONE coin for the whole ensemble decides
@@ -630,7 +736,7 @@ class RLDaisyWorld:
         B, N, n = self._shape
         a8 = None
         if policy == "replay":
-            a8 = np.ascontiguousarray(np.asarray(actions).reshape(-1, B, n)[:K], dtype=np.int8)
+            a8 = np.ascontiguousarray(canonical_actions8(np.asarray(actions).reshape(-1, B, n)[:K]))
             if a8.shape[0] < K:
                 raise ValueError("replay needs at least K action frames")
         if self.collision_mode == 1 and n:
@@ -649,8 +755,6 @@ class RLDaisyWorld:
         """run() with collision_mode == 1: the collision noise comes from the caller's NumPy stream every step (reference
         :220-242), so the loop is driven from here, one materialising step at a time; policy decisions, moves, grazing,
         collisions, forward and the lifespan counters stay on the device."""
-        if policy == "mlp":
-            raise NotImplementedError("collision_mode == 1 with the device MLP policy: pass the MLP's actions (policy='replay')")
         steps, alive, hit = 0, self._shape[0], False
         count = C.c_int64(0)
         self._push()                 # once: inside the loop the clock lives on the device (a push would rewind it)
@@ -693,6 +797,12 @@ class RLDaisyWorld:
         self._dead_L = self.L
         self._diag_cache = {}
         self._pending_agents = None
+
+    def residency(self):
+        """Where the live state sits on the device: dict(grid=, lattice=, cover_planes=, pre=) (dw_debug_state)."""
+        f = (C.c_int32 * 4)()
+        self._check(self._lib.dw_debug_state(self._h, f), "dw_debug_state")
+        return dict(grid=bool(f[0]), lattice=bool(f[1]), cover_planes=bool(f[2]), pre=int(f[3]))
 
     def synchronize(self):
         self._check(self._lib.dw_synchronize(self._h), "dw_synchronize")
