@@ -15,7 +15,9 @@ one NCCL all-reduce of the 8-double lifespan-statistics vector per bench step, i
 
 The same JSON line carries, under "giant_grid", a second measured workload (not the headline): BASELINE configs[4], one
 16384x16384 toroidal world with 16384 greedy agents, row-banded over the N GPUs (strong scaling; halo rows + two small
-all-reduces per step over NCCL), timed with CUDA events, max over ranks.  --no-extras skips it.
+all-reduces per step over NCCL), timed with CUDA events, max over ranks; under "sustained" seconds-long whole-life
+ensembles (configs[2] shape at N = 1, configs[3] at N > 1) with the clocks sampled; under "dropin_step" single env.step()
+calls through the Python drop-in.  --no-extras skips the three.
 """
 import argparse
 import ctypes as C
@@ -46,30 +48,53 @@ WORKLOAD = (f"BASELINE configs[1]: {WORLDS}-world ensemble per GPU, {N}x{N}, lig
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def _ref_worker(args):
-    """One host process: its share of the ensemble stepped by the NumPy port (FFT convolutions like the reference)."""
-    rank, worlds, steps_per_sample, n_samples, warm = args
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def have_reference():
+    """The UNMODIFIED reference installed by baseline/install_ref.py (git-ignored, travels with the snapshot)."""
+    return os.path.exists(os.path.join(REF_DIR, "daisy", "nn", "functional.py"))
+
+
+def make_cpu_env(worlds, seed):
+    """(env, policy, kind): the reference's own RLDaisyWorld + Greedy from baseline/_ref when present ("reference"), else
+    the NumPy port with the same FFT convolutions and Python agent loops ("port")."""
     import warnings
     warnings.filterwarnings("ignore")
-    from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy
-    os.environ["OMP_NUM_THREADS"] = "1"
-    np.random.seed(SEED + rank)
-    env = OracleDaisyWorld(conv="fft", grid_dimension=N, n_agents=N_AGENTS)
+    np.random.seed(seed)
+    if have_reference():
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        from daisy.daisy_world_rl import RLDaisyWorld as RefWorld
+        from daisy.agents.greedy import Greedy
+        env = RefWorld(grid_dimension=N, n_agents=N_AGENTS)
+        agent, kind = Greedy(), "reference"
+    else:
+        from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy
+        env = OracleDaisyWorld(conv="fft", grid_dimension=N, n_agents=N_AGENTS)
+        agent, kind = OracleGreedy(), "port"
     env.batch_size = worlds
+    return env, agent, kind
+
+
+def _ref_worker(args):
+    """One host process: its share of the ensemble stepped by the reference's CPU implementation."""
+    rank, worlds, steps_per_sample, n_samples, warm = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    env, agent, kind = make_cpu_env(worlds, SEED + rank)
     obs = env.reset()
-    agent = OracleGreedy()
     out = []
     for s in range(warm + n_samples):
         t0 = time.perf_counter()
         for _ in range(steps_per_sample):
             obs, _, _, _ = env.step(agent(obs))
         out.append(time.perf_counter() - t0)
-    return out[warm:]
+    return out[warm:], kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's NumPy CPU path (oracle port: the reference is Python and cannot travel to the
-    GPU box), all host cores, on a bounded sample of the same workload."""
+    """--impl reference: the reference's own NumPy CPU path (the unmodified reference from baseline/_ref when it travelled,
+    else the oracle port), all host cores, on a bounded sample of the same workload."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -82,19 +107,22 @@ def run_reference(args):
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        times = pool.map(_ref_worker, [(i, per[i], steps_per_sample, K, W) for i in range(procs)])
+        res = pool.map(_ref_worker, [(i, per[i], steps_per_sample, K, W) for i in range(procs)])
+    times, kind = [r[0] for r in res], res[0][1]
     per_step = np.max(np.array(times), axis=0)          # slowest process bounds each step
     total = float(per_step.sum())
     cells = WORLDS * N * N * steps_per_sample * K
     value = cells / total
-    sample = f"{WORLDS} worlds x {steps_per_sample} env steps per bench step, split over {procs} processes"
+    sample = (f"{WORLDS} worlds x {steps_per_sample} env steps per bench step, split over {procs} processes; "
+              + ("unmodified reference RLDaisyWorld + Greedy from baseline/_ref" if kind == "reference"
+                 else "NumPy port (oracle/daisy_numpy.py, FFT convolutions): baseline/_ref absent"))
     line = {
         "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "env_steps_per_s": WORLDS * steps_per_sample * K / total,
-        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -181,24 +209,76 @@ def load_traffic():
 
 
 def cpu_baseline_sample():
-    """Reference NumPy path (oracle port, FFT convolutions, Python agent loops), 1 core, bounded sample."""
-    import warnings
-    warnings.filterwarnings("ignore")
-    from oracle.daisy_numpy import OracleDaisyWorld, OracleGreedy
-    np.random.seed(SEED)
-    env = OracleDaisyWorld(conv="fft", grid_dimension=N, n_agents=N_AGENTS)
-    env.batch_size = WORLDS
+    """The reference's CPU path (unmodified reference from baseline/_ref when present, else the NumPy port), 1 core,
+    bounded sample."""
+    env, agent, kind = make_cpu_env(WORLDS, SEED)
     obs = env.reset()
-    agent = OracleGreedy()
     obs, _, _, _ = env.step(agent(obs))                   # warm-up
     steps = 5
     t0 = time.perf_counter()
     for _ in range(steps):
         obs, _, _, _ = env.step(agent(obs))
     dt = time.perf_counter() - t0
-    return {"value": WORLDS * N * N * steps / dt, "unit": "cell-updates/s", "cores": 1, "kind": "port",
-            "sample": f"{WORLDS} worlds x {N}x{N} x {steps} env steps after 1 warm-up, NumPy port with FFT convolutions",
+    what = "unmodified reference (baseline/_ref)" if kind == "reference" else "NumPy port with FFT convolutions"
+    return {"value": WORLDS * N * N * steps / dt, "unit": "cell-updates/s", "cores": 1, "kind": kind,
+            "sample": f"{WORLDS} worlds x {N}x{N} x {steps} env steps after 1 warm-up, {what}",
             "env_steps_per_s": WORLDS * steps / dt, "seconds": dt}
+
+
+# ----------------------------------------------------------------------------------------------- sustained ensembles
+def sustained_bench(rank, world, local):
+    """Seconds-long runs on the fused path, device-timed, clocks sampled (the headline's timed region is ~0.1 s).
+    N = 1: BASELINE configs[2] shape -- 100 000 worlds of 64x64 with 4 agents, WHOLE LIVES under the notebook's stopping rule
+    (64-step segments, device checkpoint + rewind), four of its conditions back to back (>= 2 s of device time).
+    N > 1: BASELINE configs[3] -- 125 000 worlds per GPU (10^6 at N = 8), random agents, whole lives, worlds sharded with no
+    data-path collective; per 64-step segment one MIN all-reduce of the all-done flags, at the end ONE NCCL all-reduce of the
+    8-double lifespan statistics."""
+    import torch
+    import torch.distributed as dist
+    from therldaisyworld_b200 import RLDaisyWorld
+    from therldaisyworld_b200.ensemble import DeviceShard, shard_range, simulate_lifespan
+    total = 100_000 if world == 1 else 125_000 * world
+    lo, hi = shard_range(total, world, rank)
+    np.random.seed(0)
+    env = RLDaisyWorld(grid_dimension=N, n_agents=N_AGENTS, device=local)
+    env.batch_size = hi - lo
+    conditions = ([("light/dark", "greedy"), ("light/dark", "random"), ("neutral", "greedy"), ("neutral", "antigreedy")]
+                  if world == 1 else [("light/dark", "random")])
+    sampler = ClockSampler(local) if rank == 0 else None
+    out, dev_ms, cells = [], 0.0, 0
+    for albedo, policy in conditions:
+        env.albedo_light, env.albedo_dark = (0.75, 0.25) if albedo == "light/dark" else (0.5, 0.5)
+        env.reset_on_device(seed=SEED, world_offset=lo)
+        env.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = simulate_lifespan(DeviceShard(env, world_offset=lo), policy=policy, seed=7, device="cuda")
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        c = r["worlds"] * N * N * r["steps"]
+        dev_ms += ms
+        cells += c
+        out.append({"albedo": albedo, "policy": policy, "worlds": r["worlds"], "steps_to_last_death": r["steps"], "device_ms": ms,
+                    "cell_updates_per_s": c / (ms * 1e-3), "env_steps_per_s": r["worlds"] * r["steps"] / (ms * 1e-3),
+                    "biosphere_lifespan": [r["biosphere_lifespan_mean"], r["biosphere_lifespan_sem"]],
+                    "agent_lifespan": [r.get("agent_lifespan_mean"), r.get("agent_lifespan_sem")]})
+    clocks = sampler.stop() if sampler else None
+    del env
+    torch.cuda.empty_cache()
+    return {"workload": (f"BASELINE configs[2] shape: {total} worlds x {N}x{N}, {N_AGENTS} agents, whole lives (stopping rule, "
+                         "checkpoint + rewind per 64-step segment), 4 conditions") if world == 1 else
+                        (f"BASELINE configs[3]: {total} worlds ({total // world} per GPU) x {N}x{N}, random agents, whole lives, "
+                         "one NCCL all-reduce of the 8-double statistics + one MIN all-reduce per 64-step segment"),
+            "metric": "cell_updates_per_s", "value": cells / (dev_ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world,
+            "device_seconds": dev_ms * 1e-3, "scaling": "weak", "conditions": out, "clocks": clocks,
+            "timing": "CUDA events around each condition (incl. the segment read-backs and checkpoints), max over ranks"}
 
 
 # ----------------------------------------------------------------------------------------------- giant grid (configs[4])
@@ -459,6 +539,12 @@ def run_product(args):
         except Exception as e:                                    # the headline line must survive
             giant = {"error": repr(e)}
 
+    sustained = None
+    if not args.no_extras:
+        try:
+            sustained = sustained_bench(rank, world, local)
+        except Exception as e:
+            sustained = {"error": repr(e)}
     dropin = None
     if rank == 0 and not args.no_extras:
         # the path every reference caller uses: ONE env.step() per step through the Python drop-in (lattice-resident state,
@@ -514,6 +600,7 @@ def run_product(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "giant_grid": giant,
+            "sustained": sustained,
             "dropin_step": dropin,
             "check": {"mean_done_at_after_T": mean_life, "mean_done_at_after_T_e2e": mean_life_e2e, "expected": float(T_STEPS),
                       "ensemble_stats": stats.tolist(),

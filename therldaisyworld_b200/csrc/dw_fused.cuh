@@ -678,17 +678,25 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
     const int tx = tid & 15, r0 = (tid >> 4) * 4;
     const int n_items = A.n_pairs * A.n_chunks;      // n_pairs = number of worlds for this kernel
 
-    for (;;) {
-        if (tid == 0) sm.item = (int)atomicAdd(A.queue, 1u);
-        __syncthreads();
-        const int t = sm.item;
+    for (int it = 0;; ++it) {
+        int t;
+        if (A.queue) {                       // dynamic work queue (multi-chunk launches)
+            if (tid == 0) sm.item = (int)atomicAdd(A.queue, 1u);
+            __syncthreads();
+            t = sm.item;
+        } else {                             // single-chunk launch (step()): static round-robin, nothing to zero beforehand
+            t = blockIdx.x + it * gridDim.x;
+            __syncthreads();                 // shared memory of the previous item is free
+        }
         if (t >= n_items) break;
         const int c = t / A.n_pairs, b = t - c * A.n_pairs;
-        if (tid == 0) {
-            while (atomicAdd(A.pair_done + b, 0u) < (unsigned)c) __nanosleep(200);
-            __threadfence();
+        if (A.queue) {
+            if (tid == 0) {
+                while (atomicAdd(A.pair_done + b, 0u) < (unsigned)c) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
         }
-        __syncthreads();
         const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
         {
             const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat + (size_t)b * NN);
@@ -711,7 +719,9 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             const int j = j0 + jl;
             uint32_t *cb = sm.buf[jl & 1], *nb = sm.buf[(jl + 1) & 1];
             if (warp == 0 && n > 0) dw_agents_phase32(A, j, b, cb, sm, lane, n);
-            __syncthreads();
+#ifndef DW_X_NOSYNC1            // timing experiments only (results are garbage without the barriers): upper bound of what removing
+            __syncthreads();    // a barrier could buy, see DESIGN.md section 4
+#endif
             if (j == A.K - 1) {
                 uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
 #pragma unroll
@@ -736,7 +746,9 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
                 cd = __reduce_add_sync(0xffffffffu, cd);
                 if (lane == 0) { atomicAdd(&s_tsum, tsum); atomicAdd(&s_cov[0], cl); atomicAdd(&s_cov[1], cd); }
             }
+#ifndef DW_X_NOSYNC2
             __syncthreads();
+#endif
             if (DIAG && tid == 0) {
                 atomicAdd(A.series_T + j, s_tsum);
                 atomicAdd(A.series_l + j, (unsigned long long)s_cov[0]);
@@ -774,7 +786,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (A.queue && tid == 0) {
             __threadfence();
             atomicExch(A.pair_done + b, (unsigned)(c + 1));
         }
@@ -949,17 +961,25 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
     const int row_base = (ty / TX) * N, lr0 = (ty % TX) * 4, r0 = ty * 4;
     const int n_items = A.n_pairs * A.n_chunks;        // n_pairs = number of world groups
 
-    for (;;) {
-        if (tid == 0) sm.item = (int)atomicAdd(A.queue, 1u);
-        __syncthreads();
-        const int t = sm.item;
+    for (int it = 0;; ++it) {
+        int t;
+        if (A.queue) {
+            if (tid == 0) sm.item = (int)atomicAdd(A.queue, 1u);
+            __syncthreads();
+            t = sm.item;
+        } else {                             // single-chunk launch: static round-robin (see k_fused_n64_persist)
+            t = blockIdx.x + it * gridDim.x;
+            __syncthreads();
+        }
         if (t >= n_items) break;
         const int c = t / A.n_pairs, g = t - c * A.n_pairs;
-        if (tid == 0) {
-            while (atomicAdd(A.pair_done + g, 0u) < (unsigned)c) __nanosleep(200);
-            __threadfence();
+        if (A.queue) {
+            if (tid == 0) {
+                while (atomicAdd(A.pair_done + g, 0u) < (unsigned)c) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
         }
-        __syncthreads();
         const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
         const int n_worlds = min(W, B - g * W);
         const int n_act = n_worlds * n;
@@ -1049,7 +1069,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (A.queue && tid == 0) {
             __threadfence();
             atomicExch(A.pair_done + g, (unsigned)(c + 1));
         }

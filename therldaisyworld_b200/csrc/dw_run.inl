@@ -169,11 +169,13 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         if (A.Kc < 1) A.Kc = 1;
         A.n_pairs = h->cfg.batch;
         A.n_chunks = (K + A.Kc - 1) / A.Kc;
-        rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
-        if (rc) return rc;
-        DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
-        A.queue = h->persist_sync;
-        A.pair_done = h->persist_sync + 1;
+        if (A.n_chunks > 1) {
+            rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
+            if (rc) return rc;
+            DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
+            A.queue = h->persist_sync;
+            A.pair_done = h->persist_sync + 1;
+        }                                             // else: one chunk per world (step()): static assignment, no queue to zero
         A.lat = h->lat[h->lcur];                      // in place
         const long long items = (long long)A.n_pairs * A.n_chunks;
         const int grid = (int)(items < h->persist_blocks ? items : h->persist_blocks);
@@ -204,11 +206,13 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         if (A.Kc < 1) A.Kc = 1;
         A.n_pairs = (h->cfg.batch + W - 1) / W;
         A.n_chunks = (K + A.Kc - 1) / A.Kc;
-        rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
-        if (rc) return rc;
-        DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
-        A.queue = h->persist_sync;
-        A.pair_done = h->persist_sync + 1;
+        if (A.n_chunks > 1) {
+            rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
+            if (rc) return rc;
+            DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
+            A.queue = h->persist_sync;
+            A.pair_done = h->persist_sync + 1;
+        }
         A.lat = h->lat[h->lcur];                      // in place
         const long long items = (long long)A.n_pairs * A.n_chunks;
         const int grid = (int)(items < blocks ? items : blocks);
