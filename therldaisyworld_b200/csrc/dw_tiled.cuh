@@ -470,6 +470,62 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
     }
 }
 
+// ---- look-ahead decisions (peer-memory mode) ---------------------------------------------------------------------------
+// The greedy decision of step j+1 reads the four neighbours of the agent in the lattice step j PRODUCES -- 4 cells per
+// agent out of N x R. Waiting for the whole stencil to finish puts decide + its barrier on the critical path of every
+// step; instead the owner band re-evaluates just those cells itself from the step's INPUT lattice (post-graze `lat_old`,
+// same fast path + literal tie fix-up as k_tiled_step, hence the same values) while the interior tiles are still being
+// computed on the main stream. Neighbours that sit in a ghost row belong to the neighbouring band: those come from the
+// NEW ghost rows, which the halo push + barrier that precede this kernel on the side stream have delivered.
+struct LookArgs {
+    DevParams P;
+    FastCoef F;
+    StepCoef C;
+};
+__device__ __forceinline__ uint32_t dwt_new_cell(const LookArgs &A, const BandGeom &G, const uint32_t *__restrict__ lat_old,
+                                                 const uint32_t *__restrict__ lat_new, int r, int yc) {
+    if (r == 0 || r == G.R + 1) return lat_new[(size_t)r * G.pitch + G.c0 + yc];
+    const uint32_t *p = lat_old + (size_t)r * G.pitch + G.c0 + yc;
+    const uint32_t *q0 = p - G.pitch, *q2 = p + G.pitch;
+    const uint32_t E = p[-1] + p[1] + q0[0] + q2[0];
+    const uint32_t S8 = E + q0[-1] + q0[1] + q2[-1] + q2[1];
+    unsigned tiemin = 0xffffffffu;
+    uint32_t v = dw_fast_cell(A.F, A.C, p[0], E, S8, &tiemin);
+    if (tiemin < A.F.tie_thresh) {
+        double l9[9], d9[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t w = p[(a - 1) * G.pitch + (c - 1)];
+                l9[a * 3 + c] = dw_milli(w & 0xffffu);
+                d9[a * 3 + c] = dw_milli(w >> 16);
+            }
+        const LitCell lc = dw_literal_cell(A.P, A.C.SL, l9, d9);
+        v = dw_pack((int)rint(lc.nl * 1000.0), (int)rint(lc.nd * 1000.0));
+    }
+    return v;
+}
+__global__ void __launch_bounds__(256) k_band_lookahead_decide(BandGeom G, const uint32_t *__restrict__ lat_old,
+                                                               const uint32_t *__restrict__ lat_new, const int32_t *__restrict__ xy, int n,
+                                                               int policy, PeerTable PT, const __grid_constant__ LookArgs A,
+                                                               unsigned int epoch, unsigned int *timed_out, unsigned int *ticket) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int x = xy[2 * i], y = xy[2 * i + 1];
+        const int lr = band_owned_row(G, x);
+        if (lr >= 0) {
+            const int ym = y == 0 ? G.N - 1 : y - 1, yp = y == G.N - 1 ? 0 : y + 1;
+            // candidates in action order 4..7 = (x, y-1), (x-1, y), (x+1, y), (x, y+1), like k_band_decide_one
+            const double food[4] = {dw_food(dwt_new_cell(A, G, lat_old, lat_new, lr, ym)), dw_food(dwt_new_cell(A, G, lat_old, lat_new, lr - 1, y)),
+                                    dw_food(dwt_new_cell(A, G, lat_old, lat_new, lr + 1, y)), dw_food(dwt_new_cell(A, G, lat_old, lat_new, lr, yp))};
+            const double out = (double)(dw_greedy_pick(food, policy == DW_POLICY_GREEDY) + 1);
+            for (int p = 0; p < PT.R; ++p) PT.exch[p][2 * (size_t)n + i] = out;     // owner publishes to every rank
+        }
+    }
+    dw_last_block_barrier(PT, epoch, timed_out, ticket);
+}
+
 // ---- materialisation / synthetic reset -------------------------------------------------------------------------------
 // full reference grid [7, R, N] of the band, materialised by a literal forward from the post-graze state the last step
 // started from: the other lattice buffer, or the fp64 planes when that step was the first one after a reset

@@ -35,6 +35,14 @@ struct dwt_handle {
     int gain_parity = 0, pending_parity = 0;
     unsigned int decide_epoch = 0;             // != 0: the next dwt_decide launch ends in a barrier with this epoch
     bool p2p_gain_pending = false;
+    // peer-memory mode, two-stream step: side stream for the halo push / barriers / look-ahead decisions, which run under
+    // the interior tiles of the stencil on the main stream
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_edge = nullptr, ev_side = nullptr;
+    bool look_valid = false;                   // act[] already holds the decisions of the NEXT step (k_band_lookahead_decide)
+    int look_policy = -1;
+    int64_t look_step = -1;
+    int overlap = 1;                           // DW_P2P_OVERLAP=0: the one-stream sequence of round 1 (for comparison)
     bool step_open = false;      // dwt_stencil(part 1) done, part 2 pending
     uint8_t *gz = nullptr, *done = nullptr;
     int8_t *replay = nullptr;
@@ -141,6 +149,9 @@ extern "C" int dwt_destroy(dwt_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
+    if (h->ev_edge) cudaEventDestroy(h->ev_edge);
+    if (h->ev_side) cudaEventDestroy(h->ev_side);
     void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->claim2, h->agent_xy, h->agent_state, h->exch, h->flags, h->reward, h->gz,
                     h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch, h->csum};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -180,6 +191,7 @@ static void dwt_state_reset(dwt_handle *h) {
     h->on_lattice = false;
     h->have_pre = false;
     h->chunk_j = 0;
+    h->look_valid = false;
 }
 
 extern "C" int dwt_upload_covers(dwt_handle *h, const double *light, const double *dark) {
@@ -575,7 +587,7 @@ extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, vo
         const void *ks[] = {(const void *)k_band_decide<LatCells>, (const void *)k_band_decide<PlaneCells>, (const void *)k_band_move_claim,
                             (const void *)k_band_graze<LatCells>, (const void *)k_band_graze<PlaneCells>, (const void *)k_band_finish,
                             (const void *)k_band_first_step, (const void *)k_tiled_step, (const void *)k_band_push_halo,
-                            (const void *)k_band_finish_move_claim,
+                            (const void *)k_band_finish_move_claim, (const void *)k_band_lookahead_decide,
                             (const void *)k_peer_barrier, (const void *)k_band_covers, (const void *)k_band_materialise<PreLattice>,
                             (const void *)k_band_materialise<PrePlanes>, (const void *)k_band_stamp_claim, (const void *)k_band_stamp_write,
                             (const void *)k_band_ghost_rows_wrap, (const void *)k_band_init_random};
@@ -593,6 +605,13 @@ extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, vo
     h->epoch = 0;
     h->gain_parity = 0;
     h->p2p_gain_pending = false;
+    h->look_valid = false;
+    if (!h->stream_b) {
+        DWT_TRY(h, cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking));
+        DWT_TRY(h, cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
+        DWT_TRY(h, cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+    }
+    if (const char *ov = getenv("DW_P2P_OVERLAP")) h->overlap = atoi(ov);
     return DW_OK;
 }
 
@@ -617,20 +636,34 @@ extern "C" int dwt_ipc_attach(dwt_handle *h, int32_t rank, int32_t n_ranks, cons
 // One env step of a band in peer-memory mode: no collective, no host synchronisation. Every rank must call it the same
 // number of times with the same policy. The agents of the step are finished (state += gain, reward/done) at the start of
 // the next step or by dwt_flush_p2p.
+//
+// Two streams (h->overlap, default): the main stream runs   [decide + barrier, only when no look-ahead decisions exist]
+//   finish(j-1)+move+claim(j) -> graze(j) -> stencil of the two EDGE tile rows -> stencil of the interior tile rows;
+// the side stream, started by an event after the edge tiles, runs under the interior tiles
+//   push of the new edge rows into the neighbours' ghost rows + closing barrier of step j
+//   -> look-ahead decisions of step j+1 (k_band_lookahead_decide) + barrier,
+// and the main stream waits for it before the next step's move. What is left on the critical path of a step besides the
+// stencil are the two small agent kernels.
 extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed) {
     if (!h) return DW_E_INVALID;
     if (!h->pt.on) return dwt_fail(h, DW_E_STATE, "dwt_step_p2p", "attach the peers first (dwt_ipc_attach / dwt_attach_peers)");
     int rc = DW_OK;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    const bool overlap = h->overlap != 0;
+    const bool was_on_lattice = h->on_lattice;
     if (h->n) {
         // decisions that read the world are published by the owner ranks: the decide kernel ends in a barrier (raised by
         // its last block) so that everyone has every decision before anyone moves
         const int pol = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)h->clk.step_count);
         const bool world_policy = pol == DW_POLICY_GREEDY || pol == DW_POLICY_ANTIGREEDY;
-        h->decide_epoch = world_policy ? ++h->epoch : 0u;
-        rc = dwt_decide(h, policy, actions, seed);
-        h->decide_epoch = 0u;
-        if (rc) return rc;
+        const bool have = h->look_valid && h->look_policy == pol && h->look_step == h->clk.step_count;
+        h->look_valid = false;
+        if (!have) {
+            h->decide_epoch = world_policy ? ++h->epoch : 0u;
+            rc = dwt_decide(h, policy, actions, seed);
+            h->decide_epoch = 0u;
+            if (rc) return rc;
+        }
         // finish of the previous step (its gains are complete since its closing barrier) + move + claims, one launch
         const BandGeom G = h->on_lattice ? dwt_geom_lat(h) : dwt_geom_planes(h);
         double *gain_prev = h->pending_parity ? h->exch : h->exch + h->n;
@@ -645,15 +678,48 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
         h->pending_parity = h->gain_parity;
         h->gain_parity ^= 1;
     }
-    rc = dwt_stencil(h, 0);
-    if (rc) return rc;
-    // edge rows into the neighbours' ghost rows, then the closing barrier of the step (same launch)
     const int up = (h->pt.rank + h->pt.R - 1) % h->pt.R, down = (h->pt.rank + 1) % h->pt.R;
+    if (!overlap) {
+        rc = dwt_stencil(h, 0);
+        if (rc) return rc;
+        // edge rows into the neighbours' ghost rows, then the closing barrier of the step (same launch)
+        h->epoch += 1;
+        k_band_push_halo<<<dwt_blocks(h->pitch), 256, 0, h->stream>>>(h->lat[h->cur], h->R, h->pitch,
+                                                                      h->peer_lat[h->cur][up] + (size_t)(h->R + 1) * h->pitch,
+                                                                      h->peer_lat[h->cur][down], h->pt, h->epoch, h->timed_out, h->ticket);
+        DWT_LAUNCHED(h);
+        return DW_OK;
+    }
+    // the coefficients of THIS step (the look-ahead re-evaluates cells of the lattice this step produces)
+    LookArgs LA{};
+    LA.P = dwt_params(h);
+    make_fast_coef(h->cfg, LA.F);
+    make_step_coef(h->cfg, h->clk.L, LA.C);
+    rc = dwt_stencil(h, 1);                              // edge tile rows (or the whole literal first step)
+    if (rc) return rc;
+    DWT_TRY(h, cudaEventRecord(h->ev_edge, h->stream));
+    rc = dwt_stencil(h, 2);                              // interior tile rows; advances the clock
+    if (rc) return rc;
+    DWT_TRY(h, cudaStreamWaitEvent(h->stream_b, h->ev_edge, 0));
     h->epoch += 1;
-    k_band_push_halo<<<dwt_blocks(h->pitch), 256, 0, h->stream>>>(h->lat[h->cur], h->R, h->pitch,
-                                                                  h->peer_lat[h->cur][up] + (size_t)(h->R + 1) * h->pitch,
-                                                                  h->peer_lat[h->cur][down], h->pt, h->epoch, h->timed_out, h->ticket);
+    k_band_push_halo<<<dwt_blocks(h->pitch), 256, 0, h->stream_b>>>(h->lat[h->cur], h->R, h->pitch,
+                                                                    h->peer_lat[h->cur][up] + (size_t)(h->R + 1) * h->pitch,
+                                                                    h->peer_lat[h->cur][down], h->pt, h->epoch, h->timed_out, h->ticket);
     DWT_LAUNCHED(h);
+    if (h->n && was_on_lattice) {
+        const int pol_next = dw_resolve_policy(policy, h->epsilon, seed, (uint32_t)h->clk.step_count);
+        if (pol_next == DW_POLICY_GREEDY || pol_next == DW_POLICY_ANTIGREEDY) {
+            h->epoch += 1;
+            k_band_lookahead_decide<<<dwt_blocks(h->n), 256, 0, h->stream_b>>>(dwt_geom_lat(h), h->lat[1 - h->cur], h->lat[h->cur], h->agent_xy,
+                                                                               h->n, pol_next, h->pt, LA, h->epoch, h->timed_out, h->ticket);
+            DWT_LAUNCHED(h);
+            h->look_valid = true;
+            h->look_policy = pol_next;
+            h->look_step = h->clk.step_count;
+        }
+    }
+    DWT_TRY(h, cudaEventRecord(h->ev_side, h->stream_b));
+    DWT_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side, 0));
     return DW_OK;
 }
 
