@@ -86,11 +86,20 @@ def run_threads(worlds, fn):
             except Exception:
                 pass
 
-    ts = [threading.Thread(target=wrap, args=(w,)) for w in worlds]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
+    # Garbage from earlier tests (banded worlds sit in reference cycles) must not be collected while bands are stepping:
+    # freeing a handle calls cudaFree, which waits for the device to drain -- but a band spinning in a peer barrier only
+    # finishes once THIS thread has launched its next kernels, so the collection would stall until the spin times out.
+    import gc
+    gc.collect()
+    gc.disable()
+    try:
+        ts = [threading.Thread(target=wrap, args=(w,)) for w in worlds]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    finally:
+        gc.enable()
     if errs:
         raise errs[0]
 

@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+# the multi-band tests run several bands of ONE process on one GPU, each with two streams that spin on each other's flags:
+# with the default 8 hardware queues two such streams can share a queue and serialise behind a spinning kernel
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def pytest_configure(config):

@@ -607,7 +607,12 @@ extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, vo
     h->p2p_gain_pending = false;
     h->look_valid = false;
     if (!h->stream_b) {
-        DWT_TRY(h, cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking));
+        // HIGHEST priority: its small kernels must get CTA slots while thousands of interior-tile CTAs of the main stream
+        // are still queued (at equal priority the block scheduler drains the earlier grid first and nothing overlaps)
+        int prio_lo = 0, prio_hi = 0;
+        DWT_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        if (const char *pr = getenv("DW_P2P_SIDE_PRIO")) { if (!atoi(pr)) prio_hi = prio_lo; }     // experiments: 0 = equal priority
+        DWT_TRY(h, cudaStreamCreateWithPriority(&h->stream_b, cudaStreamNonBlocking, prio_hi));
         DWT_TRY(h, cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
         DWT_TRY(h, cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     }
@@ -714,6 +719,15 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
                                                                                h->n, pol_next, h->pt, LA, h->epoch, h->timed_out, h->ticket);
             DWT_LAUNCHED(h);
             h->look_valid = true;
+        } else if (pol_next == DW_POLICY_NONE || pol_next == DW_POLICY_RANDOM) {
+            // policies that do not read the world: every rank fills its own act[] (no exchange, no barrier), off the main stream too
+            k_band_decide<LatCells><<<dwt_blocks(h->n), 256, 0, h->stream_b>>>(dwt_geom_lat(h), LatCells{h->lat[h->cur]}, h->agent_xy, h->n, pol_next,
+                                                                              h->replay, seed, (uint32_t)h->clk.step_count, h->pt, h->act, 0u,
+                                                                              h->timed_out, h->ticket);
+            DWT_LAUNCHED(h);
+            h->look_valid = true;
+        }
+        if (h->look_valid) {
             h->look_policy = pol_next;
             h->look_step = h->clk.step_count;
         }

@@ -13,6 +13,10 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+MODES = os.environ.get("BANDED_MODES", "nccl,p2p").split(",")
+PARTS = os.environ.get("BANDED_PARTS", "parity,timing,fullsize").split(",")
+
+
 def gather_rows(x):
     t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
     out = [torch.empty_like(t) for _ in range(world)]
@@ -23,13 +27,16 @@ def gather_rows(x):
 from band_helpers import full_oracle, make_state
 N, n, steps = 64 * world * 2, 150, 40
 failed = False
-for mode, policy in [(m, p) for m in ("nccl", "p2p") for p in ("none", "replay", "greedy")]:
+for mode, policy in [(m, p) for m in MODES for p in ("none", "replay", "greedy") if "parity" in PARTS]:
     light, dark, ai, st = make_state(N, n, seed=9, clustered=True)
     ai[n // 2:, 0] = (ai[n // 2:, 0] + N // world) % N
     w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local, mode=mode)
     w.load_state(light, dark, ai, st)
     ref = full_oracle(w, light, dark, ai, st) if rank == 0 else None       # before the run: takes the clock from w
     acts = np.random.RandomState(2).randint(9, size=(steps, n)) if policy == "replay" else None
+    # rank 0 has just spent host time in the CPU oracle: without this barrier the other ranks would already spin in the
+    # device-side flag barriers of step 1, whose bounded spin (seconds) turns a slow peer into an error (by design)
+    dist.barrier()
     w.run(steps, policy, actions=acts, chunk=16)
     covers = gather_rows(w.local_covers())
     grid = gather_rows(w.local_grid())
@@ -55,7 +62,7 @@ if float(flag[0]) > 0:
     dist.destroy_process_group()
     sys.exit(1)
 N, n, K = 16384, 16384, 64
-for mode in ("nccl", "p2p"):
+for mode in (MODES if "timing" in PARTS else []):
     w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local, mode=mode)
     w.reset_on_device(seed=1)
     w.run(3, "greedy")
@@ -86,12 +93,11 @@ def checksum(cov):          # exact: milli-cover integers
     return np.array([k[0].sum(), k[1].sum(), (k[0] * w).sum(), (k[1] * w).sum()], dtype=np.int64)
 
 N, n, K = 16384, 16384, 16
-for mode in ("p2p", "nccl"):
+for mode in (MODES if "fullsize" in PARTS else []):
     w = BandedDaisyWorld(N, n, rank=rank, world_size=world, device=local, mode=mode)
     w.reset_on_device(seed=2)
     w.run(K, "greedy", chunk=8)
-    cs = torch.from_numpy(checksum(w.local_covers())).cuda()
-    dist.all_reduce(cs)
+    cs = w.cover_checksum()                       # device-side, summed over the bands
     ai, st = w.agents()
     life = w.lifespans()
     del w
@@ -100,13 +106,13 @@ for mode in ("p2p", "nccl"):
         one = BandedDaisyWorld(N, n, device=local)
         one.reset_on_device(seed=2)
         one.run(K, "greedy", chunk=8)
-        ref_cs = checksum(one.local_covers())
+        ref_cs = one.cover_checksum()
         ai1, st1 = one.agents()
         life1 = one.lifespans()
-        ok = (np.array_equal(cs.cpu().numpy(), ref_cs) and np.array_equal(ai, ai1) and np.array_equal(st, st1)
+        ok = (cs == ref_cs and np.array_equal(ai, ai1) and np.array_equal(st, st1)
               and life[0] == life1[0] and np.array_equal(life[1], life1[1]))
         print(f"FULLSIZE N={N} n={n} {K} greedy steps, {world} bands ({mode}) vs 1 band: {'IDENTICAL' if ok else 'MISMATCH'} "
-              f"checksums {cs.cpu().numpy().tolist()} vs {ref_cs.tolist()}", flush=True)
+              f"checksums {cs} vs {ref_cs}", flush=True)
         del one
         torch.cuda.empty_cache()
     dist.barrier()
