@@ -338,17 +338,26 @@ def giant_grid_bench(rank, world, local, fp64_peak_tflops):
     cover_cs = w.cover_checksum()
     ai, st = w.agents()
     agent_cs = [int((ai[:, 0].astype(np.int64) * 16411 + ai[:, 1]).sum()), float(np.sum(st)), int(np.sum(ada))]
+    # compute floor of a step: this band's stencil kernel alone, back to back (max over ranks); the rest of a step is the
+    # agent kernels, the halo push, the barriers and launch gaps
+    ts = torch.tensor([w.band.time_stencil(20)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    us_stencil = float(ts[0])
     out = {
         "workload": f"BASELINE configs[4]: single {GIANT_N}x{GIANT_N} toroidal world, {GIANT_N} greedy agents, row-banded over "
                     f"{world} GPU(s) ({GIANT_N // world} rows each), {GIANT_STEPS} steps after 3 warm-up steps",
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "scaling": "strong", "n_gpus": world,
-        "us_per_step": best * 1e3 / GIANT_STEPS, "env_steps_per_s": GIANT_STEPS / (best * 1e-3),
+        "us_per_step": best * 1e3 / GIANT_STEPS, "us_stencil": us_stencil, "us_exchange": best * 1e3 / GIANT_STEPS - us_stencil,
+        "env_steps_per_s": GIANT_STEPS / (best * 1e-3),
         "hbm_gbs_algorithmic_per_gpu": 8.0 * value / world / 1e9,
         "fp64_roofline_frac": value * FLOP_PER_CELL_UPDATE / 1e12 / (fp64_peak_tflops * world) if fp64_peak_tflops else None,
         "exchange_mode": mode,
         "exchanges_per_step": {"local": "none (toroidal wrap on the device)",
                                "p2p": "owner-publishes P2P stores of decisions/gains into every rank's exchange vector, edge rows pushed "
-                                      "into the neighbours' ghost rows, 2 device-side flag barriers; no collective",
+                                      "into the neighbours' ghost rows, 2 device-side flag barriers; no collective. Two streams: edge "
+                                      "tiles, halo push, barriers and the look-ahead decisions of the next step run on a high-priority "
+                                      "side stream under the interior tiles",
                                "nccl": "1 all-reduce(SUM, 2n doubles) + 1 ring halo exchange overlapped with the interior tiles"}[mode],
         "peer_barrier_timed_out": bool(w.band.peer_timed_out()) if mode == "p2p" else None,
         "literal_recomputations": w.band.slow_count(), "biosphere_alive_steps": done_at,

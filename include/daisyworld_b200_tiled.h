@@ -118,6 +118,10 @@ int dwt_get_grid(dwt_handle *h, double *grid);
    GPU (bench.py prints it so that the 1/2/4/8-GPU runs can be compared; the reference quantity is env.grid[0, 1:3]). */
 int dwt_cover_checksum(dwt_handle *h, uint64_t *out /*[4]*/);
 int dwt_debug_slow_count(dwt_handle *h, uint64_t *count);
+/* Measurement hook: average duration (microseconds, CUDA events) of `reps` back-to-back launches of the band's stencil
+   kernel on the current state -- the compute floor of one step, against which bench.py states the per-step exchange /
+   agent overhead. Overwrites the recorded pre-state (dwt_get_grid needs a new step afterwards). */
+int dwt_debug_time_stencil(dwt_handle *h, int32_t reps, double *us_per_launch);
 
 #ifdef __cplusplus
 }

@@ -29,3 +29,47 @@ def test_shared_cell_offsets_match_the_reference_scan():
     pos[1, :, 1] = np.arange(6)
     np.testing.assert_array_equal(shared_cell_offsets(pos, 8), [0, 1, 1])
     assert shared_cell_offsets(np.zeros((3, 0, 2), dtype=np.int64), 8).tolist() == [0, 0, 0, 0]
+
+
+def test_pinned_pool_recycles_blocks_as_soon_as_the_arrays_are_dropped():
+    """env._PinnedPool hands out page-locked blocks for step()'s outputs; a block must return to the pool the moment the
+    caller drops the arrays carved from it (no reference cycle that would wait for the cyclic GC), and callers that keep
+    everything must fall back to ordinary memory instead of pinning without bound. (Host logic only: a malloc stand-in
+    replaces dw_host_alloc.)"""
+    import ctypes as C
+    import gc
+    from therldaisyworld_b200.env import _PinnedPool
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    allocs = []
+
+    class FakeLib:
+        def dw_host_alloc(self, n, pp):
+            addr = libc.malloc(n.value)
+            allocs.append(addr)
+            C.cast(pp, C.POINTER(C.c_void_p))[0] = addr
+            return 0
+
+        def dw_host_free(self, p):
+            return 0
+
+    pool = _PinnedPool(FakeLib())
+    gc.disable()
+    try:
+        def views(nbytes=4096):
+            buf = pool.take(nbytes)
+            if buf is None:
+                return None
+            ptr = C.c_void_p(C.addressof(buf))
+            a = np.frombuffer(buf, dtype=np.float64, count=16, offset=0).reshape(4, 4)
+            b = np.frombuffer(buf, dtype=np.uint8, count=16, offset=2048).view(np.bool_)
+            return ptr, a, b
+        for _ in range(100):
+            out = views()
+        assert len(allocs) <= 2 and pool._live == 1            # two blocks alternate
+        kept = [views() for _ in range(40)]
+        assert sum(k is None for k in kept) == 40 - (_PinnedPool.MAX_LIVE - 1)   # beyond the limit: fall back
+        del kept, out
+        assert pool._live == 0
+    finally:
+        gc.enable()

@@ -50,7 +50,7 @@ TILED_SYMBOLS = [
     "dwt_synchronize", "dwt_upload_covers", "dwt_upload_agents", "dwt_init_random", "dwt_decide", "dwt_move_graze",
     "dwt_finish_agents", "dwt_stencil", "dwt_halo_wrap", "dwt_get_ptrs", "dwt_run", "dwt_end_chunk",
     "dwt_reset_lifespans", "dwt_get_lifespans", "dwt_get_agents", "dwt_get_reward_done", "dwt_get_covers", "dwt_get_grid",
-    "dwt_debug_slow_count", "dwt_cover_checksum", "dwt_ipc_export", "dwt_ipc_attach", "dwt_get_peer_buffers", "dwt_attach_peers", "dwt_step_p2p",
+    "dwt_debug_slow_count", "dwt_debug_time_stencil", "dwt_cover_checksum", "dwt_ipc_export", "dwt_ipc_attach", "dwt_get_peer_buffers", "dwt_attach_peers", "dwt_step_p2p",
     "dwt_flush_p2p", "dwt_peer_status",
 ]
 
@@ -170,6 +170,7 @@ def load():
         "dwt_get_grid": (C.c_int, [vp, pd]),
         "dwt_debug_slow_count": (C.c_int, [vp, C.POINTER(u64)]),
         "dwt_cover_checksum": (C.c_int, [vp, C.POINTER(u64)]),
+        "dwt_debug_time_stencil": (C.c_int, [vp, i32, pd]),
         "dwt_ipc_export": (C.c_int, [vp, vp]),
         "dwt_ipc_attach": (C.c_int, [vp, i32, i32, vp]),
         "dwt_get_peer_buffers": (C.c_int, [vp, C.POINTER(vp)]),

@@ -212,6 +212,11 @@ class DeviceBand:
         self._check(self._lib.dwt_cover_checksum(self._h, out), "dwt_cover_checksum")
         return [int(v) for v in out]
 
+    def time_stencil(self, reps=20):
+        us = C.c_double(0.0)
+        self._check(self._lib.dwt_debug_time_stencil(self._h, int(reps), C.byref(us)), "dwt_debug_time_stencil")
+        return us.value
+
     def peer_timed_out(self):
         v = C.c_int32(0)
         self._check(self._lib.dwt_peer_status(self._h, C.byref(v)), "dwt_peer_status")

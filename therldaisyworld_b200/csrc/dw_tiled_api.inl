@@ -43,6 +43,7 @@ struct dwt_handle {
     int look_policy = -1;
     int64_t look_step = -1;
     int overlap = 1;                           // DW_P2P_OVERLAP=0: the one-stream sequence of round 1 (for comparison)
+    cudaStream_t stencil_stream = nullptr;     // != nullptr: dwt_stencil launches there instead of h->stream (edge tiles of the two-stream step)
     bool step_open = false;      // dwt_stencil(part 1) done, part 2 pending
     uint8_t *gz = nullptr, *done = nullptr;
     int8_t *replay = nullptr;
@@ -318,12 +319,13 @@ extern "C" int dwt_stencil(dwt_handle *h, int32_t part) {
     if (h->chunk_j >= DW_FUSED_MAX_STEPS) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "call dwt_end_chunk at least every 4096 steps");
     if ((part == 2) != h->step_open) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "part 2 must follow part 1");
     int *smax = h->stepmax + 2 * h->chunk_j;
+    cudaStream_t st = h->stencil_stream ? h->stencil_stream : h->stream;
     const int tiles_y = h->R / DWT_TILE;
     if (!h->on_lattice || (part == 2 && h->pre_is_planes)) {
         if (part != 2) {
             if (!h->pl) return dwt_fail(h, DW_E_STATE, "dwt_stencil", "no state uploaded");
             // the reset state is off the 0.001 lattice: first step in literal arithmetic, planes -> lattice (not split)
-            k_band_first_step<<<grid_for((size_t)h->R * h->N), 256, 0, h->stream>>>(dwt_params(h), h->cfg.S * h->clk.L, dwt_geom_planes(h),
+            k_band_first_step<<<grid_for((size_t)h->R * h->N), 256, 0, st>>>(dwt_params(h), h->cfg.S * h->clk.L, dwt_geom_planes(h),
                                                                                      h->pl, h->pd, dwt_geom_lat(h), h->lat[h->cur], smax);
             DWT_LAUNCHED(h);
             h->on_lattice = true;
@@ -351,7 +353,7 @@ extern "C" int dwt_stencil(dwt_handle *h, int32_t part) {
             A.tr_first = 1;
         }
         if (rows_of_tiles > 0) {
-            k_tiled_step<<<A.tiles_x * rows_of_tiles, 256, 0, h->stream>>>(h->tmap[1 - h->cur], A);
+            k_tiled_step<<<A.tiles_x * rows_of_tiles, 256, 0, st>>>(h->tmap[1 - h->cur], A);
             DWT_LAUNCHED(h);
         }
         if (part != 2) h->pre_is_planes = false;
@@ -511,6 +513,46 @@ extern "C" int dwt_get_grid(dwt_handle *h, double *grid) {
     return DW_OK;
 }
 
+// Measurement hook: the stencil kernel of one step over the whole band (k_tiled_step, all tile rows), `reps` launches back to
+// back on the current state, timed with CUDA events -> *us_per_launch. The output goes to the buffer that holds the
+// pre-state of the last step, so the lazily materialised grid / diagnostics of that step are gone afterwards (have_pre is
+// cleared); covers, agents, clock and counters are untouched.
+extern "C" int dwt_debug_time_stencil(dwt_handle *h, int32_t reps, double *us_per_launch) {
+    if (!h || reps < 1 || !us_per_launch) return DW_E_INVALID;
+    DWT_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->on_lattice) return dwt_fail(h, DW_E_STATE, "dwt_debug_time_stencil", "the state is off the lattice until the first step has run");
+    TiledArgs A{};
+    A.P = dwt_params(h);
+    make_fast_coef(h->cfg, A.F);
+    make_step_coef(h->cfg, h->clk.L, A.C);
+    A.out = h->lat[1 - h->cur];
+    A.pitch = h->pitch;
+    A.N = h->N;
+    A.tiles_x = h->N / DWT_TILE;
+    if (!h->csum) DWT_TRY(h, cudaMalloc((void **)&h->csum, 4 * sizeof(unsigned long long)));
+    A.stepmax = reinterpret_cast<int *>(h->csum);           // scratch: the lifespan bookkeeping must not see these launches
+    A.slow_count = nullptr;
+    const int tiles_y = h->R / DWT_TILE;
+    A.tr_first = 0; A.tr_skip_lo = tiles_y; A.tr_skip_hi = tiles_y;
+    cudaEvent_t e0, e1;
+    DWT_TRY(h, cudaEventCreate(&e0));
+    DWT_TRY(h, cudaEventCreate(&e1));
+    k_tiled_step<<<A.tiles_x * tiles_y, 256, 0, h->stream>>>(h->tmap[h->cur], A);      // warm-up
+    DWT_TRY(h, cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps; ++r) k_tiled_step<<<A.tiles_x * tiles_y, 256, 0, h->stream>>>(h->tmap[h->cur], A);
+    DWT_LAUNCHED(h);
+    DWT_TRY(h, cudaEventRecord(e1, h->stream));
+    DWT_TRY(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DWT_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->have_pre = false;
+    h->look_valid = false;
+    *us_per_launch = (double)ms * 1e3 / reps;
+    return DW_OK;
+}
+
 extern "C" int dwt_cover_checksum(dwt_handle *h, uint64_t *out) {
     if (!h || !out) return DW_E_INVALID;
     DWT_TRY(h, cudaSetDevice(h->cfg.device));
@@ -643,10 +685,11 @@ extern "C" int dwt_ipc_attach(dwt_handle *h, int32_t rank, int32_t n_ranks, cons
 // the next step or by dwt_flush_p2p.
 //
 // Two streams (h->overlap, default): the main stream runs   [decide + barrier, only when no look-ahead decisions exist]
-//   finish(j-1)+move+claim(j) -> graze(j) -> stencil of the two EDGE tile rows -> stencil of the interior tile rows;
-// the side stream, started by an event after the edge tiles, runs under the interior tiles
-//   push of the new edge rows into the neighbours' ghost rows + closing barrier of step j
-//   -> look-ahead decisions of step j+1 (k_band_lookahead_decide) + barrier,
+//   finish(j-1)+move+claim(j) -> graze(j) -> stencil of the INTERIOR tile rows;
+// the side stream (highest priority, so its CTAs are scheduled ahead of the queued interior tiles), started by an event
+// after the graze, runs concurrently
+//   stencil of the two EDGE tile rows -> push of the new edge rows into the neighbours' ghost rows + closing barrier of
+//   step j -> look-ahead decisions of step j+1 (k_band_lookahead_decide) + barrier,
 // and the main stream waits for it before the next step's move. What is left on the critical path of a step besides the
 // stencil are the two small agent kernels.
 extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions, uint64_t seed) {
@@ -700,12 +743,16 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
     LA.P = dwt_params(h);
     make_fast_coef(h->cfg, LA.F);
     make_step_coef(h->cfg, h->clk.L, LA.C);
-    rc = dwt_stencil(h, 1);                              // edge tile rows (or the whole literal first step)
-    if (rc) return rc;
+    // agents done: the edge tile rows go to the (high-priority) side stream, the interior tile rows stay on the main
+    // stream -- disjoint output rows of the same step, both read the post-graze input buffer
     DWT_TRY(h, cudaEventRecord(h->ev_edge, h->stream));
+    DWT_TRY(h, cudaStreamWaitEvent(h->stream_b, h->ev_edge, 0));
+    h->stencil_stream = h->stream_b;
+    rc = dwt_stencil(h, 1);                              // edge tile rows (or the whole literal first step)
+    h->stencil_stream = nullptr;
+    if (rc) return rc;
     rc = dwt_stencil(h, 2);                              // interior tile rows; advances the clock
     if (rc) return rc;
-    DWT_TRY(h, cudaStreamWaitEvent(h->stream_b, h->ev_edge, 0));
     h->epoch += 1;
     k_band_push_halo<<<dwt_blocks(h->pitch), 256, 0, h->stream_b>>>(h->lat[h->cur], h->R, h->pitch,
                                                                     h->peer_lat[h->cur][up] + (size_t)(h->R + 1) * h->pitch,

@@ -633,7 +633,8 @@ class RLDaisyWorld:
             buf = np.empty(nbytes, dtype=np.uint8)
             ptr = buf.ctypes.data_as(C.c_void_p)
         else:
-            ptr = C.cast(buf, C.c_void_p)
+            ptr = C.c_void_p(C.addressof(buf))       # NOT ctypes.cast: it stores the source in its own _objects (a cycle), and
+                                                     # the block would only return to the pool when the cyclic GC runs
         m = n if n else 2
         reward = np.frombuffer(buf, dtype=np.float64, count=B * m, offset=r_off).reshape((B, n, 1) if n else (B, 2))
         done = np.frombuffer(buf, dtype=np.uint8, count=B * m, offset=d_off).reshape(reward.shape).view(np.bool_)

@@ -33,3 +33,19 @@ for mb in (0.036, 0.5, 2.0, 8.0):
     def cp(dst):
         dst.copy_(d, non_blocking=True); torch.cuda.synchronize()
     print(f"D2H {mb} MB: pinned {t_of(lambda: cp(hp)):.1f} us, pageable {t_of(lambda: cp(hq)):.1f} us", flush=True)
+
+# the C call alone (no Python array work): packed step into one pre-allocated pinned block / one pageable block
+import ctypes as C
+from therldaisyworld_b200._lib import DwClock
+np.random.seed(13)
+env = RLDaisyWorld(grid_dimension=64); env.batch_size = 1000; env.reset(); env.step_policy("greedy")
+lib, h = env._lib, env._h
+lay = (C.c_int64 * 4)(); lib.dw_step_out_layout(h, lay)
+pin = C.c_void_p(); lib.dw_host_alloc(C.c_uint64(lay[3]), C.byref(pin))
+page = np.empty(lay[3], dtype=np.uint8)
+clk = DwClock()
+for name, ptr in (("pinned", pin), ("pageable", page.ctypes.data_as(C.c_void_p))):
+    for want in (0, 1):
+        f = lambda: lib.dw_step_packed(h, None, 0, 0, 1, C.c_uint64(0), want, ptr, C.byref(clk))
+        print(f"C call dw_step_packed B=1000 {name} want_obs={want}: {t_of(f):.1f} us", flush=True)
+print("pool live/free:", env._pool._live, {k: len(v) for k, v in env._pool._free.items()})
