@@ -42,9 +42,14 @@ struct FastCoef {        // launch-constant coefficients of the fast path (host-
     // rounding + tie filter (see DW rounding note below): magic = 1.5*2^32 + 0.5 + eps*2^-FIX, tie_thresh = (2 eps) << (32-FIX)
     double magic;
     unsigned int tie_thresh, pad_;
+    // exponent-biased operands (DW_BIAS_MASK, dw_half2d): constants of the linear forms with the 2^20 offsets of the biased
+    // operands taken out -- rc: start value of rho's accumulation, magic_b: magic minus the offset of the centre cover,
+    // t0_b: t0 of the series mode
+    double rc, magic_b, t0_b;
 };
 struct StepCoef {        // per-step (luminosity dependent) coefficients
     double x0;           // g^2 * (cL + (q-cL)*A0 + (q2-q)*Al0 - q2*al)
+    double x0_b;         // x0 minus 2^20 * (the X coefficients of the exponent-biased operands), dw_fast_cells only
     double xs_l, xs_d;   // g^2 * (q-cL)*a*(al-ab)/1000, g^2 * (q-cL)*a*(ad-ab)/1000   (a = adjacent tap)
     double SL;           // S*L for the literal path
     int policy, pad_;    // the policy of this step (DW_POLICY_EPS_GREEDY resolved to GREEDY / RANDOM on the host)
@@ -93,8 +98,29 @@ __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f6
 #ifndef DW_I2F_MASK
 #define DW_I2F_MASK 0x3F
 #endif
+// Third route, no conversion at all: the 16-bit half k is dropped into the top mantissa bits of 2^20 by ONE byte permute
+// (hi word = 0x41300000 | k, lo word = 0), which IS the double 2^20 + k exactly (k < 2^20). Every use is a linear form
+// accumulated by FMAs, so the 2^20 offsets are taken out of the forms' constants on the host (FastCoef::rc, magic_b,
+// StepCoef::x0_b). Price: the partial sums are ~2^20 * coefficient instead of ~2^13 * coefficient, i.e. each FMA rounds
+// at a 2^7 times coarser ulp -- 2^-53 * 2^20 * (w0 + w12 + w2) * 3 = 1e-10 milli-cover on rho and 4 * 2^-53 * 2^20 * |xs| / X
+// = 5e-14 relative on X, both far inside the fast path's error budget. DW_BIAS_MASK: same bit per
+// operand as DW_I2F_MASK (kl and kd share bit 0 and 1 -- they must use the same route because of magic_b).
+#ifndef DW_BIAS_MASK
+#define DW_BIAS_MASK 0x00
+#endif
+#ifndef DW_ROOT_ALT
+#define DW_ROOT_ALT 1                  // Newton step of the fourth root with one fp64 operation less (see dw_fast_cells)
+#endif
+#ifndef DW_AGENT_WARP
+#define DW_AGENT_WARP 0                // which warp of the 64x64 persistent kernel runs the agent phase (scheduling experiment)
+#endif
+#define DW_BIAS_OFFSET 1048576.0        // 2^20
+static_assert(((DW_BIAS_MASK & 1) != 0) == ((DW_BIAS_MASK & 2) != 0) && ((DW_BIAS_MASK & 4) != 0) == ((DW_BIAS_MASK & 8) != 0) &&
+              ((DW_BIAS_MASK & 16) != 0) == ((DW_BIAS_MASK & 32) != 0), "the two species of an operand share the conversion route (rc, magic_b)");
 template <int BIT>
 __device__ __forceinline__ double dw_half2d(uint32_t p) {
+    if (DW_BIAS_MASK & (1 << BIT))
+        return __hiloint2double((int)__byte_perm(p, 0x41300000u, (BIT & 1) ? 0x7632 : 0x7610), 0);
     if (BIT & 1) {
         if (DW_I2F_MASK & (1 << BIT)) return (double)(unsigned short)(p >> 16);
         return dw_u2d(p >> 16);
@@ -147,14 +173,14 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
 #pragma unroll
     for (int i = 0; i < W; ++i) { Sl[i] = dw_half2d<2>(S[i]); Sd[i] = dw_half2d<3>(S[i]); }
 #pragma unroll
-    for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(F.xk_l, kl[i], __fma_rn(F.xk_d, kd[i], C.x0));
+    for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(F.xk_l, kl[i], __fma_rn(F.xk_d, kd[i], DW_BIAS_MASK ? C.x0_b : C.x0));
 #pragma unroll
     for (int i = 0; i < W; ++i) Xl[i] = __fma_rn(C.xs_l, Sl[i], __fma_rn(C.xs_d, Sd[i], Xl[i]));
 #pragma unroll
     for (int i = 0; i < W; ++i) Xd[i] = Xl[i] + F.xdd;
     if (DIAG) {              // series mode: the (unrounded) temperature of the cell itself, sqrt(g)*T, summed per thread
 #pragma unroll
-        for (int i = 0; i < W; ++i) *tsum += dw_root4_fast(__fma_rn(F.tk_l, kl[i], __fma_rn(F.tk_d, kd[i], Xl[i] + F.t0)));
+        for (int i = 0; i < W; ++i) *tsum += dw_root4_fast(__fma_rn(F.tk_l, kl[i], __fma_rn(F.tk_d, kd[i], Xl[i] + (DW_BIAS_MASK ? F.t0_b : F.t0))));
     }
     // seeds first: the MUFU latency (27 cycles) overlaps the rho arithmetic below
     double s1l[W], s1d[W], y0l[W], y0d[W];
@@ -163,7 +189,10 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
 #pragma unroll
     for (int i = 0; i < W; ++i) { El[i] = dw_half2d<4>(E[i]); Ed[i] = dw_half2d<5>(E[i]); }
 #pragma unroll
-    for (int i = 0; i < W; ++i) { Rl[i] = F.w0 * kl[i]; Rd[i] = F.w0 * kd[i]; }
+    for (int i = 0; i < W; ++i) {
+        if (DW_BIAS_MASK) { Rl[i] = __fma_rn(F.w0, kl[i], F.rc); Rd[i] = __fma_rn(F.w0, kd[i], F.rc); }
+        else { Rl[i] = F.w0 * kl[i]; Rd[i] = F.w0 * kd[i]; }
+    }
 #pragma unroll
     for (int i = 0; i < W; ++i) { y0l[i] = dw_rsqrt_approx(s1l[i]); y0d[i] = dw_rsqrt_approx(s1d[i]); }
 #pragma unroll
@@ -174,6 +203,22 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
     for (int i = 0; i < W; ++i) rb[i] = __fma_rn(-F.dtm, Rl[i] + Rd[i], F.dtp);
     // Newton step on y^4 = X for both species of all cells, stage by stage
     double zl[W], zd[W], al[W], ad[W];
+#if DW_ROOT_ALT
+    // Same step, one fp64 operation less per root: T = y0 + (X - y0^4) * (s1/2)^2 * y0 with s1/2 made by an integer subtract on the
+    // exponent (ALU pipe; the MUFU seed's low word is zero), and Topt - T folded into the last FMA:
+    // dT = (Topt - y0) - ((X - y0^4) * (s1/2)^2) * y0.
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double hl = __hiloint2double(__double2hiint(s1l[i]) - 0x00100000, 0), hd = __hiloint2double(__double2hiint(s1d[i]) - 0x00100000, 0);
+        zl[i] = y0l[i] * y0l[i]; zd[i] = y0d[i] * y0d[i]; al[i] = hl * hl; ad[i] = hd * hd;
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-zl[i], zl[i], Xl[i]); zd[i] = __fma_rn(-zd[i], zd[i], Xd[i]); }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = zl[i] * al[i]; zd[i] = zd[i] * ad[i]; al[i] = F.topt - y0l[i]; ad[i] = F.topt - y0d[i]; }
+#pragma unroll
+    for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-zl[i], y0l[i], al[i]); zd[i] = __fma_rn(-zd[i], y0d[i], ad[i]); }   // sqrt(g)*(Topt-T)
+#else
 #pragma unroll
     for (int i = 0; i < W; ++i) { zl[i] = y0l[i] * y0l[i]; zd[i] = y0d[i] * y0d[i]; al[i] = s1l[i] * s1l[i]; ad[i] = s1d[i] * s1d[i]; }
 #pragma unroll
@@ -184,6 +229,7 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(zl[i], 0.25, y0l[i]); zd[i] = __fma_rn(zd[i], 0.25, y0d[i]); }      // T_l, T_d
 #pragma unroll
     for (int i = 0; i < W; ++i) { zl[i] = F.topt - zl[i]; zd[i] = F.topt - zd[i]; }                                   // sqrt(g)*(Topt-T)
+#endif
 #pragma unroll
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(-zl[i], zl[i], 1.0); zd[i] = __fma_rn(-zd[i], zd[i], 1.0); }       // beta_l, beta_d
 #pragma unroll
@@ -192,7 +238,8 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
     for (int i = 0; i < W; ++i) { zl[i] = __fma_rn(Rl[i], zl[i], kl[i]); zd[i] = __fma_rn(Rd[i], zd[i], kd[i]); }     // l + dt*dl (milli)
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        const int fl = __double2loint(zl[i] + F.magic), fd = __double2loint(zd[i] + F.magic);
+        const double mg = (DW_BIAS_MASK & 1) ? F.magic_b : F.magic;     // biased centre: zl = x + 2^20, the offset is in magic_b
+        const int fl = __double2loint(zl[i] + mg), fd = __double2loint(zd[i] + mg);
         *tiemin = __vimin3_u32(*tiemin, (unsigned)fl << (32 - DW_FIX_BITS), (unsigned)fd << (32 - DW_FIX_BITS));
         const unsigned packed = __byte_perm((unsigned)(fl >> DW_FIX_BITS), (unsigned)(fd >> DW_FIX_BITS), 0x5410);
         out[i] = __vimin_s16x2_relu(packed, 1000u | (1000u << 16));
@@ -718,7 +765,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
         for (int jl = 0; jl < kc; ++jl) {
             const int j = j0 + jl;
             uint32_t *cb = sm.buf[jl & 1], *nb = sm.buf[(jl + 1) & 1];
-            if (warp == 0 && n > 0) dw_agents_phase32(A, j, b, cb, sm, lane, n);
+            if (warp == DW_AGENT_WARP && n > 0) dw_agents_phase32(A, j, b, cb, sm, lane, n);
 #ifndef DW_X_NOSYNC1            // timing experiments only (results are garbage without the barriers): upper bound of what removing
             __syncthreads();    // a barrier could buy, see DESIGN.md section 4
 #endif

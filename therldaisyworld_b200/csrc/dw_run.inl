@@ -52,6 +52,12 @@ static void make_fast_coef(const dw_config &c, FastCoef &F) {
     F.magic = 6442450944.0 + 0.5 + eps / (double)(1 << DW_FIX_BITS);
     F.tie_thresh = (2u * (unsigned int)eps) << (32 - DW_FIX_BITS);
     F.pad_ = 0;
+    // exponent-biased operands (dw_half2d, DW_BIAS_MASK bit: 0 kl, 1 kd, 2 Sl, 3 Sd, 4 El, 5 Ed): offsets out of the constants.
+    // magic - 2^20 is exact (multiple of 2^-20 below 2^33); rc is rounded once (|rc| < 2^20: ulp 1.2e-10).
+    const int bm = DW_BIAS_MASK;
+    F.rc = -DW_BIAS_OFFSET * (((bm & 1) ? F.w0 : 0.0) + ((bm & 16) ? F.w12 : 0.0) + ((bm & 4) ? F.w2 : 0.0));
+    F.magic_b = F.magic - ((bm & 1) ? DW_BIAS_OFFSET : 0.0);
+    F.t0_b = F.t0 - DW_BIAS_OFFSET * (((bm & 1) ? F.tk_l : 0.0) + ((bm & 2) ? F.tk_d : 0.0));
 }
 
 static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
@@ -64,6 +70,9 @@ static void make_step_coef(const dw_config &c, double L, StepCoef &s) {
     s.xs_l = g2 * ((c.q - cL) * a * cl);
     s.xs_d = g2 * ((c.q - cL) * a * cd);
     s.SL = c.S * L;
+    const int bm = DW_BIAS_MASK;
+    const double xk_l = g2 * ((c.q2 - c.q) * cl), xk_d = g2 * ((c.q2 - c.q) * cd);       // FastCoef::xk_l, xk_d
+    s.x0_b = s.x0 - DW_BIAS_OFFSET * (((bm & 1) ? xk_l : 0.0) + ((bm & 2) ? xk_d : 0.0) + ((bm & 4) ? s.xs_l : 0.0) + ((bm & 8) ? s.xs_d : 0.0));
 }
 
 static int ensure_lattice_buffers(dw_handle *h) {

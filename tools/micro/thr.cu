@@ -33,6 +33,16 @@ __global__ void k(double* out, long long* cyc, int iters, double a, double b, un
                 double t = __hiloint2double(0x43300000, (int)(u[i] & 0xffffu)) - 4503599627370496.0; u[i] = __double2loint(t) + u[i] + 1; v[i] = t;
             }
             else if (OP==10) { unsigned m = __match_any_sync(0xffffffffu, u[i] & 7u); u[i] += m; }
+            else if (OP==12) { float f = __int_as_float(u[i] | 0x3f800000u); f = __fmaf_rn(f, 1.0000001f, 1e-9f); u[i] = __float_as_int(f) & 0x007fffffu; }   // FFMA chain
+            else if (OP==13) { float f; asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(u[i] & 0xffffu)); u[i] = __float_as_int(f) ^ u[i]; }        // I2FP.F32.U32 (+LOP)
+            else if (OP==14) { float f; asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(__int_as_float(u[i] | 0x40000000u))); u[i] = __float_as_int(f) ^ u[i]; }  // MUFU.RSQ
+            else if (OP==15) { float f = __int_as_float(u[i] | 0x40000000u); double t = (double)f; u[i] = __double2hiint(t) ^ u[i]; v[i] = t; }           // F2F.F64.F32
+            else if (OP==16) { float f = (float)v[i]; u[i] = __float_as_int(f) ^ u[i]; v[i] = __hiloint2double((int)(u[i] | 0x40000000u) & 0x4fffffff, 0); }   // F2F.F32.F64
+            else if (OP==17) { double t = __hiloint2double((int)__byte_perm(u[i], 0x41300000u, 0x7610), 0); v[i] = __fma_rn(t, a, v[i]); u[i] += 3; }     // bias trick + DFMA
+            else if (OP==18) { double t; unsigned short h = (unsigned short)(u[i]); asm volatile("cvt.rn.f64.u16 %0, %1;" : "=d"(t) : "h"(h)); v[i] = __fma_rn(t, a, v[i]); u[i] += 3; }  // I2F.F64.U16 + DFMA
+            else if (OP==19) { float f = __int_as_float(u[i] | 0x40000000u); float r; asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+                               f = __fmaf_rn(r, f, 1.0f); f = __fmaf_rn(r, f, 1.0f); f = __fmaf_rn(r, f, 1.0f); f = __fmaf_rn(r, f, 1.0f); u[i] = __float_as_int(f) & 0x3fffffffu; }   // MUFU.RSQ + 4 FFMA
+            else if (OP==20) { int q; asm volatile("cvt.rni.s32.f32 %0, %1;" : "=r"(q) : "f"(__int_as_float((u[i] & 0x007fffffu) | 0x42000000u))); u[i] += q; }   // F2I
             else if (OP==11) { float f = __uint2float_rn(u[i] & 0xffffu); double t = (double)f; u[i] = __double2hiint(t) ^ u[i]; v[i] = t; }  // I2F.F32 + F2F.F64.F32
         }
     }
@@ -57,6 +67,9 @@ int main(){
         run<4>("IMAD.WIDE.U32", w, 1); run<5>("MUFU.RSQ64H(+mov)", w, 1); run<6>("MUFU.RCP64H(+mov)", w, 1);
         run<7>("DFMA+cvt.f64.u32 pair", w, 1); run<8>("DFMA+RSQ64H pair", w, 1); run<9>("magic u2d (LOP+MOV+DADD)", w, 1);
         run<10>("MATCH.ANY", w, 1); run<11>("I2F.F32+F2F.F64.F32", w, 1);
+        run<12>("FFMA (+2 LOP)", w, 1); run<13>("I2FP.F32.U32 (+2 LOP)", w, 1); run<14>("MUFU.RSQ f32 (+2 LOP)", w, 1);
+        run<15>("F2F.F64.F32 (+LOP)", w, 1); run<16>("F2F.F32.F64 (+LOPs)", w, 1); run<17>("PRMT bias + DFMA", w, 1);
+        run<18>("I2F.F64.U16 + DFMA", w, 1); run<19>("MUFU.RSQ + 4 FFMA", w, 1); run<20>("F2I.S32.F32 (+LOPs)", w, 1);
     }
     return 0;
 }
