@@ -281,6 +281,41 @@ def sustained_bench(rank, world, local):
             "timing": "CUDA events around each condition (incl. the segment read-backs and checkpoints), max over ranks"}
 
 
+# ----------------------------------------------------------------------------------------------- fp32 mode
+def materialise_bench(local, peaks, worlds=4000, reps=10):
+    """Device time of materialising env.grid of a lattice-resident ensemble: fp64 (k_forward_x2 + stamp) vs the fp32 mode
+    (k_forward_f32 + stamp, fp32 arithmetic from the packed lattice). Algorithmic HBM bytes per cell: fp64 4 (lattice) + 7 * 8;
+    fp32 4 + 4 (the two lattices) + 7 * 4."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    np.random.seed(SEED)
+    env = RLDaisyWorld(grid_dimension=N, n_agents=N_AGENTS, device=local)
+    env.batch_size = worlds
+    env.reset_on_device(seed=SEED)
+    env.run(40, policy="greedy")
+    lib, h = env._lib, env._h
+    out = {"worlds": worlds, "grid": N, "reps": reps}
+    hbm = peaks.get("hbm_gbs") if peaks else 6650.0
+    for name, flag, bytes_per_cell in (("fp64", 0, 4 + 7 * 8), ("fp32", 1, 8 + 7 * 4)):
+        ms = C.c_double()
+        _lib_check(lib, h, lib.dw_debug_time_materialise(h, flag, reps, C.byref(ms)), "dw_debug_time_materialise")
+        gbs = worlds * N * N * bytes_per_cell / (ms.value * 1e-3) / 1e9
+        out[name] = {"ms": ms.value, "cell_updates_per_s": worlds * N * N / (ms.value * 1e-3), "algorithmic_bytes_per_cell": bytes_per_cell,
+                     "hbm_gbs": gbs, "hbm_frac": gbs / hbm}
+    st = env.f32_stats()
+    out["fp32"]["cells_to_fp64_tier"] = st["fp64_tier"] / max(1, st["cells"])
+    out["fp32"]["cells_to_literal"] = st["literal"] / max(1, st["cells"])
+    out["hbm_peak_gbs"] = hbm
+    out["what"] = ("env.grid of a lattice-resident ensemble materialised on the device, CUDA events; fp32: covers/bare fraction exact "
+                   "(as binary32), temperatures in fp32 arithmetic (1e-5 tolerance of the north_star's fp32 mode)")
+    del env
+    return out
+
+
+def _lib_check(lib, h, rc, what):
+    from therldaisyworld_b200 import _lib
+    _lib.check(lib, h, rc, what)
+
+
 # ----------------------------------------------------------------------------------------------- giant grid (configs[4])
 GIANT_N = 16384
 GIANT_STEPS = 64
@@ -566,6 +601,14 @@ def run_product(args):
                               "(obs download + action upload every step), device policy with / without the observation download")
         except Exception as e:
             dropin = {"error": repr(e)}
+    materialise = None
+    if rank == 0 and not args.no_extras:
+        # fp32 mode: the 7-channel grid of a lattice-resident state materialised with fp32 arithmetic (k_forward_f32) against the
+        # fp64 materialisation (k_forward_x2), both HBM-bound; 4000 worlds so that the output (0.46 / 0.92 GB) exceeds the L2
+        try:
+            materialise = materialise_bench(local, load_peaks())
+        except Exception as e:
+            materialise = {"error": repr(e)}
     if rank == 0:
         peaks = load_peaks()
         fused_s = prof.fused_ms * 1e-3
@@ -611,6 +654,7 @@ def run_product(args):
             "giant_grid": giant,
             "sustained": sustained,
             "dropin_step": dropin,
+            "fp32_mode": materialise,
             "check": {"mean_done_at_after_T": mean_life, "mean_done_at_after_T_e2e": mean_life_e2e, "expected": float(T_STEPS),
                       "ensemble_stats": stats.tolist(),
                       "wall_s_resident": wall_res},

@@ -205,11 +205,22 @@ int dw_get_obs_at(dw_handle *h, const int64_t *agent_indices, int32_t b, int32_t
 
 /* Getters (device -> host, synchronise). */
 int dw_get_grid(dw_handle *h, double *grid);                              /* env.grid */
-/* fp32 export ("fp32 mode" of the fields): env.grid / the observations converted to binary32 on the device, half the
-   device->host bytes. The state itself lives on the exact 0.001 lattice, so this is a rounding of exact fp64 fields:
-   |rel. error| <= 2^-24 = 6e-8, inside the 1e-5 tolerance BASELINE.json states for fp32. */
+/* fp32 mode (BASELINE.json north_star: "1e-5 in fp32 mode"): env.grid / the observations as binary32.
+   Lattice-resident state (after fused steps / lattice-resident step()) with the fast path's constants: the grid is
+   materialised with fp32 ARITHMETIC straight from the packed lattice (k_forward_f32: FFMA + MUFU.RSQ temperatures, 32 B of
+   HBM traffic per cell instead of 64+). The covers (ch 1, 2) and the bare fraction (ch 0; fp32 evaluation screened by its
+   error bound, fp64 fast path, then the literal cell) are the fp32 roundings of the reference's values; the temperatures
+   (ch 3..5) are within ~5e-7 relative plus a possible 0.001 K rounding flip (3e-6). Any other state: the fp64
+   materialisation converted to binary32 (2^-24 relative). Replaces reading RLDaisyWorld.grid (daisy_world_rl.py:434-461) /
+   get_obs (:246-263) in a float32 pipeline. */
 int dw_get_grid_f32(dw_handle *h, float *grid);                           /* [B,7,N,N] */
 int dw_get_obs_f32(dw_handle *h, float *obs);                             /* [B,n,7,3,3] */
+/* out[0] = cells materialised by the fp32-arithmetic path so far, out[1] = of those, cells whose bare fraction went on to the
+   fp64 tier, out[2] = cells that needed the literal cell */
+int dw_f32_stats(dw_handle *h, uint64_t *out /*[3]*/);
+/* measurement hook: device time (CUDA events) of `reps` materialisations of the current lattice-resident state, fp32 != 0:
+   k_forward_f32 (+ stamp), else the fp64 k_forward (+ stamp) */
+int dw_debug_time_materialise(dw_handle *h, int32_t fp32, int32_t reps, double *ms_per_call);
 int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states);
 int dw_get_obs(dw_handle *h, double *obs);                                /* obs of the last step / current state */
 int dw_get_reward_done(dw_handle *h, double *reward, uint8_t *done);      /* [B,n] (or [B,2] when n_agents==0) */
@@ -269,6 +280,9 @@ int dw_debug_screen_error(dw_handle *h, const double *grid, double *out);
 /* number of integers k in [-kmax,kmax] for which the division-free k/1000 used by the kernels differs from the IEEE
    quotient (must be 0) */
 int dw_debug_markstein(dw_handle *h, uint32_t kmax, uint32_t *bad);
+/* the binary32 twin used by the fp32 mode (dw_div1000f): integers |k| <= kmax whose division-free k/1000 differs from the
+   correctly rounded quotient; exact up to 2^19 */
+int dw_debug_markstein_f32(dw_handle *h, uint32_t kmax, uint32_t *bad);
 /* Measured FP64 FMA peak of the handle's device (dependent DFMA chains, full occupancy): best of `reps` launches of
    `iters` x 8 FMAs per thread, in TFLOP/s (FMA = 2 flop).  Roofline denominator of the fused kernel. */
 int dw_debug_fp64_peak(dw_handle *h, int32_t iters, int32_t reps, double *tflops_best, double *ms_best);

@@ -100,6 +100,10 @@ def test_division_free_rounding_is_exact_on_device():
     bad = C.c_uint32(123)
     assert env._lib.dw_debug_markstein(env._h, 2000000, C.byref(bad)) == 0
     assert bad.value == 0
+    # binary32 twin of the fp32 mode: every integer the fp32 grid divides by 1000 (covers <= 1000, 1000 T <= 4e5 < 2^19)
+    bad = C.c_uint32(123)
+    assert env._lib.dw_debug_markstein_f32(env._h, 1 << 19, C.byref(bad)) == 0
+    assert bad.value == 0
 
 
 def test_eps_greedy_limits_and_kernel_consistency():

@@ -38,10 +38,10 @@ SYMBOLS = [
     "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_set_mlp_population", "dw_run_population", "dw_get_population_results",
     "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_collect", "dw_step_out_layout", "dw_step_packed", "dw_host_alloc", "dw_host_free", "dw_step_policy", "dw_update_agents",
     "dw_agents_begin", "dw_agents_collide", "dw_step_tail_collect", "dw_step_tail_counted",
-    "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_grid_f32", "dw_get_obs_f32", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
+    "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_grid_f32", "dw_get_obs_f32", "dw_f32_stats", "dw_debug_time_materialise", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
     "dw_run", "dw_run_chunk", "dw_run_series", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count", "dw_debug_state",
-    "dw_debug_root4", "dw_debug_markstein", "dw_debug_fp64_peak", "dw_debug_screen_error",
+    "dw_debug_root4", "dw_debug_markstein", "dw_debug_markstein_f32", "dw_debug_fp64_peak", "dw_debug_screen_error",
 ]
 
 # every symbol include/daisyworld_b200_tiled.h declares (single giant grid, row bands)
@@ -116,6 +116,8 @@ def load():
         "dw_get_grid": (C.c_int, [vp, pd]),
         "dw_get_grid_f32": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "dw_get_obs_f32": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "dw_f32_stats": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+        "dw_debug_time_materialise": (C.c_int, [vp, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
         "dw_get_agents": (C.c_int, [vp, pi64, pd]),
         "dw_get_obs": (C.c_int, [vp, pd]),
         "dw_get_reward_done": (C.c_int, [vp, pd, pu8]),
@@ -137,6 +139,7 @@ def load():
         "dw_debug_root4": (C.c_int, [vp, pd, pd, i32]),
         "dw_debug_screen_error": (C.c_int, [vp, pd, pd]),
         "dw_debug_markstein": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "dw_debug_markstein_f32": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "dw_debug_fp64_peak": (C.c_int, [vp, i32, i32, pd, pd]),
     }
     assert set(sig) == set(SYMBOLS)

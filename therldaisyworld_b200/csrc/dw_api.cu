@@ -10,6 +10,7 @@
 #include "dw_common.cuh"
 #include "dw_generic.cuh"
 #include "dw_fused.cuh"
+#include "dw_f32.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -68,6 +69,10 @@ struct dw_handle {
     size_t scratch_cap = 0;
     double *fwd_in = nullptr, *fwd_out = nullptr;
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
+    // fp32 mode (dw_f32.cuh): float [B,7,N,N] grid materialised with fp32 arithmetic, tier counters {fp64-tier cells, literal cells}
+    float *grid32 = nullptr;
+    unsigned long long *f32_stats = nullptr;
+    unsigned long long f32_cells = 0;          // cells materialised by the fp32 path so far
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
     double epsilon = 0.0;                      // Greedy.epsilon of DW_POLICY_EPS_GREEDY
     // series mode of the fused kernel (dw_run_series)
@@ -358,7 +363,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
+    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->grid32, h->f32_stats, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
@@ -1109,9 +1114,74 @@ static int export_f32(dw_handle *h, const double *src, size_t count, float *dst)
     return DW_OK;
 }
 
+// ---- fp32 mode: the grid of a lattice-resident state materialised with fp32 arithmetic (dw_f32.cuh) ------------------------
+static bool dw_fast_path_cfg_ok(const dw_config &c);
+static void make_fast_coef(const dw_config &c, FastCoef &F);
+static void make_step_coef(const dw_config &c, double L, StepCoef &s);
+
+// the state must be on the lattice with the post-graze lattice of the last step at hand, and the constants must be the
+// fast path's (D4-symmetric kernels, g > 0); everything else is served by the fp64 materialisation + conversion
+static bool f32_arith_ok(const dw_handle *h) {
+    return h->lat_valid && h->pre == PRE_LAT && h->lat_pre && dw_fast_path_cfg_ok(h->cfg) && !getenv("DW_F32_EXPORT_ONLY");
+}
+
+static void make_f32_coef(const dw_config &c, const FastCoef &F, const StepCoef &S, const DevParams &P, F32Coef &Q) {
+    Q.w0 = (float)F.w0; Q.w12 = (float)F.w12; Q.w2 = (float)F.w2;
+    Q.dtp = (float)F.dtp; Q.dtm = (float)F.dtm; Q.dtg = (float)F.dtg;
+    Q.xk_l = (float)F.xk_l; Q.xk_d = (float)F.xk_d; Q.xdd = (float)F.xdd; Q.topt = (float)F.topt;
+    Q.t0 = (float)F.t0; Q.tk_l = (float)F.tk_l; Q.tk_d = (float)F.tk_d;
+    Q.x0 = (float)S.x0; Q.xs_l = (float)S.xs_l; Q.xs_d = (float)S.xs_d;
+    Q.inv_sqrt_g = (float)(1.0 / sqrt(c.g));
+    Q.p1000 = (float)(1000.0 * c.p);
+    // error bound of the fp32 evaluation (derivation in dw_f32.cuh), safety factor 2 included
+    const double u = 5.9604644775390625e-8, sg = sqrt(c.g), dt = fabs(c.dt);
+    const double eD = sg * (400.0 * 4.5e-7 + 2.0 * u * fabs(c.temp_optimal));
+    const double rbmax = dt * fmax(fabs(c.p), fabs(c.p - 2.0));
+    Q.k1 = (float)(2.0 * (2.0 * eD * rbmax));
+    Q.k2 = (float)(2.0 * (u * (17.0 * rbmax + 8.0 * dt)));
+    Q.c0 = (float)(2.0 * (u * (2000.0 + 6000.0 * dt * fabs(c.gamma))));
+    Q.c0b = (float)(4.0 * u * 1000.0 * fmax(1.0, fabs(c.p)));
+    const double g2 = c.g * c.g;
+    Q.xlo = (float)(g2 * P.xlo * 1.0001);
+    Q.xhi = (float)(g2 * P.xhi * 0.9999);
+}
+
+// grid32 <- the current state (channels 0..6, agent stamp included)
+static int materialise_f32(dw_handle *h) {
+    const size_t B = h->cfg.batch, NN = h->NN;
+    int rc = dev_alloc(h, &h->grid32, B * 7 * NN);
+    if (!rc) rc = dev_alloc(h, &h->f32_stats, (size_t)2);
+    if (rc) return rc;
+    const DevParams P = make_params(h);
+    FastCoef F;
+    StepCoef S;
+    F32Coef Q;
+    make_fast_coef(h->cfg, F);
+    make_step_coef(h->cfg, h->L_last, S);
+    make_f32_coef(h->cfg, F, S, P, Q);
+    if ((P.N & 1) == 0)
+        k_forward_f32<2><<<grid_for(B * NN / 2), 256, 0, h->stream>>>(P, F, S, Q, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
+    else
+        k_forward_f32<1><<<grid_for(B * NN), 256, 0, h->stream>>>(P, F, S, Q, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
+    DW_LAUNCHED(h);
+    if (P.n_agents > 0) {
+        k_stamp_f32<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid32, h->agent_xy, h->agent_state);
+        DW_LAUNCHED(h);
+    }
+    h->f32_cells += B * NN;
+    return DW_OK;
+}
+
 extern "C" int dw_get_grid_f32(dw_handle *h, float *grid) {
     if (!h || !grid) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (f32_arith_ok(h)) {
+        int rc = materialise_f32(h);
+        if (rc) return rc;
+        DW_CUDA_TRY(h, cudaMemcpyAsync(grid, h->grid32, (size_t)h->cfg.batch * 7 * h->NN * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return DW_OK;
+    }
     int rc = ensure_grid(h);
     if (rc) return rc;
     return export_f32(h, h->grid[h->cur], (size_t)h->cfg.batch * 7 * h->NN, grid);
@@ -1121,10 +1191,58 @@ extern "C" int dw_get_obs_f32(dw_handle *h, float *obs) {
     if (!h) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t count = (size_t)h->cfg.batch * h->cfg.n_agents * 63;
+    if (count && f32_arith_ok(h)) {
+        if (!obs) return DW_E_INVALID;
+        int rc = materialise_f32(h);
+        if (!rc) rc = ensure_scratch(h, (count + 1) / 2);
+        if (rc) return rc;
+        float *tmp = reinterpret_cast<float *>(h->scratch);
+        const DevParams P = make_params(h);
+        k_obs_f32<<<grid_for(count), 256, 0, h->stream>>>(P, h->grid32, h->agent_xy, P.B, P.n_agents, tmp);
+        DW_LAUNCHED(h);
+        DW_CUDA_TRY(h, cudaMemcpyAsync(obs, tmp, count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return DW_OK;
+    }
     int rc = compute_obs(h);
     if (rc || !count) return rc;
     if (!obs) return DW_E_INVALID;
     return export_f32(h, h->obs, count, obs);
+}
+
+extern "C" int dw_f32_stats(dw_handle *h, uint64_t *out) {
+    if (!h || !out) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    unsigned long long t[2] = {0, 0};
+    if (h->f32_stats) {
+        DW_CUDA_TRY(h, cudaMemcpyAsync(t, h->f32_stats, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
+        DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    out[0] = h->f32_cells; out[1] = t[0]; out[2] = t[1];
+    return DW_OK;
+}
+
+extern "C" int dw_debug_time_materialise(dw_handle *h, int32_t fp32, int32_t reps, double *ms_per_call) {
+    if (!h || !ms_per_call || reps < 1) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!f32_arith_ok(h)) return dw_fail(h, DW_E_STATE, "dw_debug_time_materialise", "needs a lattice-resident state (run fused steps first)");
+    cudaEvent_t e0, e1;
+    DW_CUDA_TRY(h, cudaEventCreate(&e0));
+    DW_CUDA_TRY(h, cudaEventCreate(&e1));
+    int rc = DW_OK;
+    for (int r = -1; r < reps && !rc; ++r) {           // r = -1: warm-up (allocations)
+        if (r == 0) DW_CUDA_TRY(h, cudaEventRecord(e0, h->stream));
+        if (fp32) rc = materialise_f32(h);
+        else { h->grid_valid = false; rc = ensure_grid(h); }
+    }
+    DW_CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+    DW_CUDA_TRY(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DW_CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_call = (double)ms / reps;
+    return rc;
 }
 
 extern "C" int dw_get_agents(dw_handle *h, int64_t *agent_indices, double *agent_states) {
@@ -1475,6 +1593,19 @@ extern "C" int dw_debug_markstein(dw_handle *h, uint32_t kmax, uint32_t *bad) {
     if (rc) return rc;
     DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
     k_debug_markstein<<<148 * 4, 256, 0, h->stream>>>(kmax, h->slow_count + 1);
+    DW_CUDA_TRY(h, cudaGetLastError());
+    DW_CUDA_TRY(h, cudaMemcpyAsync(bad, h->slow_count + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DW_OK;
+}
+
+extern "C" int dw_debug_markstein_f32(dw_handle *h, uint32_t kmax, uint32_t *bad) {
+    if (!h || !bad) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = dev_alloc(h, &h->slow_count, (size_t)2);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->slow_count + 1, 0, sizeof(unsigned int), h->stream));
+    k_debug_markstein_f32<<<148 * 4, 256, 0, h->stream>>>(kmax, h->slow_count + 1);
     DW_CUDA_TRY(h, cudaGetLastError());
     DW_CUDA_TRY(h, cudaMemcpyAsync(bad, h->slow_count + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -695,8 +695,10 @@ class RLDaisyWorld:
         return obs
 
     def grid_f32(self):
-        """env.grid as float32, converted on the device (half the download). The covers are exact lattice values, so this is
-        one rounding of the exact fp64 fields: relative error <= 6e-8 (BASELINE's fp32 tolerance is 1e-5)."""
+        """env.grid as float32 -- the fp32 mode. Lattice-resident state (after run() / lattice-resident step()): materialised
+        with fp32 arithmetic from the packed lattice (k_forward_f32): covers and bare fraction are the float32 roundings of
+        the reference values, temperatures within 1e-5 relative (observed 3e-6). Otherwise: env.grid converted on the device
+        (6e-8). Half the download either way."""
         B, N, n = self._shape
         out = np.empty((B, self.ch, N, N), dtype=np.float32)
         self._push()
@@ -704,12 +706,19 @@ class RLDaisyWorld:
         return out
 
     def observe_f32(self):
-        """observe() as float32 (what an fp32 policy network consumes), converted on the device."""
+        """observe() as float32 (what an fp32 policy network consumes): the agents' windows of grid_f32()."""
         B, N, n = self._shape
         out = np.zeros((B, n, self.ch, 3, 3), dtype=np.float32)
         self._push()
         self._check(self._lib.dw_get_obs_f32(self._h, _ptr(out, C.c_float)), "dw_get_obs_f32")
         return out
+
+    def f32_stats(self):
+        """Tier counters of the fp32-arithmetic materialisation: cells evaluated, cells whose bare fraction went on to the fp64
+        fast path (fp32 value within its error bound of a rounding tie), cells that needed the literal cell."""
+        out = (C.c_uint64 * 3)()
+        self._check(self._lib.dw_f32_stats(self._h, out), "dw_f32_stats")
+        return {"cells": int(out[0]), "fp64_tier": int(out[1]), "literal": int(out[2])}
 
     def set_mlp(self, parameters):
         """Weights of the reference's MLP policy (daisy/agents/mlp.py: MLP.get_parameters()) for policy="mlp": the
