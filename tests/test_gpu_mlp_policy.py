@@ -81,3 +81,37 @@ def test_mlp_policy_needs_weights():
         env.run(2, policy="mlp")
     with pytest.raises(DaisyWorldError):
         env.set_mlp(np.zeros(7))
+
+
+def test_in_kernel_mlp_equals_the_per_step_policy_path(monkeypatch):
+    """64x64 worlds: windows + network run inside the persistent fused kernel (dw_mlp_decide64). Same worlds through the
+    per-step path (k_obs_mlp between one-step launches, DW_MLP_UNFUSED=1): identical state, agents, rewards and lifespans.
+    70 steps = several 16-step work items per world (the pre-state is handed from item to item through lat_pre), 300 worlds
+    = more work items than resident CTAs."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    rng = np.random.RandomState(11)
+    params = rng.randn(1808) * 1.5
+    out = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("DW_MLP_UNFUSED", "1")
+        else:
+            monkeypatch.delenv("DW_MLP_UNFUSED", raising=False)
+        np.random.seed(5)
+        env = RLDaisyWorld(grid_dimension=64, n_agents=7)
+        env.batch_size = 300
+        env.reset()
+        env.set_mlp(params)
+        env.reset_lifespans()
+        env.run(3, policy="mlp")
+        env.run(70, policy="mlp")
+        obs = env.observe()
+        out.append((env.grid.copy(), env.agent_indices.copy(), env.agent_states.copy(), obs, env.lifespans()))
+    a, b = out
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[4][0], b[4][0])
+    np.testing.assert_array_equal(a[4][1], b[4][1])
+    assert len(np.unique(a[1])) > 10          # the agents did move around

@@ -101,6 +101,7 @@ struct dw_handle {
     dw_config sc_cfg{};
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
     int persist_blocks = 0, sub64_blocks = 0;  // resident CTAs of the persistent kernels on this device
+    int persist_blocks_mlp = 0;                // the same for the kernel with the in-kernel MLP policy (more shared memory)
     int tile4_threads = 0;                     // block size chosen for k_fused_tile4 (world side a multiple of 4)
     // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
     dw_profile prof{};

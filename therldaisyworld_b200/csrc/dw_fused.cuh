@@ -12,6 +12,7 @@
 //
 // Roofline: the kernel is bound by the FP64 pipe (64 DFMA/clk/SM); HBM traffic is 8 B per cell per LAUNCH.
 #pragma once
+#include <type_traits>
 #include "dw_common.cuh"
 
 #ifndef DW_N64_ROW_UNROLL
@@ -86,6 +87,10 @@ struct FusedArgs {
     int n_pairs, n_chunks;      // work items = n_pairs (worlds) * n_chunks, chunk-major
     unsigned int *queue;        // [1] next work item (zeroed before the launch)
     unsigned int *pair_done;    // [n_pairs] chunks completed per world (zeroed before the launch)
+    // DW_POLICY_MLP inside the persistent 64x64 kernel (k_fused_n64_persist<.., true>)
+    const double *mlp_w;        // [sets][DW_MLP_PARAMS] network weights (device)
+    int mlp_wpm, mlp_half, mlp_adv, pad3_;   // population mode (wpm > 0): worlds per member, agents on the member's net, adversary set
+    double SL_prev;             // S*L of the step before the launch's first one (observation windows of step 0)
 };
 
 __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
@@ -668,7 +673,8 @@ struct __align__(16) N64Smem {
 // daisy_world_rl.py:186-216, resolved in parallel): every lane decides from the pre-move state, moves, and the grazers of
 // one cell are ordered by MATCH.ANY -- the lowest lane eats, later ones find the cell empty and gain 0.0 (App. B.8).
 // Also does the per-step agent bookkeeping (agents_done_at += !done, done = reward < 0.1) since the state is final here.
-__device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int b, uint32_t *cb, N64Smem &sm, int lane, int n) {
+__device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int b, uint32_t *cb, N64Smem &sm, int lane, int n,
+                                                  const int *mlp_act = nullptr) {
     constexpr int N = 64;
     const bool active = lane < n;
     double st = 0.0;
@@ -680,6 +686,7 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
         const int pol = A.sc[j].policy;
         if (pol == DW_POLICY_REPLAY) a = A.actions[((size_t)j * A.P.B + b) * n + lane];
         else if (pol == DW_POLICY_RANDOM) a = (int)(dw_hash_rng(A.seed, A.world0 + b, lane, A.step0 + j) % 9u);
+        else if (pol == DW_POLICY_MLP) a = mlp_act[lane];        // decided by dw_mlp_decide64 before this phase
         else if (pol != DW_POLICY_NONE) {
             const int xm = (x + N - 1) & (N - 1), xp = (x + 1) & (N - 1), ym = (y + N - 1) & (N - 1), yp = (y + 1) & (N - 1);
             const uint32_t c0 = cb[x * N + ym], c1 = cb[xm * N + y], c2 = cb[xp * N + y], c3 = cb[x * N + yp];
@@ -714,11 +721,92 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
     }
 }
 
-template <bool DIAG>
+// ---- DW_POLICY_MLP inside the fused kernel (row N1: MLP.get_action, daisy/agents/mlp.py:97-116) ------------------------------
+// What the policy sees at step j is the observation the previous step returned: the 3x3x7 window of the grid that step's
+// forward wrote (daisy_world_rl.py:246-263). Fused steps never write that grid, but the buffer the NEXT stencil will overwrite
+// still holds the post-graze state the previous step started from, so the nine window cells are re-evaluated from it exactly
+// as forward stored them (screened cell, literal next to ties; b' from the unrounded covers, rounded temperatures, agent
+// stamp: last agent on a cell wins) -- the same arithmetic as k_obs_mlp, which stays the path of every other kernel family.
+// One warp per agent: lanes 0..8 the window cells, then lanes = output neurons (16, 32, 9), sequential sums in k order.
+struct MlpSmem {
+    double x[8][64], h1[8][16], h2[8][32], o[8][16];
+    int act[DW_N64_MAX_AGENTS];
+};
+#define DW_MLP_W1 (63 * 16)
+#define DW_MLP_W2 (16 * 32)
+#define DW_MLP_NPARAMS (63 * 16 + 16 * 32 + 32 * 9)
+
+__device__ __noinline__ void dw_mlp_decide64(const FusedArgs *Ap, double SL, const uint32_t *pb, const N64Smem *smp, MlpSmem *ms, int n,
+                                             int agent, int b, int lane, int wib) {
+    const FusedArgs &A = *Ap;
+    const N64Smem &sm = *smp;
+    const DevParams &P = A.P;
+    double *x = ms->x[wib];
+    if (lane < 9) {
+        const double m = P.mask[lane];
+        const int cx = ((sm.xy[agent] & 0xffff) + lane / 3 + 63) & 63, cy = ((sm.xy[agent] >> 16) + lane % 3 + 63) & 63;
+        double l9[9], d9[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t k = pb[((cx + a + 63) & 63) * 64 + ((cy + c + 63) & 63)];
+                l9[a * 3 + c] = dw_milli(k & 0xffffu);
+                d9[a * 3 + c] = dw_milli(k >> 16);
+            }
+        ScrCell c;
+        if (!(P.screen && dw_screened_cell(P, SL / P.sigma, l9, d9, c))) dw_literal_rounded(P, SL, l9, d9, c);
+        double ch4 = dw_k2v(c.k[4]);
+        for (int k = 0; k < n; ++k)
+            if ((sm.xy[k] & 0xffff) == cx && (sm.xy[k] >> 16) == cy) ch4 = sm.st[k];
+        x[lane] = dw_k2v(c.k[0]) * m;
+        x[9 + lane] = dw_k2v(c.k[1]) * m;
+        x[18 + lane] = dw_k2v(c.k[2]) * m;
+        x[27 + lane] = dw_k2v(c.k[3]) * m;
+        x[36 + lane] = ch4 * m;
+        x[45 + lane] = dw_k2v(c.k[5]) * m;
+        x[54 + lane] = 0.0 * m;
+    }
+    __syncwarp();
+    const double *w = A.mlp_w;
+    if (A.mlp_wpm > 0) w += (size_t)(agent < A.mlp_half ? b / A.mlp_wpm : A.mlp_adv) * DW_MLP_NPARAMS;
+    const double *w1 = w, *w2 = w + DW_MLP_W1, *w3 = w2 + DW_MLP_W2;
+    if (lane < 16) {
+        double h = 0.0;
+        for (int k = 0; k < 63; ++k) h = h + x[k] * __ldg(w1 + k * 16 + lane);
+        ms->h1[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    {
+        double h = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) h = h + ms->h1[wib][k] * __ldg(w2 + k * 32 + lane);
+        ms->h2[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    if (lane < 9) {
+        double o = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o = o + ms->h2[wib][k] * __ldg(w3 + k * 9 + lane);
+        ms->o[wib][lane] = o;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int best = 0;
+        double bv = ms->o[wib][0];
+#pragma unroll
+        for (int o = 1; o < 9; ++o) if (ms->o[wib][o] > bv) { bv = ms->o[wib][o]; best = o; }
+        ms->act[agent] = best;
+    }
+    __syncwarp();
+}
+
+template <bool DIAG, bool MLP = false>
 __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(const __grid_constant__ FusedArgs A) {
     __shared__ N64Smem sm;
     __shared__ double s_tsum;
     __shared__ unsigned int s_cov[2];
+    __shared__ typename std::conditional<MLP, MlpSmem, int>::type s_mlp;
     constexpr int NN = 4096;
     const int n = A.P.n_agents;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -750,6 +838,11 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
 #pragma unroll
             for (int k = 0; k < 4; ++k) reinterpret_cast<uint4 *>(sm.buf[0])[tid + k * 256] = __ldcg(gin + tid + k * 256);
         }
+        if (MLP) {       // the post-graze state the step before this item started from: observation windows of the item's first step
+            const uint4 *gp = reinterpret_cast<const uint4 *>(A.lat_pre + (size_t)b * NN);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) reinterpret_cast<uint4 *>(sm.buf[1])[tid + k * 256] = __ldcg(gp + tid + k * 256);
+        }
         if (tid < n) {
             const size_t g = (size_t)b * n + tid;
             sm.st[tid] = __ldcg(A.agent_state + g);
@@ -765,11 +858,20 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
         for (int jl = 0; jl < kc; ++jl) {
             const int j = j0 + jl;
             uint32_t *cb = sm.buf[jl & 1], *nb = sm.buf[(jl + 1) & 1];
-            if (warp == DW_AGENT_WARP && n > 0) dw_agents_phase32(A, j, b, cb, sm, lane, n);
+            const int *mlp_act = nullptr;
+            if constexpr (MLP) {
+                if (n > 0 && A.sc[j].policy == DW_POLICY_MLP) {
+                    const double SLp = j == 0 ? A.SL_prev : A.sc[j - 1].SL;
+                    for (int i = warp; i < n; i += 8) dw_mlp_decide64(&A, SLp, nb, &sm, &s_mlp, n, i, b, lane, warp);
+                }
+                mlp_act = s_mlp.act;
+                __syncthreads();
+            }
+            if (warp == DW_AGENT_WARP && n > 0) dw_agents_phase32(A, j, b, cb, sm, lane, n, mlp_act);
 #ifndef DW_X_NOSYNC1            // timing experiments only (results are garbage without the barriers): upper bound of what removing
             __syncthreads();    // a barrier could buy, see DESIGN.md section 4
 #endif
-            if (j == A.K - 1) {
+            if (!MLP && j == A.K - 1) {
                 uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) gp[tid + k * 256] = reinterpret_cast<const uint4 *>(cb)[tid + k * 256];
@@ -814,6 +916,11 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             uint4 *gout = reinterpret_cast<uint4 *>(A.lat + (size_t)b * NN);
 #pragma unroll
             for (int k = 0; k < 4; ++k) gout[tid + k * 256] = reinterpret_cast<const uint4 *>(sm.buf[kc & 1])[tid + k * 256];
+        }
+        if (MLP) {      // post-graze state of the item's last step (still intact in the other buffer): next item's windows / lazy grid
+            uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gp[tid + k * 256] = reinterpret_cast<const uint4 *>(sm.buf[(kc + 1) & 1])[tid + k * 256];
         }
         if (tid < n) {
             const size_t g = (size_t)b * n + tid;

@@ -157,6 +157,15 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     const char *impl = getenv("DW_FUSED_IMPL");
     const bool n64 = h->cfg.dim == 64 && !(impl && !strcmp(impl, "generic"));
     const bool persist = n64 && !(impl && !strcmp(impl, "simple")) && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
+    if (policy == DW_POLICY_MLP) {           // in-kernel policy: persistent 64x64 kernel only (callers check mlp_fusable)
+        if (!persist || h->series_on || !h->mlp_set || h->pre != PRE_LAT)
+            return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "DW_POLICY_MLP is fused only in the persistent 64x64 kernel");
+        A.mlp_w = h->mlp_dev;
+        A.mlp_wpm = h->pop_members ? h->cfg.batch / h->pop_members : 0;
+        A.mlp_half = h->cfg.n_agents / 2;
+        A.mlp_adv = h->pop_adversary;
+        A.SL_prev = h->cfg.S * h->L_last;
+    }
     const int dimN = h->cfg.dim;
     const bool sub64 = !(impl && !strcmp(impl, "generic")) && (dimN == 8 || dimN == 16 || dimN == 32) &&
                        (64 / dimN) * (64 / dimN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
@@ -188,7 +197,19 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         A.lat = h->lat[h->lcur];                      // in place
         const long long items = (long long)A.n_pairs * A.n_chunks;
         const int grid = (int)(items < h->persist_blocks ? items : h->persist_blocks);
-        if (h->series_on) {
+        if (policy == DW_POLICY_MLP) {
+            if (!h->persist_blocks_mlp) {
+                int per_sm = 0, sms = 0;
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64_persist<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    cudaSharedmemCarveoutMaxShared));
+                DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_n64_persist<false, true>, 256, 0));
+                DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+                if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "persistent MLP kernel does not fit on an SM");
+                h->persist_blocks_mlp = per_sm * sms;
+            }
+            const int gm = (int)(items < h->persist_blocks_mlp ? items : h->persist_blocks_mlp);
+            k_fused_n64_persist<false, true><<<gm, 256, 0, h->stream>>>(A);
+        } else if (h->series_on) {
             A.series_T = h->series_T + h->series_pos;
             A.series_l = h->series_l + h->series_pos;
             A.series_d = h->series_d + h->series_pos;
@@ -331,6 +352,15 @@ static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_de
     return launch_fused(h, K, policy, act_dev, seed, alive);
 }
 
+// DW_POLICY_MLP inside the fused kernel: 64x64 worlds with <= 32 agents whose state is on the lattice with the post-graze
+// lattice of the last step at hand (the observation windows of the first fused step come from it)
+static bool mlp_fusable(const dw_handle *h) {
+    if (getenv("DW_MLP_UNFUSED")) return false;
+    const char *impl = getenv("DW_FUSED_IMPL");
+    return h->cfg.dim == 64 && h->cfg.n_agents > 0 && h->cfg.n_agents <= DW_N64_MAX_AGENTS && dw_fused_supported(h) && h->lat_valid &&
+           h->pre == PRE_LAT && h->mlp_set && !h->series_on && !impl;
+}
+
 static int stage_actions8(dw_handle *h, const int8_t *actions, size_t count) {
     if (h->action_cap < count) {
         if (h->action_dev) cudaFree(h->action_dev);
@@ -363,9 +393,14 @@ static int run_chunk_impl(dw_handle *h, int K, int policy, const int8_t *act_dev
     DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, DW_FUSED_MAX_STEPS * sizeof(unsigned int), h->stream));
     int rc = DW_OK;
     if (policy == DW_POLICY_MLP) {
-        // the policy runs between steps on the device (observation windows from the last pre-state, then the network);
-        // each step is a one-step launch replaying the device-resident actions
+        // 64x64 worlds on the lattice: windows + network inside the persistent kernel, all remaining steps in one launch
+        // (mlp_fusable). Elsewhere the policy runs between steps on the device (observation windows from the last pre-state,
+        // then the network) and each step is a one-step launch replaying the device-resident actions.
         for (int j = 0; j < K && !rc; ++j) {
+            if (mlp_fusable(h)) {
+                rc = launch_fused(h, K - j, DW_POLICY_MLP, nullptr, seed, h->alive + j);
+                break;
+            }
             rc = mlp_actions(h);
             if (rc) break;
             rc = dw_fused_supported(h) ? run_steps_fused(h, 1, DW_POLICY_REPLAY, h->action_dev, seed, h->alive + j)

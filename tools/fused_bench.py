@@ -28,7 +28,7 @@ if __name__ == "__main__":
         print("lib:", os.environ.get("DW_LIB", "default"))
         bench(1000, 4, "greedy"); bench(4736, 4, "greedy"); bench(4736, 0, "none")
         sys.exit(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "mlp":     # policy evaluated between one-step launches: wall time is the measure
+    if len(sys.argv) > 1 and sys.argv[1] == "mlp":     # wall time is the measure (DW_MLP_UNFUSED=1: policy between one-step launches)
         for B in (1000, 10000, 100000):
             bench(B, 4, "mlp", T=128 if B > 20000 else 383)
         sys.exit(0)
