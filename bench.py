@@ -311,6 +311,34 @@ def materialise_bench(local, peaks, worlds=4000, reps=10):
     return out
 
 
+def mlp_policy_bench(local, worlds=WORLDS, steps=T_STEPS - 1, reps=3):
+    """Row N1 at the bench's ensemble shape: the reference's MLP policy (63-16-32-9, random weights) chosen on the device every
+    step. 64x64 worlds: windows + network inside the persistent fused kernel; wall time of env.run incl. the final sync."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    np.random.seed(SEED)
+    env = RLDaisyWorld(grid_dimension=N, n_agents=N_AGENTS, device=local)
+    env.batch_size = worlds
+    env.reset()
+    env.set_mlp(np.random.RandomState(0).randn(1808))
+    env.run(1, policy="mlp")
+    lib, h = env._lib, env._h
+    _lib_check(lib, h, lib.dw_checkpoint_save(h), "dw_checkpoint_save")
+    best = None
+    for _ in range(reps):
+        _lib_check(lib, h, lib.dw_checkpoint_restore(h), "dw_checkpoint_restore")
+        env._pull_clock()
+        env.synchronize()
+        t0 = time.perf_counter()
+        env.run(steps, policy="mlp")
+        env.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    del env
+    return {"worlds": worlds, "grid": N, "n_agents": N_AGENTS, "env_steps": steps, "ms": best * 1e3,
+            "cell_updates_per_s": worlds * N * N * steps / best, "env_steps_per_s": worlds * steps / best,
+            "what": "env.run(policy='mlp'): MLP.get_action (daisy/agents/mlp.py:97-116) evaluated inside the fused kernel, wall clock"}
+
+
 def _lib_check(lib, h, rc, what):
     from therldaisyworld_b200 import _lib
     _lib.check(lib, h, rc, what)
@@ -609,6 +637,12 @@ def run_product(args):
             materialise = materialise_bench(local, load_peaks())
         except Exception as e:
             materialise = {"error": repr(e)}
+    mlp_rec = None
+    if rank == 0 and not args.no_extras:
+        try:
+            mlp_rec = mlp_policy_bench(local)
+        except Exception as e:
+            mlp_rec = {"error": repr(e)}
     if rank == 0:
         peaks = load_peaks()
         fused_s = prof.fused_ms * 1e-3
@@ -655,6 +689,7 @@ def run_product(args):
             "sustained": sustained,
             "dropin_step": dropin,
             "fp32_mode": materialise,
+            "mlp_policy": mlp_rec,
             "check": {"mean_done_at_after_T": mean_life, "mean_done_at_after_T_e2e": mean_life_e2e, "expected": float(T_STEPS),
                       "ensemble_stats": stats.tolist(),
                       "wall_s_resident": wall_res},

@@ -67,15 +67,18 @@ def test_in_kernel_series_matches_oracle_per_step():
         np.testing.assert_allclose(s2[t], [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()], rtol=1e-9)
 
 
-def test_series_for_other_world_sizes_matches_oracle_per_step():
-    """run_series on a shape outside the in-kernel series mode (16x16): same per-step means, sampled between one-step launches."""
+@pytest.mark.parametrize("name,policy", [("greedy_n16_b4_todeath", "greedy"), ("antigreedy_n8_b16_todeath", "antigreedy"),
+                                         ("greedy_n17_b2_params_200", "greedy")])
+def test_series_for_other_world_sizes_matches_oracle_per_step(name, policy):
+    """run_series on the other shapes: 16x16 and 8x8 (in-kernel series mode of the sub-64 persistent kernel; the 8x8 case fills
+    16 of the 64 world slots of a CTA) and 17x17 (sampled between one-step launches): same per-step means as the oracle."""
     from oracle.daisy_numpy import OracleGreedy, env_from_golden
-    z, meta = load_golden("greedy_n16_b4_todeath")
+    z, meta = load_golden(name)
     env = product_env_from_golden(z, meta)
     K = 40
-    series = env.run_series(K, policy="greedy")
+    series = env.run_series(K, policy=policy)
     oenv, _ = env_from_golden(z)
-    agent = OracleGreedy()
+    agent = OracleGreedy(greedy=policy == "greedy")
     obs = oenv.get_obs(oenv.agent_indices)
     for t in range(K):
         obs, _, _, _ = oenv.step(agent(obs))

@@ -101,6 +101,7 @@ struct dw_handle {
     dw_config sc_cfg{};
     unsigned int *persist_sync = nullptr;      // [1 + B] work queue + per-world progress of the persistent kernel
     int persist_blocks = 0, sub64_blocks = 0;  // resident CTAs of the persistent kernels on this device
+    int sub64_blocks_series = 0;               // sub-64 kernel in series mode
     int persist_blocks_mlp = 0;                // the same for the kernel with the in-kernel MLP policy (more shared memory)
     int tile4_threads = 0;                     // block size chosen for k_fused_tile4 (world side a multiple of 4)
     // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
@@ -1154,16 +1155,15 @@ static int materialise_f32(dw_handle *h) {
     if (!rc) rc = dev_alloc(h, &h->f32_stats, (size_t)2);
     if (rc) return rc;
     const DevParams P = make_params(h);
-    FastCoef F;
-    StepCoef S;
-    F32Coef Q;
-    make_fast_coef(h->cfg, F);
-    make_step_coef(h->cfg, h->L_last, S);
-    make_f32_coef(h->cfg, F, S, P, Q);
+    F32Args A{};
+    A.P = P;
+    make_fast_coef(h->cfg, A.F);
+    make_step_coef(h->cfg, h->L_last, A.C);
+    make_f32_coef(h->cfg, A.F, A.C, P, A.Q);
     if ((P.N & 1) == 0)
-        k_forward_f32<2><<<grid_for(B * NN / 2), 256, 0, h->stream>>>(P, F, S, Q, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
+        k_forward_f32<2><<<grid_for(B * NN / 2), 256, 0, h->stream>>>(A, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
     else
-        k_forward_f32<1><<<grid_for(B * NN), 256, 0, h->stream>>>(P, F, S, Q, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
+        k_forward_f32<1><<<grid_for(B * NN), 256, 0, h->stream>>>(A, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
     DW_LAUNCHED(h);
     if (P.n_agents > 0) {
         k_stamp_f32<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid32, h->agent_xy, h->agent_state);

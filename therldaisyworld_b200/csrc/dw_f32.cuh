@@ -66,13 +66,21 @@ __device__ __forceinline__ void dw_fast_x(const FastCoef &F, const StepCoef &C, 
     xd = __fma_rn(Rd, __fma_rn(rb, __fma_rn(-dTd, dTd, 1.0), -F.dtg), kd);
 }
 
-// fp64 tier of the bare fraction of one cell (rare: ~2 % of cells; kept out of line)
-__device__ __noinline__ float dw_f32_bare_slow(const DevParams &P, const FastCoef &F, const StepCoef &C, const uint32_t *g, unsigned N,
-                                               unsigned x, unsigned y, uint32_t pc, uint32_t E, uint32_t S, unsigned *nlit) {
+// fp64 tier of the bare fraction of one cell (rare: ~2 % of cells; out of line, called after the thread's stores so that
+// nothing of the fp32 evaluation is live across the call). Returns 1000 b' as the reference rounds it.
+__device__ __noinline__ float dw_f32_bare_slow(const DevParams *Pp, const FastCoef *Fp, const StepCoef *Cp, const uint32_t *g, unsigned N,
+                                               unsigned x, unsigned y, unsigned *nlit) {
+    const DevParams &P = *Pp;
+    const unsigned xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
+    const unsigned ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
+    const uint32_t *r0 = g + xm * N, *r1 = g + x * N, *r2 = g + xp * N;
+    const uint32_t pc = r1[y];
+    const uint32_t E = r1[ym] + r1[yp] + r0[y] + r2[y];
+    const uint32_t S = E + r0[ym] + r0[yp] + r2[ym] + r2[yp];
     // lattice fast path, unrounded covers -> b' with the tie filter of the screened forward (P.eps_b, units of 0.001);
     // then the literal cell. (Range failures come here too: the fp64 fast path is exact-or-flagged on its own.)
     double dxl, dxd;
-    dw_fast_x(F, C, pc, E, S, dxl, dxd);
+    dw_fast_x(*Fp, *Cp, pc, E, S, dxl, dxd);
     dxl = fmin(fmax(dxl, 0.0), 1000.0);
     dxd = fmin(fmax(dxd, 0.0), 1000.0);
     const double dxb = (1000.0 * P.p - dxl) - dxd;
@@ -80,8 +88,6 @@ __device__ __noinline__ float dw_f32_bare_slow(const DevParams &P, const FastCoe
     const bool in_range = dxl == dxl && dxd == dxd && P.screen;     // NaN (X' <= 0): literal
     if (!in_range || !(0.5 - fabs(dxb - kb64) > P.eps_b)) {
         *nlit += 1;
-        const unsigned xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
-        const unsigned ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
         double l9[9], d9[9];
         const unsigned xs[3] = {xm, x, xp}, ys[3] = {ym, y, yp};
 #pragma unroll
@@ -92,7 +98,7 @@ __device__ __noinline__ float dw_f32_bare_slow(const DevParams &P, const FastCoe
                 l9[a * 3 + c] = dw_milli(k & 0xffffu);
                 d9[a * 3 + c] = dw_milli(k >> 16);
             }
-        const LitCell o = dw_literal_cell(P, C.SL, l9, d9);
+        const LitCell o = dw_literal_cell(P, Cp->SL, l9, d9);
         kb64 = rint(o.nb * 1000.0);
     }
     return (float)kb64;
@@ -134,10 +140,13 @@ __device__ __forceinline__ F32Out dw_f32_cell(const F32Coef &Q, uint32_t pc, uin
 // W cells per thread (W = 2: horizontally adjacent, N even, 8-byte loads and stores; W = 1: any N). pre: post-graze lattice
 // the last step started from; cur: the lattice after that step (exact new covers). out: float [B,7,N,N], channels 0..6
 // written (4 before the agent stamp). stats[0] += cells sent to the fp64 tier, stats[1] += cells that needed the literal cell.
+struct F32Args { DevParams P; FastCoef F; StepCoef C; F32Coef Q; };
 template <int W>
-__global__ void __launch_bounds__(256) k_forward_f32(DevParams P, FastCoef F, StepCoef C, F32Coef Q, const uint32_t *__restrict__ pre,
-                                                     const uint32_t *__restrict__ cur, float *__restrict__ out,
-                                                     unsigned long long *stats) {
+__global__ void __launch_bounds__(256, 4) k_forward_f32(const __grid_constant__ F32Args A, const uint32_t *__restrict__ pre,
+                                                        const uint32_t *__restrict__ cur, float *__restrict__ out,
+                                                        unsigned long long *stats) {
+    const DevParams &P = A.P;
+    const F32Coef &Q = A.Q;
     const unsigned N = (unsigned)P.N, NN = N * N, GN = NN / W, gN = N / W;
     const size_t total = (size_t)P.B * GN, stride = (size_t)gridDim.x * blockDim.x;
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -165,18 +174,15 @@ __global__ void __launch_bounds__(256) k_forward_f32(DevParams P, FastCoef F, St
             pn[0] = v.x; pn[W - 1] = v.y;
         } else pn[0] = cur[(size_t)w.b * NN + x * N + y];
         float ch[7][W];
+        bool ok[W];
 #pragma unroll
         for (int c = 0; c < W; ++c) {
             const uint32_t pc = row[1][c + 1];
             const uint32_t E = row[1][c] + row[1][c + 2] + row[0][c + 1] + row[2][c + 1];
             const uint32_t S = E + row[0][c] + row[0][c + 2] + row[2][c] + row[2][c + 2];
             const F32Out o = dw_f32_cell(Q, pc, E, S);
-            float kb = o.b;
-            if (!o.ok) {
-                n64 += 1;
-                kb = dw_f32_bare_slow(P, F, C, g, N, x, y + c, pc, E, S, &nlit);
-            }
-            ch[0][c] = dw_div1000f(kb);
+            ok[c] = o.ok;
+            ch[0][c] = dw_div1000f(o.b);
             ch[1][c] = dw_div1000f(dw_half2f<0>(pn[c]));
             ch[2][c] = dw_div1000f(dw_half2f<1>(pn[c]));
             ch[3][c] = dw_round3f(o.T * Q.inv_sqrt_g);
@@ -189,6 +195,15 @@ __global__ void __launch_bounds__(256) k_forward_f32(DevParams P, FastCoef F, St
         for (int q = 0; q < 7; ++q) {
             if (W == 2) *reinterpret_cast<float2 *>(ob + (size_t)q * NN) = make_float2(ch[q][0], ch[q][W - 1]);
             else ob[(size_t)q * NN] = ch[q][0];
+        }
+        // cells whose fp32 bare fraction sits within its error bound of a rounding tie (or outside the accepted range):
+        // fp64 tier, the stored channel 0 is overwritten
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+            if (!ok[c]) {
+                n64 += 1;
+                ob[c] = dw_div1000f(dw_f32_bare_slow(&A.P, &A.F, &A.C, g, N, x, y + c, &nlit));
+            }
         }
     }
     if (stats) {

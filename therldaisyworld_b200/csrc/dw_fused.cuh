@@ -772,8 +772,17 @@ __device__ __noinline__ void dw_mlp_decide64(const FusedArgs *Ap, double SL, con
     if (A.mlp_wpm > 0) w += (size_t)(agent < A.mlp_half ? b / A.mlp_wpm : A.mlp_adv) * DW_MLP_NPARAMS;
     const double *w1 = w, *w2 = w + DW_MLP_W1, *w3 = w2 + DW_MLP_W2;
     if (lane < 16) {
+        // products first (independent loads and multiplications, 21 at a time), then the sum in k order: the dependent chain is
+        // 63 additions instead of 63 x (load + multiply + add)
         double h = 0.0;
-        for (int k = 0; k < 63; ++k) h = h + x[k] * __ldg(w1 + k * 16 + lane);
+#pragma unroll 1
+        for (int k0 = 0; k0 < 63; k0 += 21) {
+            double pr[21];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) pr[k] = x[k0 + k] * __ldg(w1 + (k0 + k) * 16 + lane);
+#pragma unroll
+            for (int k = 0; k < 21; ++k) h = h + pr[k];
+        }
         ms->h1[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
     }
     __syncwarp();
@@ -1104,10 +1113,12 @@ __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, i
     }
 }
 
-template <int N>
+template <int N, bool DIAG = false>
 __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(const __grid_constant__ FusedArgs A) {
     constexpr int WX = 64 / N, W = WX * WX, TX = N / 4;
     __shared__ Sub64Smem<N> sm;
+    __shared__ double s_tsum;               // series mode (DIAG): per-step sums over the CTA's worlds, see k_fused_n64_persist
+    __shared__ unsigned int s_cov[2];
     const int n = A.P.n_agents, B = A.P.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
@@ -1153,6 +1164,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
         }
         for (int q = tid; q < 2 * W * 2; q += 256) (&sm.smax[0][0][0])[q] = 0;
         if (tid < W) sm.life[tid] = 0;
+        if (DIAG && tid == 0) { s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u; }
         __syncthreads();
 
 #pragma unroll 1
@@ -1176,13 +1188,36 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
             }
             const StepCoef C = A.sc[j];
             unsigned tiemin = 0xffffffffu;
-            const uint32_t mx = dw_tile_core(A.F, C, RowsSub64<N>{cb, row_base, lr0, tx, lane}, StoreWorld64{nb, r0, tx}, &tiemin);
+            double tsum = 0.0;
+            const uint32_t mx = dw_tile_core<RowsSub64<N>, StoreWorld64, DIAG>(A.F, C, RowsSub64<N>{cb, row_base, lr0, tx, lane},
+                                                                                 StoreWorld64{nb, r0, tx}, &tiemin, &tsum);
             int (*smx)[2] = sm.smax[jl & 1];
             bool stale = false;
             const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < A.F.tie_thresh);
             if (flagged) stale = dw_fix_warp_sub<N>(&A, &A.sc[j], cb, nb, flagged, r0, tx * 4, lane, smx);
             if (!stale && mx) { atomicMax(&smx[wl][0], (int)(mx & 0xffffu)); atomicMax(&smx[wl][1], (int)(mx >> 16)); }
+            if (DIAG) {
+                // series mode: this thread's tile (fix-ups included) and temperature sum, unless its world slot is empty
+                unsigned int cl = 0, cd = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(nb + (r0 + i) * 64 + tx * 4);
+                    cl += (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu) + (v.w & 0xffffu);
+                    cd += (v.x >> 16) + (v.y >> 16) + (v.z >> 16) + (v.w >> 16);
+                }
+                if (wl >= n_worlds) { tsum = 0.0; cl = 0; cd = 0; }
+                for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+                cl = __reduce_add_sync(0xffffffffu, cl);
+                cd = __reduce_add_sync(0xffffffffu, cd);
+                if (lane == 0) { atomicAdd(&s_tsum, tsum); atomicAdd(&s_cov[0], cl); atomicAdd(&s_cov[1], cd); }
+            }
             __syncthreads();
+            if (DIAG && tid == 32) {               // warp 1: warp 0 does the lifespan bookkeeping below
+                atomicAdd(A.series_T + j, s_tsum);
+                atomicAdd(A.series_l + j, (unsigned long long)s_cov[0]);
+                atomicAdd(A.series_d + j, (unsigned long long)s_cov[1]);
+                s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u;      // the next adds come after the next step's first barrier
+            }
             if (warp == 0) {
                 // lifespan bookkeeping of step j for the CTA's worlds (notebook cell 2): grid_done = max(grid[:,1:3]) <= 0.005
                 unsigned alive = 0;

@@ -222,7 +222,14 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         // worlds of 8x8, 16x16 or 32x32: (64/N)^2 of them per CTA in the 4x4-tile kernel, same persistent queue
         const int N = h->cfg.dim, W = (64 / N) * (64 / N);
         void (*kern)(const FusedArgs) = N == 8 ? k_fused_sub64_persist<8> : (N == 16 ? k_fused_sub64_persist<16> : k_fused_sub64_persist<32>);
-        int &blocks = h->sub64_blocks;
+        if (h->series_on) {
+            kern = N == 8 ? k_fused_sub64_persist<8, true> : (N == 16 ? k_fused_sub64_persist<16, true> : k_fused_sub64_persist<32, true>);
+            A.series_T = h->series_T + h->series_pos;
+            A.series_l = h->series_l + h->series_pos;
+            A.series_d = h->series_d + h->series_pos;
+            h->series_pos += K;
+        }
+        int &blocks = h->series_on ? h->sub64_blocks_series : h->sub64_blocks;
         if (!blocks) {
             int per_sm = 0, sms = 0;
             DW_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -566,8 +573,12 @@ extern "C" int dw_get_population_results(dw_handle *h, double *fitness, int64_t 
 extern "C" int dw_run_series(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed, double *out) {
     if (!h || !out || K < 1 || K > DW_FUSED_MAX_STEPS) return DW_E_INVALID;
     DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    if (h->cfg.dim != 64 || h->cfg.n_agents > DW_N64_MAX_AGENTS || !dw_fused_supported(h) || policy == DW_POLICY_MLP)
-        return dw_fail(h, DW_E_UNSUPPORTED, "dw_run_series", "series mode runs in the persistent 64x64 kernel (n_agents <= 32, built-in policies)");
+    const int dN = h->cfg.dim;
+    const bool n64_ok = dN == 64 && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
+    const bool sub_ok = (dN == 8 || dN == 16 || dN == 32) && (64 / dN) * (64 / dN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
+    if (!(n64_ok || sub_ok) || !dw_fused_supported(h) || policy == DW_POLICY_MLP || getenv("DW_FUSED_IMPL"))
+        return dw_fail(h, DW_E_UNSUPPORTED, "dw_run_series",
+                       "series mode runs in the persistent kernels (64x64 with <= 32 agents; 8x8, 16x16, 32x32 with <= 256 agents per CTA; built-in policies)");
     int rc = dev_alloc(h, &h->series_T, (size_t)DW_FUSED_MAX_STEPS);
     if (!rc) rc = dev_alloc(h, &h->series_l, (size_t)DW_FUSED_MAX_STEPS);
     if (!rc) rc = dev_alloc(h, &h->series_d, (size_t)DW_FUSED_MAX_STEPS);

@@ -419,15 +419,16 @@ class RLDaisyWorld:
 
     def run_series(self, K, policy="greedy", actions=None, seed=0):
         """run() that also returns the per-step ensemble means [K, 3] = (global mean temperature of that step's forward --
-        env.temp.mean() --, mean light cover, mean dark cover): reduced inside the fused kernel for 64x64 worlds with at most 32
-        agents, sampled between one-step launches for every other shape."""
+        env.temp.mean() --, mean light cover, mean dark cover): reduced inside the persistent fused kernels (64x64 worlds with at
+        most 32 agents; 8x8, 16x16 and 32x32 worlds), sampled between one-step launches for every other shape."""
         B, N, n = self._shape
         colliding = self.collision_mode == 1 and n      # noise from the caller's NumPy stream every step: host-driven loop
         a8 = None
         if policy == "replay":
             a8 = np.ascontiguousarray(canonical_actions8(np.asarray(actions).reshape(-1, B, n)[:K]))
         out = np.zeros((int(K), 3))
-        if N != 64 or n > 32 or policy == "mlp" or colliding:
+        in_kernel = (N == 64 and n <= 32) or (N in (8, 16, 32) and (64 // N) ** 2 * n <= 256)
+        if not in_kernel or policy == "mlp" or colliding:
             # other shapes: one fused step per sample, the same three means from the device-side reductions
             for t in range(int(K)):
                 self.run(1, policy=policy, actions=None if a8 is None else a8[t:t + 1], seed=seed)
