@@ -45,3 +45,30 @@ def test_population_rollout_at_n64_matches_oracle():
         assert steps == member_steps[m]
         np.testing.assert_array_equal(ts, total_steps[m])
         np.testing.assert_allclose(fitness[m], f, rtol=1e-12)
+
+
+@pytest.mark.parametrize("N,P,W,n,max_steps", [(16, 6, 32, 4, 200), (8, 5, 20, 6, 150), (64, 3, 8, 6, 90)])
+def test_fused_population_segments_equal_the_per_step_path(monkeypatch, N, P, W, n, max_steps):
+    """Population rollouts run as fused 64-step segments (policy inside the persistent kernels, per-step agent states recorded,
+    members' bookkeeping in one post-pass, k_pop_post); DW_POP_UNFUSED=1 keeps the per-step launch sequence: same fitness bit
+    for bit (same summation order), same stopping steps and step totals."""
+    from therldaisyworld_b200.es import evaluate_population
+    rng = np.random.RandomState(9)
+    members = rng.randn(P, 1808) * 0.7
+    members[0] = 0.0
+    out = []
+    monkeypatch.setenv("DW_MLP_FUSE_SUB64", "1")          # the sub-64 kernel's in-kernel policy is opt-in (slower on this shape)
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("DW_POP_UNFUSED", "1")
+        else:
+            monkeypatch.delenv("DW_POP_UNFUSED", raising=False)
+        np.random.seed(21)
+        fitness, total_steps, member_steps, env = evaluate_population(members, adversary_idx=1, max_steps=max_steps, worlds_per_member=W,
+                                                                       grid_dimension=N, n_agents=n)
+        out.append((fitness, total_steps, member_steps, env.agent_states.copy(), env.agent_indices.copy()))
+    a, b = out
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[0], b[0])
+    assert (a[2] > 1).all()

@@ -91,6 +91,7 @@ struct FusedArgs {
     const double *mlp_w;        // [sets][DW_MLP_PARAMS] network weights (device)
     int mlp_wpm, mlp_half, mlp_adv, pad3_;   // population mode (wpm > 0): worlds per member, agents on the member's net, adversary set
     double SL_prev;             // S*L of the step before the launch's first one (observation windows of step 0)
+    double *rew_series;         // [K][B*n] agent states after each step's update_agents (population post-pass, k_pop_post), or NULL
 };
 
 __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
@@ -718,6 +719,7 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
         sm.st[lane] = st;
         sm.xy[lane] = x | (y << 16);
         sm.ada[lane] += (st < 0.1) ? 0 : 1;
+        if (A.rew_series) A.rew_series[((size_t)j * A.P.B + b) * n + lane] = st;
     }
 }
 
@@ -728,20 +730,140 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
 // as forward stored them (screened cell, literal next to ties; b' from the unrounded covers, rounded temperatures, agent
 // stamp: last agent on a cell wins) -- the same arithmetic as k_obs_mlp, which stays the path of every other kernel family.
 // One warp per agent: lanes 0..8 the window cells, then lanes = output neurons (16, 32, 9), sequential sums in k order.
-struct MlpSmem {
-    double x[8][64], h1[8][16], h2[8][32], o[8][16];
-    int act[DW_N64_MAX_AGENTS];
+// Four agents of one world per warp (lane utilisation: one warp per agent keeps 9-16 of 32 lanes busy and costs ~1200
+// warp-instructions per agent; packed it is ~1700 per four agents). Every output neuron is still ONE accumulator summed in k
+// order with separate multiply and add, so the values are those of k_mlp_act / k_obs_mlp bit for bit.
+struct MlpScratch {            // per warp; h2 aliases x (dead after layer 1), o aliases h1 (dead after layer 2)
+    double x[4][64];
+    double h1[4][16];
 };
 #define DW_MLP_W1 (63 * 16)
 #define DW_MLP_W2 (16 * 32)
 #define DW_MLP_NPARAMS (63 * 16 + 16 * 32 + 32 * 9)
 
-__device__ __noinline__ void dw_mlp_decide64(const FusedArgs *Ap, double SL, const uint32_t *pb, const N64Smem *smp, MlpSmem *ms, int n,
-                                             int agent, int b, int lane, int wib) {
+// pb: the post-graze lattice the previous step started from, 64 words per row, world of side N at (r0w, c0w); xyw / stw: the
+// world's agents (x | y << 16, state after the previous step); agents a0 .. a0+3 (those < n) get their action in actw[].
+// wset[q]: weight set of agent a0 + q.
+template <int N>
+__device__ __noinline__ void dw_mlp_decide4(const FusedArgs *Ap, double SL, const uint32_t *pb, int r0w, int c0w, const int *xyw,
+                                            const double *stw, int n, int a0, const int (&wset)[4], MlpScratch *ms, int *actw, int lane) {
+    const FusedArgs &A = *Ap;
+    const DevParams &P = A.P;
+    // ---- observation windows: task t = cell * 4 + agent (the corner cell 8 of all four agents forms the second pass, which a
+    // Von Neumann mask skips); cells with a zero mask contribute exact zeros and are not evaluated
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int t = lane + 32 * pass;
+        const int cell = t >> 2, q = t & 3, a = a0 + q;
+        const bool in = t < 36;
+        const double m = in ? P.mask[cell] : 0.0;
+        const bool eval = in && a < n && m != 0.0;
+        if (pass == 1 && !__any_sync(0xffffffffu, eval)) {
+            if (in) for (int ch = 0; ch < 7; ++ch) ms->x[q][ch * 9 + cell] = 0.0;
+            break;
+        }
+        double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (eval) {
+            const int cx = ((xyw[a] & 0xffff) + cell / 3 + N - 1) & (N - 1), cy = ((xyw[a] >> 16) + cell % 3 + N - 1) & (N - 1);
+            double l9[9], d9[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t k = pb[(r0w + ((cx + i + N - 1) & (N - 1))) * 64 + c0w + ((cy + c + N - 1) & (N - 1))];
+                    l9[i * 3 + c] = dw_milli(k & 0xffffu);
+                    d9[i * 3 + c] = dw_milli(k >> 16);
+                }
+            ScrCell c;
+            if (!(P.screen && dw_screened_cell(P, SL / P.sigma, l9, d9, c))) dw_literal_rounded(P, SL, l9, d9, c);
+            double ch4 = dw_k2v(c.k[4]);
+            for (int k = 0; k < n; ++k)
+                if ((xyw[k] & 0xffff) == cx && (xyw[k] >> 16) == cy) ch4 = stw[k];
+            v[0] = dw_k2v(c.k[0]) * m; v[1] = dw_k2v(c.k[1]) * m; v[2] = dw_k2v(c.k[2]) * m; v[3] = dw_k2v(c.k[3]) * m;
+            v[4] = ch4 * m; v[5] = dw_k2v(c.k[5]) * m; v[6] = 0.0 * m;
+        }
+        if (in) {
+#pragma unroll
+            for (int ch = 0; ch < 7; ++ch) ms->x[q][ch * 9 + cell] = v[ch];
+        }
+    }
+    __syncwarp();
+    const double *wq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wq[q] = A.mlp_w + (size_t)wset[q] * DW_MLP_NPARAMS;
+    // ---- layer 1: lane = (agent pair, neuron); products 21 at a time, then the sums in k order
+    {
+        const int g = lane >> 4, o = lane & 15;
+        const double *wa = wq[2 * g], *wb = wq[2 * g + 1];
+        const double *xa = ms->x[2 * g], *xb = ms->x[2 * g + 1];
+        double ha = 0.0, hb = 0.0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < 63; k0 += 21) {
+            double pa[21], pbv[21];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) {
+                pa[k] = xa[k0 + k] * __ldg(wa + (k0 + k) * 16 + o);
+                pbv[k] = xb[k0 + k] * __ldg(wb + (k0 + k) * 16 + o);
+            }
+#pragma unroll
+            for (int k = 0; k < 21; ++k) { ha = ha + pa[k]; hb = hb + pbv[k]; }
+        }
+        __syncwarp();                           // every lane is done reading x before h1 ... (h2 below aliases x)
+        ms->h1[2 * g][o] = ha * (ha > 0.0 ? 1.0 : 0.0);
+        ms->h1[2 * g + 1][o] = hb * (hb > 0.0 ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    // ---- layer 2: lane = neuron, four agents
+    double (*h2)[32] = reinterpret_cast<double (*)[32]>(&ms->x[0][0]);          // [4][32]
+    {
+        double h[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h[q] = h[q] + ms->h1[q][k] * __ldg(wq[q] + DW_MLP_W1 + k * 32 + lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h2[q][lane] = h[q] * (h[q] > 0.0 ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    // ---- layer 3: lane = (agent, output 0..7), then output 8 of the four agents on lanes 0..3
+    double (*outv)[16] = ms->h1;                                                 // [4][16], h1 is dead
+    {
+        const int q = lane >> 3, o = lane & 7;
+        const double *w3 = wq[q] + DW_MLP_W1 + DW_MLP_W2;
+        double s8 = 0.0, s9 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s8 = s8 + h2[q][k] * __ldg(w3 + k * 9 + o);
+        if (lane < 4) {
+            const double *w3b = wq[lane] + DW_MLP_W1 + DW_MLP_W2;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) s9 = s9 + h2[lane][k] * __ldg(w3b + k * 9 + 8);
+        }
+        __syncwarp();                           // layer-2 reads of h1 are long done; outv aliases it
+        outv[q][o] = s8;
+        if (lane < 4) outv[lane][8] = s9;
+    }
+    __syncwarp();
+    if (lane < 4 && a0 + lane < n) {
+        int best = 0;
+        double bv = outv[lane][0];
+#pragma unroll
+        for (int o = 1; o < 9; ++o) if (outv[lane][o] > bv) { bv = outv[lane][o]; best = o; }
+        actw[a0 + lane] = best;
+    }
+    __syncwarp();
+}
+
+// One warp per agent (the 64x64 kernel): lanes 0..8 the window cells, then lanes = output neurons (16, 32, 9). Measured
+// against the packed routine above inside k_fused_n64_persist at 1000 worlds x 4 agents: 8.7 ms vs 10.6 ms per 383 steps --
+// with 4 CTAs per SM the policy phase is bound by the latency of its dependent chain, not by its instruction count, so four
+// agents on four warps beat four agents on one.
+__device__ __noinline__ void dw_mlp_decide64(const FusedArgs *Ap, double SL, const uint32_t *pb, const N64Smem *smp, double *scr, int *act, int n,
+                                             int agent, int b, int lane) {
     const FusedArgs &A = *Ap;
     const N64Smem &sm = *smp;
     const DevParams &P = A.P;
-    double *x = ms->x[wib];
+    double *x = scr, *h2 = scr + 64, *h1 = scr + 96, *ov = scr + 112;       // per-warp scratch: x[64] | h2[32] | h1[16] | o[16]
     if (lane < 9) {
         const double m = P.mask[lane];
         const int cx = ((sm.xy[agent] & 0xffff) + lane / 3 + 63) & 63, cy = ((sm.xy[agent] >> 16) + lane % 3 + 63) & 63;
@@ -783,32 +905,38 @@ __device__ __noinline__ void dw_mlp_decide64(const FusedArgs *Ap, double SL, con
 #pragma unroll
             for (int k = 0; k < 21; ++k) h = h + pr[k];
         }
-        ms->h1[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
+        h1[lane] = h * (h > 0.0 ? 1.0 : 0.0);
     }
     __syncwarp();
     {
         double h = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) h = h + ms->h1[wib][k] * __ldg(w2 + k * 32 + lane);
-        ms->h2[wib][lane] = h * (h > 0.0 ? 1.0 : 0.0);
+        for (int k = 0; k < 16; ++k) h = h + h1[k] * __ldg(w2 + k * 32 + lane);
+        h2[lane] = h * (h > 0.0 ? 1.0 : 0.0);
     }
     __syncwarp();
     if (lane < 9) {
         double o = 0.0;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) o = o + ms->h2[wib][k] * __ldg(w3 + k * 9 + lane);
-        ms->o[wib][lane] = o;
+        for (int k = 0; k < 32; ++k) o = o + h2[k] * __ldg(w3 + k * 9 + lane);
+        ov[lane] = o;
     }
     __syncwarp();
     if (lane == 0) {
         int best = 0;
-        double bv = ms->o[wib][0];
+        double bv = ov[0];
 #pragma unroll
-        for (int o = 1; o < 9; ++o) if (ms->o[wib][o] > bv) { bv = ms->o[wib][o]; best = o; }
-        ms->act[agent] = best;
+        for (int o = 1; o < 9; ++o) if (ov[o] > bv) { bv = ov[o]; best = o; }
+        act[agent] = best;
     }
     __syncwarp();
 }
+
+
+struct MlpSmem {
+    double scratch[8][128];
+    int act[DW_N64_MAX_AGENTS];
+};
 
 template <bool DIAG, bool MLP = false>
 __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(const __grid_constant__ FusedArgs A) {
@@ -871,7 +999,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             if constexpr (MLP) {
                 if (n > 0 && A.sc[j].policy == DW_POLICY_MLP) {
                     const double SLp = j == 0 ? A.SL_prev : A.sc[j - 1].SL;
-                    for (int i = warp; i < n; i += 8) dw_mlp_decide64(&A, SLp, nb, &sm, &s_mlp, n, i, b, lane, warp);
+                    for (int i = warp; i < n; i += 8) dw_mlp_decide64(&A, SLp, nb, &sm, s_mlp.scratch[warp], s_mlp.act, n, i, b, lane);
                 }
                 mlp_act = s_mlp.act;
                 __syncthreads();
@@ -1049,7 +1177,7 @@ __device__ __noinline__ bool dw_fix_warp_sub(const FusedArgs *A, const StepCoef 
 // independent, so the warps of a CTA run their agent phases concurrently.
 template <int N>
 __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, int group, uint32_t *cb, Sub64Smem<N> &sm, int lane, int n,
-                                                    int a_lo, int n_act) {
+                                                    int a_lo, int n_act, const int *mlp_act = nullptr) {
     constexpr int WX = 64 / N, W = WX * WX;
     const int pol = A.sc[j].policy;
     // pass 1: every agent decides from the pre-move state
@@ -1058,7 +1186,8 @@ __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, i
         const int x = sm.xy[a] & 0xffff, y = sm.xy[a] >> 16;
         const size_t gw = (size_t)group * W + wl;
         int act = 0;
-        if (pol == DW_POLICY_REPLAY) act = A.actions[((size_t)j * A.P.B + gw) * n + i];
+        if (pol == DW_POLICY_MLP) act = mlp_act[a];          // decided by dw_mlp_decide4 before this phase
+        else if (pol == DW_POLICY_REPLAY) act = A.actions[((size_t)j * A.P.B + gw) * n + i];
         else if (pol == DW_POLICY_RANDOM) act = (int)(dw_hash_rng(A.seed, A.world0 + (uint32_t)gw, i, A.step0 + j) % 9u);
         else if (pol != DW_POLICY_NONE) {
             const int r = (wl / WX) * N, c = (wl % WX) * N;
@@ -1108,14 +1237,19 @@ __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, i
             sm.st[a] = st;
             sm.xy[a] = x | (y << 16);
             sm.ada[a] += (st < 0.1) ? 0 : 1;
+            if (A.rew_series) A.rew_series[((size_t)j * A.P.B + (size_t)group * W) * n + a] = st;
         }
         __syncwarp();
     }
 }
 
-template <int N, bool DIAG = false>
-__global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(const __grid_constant__ FusedArgs A) {
+// MLP = true: DW_POLICY_MLP inside the kernel like k_fused_n64_persist<.., true>; every warp runs the policy of its own worlds'
+// agents, four at a time (dw_mlp_decide4). Dynamic shared memory: 8 MlpScratch + int[DW_SUB64_MAX_AGENTS] actions.
+#define DW_SUB64_MLP_SMEM (8 * sizeof(MlpScratch) + DW_SUB64_MAX_AGENTS * sizeof(int))
+template <int N, bool DIAG = false, bool MLP = false>
+__global__ void __launch_bounds__(256, MLP ? 3 : DW_N64_MIN_BLOCKS) k_fused_sub64_persist(const __grid_constant__ FusedArgs A) {
     constexpr int WX = 64 / N, W = WX * WX, TX = N / 4;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ Sub64Smem<N> sm;
     __shared__ double s_tsum;               // series mode (DIAG): per-step sums over the CTA's worlds, see k_fused_n64_persist
     __shared__ unsigned int s_cov[2];
@@ -1156,6 +1290,15 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
             if (w < n_worlds) v = __ldcg(reinterpret_cast<const uint4 *>(A.lat + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)));
             reinterpret_cast<uint4 *>(sm.buf[0])[q] = v;
         }
+        if (MLP) {   // the post-graze state the step before this item started from (observation windows of the item's first step)
+            for (int q = tid; q < 1024; q += 256) {
+                const int R = q >> 4, C4 = (q & 15) * 4;
+                const int w = (R / N) * WX + C4 / N;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (w < n_worlds) v = __ldcg(reinterpret_cast<const uint4 *>(A.lat_pre + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)));
+                reinterpret_cast<uint4 *>(sm.buf[1])[q] = v;
+            }
+        }
         for (int a = tid; a < n_act; a += 256) {
             const size_t ga = (size_t)g * W * n + a;
             sm.st[a] = __ldcg(A.agent_state + ga);
@@ -1174,10 +1317,30 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
             {   // warp k moves the agents of worlds [k * WPW, (k + 1) * WPW) of the group
                 constexpr int WPW = (W + 7) / 8;
                 const int w_lo = warp * WPW, w_hi = min(w_lo + WPW, n_worlds);
-                if (w_lo < w_hi && n > 0) dw_agents_phase_sub<N>(A, j, g, cb, sm, lane, n, w_lo * n, w_hi * n);
+                const int *mlp_act = nullptr;
+                if constexpr (MLP) {
+                    MlpScratch *scr = reinterpret_cast<MlpScratch *>(dyn_smem) + warp;
+                    int *acts = reinterpret_cast<int *>(dyn_smem + 8 * sizeof(MlpScratch));
+                    mlp_act = acts;
+                    if (n > 0 && A.sc[j].policy == DW_POLICY_MLP) {
+                        const double SLp = j == 0 ? A.SL_prev : A.sc[j - 1].SL;
+                        for (int w = w_lo; w < w_hi; ++w) {
+                            const int gw = g * W + w;
+                            for (int a0 = 0; a0 < n; a0 += 4) {
+                                int wset[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) wset[q] = A.mlp_wpm > 0 ? (a0 + q < A.mlp_half ? gw / A.mlp_wpm : A.mlp_adv) : 0;
+                                dw_mlp_decide4<N>(&A, SLp, nb, (w / WX) * N, (w % WX) * N, sm.xy + w * n, sm.st + w * n, n, a0, wset, scr,
+                                                  acts + w * n, lane);
+                            }
+                        }
+                    }
+                    // the warp's own worlds only: decisions (reads of nb, xy, st) and moves (writes of cb, xy, st) need no CTA barrier
+                }
+                if (w_lo < w_hi && n > 0) dw_agents_phase_sub<N>(A, j, g, cb, sm, lane, n, w_lo * n, w_hi * n, mlp_act);
             }
             __syncthreads();
-            if (j == A.K - 1) {                        // post-graze state of the launch's last step (lazy materialisation)
+            if (!MLP && j == A.K - 1) {                // post-graze state of the launch's last step (lazy materialisation)
                 for (int q = tid; q < 1024; q += 256) {
                     const int R = q >> 4, C4 = (q & 15) * 4;
                     const int w = (R / N) * WX + C4 / N;
@@ -1235,9 +1398,13 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_sub64_persist(
         for (int q = tid; q < 1024; q += 256) {
             const int R = q >> 4, C4 = (q & 15) * 4;
             const int w = (R / N) * WX + C4 / N;
-            if (w < n_worlds)
+            if (w < n_worlds) {
                 *reinterpret_cast<uint4 *>(A.lat + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)) =
                     reinterpret_cast<const uint4 *>(sm.buf[kc & 1])[q];
+                if (MLP)        // post-graze state of the item's last step: next item's windows / lazy materialisation
+                    *reinterpret_cast<uint4 *>(A.lat_pre + ((size_t)g * W + w) * (N * N) + (R % N) * N + (C4 % N)) =
+                        reinterpret_cast<const uint4 *>(sm.buf[(kc + 1) & 1])[q];
+            }
         }
         for (int a = tid; a < n_act; a += 256) {
             const size_t ga = (size_t)g * W * n + a;

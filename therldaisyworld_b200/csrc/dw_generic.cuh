@@ -761,6 +761,49 @@ __global__ void __launch_bounds__(128) k_pop_accumulate(int wpm, int n, int half
     }
 }
 
+// The same bookkeeping for S steps at once from the recorded per-step agent states (fused population segments: the policy
+// and the steps ran inside one launch, FusedArgs::rew_series). rew: [S][Bn] state after each step's update_agents = the
+// step's reward (done = reward < 0.1); frozen[] advances by (1 - done) per step while the member's loop is alive, exactly
+// what copying agents_done_at does in k_pop_accumulate. Same summation order as k_pop_accumulate.
+__global__ void __launch_bounds__(128) k_pop_post(int S, int wpm, int n, int half, const double *__restrict__ rew, size_t Bn,
+                                                  double *sum_reward, int *member_done, int64_t *member_steps, int64_t *frozen,
+                                                  long long step0, unsigned int *n_done) {
+    const int m = blockIdx.x;
+    __shared__ double s_sum[4];
+    __shared__ int s_alive[4];
+    __shared__ int s_stop;
+    if (member_done[m]) return;
+    const size_t base = (size_t)m * wpm * n;
+    for (int t = 0; t < S; ++t) {
+        const double *r = rew + (size_t)t * Bn + base;
+        double sum = 0.0;
+        int alive = 0;
+        for (int k = threadIdx.x; k < wpm * n; k += blockDim.x) {
+            const double v = r[k];
+            const bool dn = v < 0.1;
+            if (k % n < half) sum += v;
+            alive += dn ? 0 : 1;
+            frozen[base + k] += dn ? 0 : 1;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            alive += __shfl_xor_sync(0xffffffffu, alive, o);
+        }
+        if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_alive[threadIdx.x >> 5] = alive; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double tot = ((s_sum[0] + s_sum[1]) + s_sum[2]) + s_sum[3];
+            const int al = s_alive[0] + s_alive[1] + s_alive[2] + s_alive[3];
+            sum_reward[m] += tot / (double)(wpm * half);
+            member_steps[m] = step0 + t + 1;
+            s_stop = al == 0;
+            if (al == 0) { member_done[m] = 1; atomicAdd(n_done, 1u); }
+        }
+        __syncthreads();
+        if (s_stop) return;
+    }
+}
+
 // ---- ensemble statistics of a field (deterministic two-stage reduction: per-block partials, then one block) --------------
 // partial[b] = {sum, sum of squares, min, max}
 __device__ __forceinline__ void dw_stats_block_reduce(double s, double q, double mn, double mx, double *out4) {

@@ -157,18 +157,19 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     const char *impl = getenv("DW_FUSED_IMPL");
     const bool n64 = h->cfg.dim == 64 && !(impl && !strcmp(impl, "generic"));
     const bool persist = n64 && !(impl && !strcmp(impl, "simple")) && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
-    if (policy == DW_POLICY_MLP) {           // in-kernel policy: persistent 64x64 kernel only (callers check mlp_fusable)
-        if (!persist || h->series_on || !h->mlp_set || h->pre != PRE_LAT)
-            return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "DW_POLICY_MLP is fused only in the persistent 64x64 kernel");
+    const int dimN = h->cfg.dim;
+    const bool sub64 = !(impl && !strcmp(impl, "generic")) && (dimN == 8 || dimN == 16 || dimN == 32) &&
+                       (64 / dimN) * (64 / dimN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
+    if (policy == DW_POLICY_MLP) {           // in-kernel policy: the persistent kernels only (callers check mlp_fusable)
+        if (!(persist || sub64) || h->series_on || !h->mlp_set || h->pre != PRE_LAT)
+            return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "DW_POLICY_MLP is fused only in the persistent kernels (64x64, 8x8, 16x16, 32x32)");
+        A.rew_series = h->pop_rew_on ? h->pop_rew : nullptr;
         A.mlp_w = h->mlp_dev;
         A.mlp_wpm = h->pop_members ? h->cfg.batch / h->pop_members : 0;
         A.mlp_half = h->cfg.n_agents / 2;
         A.mlp_adv = h->pop_adversary;
         A.SL_prev = h->cfg.S * h->L_last;
     }
-    const int dimN = h->cfg.dim;
-    const bool sub64 = !(impl && !strcmp(impl, "generic")) && (dimN == 8 || dimN == 16 || dimN == 32) &&
-                       (64 / dimN) * (64 / dimN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
     if (h->profiling) DW_CUDA_TRY(h, cudaEventRecord(h->ev[0], h->stream));
     if (persist) {
         if (!h->persist_blocks) {
@@ -222,6 +223,9 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         // worlds of 8x8, 16x16 or 32x32: (64/N)^2 of them per CTA in the 4x4-tile kernel, same persistent queue
         const int N = h->cfg.dim, W = (64 / N) * (64 / N);
         void (*kern)(const FusedArgs) = N == 8 ? k_fused_sub64_persist<8> : (N == 16 ? k_fused_sub64_persist<16> : k_fused_sub64_persist<32>);
+        const bool mlp = policy == DW_POLICY_MLP;
+        const size_t dyn = mlp ? DW_SUB64_MLP_SMEM : 0;
+        if (mlp) kern = N == 8 ? k_fused_sub64_persist<8, false, true> : (N == 16 ? k_fused_sub64_persist<16, false, true> : k_fused_sub64_persist<32, false, true>);
         if (h->series_on) {
             kern = N == 8 ? k_fused_sub64_persist<8, true> : (N == 16 ? k_fused_sub64_persist<16, true> : k_fused_sub64_persist<32, true>);
             A.series_T = h->series_T + h->series_pos;
@@ -229,11 +233,12 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
             A.series_d = h->series_d + h->series_pos;
             h->series_pos += K;
         }
-        int &blocks = h->series_on ? h->sub64_blocks_series : h->sub64_blocks;
+        int &blocks = mlp ? h->sub64_blocks_mlp : (h->series_on ? h->sub64_blocks_series : h->sub64_blocks);
         if (!blocks) {
             int per_sm = 0, sms = 0;
+            if (dyn) DW_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             DW_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+            DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, dyn));
             DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
             if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "sub-64 kernel does not fit on an SM");
             blocks = per_sm * sms;
@@ -253,7 +258,7 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         A.lat = h->lat[h->lcur];                      // in place
         const long long items = (long long)A.n_pairs * A.n_chunks;
         const int grid = (int)(items < blocks ? items : blocks);
-        kern<<<grid, 256, 0, h->stream>>>(A);
+        kern<<<grid, 256, dyn, h->stream>>>(A);
     } else {
         const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
         if (smem > 48 * 1024 && !h->fused_attr_set) {      // both one-CTA-per-world fallbacks (64x64 with > 817 agents needs it too)
@@ -359,13 +364,20 @@ static int run_steps_fused(dw_handle *h, int K, int policy, const int8_t *act_de
     return launch_fused(h, K, policy, act_dev, seed, alive);
 }
 
-// DW_POLICY_MLP inside the fused kernel: 64x64 worlds with <= 32 agents whose state is on the lattice with the post-graze
-// lattice of the last step at hand (the observation windows of the first fused step come from it)
+// DW_POLICY_MLP inside the fused kernels: 64x64 worlds with <= 32 agents, or 8x8 / 16x16 / 32x32 worlds, whose state is on the
+// lattice with the post-graze lattice of the last step at hand (the observation windows of the first fused step come from it)
 static bool mlp_fusable(const dw_handle *h) {
     if (getenv("DW_MLP_UNFUSED")) return false;
     const char *impl = getenv("DW_FUSED_IMPL");
-    return h->cfg.dim == 64 && h->cfg.n_agents > 0 && h->cfg.n_agents <= DW_N64_MAX_AGENTS && dw_fused_supported(h) && h->lat_valid &&
-           h->pre == PRE_LAT && h->mlp_set && !h->series_on && !impl;
+    const int N = h->cfg.dim, n = h->cfg.n_agents;
+    // The sub-64 kernel has the in-kernel policy too (k_fused_sub64_persist<N, false, true>, four agents per warp pass), but
+    // several worlds share a CTA there and their agents' networks run one after the other on 8 warps: measured on the ES
+    // shape (64 members x 32 worlds of 16x16, 4 agents) 37.8 us per step against 42 us for the whole per-step sequence whose
+    // k_obs_mlp spreads the 8192 agents over every SM -- and 22.8 ms vs 19.8 ms per generation. It stays opt-in
+    // (DW_MLP_FUSE_SUB64=1; the tests run both paths).
+    const bool sub = (N == 8 || N == 16 || N == 32) && (64 / N) * (64 / N) * n <= DW_SUB64_MAX_AGENTS && getenv("DW_MLP_FUSE_SUB64");
+    const bool shape = (N == 64 && n <= DW_N64_MAX_AGENTS) || sub;
+    return shape && n > 0 && dw_fused_supported(h) && h->lat_valid && h->pre == PRE_LAT && h->mlp_set && !h->series_on && !impl;
 }
 
 static int stage_actions8(dw_handle *h, const int8_t *actions, size_t count) {
@@ -530,6 +542,28 @@ extern "C" int dw_run_population(dw_handle *h, int64_t max_steps, int64_t *steps
     if (rc) return rc;
     int64_t t = 0;
     while (t < max_steps) {
+        if (mlp_fusable(h) && !getenv("DW_POP_UNFUSED")) {
+            // a segment of up to 64 steps in ONE launch (policy inside the kernel, per-step agent states recorded), then the
+            // members' bookkeeping of those steps in one post-pass; one small read-back per segment
+            const int S = (int)std::min<int64_t>(64, max_steps - t);
+            rc = dev_alloc(h, &h->pop_rew, (size_t)64 * Bn);
+            if (rc) return rc;
+            DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, DW_FUSED_MAX_STEPS * sizeof(unsigned int), h->stream));
+            const long long step0 = (long long)h->clk.step_count;
+            h->pop_rew_on = true;
+            rc = launch_fused(h, S, DW_POLICY_MLP, nullptr, 0, h->alive);
+            h->pop_rew_on = false;
+            if (rc) return rc;
+            k_pop_post<<<P, 128, 0, h->stream>>>(S, wpm, n, n / 2, h->pop_rew, Bn, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, step0,
+                                                 h->pop_ndone);
+            DW_LAUNCHED(h);
+            t += S;
+            unsigned int nd = 0;
+            DW_CUDA_TRY(h, cudaMemcpyAsync(&nd, h->pop_ndone, sizeof(nd), cudaMemcpyDeviceToHost, h->stream));
+            DW_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if ((int)nd == P) break;
+            continue;
+        }
         DW_CUDA_TRY(h, cudaMemsetAsync(h->alive, 0, sizeof(unsigned int), h->stream));
         rc = mlp_actions(h);
         if (rc) return rc;

@@ -13,6 +13,11 @@ for P, N in ((16, 16), (64, 16), (256, 16), (64, 64)):
         t0 = time.perf_counter()
         fitness, total_steps, member_steps, env = evaluate_population(members, max_steps=768, worlds_per_member=32, env=env, grid_dimension=N)
         dt = time.perf_counter() - t0
+    for rep in range(2):
+        t0 = time.perf_counter()
+        f2, _, ms2, env = evaluate_population(members, max_steps=768, worlds_per_member=32, env=env, grid_dimension=N, device_reset_seed=3)
+        dt_dev = time.perf_counter() - t0
+    print(f"P={P} N={N}: device-side reset draws: {int(ms2.max())} steps, {dt_dev * 1e3:.1f} ms wall")
     steps = int(member_steps.max())
     print(f"P={P} N={N}: {steps} steps, {dt * 1e3:.1f} ms wall (incl. host reset draws + upload) -> {P * 32 * steps / dt:.3e} env-steps/s, "
           f"{P * 32 * N * N * steps / dt:.3e} cell-updates/s; fitness[:3]={fitness[:3]}", flush=True)
