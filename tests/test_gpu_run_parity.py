@@ -161,7 +161,7 @@ def test_ensemble_sharding_is_invisible(N, sizes):
 
 
 @pytest.mark.parametrize("N,n,policy", [(8, 4, "greedy"), (16, 9, "antigreedy"), (32, 4, "random"), (64, 4, "greedy"), (96, 5, "greedy"),
-                                        (33, 3, "greedy"), (128, 6, "random")])
+                                        (33, 3, "greedy"), (128, 6, "random"), (14, 3, "greedy"), (75, 4, "antigreedy")])
 def test_torus_translation_invariance(N, n, policy):
     """A size-independent property of the path: the world is a torus and nothing in the step depends on absolute
     coordinates, so shifting the initial covers and agents by (sx, sy) must shift the whole run by (sx, sy) -- through

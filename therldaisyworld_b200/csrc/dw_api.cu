@@ -106,7 +106,8 @@ struct dw_handle {
     double *pop_rew = nullptr;                 // [64][B*n] per-step agent states of a fused population segment (k_pop_post)
     bool pop_rew_on = false;
     int persist_blocks_mlp = 0;                // the same for the kernel with the in-kernel MLP policy (more shared memory)
-    int tile4_threads = 0;                     // block size chosen for k_fused_tile4 (world side a multiple of 4)
+    int tile4_threads = 0;                     // block size chosen for k_fused_tile4
+    int tile4_blocks = 0, tile4_blocks_threads = 0;   // resident CTAs of the persistent 4x4-tile kernel (for that block size)
     // profiling (dw_set_profiling): kernel launch count, and device time of the fused kernel via events
     dw_profile prof{};
     bool profiling = false;

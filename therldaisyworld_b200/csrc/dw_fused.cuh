@@ -253,7 +253,8 @@ __device__ __forceinline__ void dw_fast_cells(const FastCoef &F, const StepCoef 
 }
 
 // Literal recomputation of one cell from the packed neighbourhood (oracle order). Rare: ~1e-5 of cell-updates.
-__device__ __noinline__ uint32_t dw_slow_cell(const FusedArgs *A, double SL, const uint32_t *cb, int N, int x, int y) {
+__device__ __noinline__ uint32_t dw_slow_cell(const FusedArgs *A, double SL, const uint32_t *cb, int N, int x, int y, int ld = 0) {
+    if (ld == 0) ld = N;
     const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
     const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
     const int xs[3] = {xm, x, xp}, ys[3] = {ym, y, yp};
@@ -262,7 +263,7 @@ __device__ __noinline__ uint32_t dw_slow_cell(const FusedArgs *A, double SL, con
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const uint32_t k = cb[xs[a] * N + ys[c]];
+            const uint32_t k = cb[xs[a] * ld + ys[c]];
             l9[a * 3 + c] = dw_milli(k & 0xffffu);
             d9[a * 3 + c] = dw_milli(k >> 16);
         }
@@ -283,8 +284,9 @@ struct AgentSmem {
 
 __device__ __forceinline__ double dw_food(uint32_t pk) { return dw_milli(pk & 0xffffu) + dw_milli(pk >> 16); }
 
-__device__ __forceinline__ void dw_agents_phase(const FusedArgs &A, int j, int b, uint32_t *cb, const AgentSmem &S, int lane) {
+__device__ __forceinline__ void dw_agents_phase(const FusedArgs &A, int j, int b, uint32_t *cb, const AgentSmem &S, int lane, int ld = 0) {
     const int N = A.P.N, n = A.P.n_agents;
+    if (ld == 0) ld = N;                 // row pitch of cb in words (k_fused_tile4 pads rows to a multiple of 4)
     // pass 1: decisions from the state the previous step left (= the observation the policy would have seen)
     const int pol = A.sc[j].policy;
     for (int i = lane; i < n; i += 32) {
@@ -296,8 +298,8 @@ __device__ __forceinline__ void dw_agents_phase(const FusedArgs &A, int j, int b
             const int x = S.xy[i] & 0xffff, y = S.xy[i] >> 16;
             const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1;
             const int ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
-            const double food[4] = {dw_food(cb[x * N + ym]), dw_food(cb[xm * N + y]), dw_food(cb[xp * N + y]),
-                                    dw_food(cb[x * N + yp])};
+            const double food[4] = {dw_food(cb[x * ld + ym]), dw_food(cb[xm * ld + y]), dw_food(cb[xp * ld + y]),
+                                    dw_food(cb[x * ld + yp])};
             a = dw_greedy_pick(food, pol == DW_POLICY_GREEDY);
         }
         S.act[i] = a;
@@ -324,7 +326,7 @@ __device__ __forceinline__ void dw_agents_phase(const FusedArgs &A, int j, int b
                         default: y = y == N - 1 ? 0 : y + 1; break;
                     }
                 }
-                if (a > 4) { wants = true; cell = x * N + y; }
+                if (a > 4) { wants = true; cell = x * ld + y; }
             }
         }
         const uint32_t pk = wants ? cb[cell] : 0u;
@@ -508,9 +510,10 @@ struct RowsWorld64 {
     }
 };
 struct StoreWorld64 {
+    static constexpr bool kMasks = false;
     uint32_t *nb;
     int r0, tx;
-    __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
+    __device__ __forceinline__ void operator()(int i, uint32_t (&q)[4]) const {
         *reinterpret_cast<uint4 *>(nb + (r0 + i) * 64 + tx * 4) = make_uint4(q[0], q[1], q[2], q[3]);
     }
 };
@@ -549,9 +552,15 @@ __device__ __forceinline__ uint32_t dw_tile_core(const FastCoef &F, const StepCo
 #else
         dw_fast_cells<4, DIAG>(F, C, mid.p, E, S8, tiemin, q, tsum);
 #endif
+        if (Store::kMasks) {               // k_fused_tile4, padded sides: the store zeroes entries that lie outside the world
+            store(i, q);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) mx = __vmaxu2(mx, q[c]);
-        store(i, q);
+            for (int c = 0; c < 4; ++c) mx = __vmaxu2(mx, q[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mx = __vmaxu2(mx, q[c]);
+            store(i, q);
+        }
         top = mid;
         mid = bot;
     }
@@ -1435,29 +1444,53 @@ __global__ void __launch_bounds__(256, MLP ? 3 : DW_N64_MIN_BLOCKS) k_fused_sub6
 // ---- any N that is a multiple of 4 (and fits in shared memory): one CTA per world, 4x4 tiles dealt round-robin to the threads ----
 // Same fast path and tile core as the 64x64 kernel; the halo columns come from shared memory instead of SHFL (the lanes
 // of a warp do not line up with a world row), the rows wrap by compare. The host picks the block size from the tile count
-// and the shared-memory footprint (launch_fused). dynamic smem: 2*N*N u32 | n doubles | 3n ints | 4 ints.
+// and the shared-memory footprint (launch_fused). Round 2: persistent CTAs with the (world, 16-step chunk) work queue of the
+// 64x64 kernel (a grid of one CTA per world ran 2.25 waves at 1000 worlds of 96x96: 25 % of the last wave idle). World sides
+// that are not a multiple of 4 (round 2): shared-memory rows are
+// padded to ld = 4 * ceil(N / 4) words, the last tile of a row takes its missing columns (and its right halo) from the
+// wrapped columns 0, 1, .., its cells outside the world are neither stored nor counted in the maxima, and the tile rows
+// below the world are computed from wrapped rows and dropped. dynamic smem: 2*N*ld u32 | n doubles | 3n ints | 4 ints.
+template <bool PAD>
 struct RowsTile4 {
     const uint32_t *cb;
-    int N, r0, c0, cl, cr;              // first row / column of the tile, wrapped left and right halo columns
+    int N, ld, r0, c0, cl, cr, valid;   // row pitch, first row / column of the tile, wrapped halo columns, columns inside the world
     __device__ __forceinline__ Row6 load(int k) const {
         int r = r0 + k;
         r = r < 0 ? r + N : (r >= N ? r - N : r);
-        const uint32_t *row = cb + r * N;
-        const uint4 v = *reinterpret_cast<const uint4 *>(row + c0);
+        const uint32_t *row = cb + r * (PAD ? ld : N);
+        uint4 v = *reinterpret_cast<const uint4 *>(row + c0);
+        if (PAD && valid < 4) {         // last tile of a row whose side is not a multiple of 4: the missing columns wrap to 0, 1, 2
+            if (valid < 2) v.y = row[1 - valid];
+            if (valid < 3) v.z = row[2 - valid];
+            v.w = row[3 - valid];
+        }
         return dw_make_row(v, row[cl], row[cr]);
     }
 };
+template <bool PAD>
 struct StoreTile4 {
+    static constexpr bool kMasks = PAD;
     uint32_t *nb;
-    int N, r0, c0;
-    __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
-        *reinterpret_cast<uint4 *>(nb + (r0 + i) * N + c0) = make_uint4(q[0], q[1], q[2], q[3]);
+    int N, ld, r0, c0, valid;
+    __device__ __forceinline__ void operator()(int i, uint32_t (&q)[4]) const {
+        if (!PAD) {
+            *reinterpret_cast<uint4 *>(nb + (r0 + i) * N + c0) = make_uint4(q[0], q[1], q[2], q[3]);
+            return;
+        }
+        if (r0 + i >= N) { q[0] = 0u; q[1] = 0u; q[2] = 0u; q[3] = 0u; return; }       // tile row below the world: nothing to keep
+        uint32_t *d = nb + (r0 + i) * ld + c0;
+        if (valid == 4) { *reinterpret_cast<uint4 *>(d) = make_uint4(q[0], q[1], q[2], q[3]); return; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < valid) d[t] = q[t];
+            else q[t] = 0u;
+        }
     }
 };
 
 // warp-cooperative tie fix-up, generic N (see dw_fix_warp64)
 __device__ __noinline__ uint32_t dw_fix_warp_tile4(const FusedArgs *A, const StepCoef *C, const uint32_t *cb, uint32_t *nb, unsigned flagged,
-                                                   uint32_t mx, int r0, int c0, int lane, int N) {
+                                                   uint32_t mx, int r0, int c0, int lane, int N, int ld) {
     uint32_t extra = 0;
     bool mine = false;
     __syncwarp();
@@ -1466,17 +1499,17 @@ __device__ __noinline__ uint32_t dw_fix_warp_tile4(const FusedArgs *A, const Ste
         flagged &= flagged - 1;
         const int tr0 = __shfl_sync(0xffffffffu, r0, L), tc0 = __shfl_sync(0xffffffffu, c0, L);
         if (lane == L) mine = true;
-        if (lane < 16) {
-            const int x = tr0 + (lane >> 2), y = tc0 + (lane & 3);
+        const int x = tr0 + (lane >> 2), y = tc0 + (lane & 3);
+        if (lane < 16 && x < N && y < N) {               // cells of an edge tile outside the world are skipped
             const int xm = x == 0 ? N - 1 : x - 1, xp = x == N - 1 ? 0 : x + 1, ym = y == 0 ? N - 1 : y - 1, yp = y == N - 1 ? 0 : y + 1;
-            const uint32_t *q0 = cb + xm * N, *q1 = cb + x * N, *q2 = cb + xp * N;
+            const uint32_t *q0 = cb + xm * ld, *q1 = cb + x * ld, *q2 = cb + xp * ld;
             const uint32_t E = q1[ym] + q1[yp] + q0[y] + q2[y];
             const uint32_t S8 = E + q0[ym] + q0[yp] + q2[ym] + q2[yp];
             unsigned tiemin = 0xffffffffu;
             uint32_t v = dw_fast_cell(A->F, *C, q1[y], E, S8, &tiemin);
             if (tiemin < A->F.tie_thresh) {
-                v = dw_slow_cell(A, C->SL, cb, N, x, y);
-                nb[x * N + y] = v;
+                v = dw_slow_cell(A, C->SL, cb, N, x, y, ld);
+                nb[x * ld + y] = v;
             }
             extra = __vmaxu2(extra, v);
         }
@@ -1485,91 +1518,136 @@ __device__ __noinline__ uint32_t dw_fix_warp_tile4(const FusedArgs *A, const Ste
     return __vmaxu2(mine ? 0u : mx, extra);
 }
 
+template <bool PAD>
 __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__ FusedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = A.P.N, n = A.P.n_agents, NN = N * N, T = N >> 2, TT = T * T;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    __shared__ int s_item;
+    const int N = A.P.N, n = A.P.n_agents, NN = N * N, T = (N + 3) >> 2, TT = T * T;
+    const int ld = PAD ? T * 4 : N, SN = N * ld;   // PAD: shared-memory rows padded to a multiple of 4 words (16-byte tile loads)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
     uint32_t *buf0 = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *buf1 = buf0 + NN;
+    uint32_t *buf1 = buf0 + SN;
     AgentSmem S;
-    S.st = reinterpret_cast<double *>(buf1 + NN);
+    S.st = reinterpret_cast<double *>(buf1 + SN);
     S.xy = reinterpret_cast<int *>(S.st + n);
     S.act = S.xy + n;
     S.ada = S.act + n;
     int *s_max = S.ada + n;
-
-    {
-        const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat_in + (size_t)b * NN);
-        for (int c = tid; c < NN / 4; c += nthr) reinterpret_cast<uint4 *>(buf0)[c] = gin[c];
-    }
-    for (int i = tid; i < n; i += nthr) {
-        S.st[i] = A.agent_state[(size_t)b * n + i];
-        S.xy[i] = A.agent_xy[((size_t)b * n + i) * 2] | (A.agent_xy[((size_t)b * n + i) * 2 + 1] << 16);
-        S.ada[i] = 0;
-    }
-    if (tid < 4) s_max[tid] = 0;
-    __syncthreads();
-
-    uint32_t *cb = buf0, *nb = buf1;
-    int life = 0;
     const int rounds = (TT + nthr - 1) / nthr;
-    for (int j = 0; j < A.K; ++j) {
-        if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane);
-        __syncthreads();
-        if (j == A.K - 1) {
-            uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
-            for (int c = tid; c < NN / 4; c += nthr) gp[c] = reinterpret_cast<const uint4 *>(cb)[c];
+    const int n_items = A.n_pairs * A.n_chunks;      // persistent CTAs, work item = (world, chunk of Kc steps), see k_fused_n64_persist
+
+    for (int it = 0;; ++it) {
+        int t;
+        if (A.queue) {
+            if (tid == 0) s_item = (int)atomicAdd(A.queue, 1u);
+            __syncthreads();
+            t = s_item;
+        } else {
+            t = blockIdx.x + it * gridDim.x;
+            __syncthreads();
         }
-        const StepCoef C = A.sc[j];
-        uint32_t mx = 0;
-        for (int r = 0; r < rounds; ++r) {                      // uniform trip count: the fix-up below is warp-collective
-            const int tile = tid + r * nthr;
-            const bool active = tile < TT;
-            const int ty = tile / T, tx = tile - ty * T;
-            const int r0 = ty * 4, c0 = tx * 4;
-            unsigned tiemin = 0xffffffffu;
-            uint32_t m = 0;
-            if (active)
-                m = dw_tile_core(A.F, C, RowsTile4{cb, N, r0, c0, c0 == 0 ? N - 1 : c0 - 1, c0 + 4 == N ? 0 : c0 + 4},
-                                 StoreTile4{nb, N, r0, c0}, &tiemin);
-            const unsigned flagged = __ballot_sync(0xffffffffu, active && tiemin < A.F.tie_thresh);
-            if (flagged) m = dw_fix_warp_tile4(&A, &A.sc[j], cb, nb, flagged, m, r0, c0, lane, N);
-            mx = __vmaxu2(mx, m);
-        }
-        const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
-        int *sm = s_max + 2 * (j & 1);
-        if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
-        __syncthreads();
-        if (warp == 0) {
-            const bool grid_done = max(sm[0], sm[1]) <= 5;
-            if (lane == 0) {
-                if (!grid_done) { life += 1; atomicAdd(A.alive + j, 1u); }
-                s_max[2 * ((j + 1) & 1)] = 0;
-                s_max[2 * ((j + 1) & 1) + 1] = 0;
+        if (t >= n_items) break;
+        const int c = t / A.n_pairs, b = t - c * A.n_pairs;
+        if (A.queue) {
+            if (tid == 0) {
+                while (atomicAdd(A.pair_done + b, 0u) < (unsigned)c) __nanosleep(200);
+                __threadfence();
             }
-            for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;
+            __syncthreads();
         }
-        uint32_t *t = cb; cb = nb; nb = t;
-    }
-    __syncthreads();
-    {
-        uint4 *gout = reinterpret_cast<uint4 *>(A.lat_out + (size_t)b * NN);
-        for (int c = tid; c < NN / 4; c += nthr) gout[c] = reinterpret_cast<const uint4 *>(cb)[c];
-    }
-    for (int i = tid; i < n; i += nthr) {
-        A.agent_state[(size_t)b * n + i] = S.st[i];
-        A.agent_xy[((size_t)b * n + i) * 2] = S.xy[i] & 0xffff;
-        A.agent_xy[((size_t)b * n + i) * 2 + 1] = S.xy[i] >> 16;
-        if (A.count_life) A.agents_done_at[(size_t)b * n + i] += S.ada[i];
-        const double r = S.st[i];
-        A.reward[(size_t)b * n + i] = r;
-        A.done[(size_t)b * n + i] = r < 0.1;
-    }
-    if (tid == 0) {
-        if (A.count_life) A.done_at[b] += life;
-        if (n == 0) {
-            const int *sm = s_max + 2 * ((A.K - 1) & 1);
-            for (int c = 0; c < 2; ++c) { A.reward[2 * b + c] = sm[c] > 0 ? 1.0 : 0.0; A.done[2 * b + c] = sm[c] > 0 ? 0 : 1; }
+        const int j0 = c * A.Kc, kc = min(A.Kc, A.K - j0);
+        if (!PAD) {
+            const uint4 *gin = reinterpret_cast<const uint4 *>(A.lat + (size_t)b * NN);
+            for (int q = tid; q < NN / 4; q += nthr) reinterpret_cast<uint4 *>(buf0)[q] = __ldcg(gin + q);
+        } else {
+            const uint32_t *gin = A.lat + (size_t)b * NN;
+            for (int q = tid; q < NN; q += nthr) buf0[(q / N) * ld + q % N] = __ldcg(gin + q);
+        }
+        for (int i = tid; i < n; i += nthr) {
+            const size_t g = (size_t)b * n + i;
+            S.st[i] = __ldcg(A.agent_state + g);
+            S.xy[i] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
+            S.ada[i] = 0;
+        }
+        if (tid < 4) s_max[tid] = 0;
+        __syncthreads();
+
+        uint32_t *cb = buf0, *nb = buf1;
+        int life = 0;
+        for (int jl = 0; jl < kc; ++jl) {
+            const int j = j0 + jl;
+            if (warp == 0 && n > 0) dw_agents_phase(A, j, b, cb, S, lane, ld);
+            __syncthreads();
+            if (j == A.K - 1) {
+                if (!PAD) {
+                    uint4 *gp = reinterpret_cast<uint4 *>(A.lat_pre + (size_t)b * NN);
+                    for (int q = tid; q < NN / 4; q += nthr) gp[q] = reinterpret_cast<const uint4 *>(cb)[q];
+                } else {
+                    uint32_t *gp = A.lat_pre + (size_t)b * NN;
+                    for (int q = tid; q < NN; q += nthr) gp[q] = cb[(q / N) * ld + q % N];
+                }
+            }
+            const StepCoef C = A.sc[j];
+            uint32_t mx = 0;
+            for (int r = 0; r < rounds; ++r) {                      // uniform trip count: the fix-up below is warp-collective
+                const int tile = tid + r * nthr;
+                const bool active = tile < TT;
+                const int ty = tile / T, tx = tile - ty * T;
+                const int r0 = ty * 4, c0 = tx * 4;
+                unsigned tiemin = 0xffffffffu;
+                uint32_t m = 0;
+                const int valid = PAD ? min(4, N - c0) : 4;
+                if (active)
+                    m = dw_tile_core(A.F, C, RowsTile4<PAD>{cb, N, ld, r0, c0, c0 == 0 ? N - 1 : c0 - 1, c0 + 4 >= N ? c0 + 4 - N : c0 + 4, valid},
+                                     StoreTile4<PAD>{nb, N, ld, r0, c0, valid}, &tiemin);
+                const unsigned flagged = __ballot_sync(0xffffffffu, active && tiemin < A.F.tie_thresh);
+                if (flagged) m = dw_fix_warp_tile4(&A, &A.sc[j], cb, nb, flagged, m, r0, c0, lane, N, ld);
+                mx = __vmaxu2(mx, m);
+            }
+            const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+            int *sm = s_max + 2 * (jl & 1);
+            if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+            __syncthreads();
+            if (warp == 0) {
+                const bool grid_done = max(sm[0], sm[1]) <= 5;
+                if (lane == 0) {
+                    if (!grid_done) { life += 1; atomicAdd(A.alive + j, 1u); }
+                    s_max[2 * ((jl + 1) & 1)] = 0;
+                    s_max[2 * ((jl + 1) & 1) + 1] = 0;
+                }
+                for (int i = lane; i < n; i += 32) S.ada[i] += (S.st[i] < 0.1) ? 0 : 1;
+            }
+            uint32_t *tmp = cb; cb = nb; nb = tmp;
+        }
+        __syncthreads();
+        if (!PAD) {
+            uint4 *gout = reinterpret_cast<uint4 *>(A.lat + (size_t)b * NN);
+            for (int q = tid; q < NN / 4; q += nthr) gout[q] = reinterpret_cast<const uint4 *>(cb)[q];
+        } else {
+            uint32_t *gout = A.lat + (size_t)b * NN;
+            for (int q = tid; q < NN; q += nthr) gout[q] = cb[(q / N) * ld + q % N];
+        }
+        for (int i = tid; i < n; i += nthr) {
+            const size_t g = (size_t)b * n + i;
+            A.agent_state[g] = S.st[i];
+            A.agent_xy[2 * g] = S.xy[i] & 0xffff;
+            A.agent_xy[2 * g + 1] = S.xy[i] >> 16;
+            if (A.count_life) A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + S.ada[i];
+            const double r = S.st[i];
+            A.reward[g] = r;
+            A.done[g] = r < 0.1;
+        }
+        if (tid == 0) {
+            if (A.count_life) A.done_at[b] = __ldcg(A.done_at + b) + life;
+            if (n == 0) {
+                const int *sm = s_max + 2 * ((kc - 1) & 1);
+                for (int ch = 0; ch < 2; ++ch) { A.reward[2 * b + ch] = sm[ch] > 0 ? 1.0 : 0.0; A.done[2 * b + ch] = sm[ch] > 0 ? 0 : 1; }
+            }
+        }
+        __syncthreads();
+        if (A.queue && tid == 0) {
+            __threadfence();
+            atomicExch(A.pair_done + b, (unsigned)(c + 1));
         }
     }
 }

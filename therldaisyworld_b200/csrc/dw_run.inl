@@ -260,20 +260,26 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
         const int grid = (int)(items < blocks ? items : blocks);
         kern<<<grid, 256, dyn, h->stream>>>(A);
     } else {
-        const size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
+        size_t smem = fused_smem_bytes(h->cfg.dim, h->cfg.n_agents);
+        // 4x4-tile kernel for every side >= 12 that fits with rows padded to a multiple of 4 words
+        const size_t smem_t4 = smem + 2 * (size_t)dimN * (size_t)(((dimN + 3) & ~3) - dimN) * sizeof(uint32_t);
+        const bool tile4_fits = smem_t4 <= 200 * 1024;
         if (smem > 48 * 1024 && !h->fused_attr_set) {      // both one-CTA-per-world fallbacks (64x64 with > 817 agents needs it too)
             DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_n64, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->fused_attr_set = true;
         }
-        const bool tile4 = !n64 && dimN % 4 == 0 && dimN >= 12 && !(impl && !strcmp(impl, "generic"));
+        const bool tile4 = !n64 && dimN >= 12 && tile4_fits && !(impl && !strcmp(impl, "generic")) && !getenv("DW_TILE4_MULT4_ONLY") ||
+                           (!n64 && dimN % 4 == 0 && dimN >= 12 && !(impl && !strcmp(impl, "generic")));
+        if (tile4) smem = smem_t4;
         if (n64) k_fused_n64<<<h->cfg.batch, 256, smem, h->stream>>>(A);
         else if (tile4) {
             // 4x4 tiles dealt round-robin to the threads: pick the block size that keeps the most useful warps resident
             // (64 registers per thread: at most 1024 threads per SM; CTAs per SM bounded by the shared-memory footprint)
             if (!h->tile4_threads) {
-                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_tile4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                const int TT = (dimN / 4) * (dimN / 4);
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_tile4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(k_fused_tile4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                const int TT = ((dimN + 3) / 4) * ((dimN + 3) / 4);
                 const int cps_max = (int)std::min<size_t>(16, (227 * 1024) / (smem + 1024));
                 double best = -1.0;
                 for (int cps = 1; cps <= std::max(1, cps_max); ++cps) {
@@ -287,9 +293,37 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
             }
             const char *tenv = getenv("DW_TILE4_THREADS");
             const int threads = tenv ? atoi(tenv) : h->tile4_threads;
-            k_fused_tile4<<<h->cfg.batch, threads, smem, h->stream>>>(A);
-        } else k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
-        h->lcur = 1 - h->lcur;
+            void (*kern)(const FusedArgs) = dimN % 4 == 0 ? k_fused_tile4<false> : k_fused_tile4<true>;
+            if (!h->tile4_blocks || h->tile4_blocks_threads != threads) {
+                int per_sm = 0, sms = 0;
+                DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+                DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+                if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "4x4-tile kernel does not fit on an SM");
+                h->tile4_blocks = per_sm * sms;
+                h->tile4_blocks_threads = threads;
+            }
+            // persistent CTAs, (world, chunk) work queue, state advanced in place (like the 64x64 kernel)
+            const char *kc_env = getenv("DW_PERSIST_KC");
+            A.Kc = kc_env ? atoi(kc_env) : 16;
+            if (A.Kc < 1) A.Kc = 1;
+            A.n_pairs = h->cfg.batch;
+            A.n_chunks = (K + A.Kc - 1) / A.Kc;
+            if (A.n_chunks > 1) {
+                rc = dev_alloc(h, &h->persist_sync, (size_t)h->cfg.batch + 1);
+                if (rc) return rc;
+                DW_CUDA_TRY(h, cudaMemsetAsync(h->persist_sync, 0, ((size_t)A.n_pairs + 1) * sizeof(unsigned int), h->stream));
+                A.queue = h->persist_sync;
+                A.pair_done = h->persist_sync + 1;
+            }
+            A.lat = h->lat[h->lcur];
+            const long long items = (long long)A.n_pairs * A.n_chunks;
+            const int grid = (int)(items < h->tile4_blocks ? items : h->tile4_blocks);
+            kern<<<grid, threads, smem, h->stream>>>(A);
+        } else {
+            k_fused_generic<<<h->cfg.batch, 256, smem, h->stream>>>(A);
+            h->lcur = 1 - h->lcur;
+        }
+        if (n64) h->lcur = 1 - h->lcur;
     }
     DW_LAUNCHED(h);
     if (h->profiling) {

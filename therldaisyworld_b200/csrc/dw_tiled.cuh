@@ -368,9 +368,10 @@ struct RowsTile72 {
     }
 };
 struct StoreGlobal {
+    static constexpr bool kMasks = false;
     uint32_t *o;            // first cell of the thread's first output row
     int pitch;
-    __device__ __forceinline__ void operator()(int i, const uint32_t (&q)[4]) const {
+    __device__ __forceinline__ void operator()(int i, uint32_t (&q)[4]) const {
         *reinterpret_cast<uint4 *>(o + (size_t)i * pitch) = make_uint4(q[0], q[1], q[2], q[3]);
     }
 };
