@@ -173,3 +173,27 @@ def test_fp32_mode_random_physics():
         st, _ = _check_f32_against_f64(env)
         tiers.append(st["fp64_tier"] / st["cells"])
     assert np.mean(tiers) < 0.25, tiers
+
+
+@pytest.mark.parametrize("N,n", [(20, 3), (48, 4), (96, 2)])
+def test_series_in_the_tile4_kernel_matches_oracle_per_step(N, n):
+    """The 4x4-tile persistent kernel's in-kernel series mode (sides that are other multiples of 4), against the NumPy oracle
+    started from the same reset state; more steps than one 16-step work item."""
+    import json
+    from therldaisyworld_b200 import RLDaisyWorld
+    from oracle.daisy_numpy import OracleGreedy, env_from_golden
+    np.random.seed(N)
+    env = RLDaisyWorld(grid_dimension=N, n_agents=n)
+    env.batch_size = 3
+    env.reset()
+    z = {"meta": json.dumps({"ctor": {"grid_dimension": N, "n_agents": n}, "attrs": {"batch_size": 3}}),
+         "init_grid": env.grid.copy(), "init_agent_indices": env.agent_indices.copy(), "init_agent_states": env.agent_states.copy()}
+    oenv, _ = env_from_golden(z)
+    K = 37
+    series = env.run_series(K, policy="greedy")
+    agent = OracleGreedy()
+    obs = oenv.get_obs(oenv.agent_indices)
+    for t in range(K):
+        obs, _, _, _ = oenv.step(agent(obs))
+        np.testing.assert_allclose(series[t], [oenv.temp.mean(), oenv.grid[:, 1].mean(), oenv.grid[:, 2].mean()], rtol=1e-9)
+    np.testing.assert_array_equal(env.grid, oenv.grid)

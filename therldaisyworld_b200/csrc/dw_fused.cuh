@@ -1518,10 +1518,13 @@ __device__ __noinline__ uint32_t dw_fix_warp_tile4(const FusedArgs *A, const Ste
     return __vmaxu2(mine ? 0u : mx, extra);
 }
 
-template <bool PAD>
+template <bool PAD, bool DIAG = false>
 __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__ FusedArgs A) {
+    static_assert(!(PAD && DIAG), "series mode: sides that are multiples of 4 (the temperature sum would include padded cells)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_item;
+    __shared__ double s_tsum;               // series mode (DIAG), see k_fused_n64_persist
+    __shared__ unsigned int s_cov[2];
     const int N = A.P.N, n = A.P.n_agents, NN = N * N, T = (N + 3) >> 2, TT = T * T;
     const int ld = PAD ? T * 4 : N, SN = N * ld;   // PAD: shared-memory rows padded to a multiple of 4 words (16-byte tile loads)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
@@ -1570,6 +1573,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__
             S.ada[i] = 0;
         }
         if (tid < 4) s_max[tid] = 0;
+        if (DIAG && tid == 0) { s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u; }
         __syncthreads();
 
         uint32_t *cb = buf0, *nb = buf1;
@@ -1589,6 +1593,8 @@ __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__
             }
             const StepCoef C = A.sc[j];
             uint32_t mx = 0;
+            double tsum = 0.0;
+            unsigned int cl = 0, cd = 0;
             for (int r = 0; r < rounds; ++r) {                      // uniform trip count: the fix-up below is warp-collective
                 const int tile = tid + r * nthr;
                 const bool active = tile < TT;
@@ -1598,16 +1604,37 @@ __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__
                 uint32_t m = 0;
                 const int valid = PAD ? min(4, N - c0) : 4;
                 if (active)
-                    m = dw_tile_core(A.F, C, RowsTile4<PAD>{cb, N, ld, r0, c0, c0 == 0 ? N - 1 : c0 - 1, c0 + 4 >= N ? c0 + 4 - N : c0 + 4, valid},
-                                     StoreTile4<PAD>{nb, N, ld, r0, c0, valid}, &tiemin);
+                    m = dw_tile_core<RowsTile4<PAD>, StoreTile4<PAD>, DIAG>(
+                        A.F, C, RowsTile4<PAD>{cb, N, ld, r0, c0, c0 == 0 ? N - 1 : c0 - 1, c0 + 4 >= N ? c0 + 4 - N : c0 + 4, valid},
+                        StoreTile4<PAD>{nb, N, ld, r0, c0, valid}, &tiemin, &tsum);
                 const unsigned flagged = __ballot_sync(0xffffffffu, active && tiemin < A.F.tie_thresh);
                 if (flagged) m = dw_fix_warp_tile4(&A, &A.sc[j], cb, nb, flagged, m, r0, c0, lane, N, ld);
                 mx = __vmaxu2(mx, m);
+                if (DIAG && active) {           // this tile's new covers (fix-ups included)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(nb + (r0 + i) * N + c0);
+                        cl += (v.x & 0xffffu) + (v.y & 0xffffu) + (v.z & 0xffffu) + (v.w & 0xffffu);
+                        cd += (v.x >> 16) + (v.y >> 16) + (v.z >> 16) + (v.w >> 16);
+                    }
+                }
             }
             const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
             int *sm = s_max + 2 * (jl & 1);
             if (lane == 0) { atomicMax(sm, (int)ml); atomicMax(sm + 1, (int)md); }
+            if (DIAG) {
+                for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+                cl = __reduce_add_sync(0xffffffffu, cl);
+                cd = __reduce_add_sync(0xffffffffu, cd);
+                if (lane == 0) { atomicAdd(&s_tsum, tsum); atomicAdd(&s_cov[0], cl); atomicAdd(&s_cov[1], cd); }
+            }
             __syncthreads();
+            if (DIAG && tid == 32) {               // warp 1 (every block size is at least two warps when TT >= 9 tiles ... see host check)
+                atomicAdd(A.series_T + j, s_tsum);
+                atomicAdd(A.series_l + j, (unsigned long long)s_cov[0]);
+                atomicAdd(A.series_d + j, (unsigned long long)s_cov[1]);
+                s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u;
+            }
             if (warp == 0) {
                 const bool grid_done = max(sm[0], sm[1]) <= 5;
                 if (lane == 0) {

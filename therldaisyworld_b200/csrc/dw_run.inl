@@ -294,13 +294,22 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
             const char *tenv = getenv("DW_TILE4_THREADS");
             const int threads = tenv ? atoi(tenv) : h->tile4_threads;
             void (*kern)(const FusedArgs) = dimN % 4 == 0 ? k_fused_tile4<false> : k_fused_tile4<true>;
-            if (!h->tile4_blocks || h->tile4_blocks_threads != threads) {
+            if (h->series_on) {
+                if (dimN % 4 != 0 || threads < 64) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "series mode of the 4x4-tile kernel: sides that are multiples of 4");
+                kern = k_fused_tile4<false, true>;
+                DW_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                A.series_T = h->series_T + h->series_pos;
+                A.series_l = h->series_l + h->series_pos;
+                A.series_d = h->series_d + h->series_pos;
+                h->series_pos += K;
+            }
+            if (!h->tile4_blocks || h->tile4_blocks_threads != threads || h->series_on) {
                 int per_sm = 0, sms = 0;
                 DW_CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
                 DW_CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
                 if (per_sm < 1) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "4x4-tile kernel does not fit on an SM");
                 h->tile4_blocks = per_sm * sms;
-                h->tile4_blocks_threads = threads;
+                h->tile4_blocks_threads = h->series_on ? 0 : threads;       // the series variant is re-queried every time
             }
             // persistent CTAs, (world, chunk) work queue, state advanced in place (like the 64x64 kernel)
             const char *kc_env = getenv("DW_PERSIST_KC");
@@ -644,9 +653,11 @@ extern "C" int dw_run_series(dw_handle *h, int64_t K, int32_t policy, const int8
     const int dN = h->cfg.dim;
     const bool n64_ok = dN == 64 && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
     const bool sub_ok = (dN == 8 || dN == 16 || dN == 32) && (64 / dN) * (64 / dN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
-    if (!(n64_ok || sub_ok) || !dw_fused_supported(h) || policy == DW_POLICY_MLP || getenv("DW_FUSED_IMPL"))
+    const bool t4_ok = dN != 64 && !sub_ok && dN >= 20 && dN % 4 == 0;     // k_fused_tile4<false, true> (>= 25 tiles: at least two warps)
+    if (!(n64_ok || sub_ok || t4_ok) || !dw_fused_supported(h) || policy == DW_POLICY_MLP || getenv("DW_FUSED_IMPL"))
         return dw_fail(h, DW_E_UNSUPPORTED, "dw_run_series",
-                       "series mode runs in the persistent kernels (64x64 with <= 32 agents; 8x8, 16x16, 32x32 with <= 256 agents per CTA; built-in policies)");
+                       "series mode runs in the persistent kernels (64x64 with <= 32 agents; 8x8, 16x16, 32x32 with <= 256 agents per CTA; "
+                       "other multiples of 4 from 20 that fit in shared memory; built-in policies)");
     int rc = dev_alloc(h, &h->series_T, (size_t)DW_FUSED_MAX_STEPS);
     if (!rc) rc = dev_alloc(h, &h->series_l, (size_t)DW_FUSED_MAX_STEPS);
     if (!rc) rc = dev_alloc(h, &h->series_d, (size_t)DW_FUSED_MAX_STEPS);

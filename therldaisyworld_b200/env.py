@@ -427,7 +427,8 @@ class RLDaisyWorld:
         if policy == "replay":
             a8 = np.ascontiguousarray(canonical_actions8(np.asarray(actions).reshape(-1, B, n)[:K]))
         out = np.zeros((int(K), 3))
-        in_kernel = (N == 64 and n <= 32) or (N in (8, 16, 32) and (64 // N) ** 2 * n <= 256)
+        in_kernel = (N == 64 and n <= 32) or (N in (8, 16, 32) and (64 // N) ** 2 * n <= 256) or \
+            (N % 4 == 0 and 20 <= N <= 156 and N not in (32, 64) and n <= 1024)
         if not in_kernel or policy == "mlp" or colliding:
             # other shapes: one fused step per sample, the same three means from the device-side reductions
             for t in range(int(K)):
