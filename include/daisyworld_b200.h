@@ -238,6 +238,16 @@ int dw_get_cover_stats(dw_handle *h, double *out /*[4]*/);
    which every world of this handle is grid_done (the notebook's loop condition). */
 int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed, int32_t stop_all_done,
            dw_run_result *res);
+/* Statistics-only variant of dw_run_chunk for lifespan ensembles (notebook cell 2 run for its counters only): the chunk may run
+   past the stopping step; the kernels record per agent in which steps of the chunk it was not done, and
+   dw_trim_lifespans(h, j) takes the steps after step j (0-based, the first step at which every world of every rank was
+   grid_done) back out of agents_done_at. done_at needs no correction (every world stays done). No checkpoint, no replay; the
+   lattice/agents/clock are left where the chunk ended. dw_trim_supported: *yes = 1 when the NEXT chunk can run this way
+   (lattice-resident state, persistent kernel families, built-in policies); otherwise use dw_checkpoint_save + dw_run_chunk +
+   dw_checkpoint_restore. */
+int dw_trim_supported(dw_handle *h, int32_t policy, int32_t *yes);
+int dw_run_chunk_masked(dw_handle *h, int32_t K, int32_t policy, const int8_t *actions, uint64_t seed, uint64_t *done_mask);
+int dw_trim_lifespans(dw_handle *h, int32_t j);
 /* Multi-rank variant: run exactly `K` (<=64) steps and return, per step, whether every world of THIS handle
    was grid_done (bit j of *done_mask = step j); the caller ANDs masks across ranks and decides. */
 int dw_run_chunk(dw_handle *h, int32_t K, int32_t policy, const int8_t *actions, uint64_t seed, uint64_t *done_mask);

@@ -190,3 +190,31 @@ def test_torus_translation_invariance(N, n, policy):
     np.testing.assert_array_equal(a.agent_states, b.agent_states)
     np.testing.assert_array_equal(a.lifespans()[0], b.lifespans()[0])
     np.testing.assert_array_equal(a.lifespans()[1], b.lifespans()[1])
+
+
+@pytest.mark.parametrize("N,B,policy", [(64, 40, "greedy"), (64, 25, "random"), (16, 70, "greedy"), (32, 9, "antigreedy")])
+def test_trimmed_lifespans_equal_checkpoint_and_replay(monkeypatch, N, B, policy):
+    """ensemble.simulate_lifespan, statistics only: segments run 'masked' past the stopping step and the surplus is trimmed out
+    of the agents' counters (dw_run_chunk_masked / dw_trim_lifespans) -- against the checkpoint + rewind + replay path
+    (DW_NO_TRIM=1): identical lifespan counters, steps and statistics."""
+    from therldaisyworld_b200 import RLDaisyWorld
+    from therldaisyworld_b200.ensemble import DeviceShard, simulate_lifespan
+    res = []
+    for no_trim in (False, True):
+        if no_trim:
+            monkeypatch.setenv("DW_NO_TRIM", "1")
+        else:
+            monkeypatch.delenv("DW_NO_TRIM", raising=False)
+        np.random.seed(3)
+        env = RLDaisyWorld(grid_dimension=N)
+        env.batch_size = B
+        env.reset_on_device(seed=11)
+        shard = DeviceShard(env)
+        out = simulate_lifespan(shard, policy=policy, seed=5, device="cuda")
+        if not no_trim:
+            assert shard.trim_supported(policy)
+        res.append((out, env.lifespans()))
+    (a, la), (b, lb) = res
+    assert a == b and a["all_done"] and a["steps"] % 64 != 0
+    np.testing.assert_array_equal(la[0], lb[0])
+    np.testing.assert_array_equal(la[1], lb[1])

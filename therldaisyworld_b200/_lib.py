@@ -38,7 +38,7 @@ SYMBOLS = [
     "dw_set_stream", "dw_set_epsilon", "dw_set_mlp", "dw_set_mlp_population", "dw_run_population", "dw_get_population_results",
     "dw_upload_state", "dw_upload_covers", "dw_init_random", "dw_init_temperatures", "dw_set_profiling", "dw_get_profile", "dw_step", "dw_step_collect", "dw_step_out_layout", "dw_step_packed", "dw_host_alloc", "dw_host_free", "dw_step_policy", "dw_update_agents",
     "dw_agents_begin", "dw_agents_collide", "dw_step_tail_collect", "dw_step_tail_counted",
-    "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_get_grid_f32", "dw_get_obs_f32", "dw_f32_stats", "dw_debug_time_materialise", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
+    "dw_forward", "dw_get_obs_at", "dw_get_grid", "dw_trim_supported", "dw_run_chunk_masked", "dw_trim_lifespans", "dw_get_grid_f32", "dw_get_obs_f32", "dw_f32_stats", "dw_debug_time_materialise", "dw_get_agents", "dw_get_obs", "dw_get_reward_done", "dw_get_diag", "dw_get_diag_stats", "dw_get_cover_stats",
     "dw_run", "dw_run_chunk", "dw_run_series", "dw_reset_lifespans", "dw_get_lifespans", "dw_lifespan_stats_device",
     "dw_checkpoint_save", "dw_checkpoint_restore", "dw_synchronize", "dw_set_world_offset", "dw_debug_slow_count", "dw_debug_state",
     "dw_debug_root4", "dw_debug_markstein", "dw_debug_markstein_f32", "dw_debug_fp64_peak", "dw_debug_screen_error",
@@ -117,6 +117,9 @@ def load():
         "dw_get_grid_f32": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "dw_get_obs_f32": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "dw_f32_stats": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+        "dw_trim_supported": (C.c_int, [vp, C.c_int32, C.POINTER(C.c_int32)]),
+        "dw_run_chunk_masked": (C.c_int, [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int8), C.c_uint64, C.POINTER(C.c_uint64)]),
+        "dw_trim_lifespans": (C.c_int, [vp, C.c_int32]),
         "dw_debug_time_materialise": (C.c_int, [vp, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
         "dw_get_agents": (C.c_int, [vp, pi64, pd]),
         "dw_get_obs": (C.c_int, [vp, pd]),

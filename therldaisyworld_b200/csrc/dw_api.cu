@@ -103,6 +103,9 @@ struct dw_handle {
     int persist_blocks = 0, sub64_blocks = 0;  // resident CTAs of the persistent kernels on this device
     int sub64_blocks_series = 0;               // sub-64 kernel in series mode
     int sub64_blocks_mlp = 0;                  // sub-64 kernel with the in-kernel MLP policy
+    // statistics-only lifespan runs (dw_run_chunk_masked / dw_trim_lifespans): per-agent "not done" bits of the last chunk
+    unsigned long long *alive_mask = nullptr;
+    bool mask_on = false, mask_complete = false;
     double *pop_rew = nullptr;                 // [64][B*n] per-step agent states of a fused population segment (k_pop_post)
     bool pop_rew_on = false;
     int persist_blocks_mlp = 0;                // the same for the kernel with the in-kernel MLP policy (more shared memory)
@@ -369,7 +372,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->grid32, h->f32_stats, h->pop_rew, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
+    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->grid32, h->f32_stats, h->pop_rew, h->alive_mask, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);

@@ -92,6 +92,9 @@ struct FusedArgs {
     int mlp_wpm, mlp_half, mlp_adv, pad3_;   // population mode (wpm > 0): worlds per member, agents on the member's net, adversary set
     double SL_prev;             // S*L of the step before the launch's first one (observation windows of step 0)
     double *rew_series;         // [K][B*n] agent states after each step's update_agents (population post-pass, k_pop_post), or NULL
+    // [B*n] bit j = "agent was not done after step j of this launch" (K <= 64), or NULL: lets a statistics-only caller that ran
+    // past the notebook's stopping step take the surplus out of agents_done_at instead of rewinding (dw_trim_lifespans)
+    unsigned long long *alive_mask;
 };
 
 __device__ __forceinline__ double dw_u2d(uint32_t k) {        // exact u32 -> f64 through the 2^52 trick
@@ -677,6 +680,7 @@ struct __align__(16) N64Smem {
     int ada[DW_N64_MAX_AGENTS];     // agents_done_at increments of this work item
     int smax[4];                    // [2 parities][2 species]
     int item;
+    unsigned long long am[DW_N64_MAX_AGENTS];   // alive_mask bits of this work item
 };
 
 // Agent phase of one step for n <= 32 agents, one lane per agent, single pass (the reference's sequential loop,
@@ -728,6 +732,7 @@ __device__ __forceinline__ void dw_agents_phase32(const FusedArgs &A, int j, int
         sm.st[lane] = st;
         sm.xy[lane] = x | (y << 16);
         sm.ada[lane] += (st < 0.1) ? 0 : 1;
+        if (A.alive_mask && !(st < 0.1)) sm.am[lane] |= 1ull << (j & 63);
         if (A.rew_series) A.rew_series[((size_t)j * A.P.B + b) * n + lane] = st;
     }
 }
@@ -994,6 +999,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             sm.st[tid] = __ldcg(A.agent_state + g);
             sm.xy[tid] = __ldcg(A.agent_xy + 2 * g) | (__ldcg(A.agent_xy + 2 * g + 1) << 16);
             sm.ada[tid] = 0;
+            sm.am[tid] = 0ull;
         }
         if (tid < 4) sm.smax[tid] = 0;
         if (DIAG && tid == 0) { s_tsum = 0.0; s_cov[0] = 0u; s_cov[1] = 0u; }
@@ -1075,6 +1081,7 @@ __global__ void __launch_bounds__(256, DW_N64_MIN_BLOCKS) k_fused_n64_persist(co
             A.agent_xy[2 * g] = sm.xy[tid] & 0xffff;
             A.agent_xy[2 * g + 1] = sm.xy[tid] >> 16;
             if (A.count_life) A.agents_done_at[g] = __ldcg(A.agents_done_at + g) + sm.ada[tid];
+            if (A.alive_mask) A.alive_mask[g] = __ldcg(A.alive_mask + g) | sm.am[tid];
             A.reward[g] = r;
             A.done[g] = r < 0.1;
         }
@@ -1109,6 +1116,7 @@ struct Sub64Smem {
     int xy[DW_SUB64_MAX_AGENTS];        // x | y << 16, world-local
     int ada[DW_SUB64_MAX_AGENTS];
     signed char act[DW_SUB64_MAX_AGENTS];
+    unsigned long long am[DW_SUB64_MAX_AGENTS];   // alive_mask bits of this work item
     int smax[2][(64 / N) * (64 / N)][2];
     int life[(64 / N) * (64 / N)];
     int item;
@@ -1246,6 +1254,7 @@ __device__ __forceinline__ void dw_agents_phase_sub(const FusedArgs &A, int j, i
             sm.st[a] = st;
             sm.xy[a] = x | (y << 16);
             sm.ada[a] += (st < 0.1) ? 0 : 1;
+            if (A.alive_mask && !(st < 0.1)) sm.am[a] |= 1ull << (j & 63);
             if (A.rew_series) A.rew_series[((size_t)j * A.P.B + (size_t)group * W) * n + a] = st;
         }
         __syncwarp();
@@ -1313,6 +1322,7 @@ __global__ void __launch_bounds__(256, MLP ? 3 : DW_N64_MIN_BLOCKS) k_fused_sub6
             sm.st[a] = __ldcg(A.agent_state + ga);
             sm.xy[a] = __ldcg(A.agent_xy + 2 * ga) | (__ldcg(A.agent_xy + 2 * ga + 1) << 16);
             sm.ada[a] = 0;
+            sm.am[a] = 0ull;
         }
         for (int q = tid; q < 2 * W * 2; q += 256) (&sm.smax[0][0][0])[q] = 0;
         if (tid < W) sm.life[tid] = 0;
@@ -1422,6 +1432,7 @@ __global__ void __launch_bounds__(256, MLP ? 3 : DW_N64_MIN_BLOCKS) k_fused_sub6
             A.agent_xy[2 * ga] = sm.xy[a] & 0xffff;
             A.agent_xy[2 * ga + 1] = sm.xy[a] >> 16;
             if (A.count_life) A.agents_done_at[ga] = __ldcg(A.agents_done_at + ga) + sm.ada[a];
+            if (A.alive_mask) A.alive_mask[ga] = __ldcg(A.alive_mask + ga) | sm.am[a];
             A.reward[ga] = r;
             A.done[ga] = r < 0.1;
         }
@@ -1629,7 +1640,7 @@ __global__ void __launch_bounds__(1024, 1) k_fused_tile4(const __grid_constant__
                 if (lane == 0) { atomicAdd(&s_tsum, tsum); atomicAdd(&s_cov[0], cl); atomicAdd(&s_cov[1], cd); }
             }
             __syncthreads();
-            if (DIAG && tid == 32) {               // warp 1 (every block size is at least two warps when TT >= 9 tiles ... see host check)
+            if (DIAG && tid == nthr - 1) {         // the last thread (any block size); warp 0's lane 0 does the bookkeeping below
                 atomicAdd(A.series_T + j, s_tsum);
                 atomicAdd(A.series_l + j, (unsigned long long)s_cov[0]);
                 atomicAdd(A.series_d + j, (unsigned long long)s_cov[1]);

@@ -761,6 +761,14 @@ __global__ void __launch_bounds__(128) k_pop_accumulate(int wpm, int n, int half
     }
 }
 
+// agents_done_at -= number of steps after step j of the last chunk in which the agent was not done (alive_mask, see FusedArgs)
+__global__ void __launch_bounds__(256) k_trim_lifespans(size_t count, int j, const unsigned long long *__restrict__ mask,
+                                                        int64_t *__restrict__ agents_done_at) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count || j >= 63) return;
+    agents_done_at[i] -= __popcll(mask[i] >> (j + 1));
+}
+
 // The same bookkeeping for S steps at once from the recorded per-step agent states (fused population segments: the policy
 // and the steps ran inside one launch, FusedArgs::rew_series). rew: [S][Bn] state after each step's update_agents = the
 // step's reward (done = reward < 0.1); frozen[] advances by (1 - done) per step while the member's loop is alive, exactly

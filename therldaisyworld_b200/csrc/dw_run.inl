@@ -152,6 +152,7 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
     A.K = K; A.policy = policy;
     A.count_life = h->count_life ? 1 : 0;
     A.slow_count = h->slow_count;
+    A.alive_mask = h->mask_on ? h->alive_mask : nullptr;
     // kernel selection: 64x64 worlds with <= 32 agents run the persistent kernel (dynamic work queue); DW_FUSED_IMPL
     // overrides for experiments: "persist" (default) | "simple" (one CTA per world) | "generic" (any N)
     const char *impl = getenv("DW_FUSED_IMPL");
@@ -295,7 +296,7 @@ static int launch_fused(dw_handle *h, int K, int policy, const int8_t *act_dev, 
             const int threads = tenv ? atoi(tenv) : h->tile4_threads;
             void (*kern)(const FusedArgs) = dimN % 4 == 0 ? k_fused_tile4<false> : k_fused_tile4<true>;
             if (h->series_on) {
-                if (dimN % 4 != 0 || threads < 64) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "series mode of the 4x4-tile kernel: sides that are multiples of 4");
+                if (dimN % 4 != 0) return dw_fail(h, DW_E_UNSUPPORTED, "launch_fused", "series mode of the 4x4-tile kernel: sides that are multiples of 4");
                 kern = k_fused_tile4<false, true>;
                 DW_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 A.series_T = h->series_T + h->series_pos;
@@ -514,6 +515,57 @@ extern "C" int dw_run_chunk(dw_handle *h, int32_t K, int32_t policy, const int8_
     return run_chunk_impl(h, K, policy, h->action_dev, seed, done_mask, nullptr);
 }
 
+// Statistics-only lifespan runs (ensemble.simulate_lifespan): the notebook's loop stops at the first step at which every world
+// is grid_done, which is only known after a chunk has run. dw_run(stop_all_done) rewinds to a checkpoint and replays up to that
+// step (exact final state); a caller that only wants the lifespan counters can instead let the chunk run on and take the
+// surplus out of agents_done_at afterwards -- done_at cannot grow after the stopping step (every world is done for good), and
+// the kernels record per agent which steps of the chunk it was not done in. No checkpoint copy, no replay.
+static bool trim_supported(const dw_handle *h, int policy) {
+    const int N = h->cfg.dim, n = h->cfg.n_agents;
+    const bool fam = (N == 64 && n <= DW_N64_MAX_AGENTS) || ((N == 8 || N == 16 || N == 32) && (64 / N) * (64 / N) * n <= DW_SUB64_MAX_AGENTS);
+    return fam && h->lat_valid && dw_fused_supported(h) && policy != DW_POLICY_MLP && !getenv("DW_FUSED_IMPL") && !getenv("DW_NO_TRIM");
+}
+
+extern "C" int dw_trim_supported(dw_handle *h, int32_t policy, int32_t *yes) {
+    if (!h || !yes) return DW_E_INVALID;
+    *yes = trim_supported(h, policy) ? 1 : 0;
+    return DW_OK;
+}
+
+extern "C" int dw_run_chunk_masked(dw_handle *h, int32_t K, int32_t policy, const int8_t *actions, uint64_t seed, uint64_t *done_mask) {
+    if (!h || K < 1 || K > 64) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = check_policy(h, policy, actions);
+    if (rc) return rc;
+    if (!trim_supported(h, policy)) return dw_fail(h, DW_E_STATE, "dw_run_chunk_masked", "ask dw_trim_supported first");
+    const size_t per_step = (size_t)h->cfg.batch * h->cfg.n_agents;
+    if (policy == DW_POLICY_REPLAY && per_step) {
+        rc = stage_actions8(h, actions, per_step * K);
+        if (rc) return rc;
+    }
+    rc = dev_alloc(h, &h->alive_mask, per_step);
+    if (rc) return rc;
+    DW_CUDA_TRY(h, cudaMemsetAsync(h->alive_mask, 0, (per_step ? per_step : 1) * sizeof(unsigned long long), h->stream));
+    h->mask_on = true;
+    rc = run_chunk_impl(h, K, policy, h->action_dev, seed, done_mask, nullptr);
+    h->mask_on = false;
+    h->mask_complete = rc == DW_OK;
+    return rc;
+}
+
+extern "C" int dw_trim_lifespans(dw_handle *h, int32_t j) {
+    if (!h || j < 0 || j > 63) return DW_E_INVALID;
+    DW_CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->mask_complete) return dw_fail(h, DW_E_STATE, "dw_trim_lifespans", "no masked chunk to trim (dw_run_chunk_masked)");
+    const size_t count = (size_t)h->cfg.batch * h->cfg.n_agents;
+    if (count) {
+        k_trim_lifespans<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(count, j, h->alive_mask, h->agents_done_at);
+        DW_LAUNCHED(h);
+    }
+    h->mask_complete = false;
+    return DW_OK;
+}
+
 extern "C" int dw_run(dw_handle *h, int64_t K, int32_t policy, const int8_t *actions, uint64_t seed, int32_t stop_all_done,
                       dw_run_result *res) {
     if (!h || K < 0) return DW_E_INVALID;
@@ -653,7 +705,7 @@ extern "C" int dw_run_series(dw_handle *h, int64_t K, int32_t policy, const int8
     const int dN = h->cfg.dim;
     const bool n64_ok = dN == 64 && h->cfg.n_agents <= DW_N64_MAX_AGENTS;
     const bool sub_ok = (dN == 8 || dN == 16 || dN == 32) && (64 / dN) * (64 / dN) * h->cfg.n_agents <= DW_SUB64_MAX_AGENTS;
-    const bool t4_ok = dN != 64 && !sub_ok && dN >= 20 && dN % 4 == 0;     // k_fused_tile4<false, true> (>= 25 tiles: at least two warps)
+    const bool t4_ok = dN != 64 && !sub_ok && dN >= 20 && dN % 4 == 0;     // k_fused_tile4<false, true>
     if (!(n64_ok || sub_ok || t4_ok) || !dw_fused_supported(h) || policy == DW_POLICY_MLP || getenv("DW_FUSED_IMPL"))
         return dw_fail(h, DW_E_UNSUPPORTED, "dw_run_series",
                        "series mode runs in the persistent kernels (64x64 with <= 32 agents; 8x8, 16x16, 32x32 with <= 256 agents per CTA; "
