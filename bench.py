@@ -229,7 +229,8 @@ def cpu_baseline_sample():
 def sustained_bench(rank, world, local):
     """Seconds-long runs on the fused path, device-timed, clocks sampled (the headline's timed region is ~0.1 s).
     N = 1: BASELINE configs[2] shape -- 100 000 worlds of 64x64 with 4 agents, WHOLE LIVES under the notebook's stopping rule
-    (64-step segments, device checkpoint + rewind), four of its conditions back to back (>= 2 s of device time).
+    (32-step segments run past the stopping step, surplus trimmed out of the agents' counters: ensemble.simulate_lifespan),
+    four of its conditions back to back (>= 2 s of device time).
     N > 1: BASELINE configs[3] -- 125 000 worlds per GPU (10^6 at N = 8), random agents, whole lives, worlds sharded with no
     data-path collective; per 64-step segment one MIN all-reduce of the all-done flags, at the end ONE NCCL all-reduce of the
     8-double lifespan statistics."""
@@ -272,13 +273,13 @@ def sustained_bench(rank, world, local):
     clocks = sampler.stop() if sampler else None
     del env
     torch.cuda.empty_cache()
-    return {"workload": (f"BASELINE configs[2] shape: {total} worlds x {N}x{N}, {N_AGENTS} agents, whole lives (stopping rule, "
-                         "checkpoint + rewind per 64-step segment), 4 conditions") if world == 1 else
+    return {"workload": (f"BASELINE configs[2] shape: {total} worlds x {N}x{N}, {N_AGENTS} agents, whole lives (stopping rule: "
+                         "32-step segments, surplus steps trimmed out of the lifespan counters), 4 conditions") if world == 1 else
                         (f"BASELINE configs[3]: {total} worlds ({total // world} per GPU) x {N}x{N}, random agents, whole lives, "
                          "one NCCL all-reduce of the 8-double statistics + one MIN all-reduce per 64-step segment"),
             "metric": "cell_updates_per_s", "value": cells / (dev_ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world,
             "device_seconds": dev_ms * 1e-3, "scaling": "weak", "conditions": out, "clocks": clocks,
-            "timing": "CUDA events around each condition (incl. the segment read-backs and checkpoints), max over ranks"}
+            "timing": "CUDA events around each condition (incl. the first literal step, the segment read-backs and the trim), max over ranks"}
 
 
 # ----------------------------------------------------------------------------------------------- fp32 mode
