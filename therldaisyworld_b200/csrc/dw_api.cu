@@ -71,8 +71,6 @@ struct dw_handle {
     unsigned int *slow_count = nullptr;        // [0] literal recomputations in fused runs, [1] scratch counter
     // fp32 mode (dw_f32.cuh): float [B,7,N,N] grid materialised with fp32 arithmetic, tier counters {fp64-tier cells, literal cells}
     float *grid32 = nullptr;
-    unsigned int *f32_list = nullptr;          // [1 + cap] work list of the fp64 tier (count, then cell indices)
-    size_t f32_list_cap = 0;
     unsigned long long *f32_stats = nullptr;
     unsigned long long f32_cells = 0;          // cells materialised by the fp32 path so far
     unsigned int world0 = 0;                   // global index of the first world (multi-rank ensembles)
@@ -374,7 +372,7 @@ extern "C" int dw_destroy(dw_handle *h) {
     if (!h) return DW_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->grid32, h->f32_stats, h->f32_list, h->pop_rew, h->alive_mask, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
+    void *ptrs[] = {h->grid[0], h->grid[1], h->cov, h->agent_idx64, h->lat[0], h->lat[1], h->lat_pre, h->agent_xy, h->agent_state, h->out_block, h->world_max, h->done_at, h->agents_done_at, h->alive, h->action_dev, h->scratch, h->fwd_in, h->slow_count, h->grid32, h->f32_stats, h->pop_rew, h->alive_mask, h->sc_dev, h->persist_sync, h->series_T, h->series_l, h->series_d, h->mlp_dev, h->pop_sum, h->pop_done, h->pop_steps, h->pop_frozen, h->pop_ndone,
                     h->fwd_out};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
@@ -1169,25 +1167,11 @@ static int materialise_f32(dw_handle *h) {
     make_fast_coef(h->cfg, A.F);
     make_step_coef(h->cfg, h->L_last, A.C);
     make_f32_coef(h->cfg, A.F, A.C, P, A.Q);
-    // fp64-tier work list: up to 1/8 of the cells (measured 2 %); world * N * N + cell must fit 32 bits, else everything in place
-    const size_t cells = B * NN;
-    unsigned int cap = cells < (1ull << 32) ? (unsigned int)(cells / 8 + 1024) : 0u;
-    if (h->f32_list_cap < (size_t)cap + 1) {
-        if (h->f32_list) cudaFree(h->f32_list);
-        h->f32_list = nullptr;
-        DW_CUDA_TRY(h, cudaMalloc((void **)&h->f32_list, ((size_t)cap + 1) * sizeof(unsigned int)));
-        h->f32_list_cap = (size_t)cap + 1;
-    }
-    DW_CUDA_TRY(h, cudaMemsetAsync(h->f32_list, 0, sizeof(unsigned int), h->stream));
     if ((P.N & 1) == 0)
-        k_forward_f32<2><<<grid_for(B * NN / 2), 256, 0, h->stream>>>(A, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats, h->f32_list, cap);
+        k_forward_f32<2><<<grid_for(B * NN / 2), 256, 0, h->stream>>>(A, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
     else
-        k_forward_f32<1><<<grid_for(B * NN), 256, 0, h->stream>>>(A, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats, h->f32_list, cap);
+        k_forward_f32<1><<<grid_for(B * NN), 256, 0, h->stream>>>(A, h->lat_pre, h->lat[h->lcur], h->grid32, h->f32_stats);
     DW_LAUNCHED(h);
-    if (cap) {
-        k_forward_f32_fix<<<grid_for(cap / 16 + 1, 128), 128, 0, h->stream>>>(A, h->lat_pre, h->grid32, h->f32_stats, h->f32_list, cap);
-        DW_LAUNCHED(h);
-    }
     if (P.n_agents > 0) {
         k_stamp_f32<<<(P.B + 127) / 128, 128, 0, h->stream>>>(P, h->grid32, h->agent_xy, h->agent_state);
         DW_LAUNCHED(h);

@@ -68,6 +68,9 @@ __device__ __forceinline__ void dw_fast_x(const FastCoef &F, const StepCoef &C, 
 
 // fp64 tier of the bare fraction of one cell (rare: ~2 % of cells; out of line, called after the thread's stores so that
 // nothing of the fp32 evaluation is live across the call). Returns 1000 b' as the reference rounds it.
+// Measured alternatives (4000 worlds of 64x64, this in-place call: 0.185 ms): deferring the ~3e5 flagged cells to a dense second
+// kernel through a work list costs more than the divergence it removes -- one shared counter 0.257 ms (the warp-aggregated
+// atomics serialise), per-warp list segments without atomics 0.230 ms.
 __device__ __noinline__ float dw_f32_bare_slow(const DevParams *Pp, const FastCoef *Fp, const StepCoef *Cp, const uint32_t *g, unsigned N,
                                                unsigned x, unsigned y, unsigned *nlit) {
     const DevParams &P = *Pp;
@@ -141,13 +144,10 @@ __device__ __forceinline__ F32Out dw_f32_cell(const F32Coef &Q, uint32_t pc, uin
 // the last step started from; cur: the lattice after that step (exact new covers). out: float [B,7,N,N], channels 0..6
 // written (4 before the agent stamp). stats[0] += cells sent to the fp64 tier, stats[1] += cells that needed the literal cell.
 struct F32Args { DevParams P; FastCoef F; StepCoef C; F32Coef Q; };
-// list / list_cap: cells whose bare fraction needs the fp64 tier are appended (one warp-aggregated atomic per warp) and
-// finished densely by k_forward_f32_fix -- 2 % of the cells spread over half of the warps would otherwise make every other
-// warp walk through the fp64 path for one or two lanes. Cells that do not fit in the list are finished in place.
 template <int W>
 __global__ void __launch_bounds__(256, 4) k_forward_f32(const __grid_constant__ F32Args A, const uint32_t *__restrict__ pre,
                                                         const uint32_t *__restrict__ cur, float *__restrict__ out,
-                                                        unsigned long long *stats, unsigned int *list, unsigned int list_cap) {
+                                                        unsigned long long *stats) {
     const DevParams &P = A.P;
     const F32Coef &Q = A.Q;
     const unsigned N = (unsigned)P.N, NN = N * N, GN = NN / W, gN = N / W;
@@ -203,18 +203,9 @@ __global__ void __launch_bounds__(256, 4) k_forward_f32(const __grid_constant__ 
         // fp64 tier, the stored channel 0 is overwritten
 #pragma unroll
         for (int c = 0; c < W; ++c) {
-            const unsigned need = __ballot_sync(__activemask(), !ok[c]);
-            if (!need) continue;
-            const unsigned am = __activemask();
-            const int leader = __ffs(am) - 1, lane = threadIdx.x & 31;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(list, (unsigned)__popc(need));          // list[0] = count, entries from list[1]
-            base = __shfl_sync(am, base, leader);
             if (!ok[c]) {
                 n64 += 1;
-                const unsigned slot = base + __popc(need & ((1u << lane) - 1u));
-                if (slot < list_cap) list[1 + slot] = (unsigned)((size_t)w.b * NN + x * N + y + c);
-                else ob[c] = dw_div1000f(dw_f32_bare_slow(&A.P, &A.F, &A.C, g, N, x, y + c, &nlit));
+                ob[c] = dw_div1000f(dw_f32_bare_slow(&A.P, &A.F, &A.C, g, N, x, y + c, &nlit));
             }
         }
     }
@@ -223,20 +214,6 @@ __global__ void __launch_bounds__(256, 4) k_forward_f32(const __grid_constant__ 
         nlit = __reduce_add_sync(__activemask(), nlit);
         if ((threadIdx.x & 31) == 0 && n64) { atomicAdd(stats, (unsigned long long)n64); atomicAdd(stats + 1, (unsigned long long)nlit); }
     }
-}
-
-// the listed cells, one thread each: fp64 tier of the bare fraction, channel 0 overwritten
-__global__ void __launch_bounds__(128) k_forward_f32_fix(const __grid_constant__ F32Args A, const uint32_t *__restrict__ pre,
-                                                         float *__restrict__ out, unsigned long long *stats,
-                                                         const unsigned int *__restrict__ list, unsigned int list_cap) {
-    const unsigned N = (unsigned)A.P.N, NN = N * N;
-    const unsigned count = min(list[0], list_cap);
-    unsigned nlit = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const unsigned cell = list[1 + i], b = cell / NN, c = cell - b * NN, x = c / N, y = c - x * N;
-        out[(size_t)b * 7 * NN + c] = dw_div1000f(dw_f32_bare_slow(&A.P, &A.F, &A.C, pre + (size_t)b * NN, N, x, y, &nlit));
-    }
-    if (stats && nlit) atomicAdd(stats + 1, (unsigned long long)nlit);
 }
 
 // debug hook: integers |k| <= kmax whose dw_div1000f differs from the correctly rounded binary32 quotient (must be 0)
