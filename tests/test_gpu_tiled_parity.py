@@ -79,13 +79,14 @@ def test_bands_on_one_gpu_match_oracle(bands, policy):
     _compare(worlds, ref, done_at, ada)
 
 
-@pytest.mark.parametrize("bands,policy", [(2, "greedy"), (4, "antigreedy"), (4, "replay"), (2, "none")])
-def test_peer_memory_mode_bands_on_one_gpu(bands, policy):
+@pytest.mark.parametrize("bands,policy,n", [(2, "greedy", 200), (4, "antigreedy", 200), (4, "replay", 200), (2, "none", 200),
+                                            (2, "greedy", 900), (4, "antigreedy", 1500)])
+def test_peer_memory_mode_bands_on_one_gpu(bands, policy, n):
     """dwt_step_p2p: owners publish decisions / gains into every band's exchange vector, edge rows are pushed into the
     neighbours' ghost rows, bands meet at device-side flag barriers. Here the 'peers' are bands of one process on one GPU,
     each on its own stream (the IPC variant of the same code path runs in tools/banded_nccl_check.py)."""
     import torch
-    N, n, steps = 256, 200, 30
+    N, steps = 256, 30               # n > 256: several blocks in the agent kernels (grid barrier of k_band_fmc_graze)
     light, dark, ai, st = make_state(N, n, seed=17, clustered=True)
     ai[n // 2:, 0] = (ai[n // 2:, 0] + N // bands) % N
     shared = ThreadComm.Shared(bands)

@@ -277,6 +277,77 @@ __global__ void __launch_bounds__(256) k_band_graze(BandGeom G, Cells C, const i
     gain[i] = got;
 }
 
+// Peer-memory mode, lattice state: k_band_finish_move_claim and k_band_graze in ONE launch. The graze needs every claim of
+// the step filed, so the two halves are separated by a grid-wide barrier (monotonic counter in global memory: the host passes
+// the value it has after this launch's blocks have all arrived). Only launched when the grid is at most one block per SM
+// (n <= 256 * SMs), so every block is resident and the spin cannot deadlock. Saves one kernel boundary per step on the
+// critical path of a step (the two agent kernels are what is left there besides the stencil).
+__global__ void __launch_bounds__(256) k_band_fmc_graze(BandGeom G, double agent_gamma, int32_t *xy, double *st, int n,
+                                                        const double *__restrict__ act, int *claim_new, uint8_t *gz, int do_finish,
+                                                        double *gain_prev, int *claim_prev, double *reward, uint8_t *done,
+                                                        int64_t *agents_done_at, LatCells C, PeerTable PT, int gain_off,
+                                                        unsigned int *bar, unsigned int target) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    int x = 0, y = 0;
+    uint8_t g = 0;
+    if (active) {
+        double s = st[i];
+        x = xy[2 * i]; y = xy[2 * i + 1];
+        if (do_finish) {
+            const double gp = gain_prev[i];
+            gain_prev[i] = 0.0;
+            if (gz[i]) {
+                s = s + gp;
+                const int lr = band_owned_row(G, x);
+                if (lr >= 0) claim_prev[(size_t)lr * G.N + y] = 0x7fffffff;
+            }
+            s = dw_clip01(s);
+            reward[i] = s;
+            done[i] = s < 0.1;
+            agents_done_at[i] += (s < 0.1) ? 0 : 1;
+        }
+        const int a = (int)act[i] - 1;
+        s = s - agent_gamma;
+        st[i] = s;
+        if (s > 0.0) {
+            if (a != 8) {
+                const int d = (a & 2) ? 1 : -1;
+                if (((a + 1) & 2) == 0) { y += d; y = y < 0 ? y + G.N : (y >= G.N ? y - G.N : y); }
+                else { x += d; x = x < 0 ? x + G.N : (x >= G.N ? x - G.N : x); }
+                xy[2 * i] = x;
+                xy[2 * i + 1] = y;
+            }
+            if (a > 4) {
+                g = 1;
+                const int lr = band_owned_row(G, x);
+                if (lr >= 0) atomicMin(claim_new + (size_t)lr * G.N + y, i);
+            }
+        }
+        gz[i] = g;
+    }
+    // every claim of the step is filed once all blocks have passed here
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while ((int)(*(volatile unsigned int *)bar - target) < 0) { }
+        __threadfence();
+    }
+    __syncthreads();
+    if (!active || !g) return;
+    double got = 0.0;
+    bool won = false, clear = true;
+    const int lr = band_owned_row(G, x);
+    if (lr >= 0) {
+        if (__ldcg(claim_new + (size_t)lr * G.N + y) == i) { got = C.food((size_t)lr * G.pitch + G.c0 + y); won = true; }
+        else clear = false;
+    }
+    if (clear)
+        band_row_images(G, x, [&](int r) { band_col_images(G, y, [&](int cc) { C.zero((size_t)r * G.pitch + cc); }); });
+    if (won) for (int p = 0; p < PT.R; ++p) PT.exch[p][(size_t)gain_off + i] = got;
+}
+
 // Phase 4 (replicated, after the gains were summed over ranks): state += gain, clip, reward/done, lifespan counter;
 // also returns the graze claims of this step to "idle".
 __global__ void __launch_bounds__(256) k_band_finish(BandGeom G, const int32_t *__restrict__ xy, int *claim, double *st, int n,

@@ -14,6 +14,9 @@ struct dwt_handle {
     uint32_t *lat[2] = {nullptr, nullptr};
     CUtensorMap tmap[2];
     int cur = 0;
+    unsigned int *gridbar = nullptr;     // grid barrier counter of k_band_fmc_graze (monotonic)
+    unsigned int gridbar_count = 0;
+    int sm_count = 0;
     bool on_lattice = false;     // false: the state lives in the fp64 planes (right after reset)
     bool have_pre = false;       // a step has run: lat[1-cur] (or the planes) hold its post-graze pre-state
     bool pre_is_planes = false;
@@ -125,8 +128,18 @@ extern "C" int dwt_create(const dw_config *cfg, int32_t rows, int32_t row0, int3
               alloc((void **)&h->flags, (DWT_MAX_RANKS + 2) * 4) &&
               alloc((void **)&h->reward, n * 8) && alloc((void **)&h->gz, n) && alloc((void **)&h->done, n) &&
               alloc((void **)&h->agents_done_at, n * 8) && alloc((void **)&h->stepmax, (size_t)DW_FUSED_MAX_STEPS * 2 * 4) &&
-              alloc((void **)&h->slow_count, 4) && alloc((void **)&h->replay, n);
+              alloc((void **)&h->slow_count, 4) && alloc((void **)&h->replay, n) &&
+              alloc((void **)&h->gridbar, 4);        // here, not lazily: a cudaMalloc between steps synchronises the whole device
     if (ok) h->replay_cap = n;
+    if (ok) ok = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess;
+    if (ok) {
+        // With lazy module loading the FIRST launch of a kernel loads its code, which can synchronise the whole device. The
+        // merged agent kernel is first launched at step 2 of a peer-memory run, when a peer band may already be spinning at a
+        // flag barrier: with several bands of one process on ONE device (the test harness) the two would wait for each other
+        // until the barrier's timeout. Load it here.
+        cudaFuncAttributes fa;
+        ok = cudaFuncGetAttributes(&fa, k_band_fmc_graze) == cudaSuccess;
+    }
     if (ok) ok = cudaMemset(h->claim, 0x7f, planes * 4) == cudaSuccess;       // 0x7f7f7f7f: "idle" (> any agent index)
     h->gain = h->exch ? h->exch + n : nullptr;
     h->act = h->exch ? h->exch + 2 * n : nullptr;
@@ -154,7 +167,7 @@ extern "C" int dwt_destroy(dwt_handle *h) {
     if (h->ev_edge) cudaEventDestroy(h->ev_edge);
     if (h->ev_side) cudaEventDestroy(h->ev_side);
     void *ptrs[] = {h->lat[0], h->lat[1], h->pl, h->pd, h->claim, h->claim2, h->agent_xy, h->agent_state, h->exch, h->flags, h->reward, h->gz,
-                    h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch, h->csum};
+                    h->done, h->replay, h->agents_done_at, h->stepmax, h->slow_count, h->scratch, h->csum, h->gridbar};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
     return DW_OK;
@@ -715,13 +728,25 @@ extern "C" int dwt_step_p2p(dwt_handle *h, int32_t policy, const int8_t *actions
         // finish of the previous step (its gains are complete since its closing barrier) + move + claims, one launch
         const BandGeom G = h->on_lattice ? dwt_geom_lat(h) : dwt_geom_planes(h);
         double *gain_prev = h->pending_parity ? h->exch : h->exch + h->n;
-        k_band_finish_move_claim<<<dwt_blocks(h->n), 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act,
-                                                                          dwt_claim(h, h->gain_parity), h->gz, h->p2p_gain_pending ? 1 : 0,
-                                                                          gain_prev, dwt_claim(h, h->pending_parity), h->reward, h->done,
-                                                                          h->agents_done_at);
-        DWT_LAUNCHED(h);
-        rc = dwt_graze(h);
-        if (rc) return rc;
+        const int nb = dwt_blocks(h->n);
+        if (h->on_lattice && nb <= h->sm_count && !getenv("DW_BAND_SPLIT_AGENT_KERNELS")) {
+            // finish(j-1) + move + claim + graze in one launch (grid barrier between claim and graze, see k_band_fmc_graze)
+            h->gridbar_count += (unsigned int)nb;
+            k_band_fmc_graze<<<nb, 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act,
+                                                        dwt_claim(h, h->gain_parity), h->gz, h->p2p_gain_pending ? 1 : 0, gain_prev,
+                                                        dwt_claim(h, h->pending_parity), h->reward, h->done, h->agents_done_at,
+                                                        LatCells{h->lat[h->cur]}, h->pt, h->gain_parity ? 0 : h->n, h->gridbar,
+                                                        h->gridbar_count);
+            DWT_LAUNCHED(h);
+        } else {
+            k_band_finish_move_claim<<<nb, 256, 0, h->stream>>>(G, h->cfg.agent_gamma, h->agent_xy, h->agent_state, h->n, h->act,
+                                                                dwt_claim(h, h->gain_parity), h->gz, h->p2p_gain_pending ? 1 : 0,
+                                                                gain_prev, dwt_claim(h, h->pending_parity), h->reward, h->done,
+                                                                h->agents_done_at);
+            DWT_LAUNCHED(h);
+            rc = dwt_graze(h);
+            if (rc) return rc;
+        }
         h->p2p_gain_pending = true;
         h->pending_parity = h->gain_parity;
         h->gain_parity ^= 1;
