@@ -490,50 +490,74 @@ __device__ __noinline__ uint32_t dwt_fix_warp(const TiledArgs *A, const uint32_t
     return __vmaxu2(mine ? 0u : mx, extra);
 }
 
-__global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledArgs A) {
-    __shared__ __align__(128) uint32_t tile[DWT_TILE_ROWS * DWT_TILE_PITCH];
-    __shared__ __align__(8) unsigned long long bar;
+// A CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the launch with TWO staged tiles: the TMA load of the next
+// tile is issued before the current one is computed. The default launch is one tile per CTA (gridDim.x = number of tiles);
+// the persistent form (gridDim.x = resident CTAs, DW_TILED_PERSISTENT=1) was measured slower, see dwt_stencil_grid.
+__device__ __forceinline__ void dwt_issue_tile(const CUtensorMap *tmap, const TiledArgs &A, int t, uint32_t smem_tile, uint32_t bar_a) {
+    const int tc = t % A.tiles_x;
+    int tr = A.tr_first + t / A.tiles_x;
+    if (tr >= A.tr_skip_lo) tr += A.tr_skip_hi - A.tr_skip_lo;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)DWT_TILE_BYTES) : "memory");
+    // box origin (word, row) of the padded lattice: tile columns 64*tc-4 .. 64*tc+67, band rows 64*tr-1 .. 64*tr+64
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_tile), "l"(tmap), "r"(bar_a), "r"(tc * DWT_TILE), "r"(tr * DWT_TILE)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledArgs A,
+                                                       int n_tiles) {
+    constexpr int kStageWords = ((DWT_TILE_BYTES + 127) / 128) * 32;      // a TMA destination must be 128-byte aligned: 19008 -> 19072 B
+    __shared__ __align__(128) uint32_t tile[2][kStageWords];
+    __shared__ __align__(8) unsigned long long bar[2];
     __shared__ int smax[2];
     const int tid = threadIdx.x, lane = tid & 31;
     const int tx = tid & 15, r0 = (tid >> 4) * 4;
-    const int tc = blockIdx.x % A.tiles_x;
-    int tr = A.tr_first + blockIdx.x / A.tiles_x;
-    if (tr >= A.tr_skip_lo) tr += A.tr_skip_hi - A.tr_skip_lo;
-    const uint32_t bar_a = dwt_smem_u32(&bar);
+    const uint32_t bar_a[2] = {dwt_smem_u32(&bar[0]), dwt_smem_u32(&bar[1])};
+    const uint32_t tile_a[2] = {dwt_smem_u32(tile[0]), dwt_smem_u32(tile[1])};
+    int t = blockIdx.x;
     if (tid == 0) {
         smax[0] = 0; smax[1] = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a[0]));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a[1]));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)DWT_TILE_BYTES) : "memory");
-        // box origin (word, row) of the padded lattice: tile columns 64*tc-4 .. 64*tc+67, band rows 64*tr-1 .. 64*tr+64
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"(dwt_smem_u32(tile)), "l"(&tmap), "r"(bar_a), "r"(tc * DWT_TILE), "r"(tr * DWT_TILE)
-                     : "memory");
+        if (t < n_tiles) dwt_issue_tile(&tmap, A, t, tile_a[0], bar_a[0]);
     }
-    __syncthreads();                                     // barrier initialised and armed before anyone polls it
-    {
-        uint32_t ok = 0;
-        while (!ok)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(ok) : "r"(bar_a) : "memory");
-    }
+    __syncthreads();                                     // barriers initialised (and the first one armed) before anyone polls
     const int tile_off = (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
-    const long long out_off = (long long)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
-    unsigned tiemin = 0xffffffffu;
-    uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile + tile_off}, StoreGlobal{A.out + out_off, A.pitch}, &tiemin);
-    const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < A.F.tie_thresh);
-    if (flagged) mx = dwt_fix_warp(&A, tile, flagged, mx, tile_off, out_off, lane);
-    // ghost columns of the produced rows: the two threads of a row group that hold column 0 / N-1 copy their (final) cells
-    if (tx == 0 && tc == 0) {
-        uint32_t *o = A.out + out_off;
+    uint32_t mx_all = 0;
+    for (int k = 0; t < n_tiles; ++k, t += gridDim.x) {
+        const int s = k & 1;
+        // the other stage was last read in iteration k-1, which ended with a CTA barrier: free to be refilled
+        if (tid == 0 && t + (int)gridDim.x < n_tiles) dwt_issue_tile(&tmap, A, t + gridDim.x, tile_a[s ^ 1], bar_a[s ^ 1]);
+        {
+            const uint32_t parity = (uint32_t)(k >> 1) & 1u;
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(bar_a[s]), "r"(parity) : "memory");
+        }
+        const int tc = t % A.tiles_x;
+        int tr = A.tr_first + t / A.tiles_x;
+        if (tr >= A.tr_skip_lo) tr += A.tr_skip_hi - A.tr_skip_lo;
+        const long long out_off = (long long)(tr * DWT_TILE + 1 + r0) * A.pitch + 4 + tc * DWT_TILE + 4 * tx;
+        unsigned tiemin = 0xffffffffu;
+        uint32_t mx = dw_tile_core(A.F, A.C, RowsTile72{tile[s] + tile_off}, StoreGlobal{A.out + out_off, A.pitch}, &tiemin);
+        const unsigned flagged = __ballot_sync(0xffffffffu, tiemin < A.F.tie_thresh);
+        if (flagged) mx = dwt_fix_warp(&A, tile[s], flagged, mx, tile_off, out_off, lane);
+        // ghost columns of the produced rows: the two threads of a row group that hold column 0 / N-1 copy their (final) cells
+        if (tx == 0 && tc == 0) {
+            uint32_t *o = A.out + out_off;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[(size_t)i * A.pitch + A.N] = o[(size_t)i * A.pitch];
-    } else if (tx == 15 && tc == A.tiles_x - 1) {
-        uint32_t *o = A.out + out_off + 3;
+            for (int i = 0; i < 4; ++i) o[(size_t)i * A.pitch + A.N] = o[(size_t)i * A.pitch];
+        } else if (tx == 15 && tc == A.tiles_x - 1) {
+            uint32_t *o = A.out + out_off + 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[(size_t)i * A.pitch - A.N] = o[(size_t)i * A.pitch];
+            for (int i = 0; i < 4; ++i) o[(size_t)i * A.pitch - A.N] = o[(size_t)i * A.pitch];
+        }
+        mx_all = __vmaxu2(mx_all, mx);
+        __syncthreads();                                 // every read of tile[s] is done before the next iteration refills it
     }
-    const unsigned ml = __reduce_max_sync(0xffffffffu, mx & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx >> 16);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, mx_all & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx_all >> 16);
     if (lane == 0) { atomicMax(&smax[0], (int)ml); atomicMax(&smax[1], (int)md); }
     __syncthreads();
     if (tid == 0) {
