@@ -504,16 +504,17 @@ __device__ __forceinline__ void dwt_issue_tile(const CUtensorMap *tmap, const Ti
                  : "memory");
 }
 
+template <int STAGES>        // 1: the default one-tile-per-CTA launch (19 KB of shared memory); 2: persistent form with prefetch
 __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledArgs A,
                                                        int n_tiles) {
     constexpr int kStageWords = ((DWT_TILE_BYTES + 127) / 128) * 32;      // a TMA destination must be 128-byte aligned: 19008 -> 19072 B
-    __shared__ __align__(128) uint32_t tile[2][kStageWords];
+    __shared__ __align__(128) uint32_t tile[STAGES][kStageWords];
     __shared__ __align__(8) unsigned long long bar[2];
     __shared__ int smax[2];
     const int tid = threadIdx.x, lane = tid & 31;
     const int tx = tid & 15, r0 = (tid >> 4) * 4;
     const uint32_t bar_a[2] = {dwt_smem_u32(&bar[0]), dwt_smem_u32(&bar[1])};
-    const uint32_t tile_a[2] = {dwt_smem_u32(tile[0]), dwt_smem_u32(tile[1])};
+    const uint32_t tile_a[2] = {dwt_smem_u32(tile[0]), dwt_smem_u32(tile[STAGES - 1])};
     int t = blockIdx.x;
     if (tid == 0) {
         smax[0] = 0; smax[1] = 0;
@@ -526,11 +527,11 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
     const int tile_off = (1 + r0) * DWT_TILE_PITCH + 4 + 4 * tx;
     uint32_t mx_all = 0;
     for (int k = 0; t < n_tiles; ++k, t += gridDim.x) {
-        const int s = k & 1;
+        const int s = STAGES == 2 ? (k & 1) : 0;
         // the other stage was last read in iteration k-1, which ended with a CTA barrier: free to be refilled
-        if (tid == 0 && t + (int)gridDim.x < n_tiles) dwt_issue_tile(&tmap, A, t + gridDim.x, tile_a[s ^ 1], bar_a[s ^ 1]);
+        if (STAGES == 2 && tid == 0 && t + (int)gridDim.x < n_tiles) dwt_issue_tile(&tmap, A, t + gridDim.x, tile_a[s ^ 1], bar_a[s ^ 1]);
         {
-            const uint32_t parity = (uint32_t)(k >> 1) & 1u;
+            const uint32_t parity = (uint32_t)(STAGES == 2 ? (k >> 1) : k) & 1u;
             uint32_t ok = 0;
             while (!ok)
                 asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -556,6 +557,7 @@ __global__ void __launch_bounds__(256, 4) k_tiled_step(const __grid_constant__ C
         }
         mx_all = __vmaxu2(mx_all, mx);
         __syncthreads();                                 // every read of tile[s] is done before the next iteration refills it
+        if (STAGES == 1 && tid == 0 && t + (int)gridDim.x < n_tiles) dwt_issue_tile(&tmap, A, t + gridDim.x, tile_a[0], bar_a[0]);
     }
     const unsigned ml = __reduce_max_sync(0xffffffffu, mx_all & 0xffffu), md = __reduce_max_sync(0xffffffffu, mx_all >> 16);
     if (lane == 0) { atomicMax(&smax[0], (int)ml); atomicMax(&smax[1], (int)md); }

@@ -377,7 +377,9 @@ extern "C" int dwt_stencil(dwt_handle *h, int32_t part) {
         }
         if (rows_of_tiles > 0) {
             const int n_tiles = A.tiles_x * rows_of_tiles;
-            k_tiled_step<<<dwt_stencil_grid(h, n_tiles), 256, 0, st>>>(h->tmap[1 - h->cur], A, n_tiles);
+            const int sgrid = dwt_stencil_grid(h, n_tiles);
+            if (sgrid == n_tiles) k_tiled_step<1><<<sgrid, 256, 0, st>>>(h->tmap[1 - h->cur], A, n_tiles);
+            else k_tiled_step<2><<<sgrid, 256, 0, st>>>(h->tmap[1 - h->cur], A, n_tiles);
             DWT_LAUNCHED(h);
         }
         if (part != 2) h->pre_is_planes = false;
@@ -562,9 +564,10 @@ extern "C" int dwt_debug_time_stencil(dwt_handle *h, int32_t reps, double *us_pe
     DWT_TRY(h, cudaEventCreate(&e0));
     DWT_TRY(h, cudaEventCreate(&e1));
     const int n_tiles = A.tiles_x * tiles_y, sgrid = dwt_stencil_grid(h, n_tiles);
-    k_tiled_step<<<sgrid, 256, 0, h->stream>>>(h->tmap[h->cur], A, n_tiles);      // warm-up
+    void (*kern)(const CUtensorMap, const TiledArgs, int) = sgrid == n_tiles ? k_tiled_step<1> : k_tiled_step<2>;
+    kern<<<sgrid, 256, 0, h->stream>>>(h->tmap[h->cur], A, n_tiles);      // warm-up
     DWT_TRY(h, cudaEventRecord(e0, h->stream));
-    for (int r = 0; r < reps; ++r) k_tiled_step<<<sgrid, 256, 0, h->stream>>>(h->tmap[h->cur], A, n_tiles);
+    for (int r = 0; r < reps; ++r) kern<<<sgrid, 256, 0, h->stream>>>(h->tmap[h->cur], A, n_tiles);
     DWT_LAUNCHED(h);
     DWT_TRY(h, cudaEventRecord(e1, h->stream));
     DWT_TRY(h, cudaEventSynchronize(e1));
@@ -653,7 +656,7 @@ extern "C" int dwt_attach_peers(dwt_handle *h, int32_t rank, int32_t n_ranks, vo
         cudaFuncAttributes fa;
         const void *ks[] = {(const void *)k_band_decide<LatCells>, (const void *)k_band_decide<PlaneCells>, (const void *)k_band_move_claim,
                             (const void *)k_band_graze<LatCells>, (const void *)k_band_graze<PlaneCells>, (const void *)k_band_finish,
-                            (const void *)k_band_first_step, (const void *)k_tiled_step, (const void *)k_band_push_halo,
+                            (const void *)k_band_first_step, (const void *)k_tiled_step<1>, (const void *)k_tiled_step<2>, (const void *)k_band_push_halo,
                             (const void *)k_band_finish_move_claim, (const void *)k_band_fmc_graze, (const void *)k_band_lookahead_decide,
                             (const void *)k_peer_barrier, (const void *)k_band_covers, (const void *)k_band_materialise<PreLattice>,
                             (const void *)k_band_materialise<PrePlanes>, (const void *)k_band_stamp_claim, (const void *)k_band_stamp_write,
